@@ -1,0 +1,206 @@
+/*
+ * pcr_b200.h -- C ABI of the B200-native k-nearest-neighbour engine that replaces the KNN hot
+ * path of nahomes-15/pointclouds-rs ("pcrs").  Plain pointers and sizes only; no C++/torch types.
+ *
+ * What each entry point replaces (reference file:line, relative to the pcrs repository root):
+ *
+ *   pcr_index_build / pcr_index_free / pcr_index_len
+ *       pointclouds_spatial::KdTree::{build,len,is_empty}      crates/spatial/src/kdtree.rs:25-54
+ *   pcr_knn                     KdTree::knn / knn_indices       crates/spatial/src/kdtree.rs:64-96
+ *   pcr_radius_count / pcr_radius_search
+ *       KdTree::radius_search[_unsorted]                        crates/spatial/src/kdtree.rs:105-163
+ *   pcr_sor                     statistical_outlier_removal     crates/filters/src/statistical_outlier.rs:4-69
+ *   pcr_radius_outlier          radius_outlier_removal          crates/filters/src/radius_outlier.rs:4-18
+ *   pcr_estimate_normals        estimate_normals_with_viewpoint crates/normals/src/estimate.rs:19-124,139-238
+ *   pcr_find_correspondences    find_correspondences            crates/registration/src/correspondence.rs:16-39
+ *   pcr_apply_transform         apply_transform                 crates/registration/src/icp.rs:39-47,77-92
+ *   pcr_icp_point_to_point      icp_point_to_point              crates/registration/src/icp.rs:125-282
+ *   pcr_icp_point_to_plane      icp_point_to_plane              crates/registration/src/icp_plane.rs:20-97,131-236
+ *   pcr_sor_normals_batch       the SOR -> normals chain of the demo pipelines, per frame
+ *                               (examples/python/kitti_obstacle_detection.py:99-101)
+ *
+ * The reference calls its kd-tree once per point inside serial loops; a per-query C call would be
+ * useless on a GPU, so the boundary is BATCHED and sits one level up: it replaces the bodies of the
+ * consumer functions and offers a batched form of the KdTree queries.  Results follow the
+ * reference on the same inputs: KNN index lists are exact under an ascending (d^2, index) order
+ * (kiddo leaves ties unspecified), d^2 = ((dx*dx)+(dy*dy))+(dz*dz) in f32 without FMA.
+ *
+ * Conventions
+ *   - Clouds are SoA: three f32 arrays x/y/z of n elements (PointCloud, crates/core/src/cloud.rs:4-11).
+ *   - The caller owns every buffer; pointers need to stay valid only for the duration of the call.
+ *     Outputs go to caller-allocated buffers.  The library only allocates the opaque handles.
+ *   - Every function returns a pcr_status (0 = ok).  pcr_last_error() gives the message.  No C++
+ *     exception and no sticky CUDA error crosses this boundary.  There is NO CPU fallback: without
+ *     a usable CUDA device the calls fail with PCR_ERR_NO_DEVICE / PCR_ERR_CUDA.
+ *   - Calls are synchronous (they return after the context's stream has drained) unless the name
+ *     ends in _async.  A pcr_ctx is single-caller: use one context per host thread.
+ *   - *_dev variants take DEVICE pointers (same layouts) and are enqueued on the context's stream
+ *     without host<->device copies; pcr_ctx_synchronize() waits for them.
+ *   - Non-finite points are left out of the index and are never returned as neighbours; as queries
+ *     they give empty results exactly like kdtree.rs:65 / statistical_outlier.rs:22-24.
+ */
+#ifndef PCR_B200_H
+#define PCR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCR_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum pcr_status {
+    PCR_OK = 0,
+    PCR_ERR_INVALID_ARG = 1,      /* null pointer, bad size, non-finite parameter */
+    PCR_ERR_NORMALS_MISMATCH = 2, /* IcpPlaneError::NormalsMismatch, icp_plane.rs:100-107 */
+    PCR_ERR_CUDA = 3,
+    PCR_ERR_NCCL = 4,
+    PCR_ERR_OOM = 5,
+    PCR_ERR_NO_DEVICE = 6,
+    PCR_ERR_UNSUPPORTED = 7,      /* e.g. k above PCR_MAX_K */
+    PCR_ERR_CAPACITY = 8          /* caller buffer too small (radius_search) */
+} pcr_status;
+
+#define PCR_MAX_K 1024 /* largest k accepted by the KNN kernels */
+
+typedef struct pcr_ctx pcr_ctx;     /* device, stream, scratch memory, optional NCCL communicator */
+typedef struct pcr_index pcr_index; /* uniform-grid index over one cloud, resident in HBM */
+
+/* ---- context ------------------------------------------------------------------------------- */
+int pcr_version(void);
+/* Number of visible CUDA devices (0 when there is none or the driver is missing). */
+int pcr_device_count(void);
+int pcr_ctx_create(int device, pcr_ctx **out);
+/* Same, but enqueue everything on an existing cudaStream_t (passed as void*), e.g. the current
+ * stream of the embedding framework.  The stream must outlive the context. */
+int pcr_ctx_create_on_stream(int device, void *cuda_stream, pcr_ctx **out);
+void pcr_ctx_destroy(pcr_ctx *ctx);
+int pcr_ctx_synchronize(pcr_ctx *ctx);
+/* Message of the last failure on this context (ctx == NULL: last failure of a create call on the
+ * calling thread).  Never NULL. */
+const char *pcr_last_error(const pcr_ctx *ctx);
+/* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
+uint64_t pcr_ctx_launch_count(const pcr_ctx *ctx);
+/* Tuning: force the grid cell size (metres) for subsequent index builds; 0 = automatic. */
+int pcr_ctx_set_cell_size(pcr_ctx *ctx, float cell_size);
+
+/* ---- multi-GPU (one process per GPU; the host exchanges the id, e.g. torch.distributed) ------ */
+#define PCR_UNIQUE_ID_BYTES 128
+int pcr_comm_unique_id(void *out_id /* PCR_UNIQUE_ID_BYTES */);
+int pcr_ctx_comm_init(pcr_ctx *ctx, const void *id, int rank, int world_size);
+int pcr_ctx_comm_rank(const pcr_ctx *ctx);
+int pcr_ctx_comm_size(const pcr_ctx *ctx);
+
+/* ---- spatial index (KdTree) ------------------------------------------------------------------ */
+/* k_hint: the k the index will mostly be queried with (0 = unknown); only steers the cell size. */
+int pcr_index_build(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n,
+                    size_t k_hint, pcr_index **out);
+int pcr_index_build_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n,
+                        size_t k_hint, pcr_index **out);
+void pcr_index_free(pcr_index *index);
+size_t pcr_index_len(const pcr_index *index); /* points of the cloud, kdtree.rs:47-49 */
+/* Grid description for diagnostics: cell size, dims[3], indexed (finite) point count. */
+int pcr_index_info(const pcr_index *index, float *cell_size, int32_t dims[3], size_t *n_indexed);
+
+/* KdTree::knn for nq queries at once.  idx, dist: row-major nq x k; row q holds counts[q] =
+ * min(k, indexed points) valid entries in ascending (distance, index) order (0 for a non-finite
+ * query or k == 0 or an empty cloud), the rest is padded with UINT32_MAX / +INF.  dist is the
+ * Euclidean distance sqrt(d^2) (kdtree.rs:76).  dist and counts may be NULL (knn_indices). */
+int pcr_knn(pcr_index *index, const float *qx, const float *qy, const float *qz, size_t nq,
+            size_t k, uint32_t *idx, float *dist, uint32_t *counts);
+int pcr_knn_dev(pcr_index *index, const float *d_qx, const float *d_qy, const float *d_qz, size_t nq,
+                size_t k, uint32_t *d_idx, float *d_dist, uint32_t *d_counts);
+
+/* radius_search_unsorted(q, r).len() per query (d^2 <= r*r, r*r rounded in f32; 0 if r <= 0,
+ * r non-finite or q non-finite, kdtree.rs:106-112). */
+int pcr_radius_count(pcr_index *index, const float *qx, const float *qy, const float *qz, size_t nq,
+                     float radius, uint32_t *counts);
+/* radius_search in CSR form: offsets[nq+1], idx[offsets[q]..offsets[q+1]) ascending by index
+ * (kdtree.rs:132).  *total receives offsets[nq]; if it exceeds cap nothing is written to idx and
+ * PCR_ERR_CAPACITY is returned (call again with a larger buffer). */
+int pcr_radius_search(pcr_index *index, const float *qx, const float *qy, const float *qz, size_t nq,
+                      float radius, uint64_t *offsets, uint32_t *idx, size_t cap, size_t *total);
+
+/* ---- filters ----------------------------------------------------------------------------------- */
+/* statistical_outlier_removal up to (not including) cloud.select(): keep[i] = 1 iff point i
+ * survives; *n_kept = number of ones.  mean_d (may be NULL) receives the per-point mean neighbour
+ * distance (INF for non-finite points).  stats (may be NULL) receives {global_mean,
+ * global_stddev, threshold}.  Empty cloud or k == 0: all zeros (the reference returns an empty
+ * cloud); n == 1: keep[0] = 1. */
+int pcr_sor(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n, size_t k,
+            float std_mul, uint8_t *keep, size_t *n_kept, float *mean_d, float *stats);
+int pcr_sor_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n,
+                size_t k, float std_mul, uint8_t *d_keep, float *d_mean_d /* may be NULL */);
+/* radius_outlier_removal: keep[i] = 1 iff #{j : d^2(i,j) <= r^2} >= min_neighbors (self counts). */
+int pcr_radius_outlier(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n,
+                       float radius, size_t min_neighbors, uint8_t *keep, size_t *n_kept);
+
+/* ---- normals ----------------------------------------------------------------------------------- */
+int pcr_estimate_normals(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n,
+                         size_t k, const float viewpoint[3], float *nx, float *ny, float *nz);
+int pcr_estimate_normals_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z,
+                             size_t n, size_t k, const float viewpoint[3], float *d_nx, float *d_ny,
+                             float *d_nz);
+
+/* ---- registration ------------------------------------------------------------------------------ */
+typedef struct pcr_icp_params { /* IcpParams, icp.rs:95-109 (defaults 50, 1e-5, INF) */
+    uint64_t max_iterations;
+    float tolerance;
+    float max_correspondence_distance;
+} pcr_icp_params;
+
+typedef struct pcr_icp_result { /* IcpResult + RigidTransform, icp.rs:8-11,112-118 */
+    float rotation[9];          /* row-major 3x3 */
+    float translation[3];
+    float fitness;
+    float rmse;
+    int32_t converged;
+    uint64_t num_iterations;
+} pcr_icp_result;
+
+/* Outputs sized ns; *count receives the number of correspondences (source order). */
+int pcr_find_correspondences(pcr_index *target, const float *sx, const float *sy, const float *sz,
+                             size_t ns, float max_distance, uint32_t *src_idx, uint32_t *tgt_idx,
+                             float *dist, size_t *count);
+int pcr_apply_transform(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n,
+                        const float rotation[9], const float translation[3], float *ox, float *oy,
+                        float *oz);
+int pcr_icp_point_to_point(pcr_ctx *ctx, const float *sx, const float *sy, const float *sz, size_t ns,
+                           const float *tx, const float *ty, const float *tz, size_t nt,
+                           const pcr_icp_params *params, pcr_icp_result *result);
+/* n_normals != nt -> PCR_ERR_NORMALS_MISMATCH (icp_plane.rs:27-32).  With a communicator
+ * (pcr_ctx_comm_init) every rank passes ITS shard of the source and the full target; the 6x6
+ * system is all-reduced each iteration and every rank returns the same result. */
+int pcr_icp_point_to_plane(pcr_ctx *ctx, const float *sx, const float *sy, const float *sz, size_t ns,
+                           const float *tx, const float *ty, const float *tz, size_t nt,
+                           const float *nx, const float *ny, const float *nz, size_t n_normals,
+                           const pcr_icp_params *params, pcr_icp_result *result);
+int pcr_icp_point_to_point_dev(pcr_ctx *ctx, const float *d_sx, const float *d_sy, const float *d_sz,
+                               size_t ns, const float *d_tx, const float *d_ty, const float *d_tz,
+                               size_t nt, const pcr_icp_params *params, pcr_icp_result *result);
+int pcr_icp_point_to_plane_dev(pcr_ctx *ctx, const float *d_sx, const float *d_sy, const float *d_sz,
+                               size_t ns, const float *d_tx, const float *d_ty, const float *d_tz,
+                               size_t nt, const float *d_nx, const float *d_ny, const float *d_nz,
+                               size_t n_normals, const pcr_icp_params *params, pcr_icp_result *result);
+
+/* ---- multi-frame batch (BASELINE config 5) ------------------------------------------------------
+ * Frames are independent clouds stored back to back: frame f = points [frame_offsets[f],
+ * frame_offsets[f+1]).  Per frame: SOR(k_sor, std_mul) then normals(k_normals, viewpoint) on the
+ * KEPT points (the reference rebuilds its tree on the filtered cloud).  keep: one byte per input
+ * point.  nx/ny/nz: one entry per input point; entries of removed points are set to 0. */
+int pcr_sor_normals_batch(pcr_ctx *ctx, const float *x, const float *y, const float *z,
+                          const uint64_t *frame_offsets, size_t n_frames, size_t k_sor,
+                          float std_mul, size_t k_normals, const float viewpoint[3], uint8_t *keep,
+                          float *nx, float *ny, float *nz, uint64_t *n_kept_per_frame);
+int pcr_sor_normals_batch_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z,
+                              const uint64_t *frame_offsets /* HOST */, size_t n_frames,
+                              size_t k_sor, float std_mul, size_t k_normals,
+                              const float viewpoint[3], uint8_t *d_keep, float *d_nx, float *d_ny,
+                              float *d_nz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCR_B200_H */

@@ -1,0 +1,448 @@
+"""pointclouds_rs_b200 -- B200-native drop-in for the KNN hot path of pointclouds-rs ("pcrs").
+
+The module mirrors the names and argument meaning of the reference's PyO3 module `pointclouds_rs`
+(crates/python/src/lib.rs:12-49) for the functions that sit on the KNN path:
+
+    PointCloud                                    crates/python/src/cloud.rs:10-88
+    statistical_outlier_removal(cloud, k, std_mul)      crates/python/src/filters.rs:36-49
+    radius_outlier_removal(cloud, radius, min_neighbors) crates/python/src/filters.rs:51-66
+    estimate_normals(cloud, k)                          crates/python/src/normals.rs:4-10
+    icp_point_to_point / icp_point_to_plane / apply_transform / IcpResult
+                                                        crates/python/src/registration.rs:4-109
+    KdTree (batched)                                    crates/spatial/src/kdtree.rs:14-164
+
+Everything runs through the C ABI (include/pcr_b200.h) of lib/libpcr_b200.so: hand-written sm_100a
+CUDA, no PyTorch on the path, no CPU fallback.  Functions outside the KNN path (voxel_downsample,
+passthrough_filter, ransac_plane, euclidean_cluster, file IO) are out of scope here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import PcrError  # noqa: F401
+
+__all__ = [
+    "PointCloud", "KdTree", "IcpResult", "Context",
+    "statistical_outlier_removal", "radius_outlier_removal", "estimate_normals",
+    "icp_point_to_point", "icp_point_to_plane", "apply_transform", "find_correspondences",
+    "sor_normals_batch", "default_context", "PcrError",
+]
+
+
+def _p(a: Optional[np.ndarray], t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+class Context:
+    """Owns a pcr_ctx (device, stream, scratch).  One per host thread."""
+
+    def __init__(self, device: Optional[int] = None, stream: Optional[int] = None):
+        lib = _ffi.load()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+            if lib.pcr_device_count() and device >= lib.pcr_device_count():
+                device = 0
+        h = C.c_void_p()
+        if stream is None:
+            st = lib.pcr_ctx_create(device, C.byref(h))
+        else:
+            st = lib.pcr_ctx_create_on_stream(device, C.c_void_p(stream), C.byref(h))
+        _ffi.check(st)
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _ffi.load().pcr_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        _ffi.check(_ffi.load().pcr_ctx_synchronize(self._h), self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(_ffi.load().pcr_ctx_launch_count(self._h))
+
+    def set_cell_size(self, cell: float):
+        _ffi.check(_ffi.load().pcr_ctx_set_cell_size(self._h, float(cell)), self._h)
+
+    # multi-GPU: the host exchanges the id (e.g. torch.distributed.broadcast_object_list)
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(_ffi.PCR_UNIQUE_ID_BYTES)
+        _ffi.check(_ffi.load().pcr_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, world_size: int):
+        buf = C.create_string_buffer(uid, _ffi.PCR_UNIQUE_ID_BYTES)
+        _ffi.check(_ffi.load().pcr_ctx_comm_init(self._h, buf, rank, world_size), self._h)
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+def _soa(a: np.ndarray):
+    x = np.ascontiguousarray(a[:, 0])
+    y = np.ascontiguousarray(a[:, 1])
+    z = np.ascontiguousarray(a[:, 2])
+    return x, y, z
+
+
+class PointCloud:
+    """SoA point cloud (crates/core/src/cloud.rs:4-11) with the PyO3 class's surface."""
+
+    def __init__(self):
+        self.x = np.empty(0, np.float32)
+        self.y = np.empty(0, np.float32)
+        self.z = np.empty(0, np.float32)
+        self.normals: Optional[np.ndarray] = None  # (N,3) f32
+
+    @staticmethod
+    def _from_xyz(x, y, z, normals=None) -> "PointCloud":
+        pc = PointCloud()
+        pc.x, pc.y, pc.z = x, y, z
+        pc.normals = normals
+        return pc
+
+    @staticmethod
+    def from_numpy(array) -> "PointCloud":
+        # crates/python/src/cloud.rs:25-37,91-137
+        if not isinstance(array, np.ndarray) or array.dtype not in (np.float32, np.float64):
+            raise TypeError("expected NumPy array with dtype float32 or float64, shape (N, 3)")
+        if array.ndim != 2:
+            raise TypeError("expected NumPy array with dtype float32 or float64, shape (N, 3)")
+        if not array.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous (row-major). Use numpy.ascontiguousarray(arr) to convert.")
+        if array.shape[1] != 3:
+            raise ValueError("expected shape (N, 3)")
+        a = array.astype(np.float32, copy=False)
+        return PointCloud._from_xyz(*_soa(a))
+
+    def to_numpy(self) -> np.ndarray:
+        return np.stack([self.x, self.y, self.z], axis=1) if len(self.x) else np.zeros((0, 3), np.float32)
+
+    def normals_to_numpy(self) -> Optional[np.ndarray]:
+        """Superset of the reference surface (it has no accessor for normals)."""
+        return None if self.normals is None else self.normals.copy()
+
+    def len(self) -> int:
+        return int(len(self.x))
+
+    def is_empty(self) -> bool:
+        return len(self.x) == 0
+
+    def __len__(self) -> int:
+        return int(len(self.x))
+
+    def __repr__(self) -> str:
+        return f"PointCloud(n={len(self.x)})"
+
+    def select(self, indices: Sequence[int]) -> "PointCloud":
+        idx = np.asarray(indices, dtype=np.int64).reshape(-1)
+        n = len(self.x)
+        bad = idx[(idx >= n) | (idx < 0)]
+        if len(bad):
+            raise IndexError(f"index {int(bad[0])} out of bounds for cloud with {n} points")
+        nr = None if self.normals is None else self.normals[idx]
+        return PointCloud._from_xyz(self.x[idx], self.y[idx], self.z[idx], nr)
+
+    def select_inverse(self, indices: Sequence[int]) -> "PointCloud":
+        idx = np.asarray(indices, dtype=np.int64).reshape(-1)
+        n = len(self.x)
+        bad = idx[(idx >= n) | (idx < 0)]
+        if len(bad):
+            raise IndexError(f"index {int(bad[0])} out of bounds for cloud with {n} points")
+        keep = np.ones(n, bool)
+        keep[idx] = False
+        return self.select(np.nonzero(keep)[0])
+
+
+class KdTree:
+    """Batched form of pointclouds_spatial::KdTree: a uniform-grid index resident in HBM."""
+
+    def __init__(self, cloud: PointCloud, k_hint: int = 0, ctx: Optional[Context] = None):
+        self._ctx = ctx or default_context()
+        lib = _ffi.load()
+        h = C.c_void_p()
+        self._n = len(cloud)
+        st = lib.pcr_index_build(self._ctx._h, _p(cloud.x, _ffi.f32p), _p(cloud.y, _ffi.f32p), _p(cloud.z, _ffi.f32p),
+                                 self._n, k_hint, C.byref(h))
+        _ffi.check(st, self._ctx._h)
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _ffi.load().pcr_index_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def len(self) -> int:
+        return int(_ffi.load().pcr_index_len(self._h))
+
+    __len__ = len
+
+    def is_empty(self) -> bool:
+        return self.len() == 0
+
+    def info(self):
+        cell = C.c_float()
+        dims = (C.c_int32 * 3)()
+        n_idx = C.c_size_t()
+        _ffi.check(_ffi.load().pcr_index_info(self._h, C.byref(cell), dims, C.byref(n_idx)))
+        return {"cell_size": cell.value, "dims": list(dims), "n_indexed": n_idx.value}
+
+    def knn(self, queries: np.ndarray, k: int):
+        """-> (idx (nq,k) u32, dist (nq,k) f32, counts (nq,) u32); rows padded with UINT32_MAX / inf."""
+        q = np.ascontiguousarray(np.asarray(queries, np.float32).reshape(-1, 3))
+        qx, qy, qz = _soa(q)
+        nq = len(qx)
+        idx = np.full((nq, max(k, 0)), 0xFFFFFFFF, np.uint32)
+        dist = np.full((nq, max(k, 0)), np.inf, np.float32)
+        cnt = np.zeros(nq, np.uint32)
+        st = _ffi.load().pcr_knn(self._h, _p(qx, _ffi.f32p), _p(qy, _ffi.f32p), _p(qz, _ffi.f32p), nq, k,
+                                 _p(idx, _ffi.u32p), _p(dist, _ffi.f32p), _p(cnt, _ffi.u32p))
+        _ffi.check(st, self._ctx._h)
+        return idx, dist, cnt
+
+    def knn_indices(self, queries: np.ndarray, k: int):
+        q = np.ascontiguousarray(np.asarray(queries, np.float32).reshape(-1, 3))
+        qx, qy, qz = _soa(q)
+        nq = len(qx)
+        idx = np.full((nq, max(k, 0)), 0xFFFFFFFF, np.uint32)
+        cnt = np.zeros(nq, np.uint32)
+        st = _ffi.load().pcr_knn(self._h, _p(qx, _ffi.f32p), _p(qy, _ffi.f32p), _p(qz, _ffi.f32p), nq, k,
+                                 _p(idx, _ffi.u32p), None, _p(cnt, _ffi.u32p))
+        _ffi.check(st, self._ctx._h)
+        return idx, cnt
+
+    def radius_count(self, queries: np.ndarray, radius: float) -> np.ndarray:
+        q = np.ascontiguousarray(np.asarray(queries, np.float32).reshape(-1, 3))
+        qx, qy, qz = _soa(q)
+        cnt = np.zeros(len(qx), np.uint32)
+        st = _ffi.load().pcr_radius_count(self._h, _p(qx, _ffi.f32p), _p(qy, _ffi.f32p), _p(qz, _ffi.f32p), len(qx),
+                                          float(radius), _p(cnt, _ffi.u32p))
+        _ffi.check(st, self._ctx._h)
+        return cnt
+
+    def radius_search(self, queries: np.ndarray, radius: float):
+        """CSR: (offsets (nq+1,) u64, idx u32) with every row ascending by index (kdtree.rs:132)."""
+        q = np.ascontiguousarray(np.asarray(queries, np.float32).reshape(-1, 3))
+        qx, qy, qz = _soa(q)
+        nq = len(qx)
+        off = np.zeros(nq + 1, np.uint64)
+        total = C.c_size_t()
+        cap = max(16 * nq, 1024)
+        lib = _ffi.load()
+        for _ in range(2):
+            idx = np.empty(cap, np.uint32)
+            st = lib.pcr_radius_search(self._h, _p(qx, _ffi.f32p), _p(qy, _ffi.f32p), _p(qz, _ffi.f32p), nq, float(radius),
+                                       _p(off, _ffi.u64p), _p(idx, _ffi.u32p), cap, C.byref(total))
+            if st == _ffi.PCR_ERR_CAPACITY:
+                cap = int(total.value)
+                continue
+            _ffi.check(st, self._ctx._h)
+            return off, idx[: total.value].copy()
+        raise PcrError(_ffi.PCR_ERR_CAPACITY, "radius_search: capacity retry failed")
+
+    def find_correspondences(self, source: PointCloud, max_distance: float = math.inf):
+        ns = len(source)
+        si = np.empty(max(ns, 1), np.uint32)
+        ti = np.empty(max(ns, 1), np.uint32)
+        dd = np.empty(max(ns, 1), np.float32)
+        m = C.c_size_t()
+        st = _ffi.load().pcr_find_correspondences(self._h, _p(source.x, _ffi.f32p), _p(source.y, _ffi.f32p), _p(source.z, _ffi.f32p),
+                                                  ns, float(max_distance), _p(si, _ffi.u32p), _p(ti, _ffi.u32p), _p(dd, _ffi.f32p),
+                                                  C.byref(m))
+        _ffi.check(st, self._ctx._h)
+        return si[: m.value].copy(), ti[: m.value].copy(), dd[: m.value].copy()
+
+
+def find_correspondences(source: PointCloud, target_tree: KdTree, max_distance: float = math.inf):
+    return target_tree.find_correspondences(source, max_distance)
+
+
+# ---------------------------------------------------------------------------------------------------
+# filters
+# ---------------------------------------------------------------------------------------------------
+
+def sor_mask(cloud: PointCloud, k: int, std_mul: float, ctx: Optional[Context] = None, want_mean: bool = False):
+    """keep mask (u8), kept count, [mean distances], (mean, std, threshold)."""
+    ctx = ctx or default_context()
+    if not math.isfinite(std_mul) or std_mul < 0.0:  # crates/python/src/filters.rs:42-46
+        raise ValueError("std_mul must be >= 0 and finite")
+    n = len(cloud)
+    keep = np.zeros(max(n, 1), np.uint8)
+    kept = C.c_size_t()
+    mean_d = np.empty(max(n, 1), np.float32) if want_mean else None
+    stats = np.zeros(3, np.float32)
+    st = _ffi.load().pcr_sor(ctx._h, _p(cloud.x, _ffi.f32p), _p(cloud.y, _ffi.f32p), _p(cloud.z, _ffi.f32p), n, k, float(std_mul),
+                             _p(keep, _ffi.u8p), C.byref(kept), _p(mean_d, _ffi.f32p), _p(stats, _ffi.f32p))
+    _ffi.check(st, ctx._h)
+    return keep[:n], int(kept.value), (mean_d[:n] if want_mean else None), stats
+
+
+def statistical_outlier_removal(cloud: PointCloud, k: int, std_mul: float, ctx: Optional[Context] = None) -> PointCloud:
+    keep, _, _, _ = sor_mask(cloud, k, std_mul, ctx)
+    return cloud.select(np.nonzero(keep)[0])  # statistical_outlier.rs:68
+
+
+def ror_mask(cloud: PointCloud, radius: float, min_neighbors: int, ctx: Optional[Context] = None):
+    ctx = ctx or default_context()
+    if not math.isfinite(radius) or radius <= 0.0:  # crates/python/src/filters.rs:57-61
+        raise ValueError("radius must be > 0 and finite")
+    n = len(cloud)
+    keep = np.zeros(max(n, 1), np.uint8)
+    kept = C.c_size_t()
+    st = _ffi.load().pcr_radius_outlier(ctx._h, _p(cloud.x, _ffi.f32p), _p(cloud.y, _ffi.f32p), _p(cloud.z, _ffi.f32p), n,
+                                        float(radius), int(min_neighbors), _p(keep, _ffi.u8p), C.byref(kept))
+    _ffi.check(st, ctx._h)
+    return keep[:n], int(kept.value)
+
+
+def radius_outlier_removal(cloud: PointCloud, radius: float, min_neighbors: int, ctx: Optional[Context] = None) -> PointCloud:
+    keep, _ = ror_mask(cloud, radius, min_neighbors, ctx)
+    return cloud.select(np.nonzero(keep)[0])
+
+
+# ---------------------------------------------------------------------------------------------------
+# normals
+# ---------------------------------------------------------------------------------------------------
+
+def normals_array(cloud: PointCloud, k: int, viewpoint=(0.0, 0.0, 0.0), ctx: Optional[Context] = None) -> np.ndarray:
+    """estimate_normals_with_viewpoint -> (N,3) f32 (empty if the cloud is empty or k == 0)."""
+    ctx = ctx or default_context()
+    n = len(cloud)
+    if n == 0 or k == 0:
+        return np.zeros((0, 3), np.float32)
+    vp = np.asarray(viewpoint, np.float32).reshape(3)
+    nx = np.empty(n, np.float32)
+    ny = np.empty(n, np.float32)
+    nz = np.empty(n, np.float32)
+    st = _ffi.load().pcr_estimate_normals(ctx._h, _p(cloud.x, _ffi.f32p), _p(cloud.y, _ffi.f32p), _p(cloud.z, _ffi.f32p), n, k,
+                                          _p(vp, _ffi.f32p), _p(nx, _ffi.f32p), _p(ny, _ffi.f32p), _p(nz, _ffi.f32p))
+    _ffi.check(st, ctx._h)
+    return np.stack([nx, ny, nz], axis=1)
+
+
+def estimate_normals(cloud: PointCloud, k: int, ctx: Optional[Context] = None) -> PointCloud:
+    """Returns a copy of the cloud with normals attached (crates/python/src/normals.rs:4-10)."""
+    nr = normals_array(cloud, k, (0.0, 0.0, 0.0), ctx)
+    return PointCloud._from_xyz(cloud.x.copy(), cloud.y.copy(), cloud.z.copy(), nr)
+
+
+# ---------------------------------------------------------------------------------------------------
+# registration
+# ---------------------------------------------------------------------------------------------------
+
+class IcpResult:
+    def __init__(self, r: _ffi.IcpResultC):
+        self.converged = bool(r.converged)
+        self.fitness = float(np.float32(r.fitness))
+        self.rmse = float(np.float32(r.rmse))
+        self.num_iterations = int(r.num_iterations)
+        self.translation = [float(v) for v in r.translation]
+        rot = [float(v) for v in r.rotation]
+        self.rotation = [rot[0:3], rot[3:6], rot[6:9]]
+
+    def __repr__(self) -> str:
+        return f"IcpResult(converged={str(self.converged).lower()}, rmse={self.rmse:.6f}, iterations={self.num_iterations})"
+
+
+def _icp_params(max_iterations, tolerance, max_correspondence_distance):
+    # crates/python/src/registration.rs:67-72,85
+    if math.isnan(tolerance) or tolerance < 0:
+        raise ValueError("tolerance must be >= 0")
+    if math.isnan(max_correspondence_distance) or max_correspondence_distance < 0:
+        raise ValueError("max_correspondence_distance must be >= 0")
+    return _ffi.IcpParams(int(max_iterations), float(tolerance), float(max_correspondence_distance))
+
+
+def icp_point_to_point(source: PointCloud, target: PointCloud, max_iterations: int = 50, tolerance: float = 1e-5,
+                       max_correspondence_distance: float = math.inf, ctx: Optional[Context] = None) -> IcpResult:
+    ctx = ctx or default_context()
+    p = _icp_params(max_iterations, tolerance, max_correspondence_distance)
+    res = _ffi.IcpResultC()
+    st = _ffi.load().pcr_icp_point_to_point(ctx._h, _p(source.x, _ffi.f32p), _p(source.y, _ffi.f32p), _p(source.z, _ffi.f32p),
+                                            len(source), _p(target.x, _ffi.f32p), _p(target.y, _ffi.f32p), _p(target.z, _ffi.f32p),
+                                            len(target), C.byref(p), C.byref(res))
+    _ffi.check(st, ctx._h)
+    return IcpResult(res)
+
+
+def icp_point_to_plane(source: PointCloud, target: PointCloud, max_iterations: int = 50, tolerance: float = 1e-5,
+                       max_correspondence_distance: float = math.inf, ctx: Optional[Context] = None) -> IcpResult:
+    ctx = ctx or default_context()
+    if target.normals is None:  # crates/python/src/registration.rs:66-71
+        raise ValueError("target cloud must have normals for point-to-plane ICP. Use estimate_normals(target, k) first.")
+    p = _icp_params(max_iterations, tolerance, max_correspondence_distance)
+    nr = np.asarray(target.normals, np.float32).reshape(-1, 3)
+    nx, ny, nz = _soa(nr)
+    res = _ffi.IcpResultC()
+    st = _ffi.load().pcr_icp_point_to_plane(ctx._h, _p(source.x, _ffi.f32p), _p(source.y, _ffi.f32p), _p(source.z, _ffi.f32p),
+                                            len(source), _p(target.x, _ffi.f32p), _p(target.y, _ffi.f32p), _p(target.z, _ffi.f32p),
+                                            len(target), _p(nx, _ffi.f32p), _p(ny, _ffi.f32p), _p(nz, _ffi.f32p), len(nx),
+                                            C.byref(p), C.byref(res))
+    _ffi.check(st, ctx._h)
+    return IcpResult(res)
+
+
+def apply_transform(cloud: PointCloud, rotation, translation, ctx: Optional[Context] = None) -> PointCloud:
+    """R*p + t for every point; the result carries xyz only (icp.rs:77-92)."""
+    ctx = ctx or default_context()
+    n = len(cloud)
+    r = np.ascontiguousarray(np.asarray(rotation, np.float32).reshape(9))
+    t = np.ascontiguousarray(np.asarray(translation, np.float32).reshape(3))
+    ox = np.empty(n, np.float32)
+    oy = np.empty(n, np.float32)
+    oz = np.empty(n, np.float32)
+    st = _ffi.load().pcr_apply_transform(ctx._h, _p(cloud.x, _ffi.f32p), _p(cloud.y, _ffi.f32p), _p(cloud.z, _ffi.f32p), n,
+                                         _p(r, _ffi.f32p), _p(t, _ffi.f32p), _p(ox, _ffi.f32p), _p(oy, _ffi.f32p), _p(oz, _ffi.f32p))
+    _ffi.check(st, ctx._h)
+    return PointCloud._from_xyz(ox, oy, oz)
+
+
+# ---------------------------------------------------------------------------------------------------
+# multi-frame batch (BASELINE config 5)
+# ---------------------------------------------------------------------------------------------------
+
+def sor_normals_batch(points: np.ndarray, frame_offsets: Sequence[int], k_sor: int, std_mul: float, k_normals: int,
+                      viewpoint=(0.0, 0.0, 0.0), ctx: Optional[Context] = None):
+    """points: (N,3) f32 of all frames back to back. -> (keep u8 (N,), normals (N,3), kept per frame)."""
+    ctx = ctx or default_context()
+    pts = np.ascontiguousarray(np.asarray(points, np.float32).reshape(-1, 3))
+    x, y, z = _soa(pts)
+    off = np.ascontiguousarray(np.asarray(frame_offsets, np.uint64))
+    nf = len(off) - 1
+    n = len(x)
+    vp = np.asarray(viewpoint, np.float32).reshape(3)
+    keep = np.zeros(max(n, 1), np.uint8)
+    nx = np.zeros(max(n, 1), np.float32)
+    ny = np.zeros(max(n, 1), np.float32)
+    nz = np.zeros(max(n, 1), np.float32)
+    kept = np.zeros(max(nf, 1), np.uint64)
+    st = _ffi.load().pcr_sor_normals_batch(ctx._h, _p(x, _ffi.f32p), _p(y, _ffi.f32p), _p(z, _ffi.f32p), _p(off, _ffi.u64p), nf,
+                                           k_sor, float(std_mul), k_normals, _p(vp, _ffi.f32p), _p(keep, _ffi.u8p),
+                                           _p(nx, _ffi.f32p), _p(ny, _ffi.f32p), _p(nz, _ffi.f32p), _p(kept, _ffi.u64p))
+    _ffi.check(st, ctx._h)
+    return keep[:n], np.stack([nx[:n], ny[:n], nz[:n]], axis=1), kept[:nf]

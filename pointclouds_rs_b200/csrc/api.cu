@@ -1,0 +1,871 @@
+// api.cu -- the extern "C" boundary (include/pcr_b200.h): argument checks, the reference's
+// degenerate-input rules, host<->device staging, and nothing else.  Every entry point catches
+// everything: no exception and no sticky CUDA error crosses the ABI.
+#include "pcr_internal.cuh"
+
+#include <stdarg.h>
+
+#include <algorithm>
+#include <new>
+
+namespace pcr {
+
+static thread_local std::string g_thread_error = "no error";
+
+void set_thread_error(const char *msg) { g_thread_error = msg ? msg : "unknown error"; }
+
+int fail(Ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_thread_error = buf;
+    return code;
+}
+
+int ensure(Ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return PCR_OK;
+    size_t want = std::max(bytes, b.cap + b.cap / 2);
+    want = (want + 255) & ~(size_t)255;
+    if (b.p) {
+        // the old block may still be in use by work queued on the stream: free it stream-ordered
+        PCR_CUDA(ctx, cudaFreeAsync(b.p, ctx->stream));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    PCR_CUDA(ctx, cudaMallocAsync(&b.p, want, ctx->stream));
+    b.cap = want;
+    return PCR_OK;
+}
+
+int ensure_pinned(Ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_cap) return PCR_OK;
+    size_t want = std::max<size_t>(bytes, 1 << 16);
+    if (ctx->pinned) {
+        PCR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        ctx->pinned_cap = 0;
+    }
+    PCR_CUDA(ctx, cudaHostAlloc(&ctx->pinned, want, cudaHostAllocMapped | cudaHostAllocPortable));
+    ctx->pinned_cap = want;
+    return PCR_OK;
+}
+
+namespace {
+
+void free_buf(Ctx *ctx, DevBuf &b) {
+    if (b.p) cudaFreeAsync(b.p, ctx->stream);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+int ctx_create(int device, void *stream, bool have_stream, Ctx **out) {
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, PCR_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= count) return fail(nullptr, PCR_ERR_INVALID_ARG, "device %d out of range [0,%d)", device, count);
+    Ctx *ctx = new (std::nothrow) Ctx();
+    if (!ctx) return fail(nullptr, PCR_ERR_OOM, "host allocation failed");
+    ctx->device = device;
+    struct Guard {
+        Ctx *c;
+        ~Guard() { delete c; }
+    } g{ctx};
+    PCR_CUDA(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PCR_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, PCR_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    ctx->sm_count = prop.multiProcessorCount;
+    if (have_stream) {
+        ctx->stream = (cudaStream_t)stream;
+        ctx->owns_stream = false;
+    } else {
+        PCR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->owns_stream = true;
+    }
+    // keep freed blocks in the stream-ordered pool: index builds allocate and free every call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+    PCR_TRY(ensure_pinned(ctx, 1 << 16));
+    g.c = nullptr;
+    *out = ctx;
+    return PCR_OK;
+}
+
+struct DevSetter {  // every entry point runs on the context's device
+    int prev = -1;
+    explicit DevSetter(Ctx *c) {
+        cudaGetDevice(&prev);
+        if (prev != c->device) cudaSetDevice(c->device);
+        else prev = -1;
+    }
+    ~DevSetter() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// stage three host arrays into one device buffer: returns device pointers
+int stage_xyz(Ctx *ctx, DevBuf &buf, const float *x, const float *y, const float *z, size_t n, float **dx, float **dy, float **dz) {
+    size_t stride = (n + 63) & ~(size_t)63;  // keeps every array 256 B aligned
+    PCR_TRY(ensure(ctx, buf, sizeof(float) * 3 * std::max<size_t>(stride, 64)));
+    float *base = (float *)buf.p;
+    *dx = base;
+    *dy = base + stride;
+    *dz = base + 2 * stride;
+    if (n) {
+        PCR_CUDA(ctx, cudaMemcpyAsync(*dx, x, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+        PCR_CUDA(ctx, cudaMemcpyAsync(*dy, y, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+        PCR_CUDA(ctx, cudaMemcpyAsync(*dz, z, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return PCR_OK;
+}
+
+#define PCR_API_BEGIN try {
+#define PCR_API_END(ctx_expr)                                                         \
+    }                                                                                 \
+    catch (const std::bad_alloc &) { return pcr::fail((ctx_expr), PCR_ERR_OOM, "host allocation failed"); } \
+    catch (...) { return pcr::fail((ctx_expr), PCR_ERR_CUDA, "unexpected C++ exception"); }
+
+}  // namespace
+}  // namespace pcr
+
+using namespace pcr;
+
+struct pcr_ctx {
+    Ctx c;
+};
+struct pcr_index {
+    Index *ix;
+    pcr_ctx *owner;
+};
+
+extern "C" {
+
+int pcr_version(void) { return PCR_B200_VERSION; }
+
+int pcr_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return count;
+}
+
+const char *pcr_last_error(const pcr_ctx *ctx) {
+    if (ctx && !ctx->c.err.empty()) return ctx->c.err.c_str();
+    return g_thread_error.c_str();
+}
+
+static int create_common(int device, void *stream, bool have, pcr_ctx **out) {
+    if (!out) return fail(nullptr, PCR_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    PCR_API_BEGIN
+    Ctx *c = nullptr;
+    PCR_TRY(ctx_create(device, stream, have, &c));
+    pcr_ctx *w = new (std::nothrow) pcr_ctx();
+    if (!w) {
+        delete c;
+        return fail(nullptr, PCR_ERR_OOM, "host allocation failed");
+    }
+    w->c = *c;  // plain members only
+    delete c;
+    *out = w;
+    return PCR_OK;
+    PCR_API_END(nullptr)
+}
+
+int pcr_ctx_create(int device, pcr_ctx **out) { return create_common(device, nullptr, false, out); }
+int pcr_ctx_create_on_stream(int device, void *cuda_stream, pcr_ctx **out) { return create_common(device, cuda_stream, true, out); }
+
+void pcr_ctx_destroy(pcr_ctx *ctx) {
+    if (!ctx) return;
+    Ctx *c = &ctx->c;
+    DevSetter ds(c);
+    cudaStreamSynchronize(c->stream);
+    comm_destroy(c);
+    free_buf(c, c->b_in);
+    free_buf(c, c->b_in2);
+    free_buf(c, c->b_out);
+    free_buf(c, c->b_misc);
+    free_buf(c, c->b_misc2);
+    free_buf(c, c->b_small);
+    free_buf(c, c->b_table);
+    cudaStreamSynchronize(c->stream);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->owns_stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete ctx;
+}
+
+int pcr_ctx_synchronize(pcr_ctx *ctx) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    DevSetter ds(&ctx->c);
+    PCR_CUDA(&ctx->c, cudaStreamSynchronize(ctx->c.stream));
+    return PCR_OK;
+}
+
+uint64_t pcr_ctx_launch_count(const pcr_ctx *ctx) { return ctx ? ctx->c.launches : 0; }
+
+int pcr_ctx_set_cell_size(pcr_ctx *ctx, float cell_size) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    if (!(cell_size >= 0.f) || !std::isfinite(cell_size)) return fail(&ctx->c, PCR_ERR_INVALID_ARG, "cell_size must be >= 0 and finite");
+    ctx->c.forced_cell = cell_size;
+    return PCR_OK;
+}
+
+int pcr_comm_unique_id(void *out_id) {
+    if (!out_id) return fail(nullptr, PCR_ERR_INVALID_ARG, "out_id is NULL");
+    PCR_API_BEGIN
+    return comm_unique_id(out_id);
+    PCR_API_END(nullptr)
+}
+int pcr_ctx_comm_init(pcr_ctx *ctx, const void *id, int rank, int world_size) {
+    if (!ctx || !id) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx/id is NULL");
+    PCR_API_BEGIN
+    DevSetter ds(&ctx->c);
+    return comm_init(&ctx->c, id, rank, world_size);
+    PCR_API_END(&ctx->c)
+}
+int pcr_ctx_comm_rank(const pcr_ctx *ctx) { return ctx ? ctx->c.rank : 0; }
+int pcr_ctx_comm_size(const pcr_ctx *ctx) { return ctx ? ctx->c.world : 1; }
+
+/* ---- index ------------------------------------------------------------------------------------ */
+static int wrap_index(pcr_ctx *ctx, Index *ix, pcr_index **out) {
+    pcr_index *w = new (std::nothrow) pcr_index();
+    if (!w) {
+        index_free(ix);
+        return fail(&ctx->c, PCR_ERR_OOM, "host allocation failed");
+    }
+    w->ix = ix;
+    w->owner = ctx;
+    *out = w;
+    return PCR_OK;
+}
+
+int pcr_index_build_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n, size_t k_hint,
+                        pcr_index **out) {
+    if (!ctx || !out) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx/out is NULL");
+    *out = nullptr;
+    if (n && (!d_x || !d_y || !d_z)) return fail(&ctx->c, PCR_ERR_INVALID_ARG, "x/y/z is NULL");
+    PCR_API_BEGIN
+    DevSetter ds(&ctx->c);
+    BuildOpts bo;
+    bo.k_hint = k_hint;
+    Index *ix = nullptr;
+    PCR_TRY(index_build_dev(&ctx->c, d_x, d_y, d_z, n, bo, &ix));
+    return wrap_index(ctx, ix, out);
+    PCR_API_END(&ctx->c)
+}
+
+int pcr_index_build(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n, size_t k_hint, pcr_index **out) {
+    if (!ctx || !out) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx/out is NULL");
+    *out = nullptr;
+    if (n && (!x || !y || !z)) return fail(&ctx->c, PCR_ERR_INVALID_ARG, "x/y/z is NULL");
+    PCR_API_BEGIN
+    Ctx *c = &ctx->c;
+    DevSetter ds(c);
+    float *dx, *dy, *dz;
+    PCR_TRY(stage_xyz(c, c->b_in, x, y, z, n, &dx, &dy, &dz));
+    BuildOpts bo;
+    bo.k_hint = k_hint;
+    Index *ix = nullptr;
+    PCR_TRY(index_build_dev(c, dx, dy, dz, n, bo, &ix));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    return wrap_index(ctx, ix, out);
+    PCR_API_END(&ctx->c)
+}
+
+void pcr_index_free(pcr_index *index) {
+    if (!index) return;
+    if (index->ix) {
+        DevSetter ds(index->ix->ctx);
+        index_free(index->ix);
+    }
+    delete index;
+}
+
+size_t pcr_index_len(const pcr_index *index) { return index && index->ix ? index->ix->n : 0; }
+
+int pcr_index_info(const pcr_index *index, float *cell_size, int32_t dims[3], size_t *n_indexed) {
+    if (!index || !index->ix) return fail(nullptr, PCR_ERR_INVALID_ARG, "index is NULL");
+    const GridDesc &g = index->ix->grids_h[0];
+    if (cell_size) *cell_size = (float)g.h;
+    if (dims)
+        for (int j = 0; j < 3; j++) dims[g.ax[j]] = g.dims[j];
+    if (n_indexed) *n_indexed = index->ix->n_indexed;
+    return PCR_OK;
+}
+
+int pcr_knn_dev(pcr_index *index, const float *d_qx, const float *d_qy, const float *d_qz, size_t nq, size_t k, uint32_t *d_idx,
+                float *d_dist, uint32_t *d_counts) {
+    if (!index || !index->ix) return fail(nullptr, PCR_ERR_INVALID_ARG, "index is NULL");
+    Ctx *c = index->ix->ctx;
+    if (nq && k && (!d_qx || !d_qy || !d_qz || !d_idx)) return fail(c, PCR_ERR_INVALID_ARG, "null query/output pointer");
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    if (k == 0 && d_counts && nq) PCR_CUDA(c, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * nq, c->stream));
+    return knn_queries_dev(index->ix, d_qx, d_qy, d_qz, nq, k, d_idx, d_dist, d_counts);
+    PCR_API_END(c)
+}
+
+int pcr_knn(pcr_index *index, const float *qx, const float *qy, const float *qz, size_t nq, size_t k, uint32_t *idx, float *dist,
+            uint32_t *counts) {
+    if (!index || !index->ix) return fail(nullptr, PCR_ERR_INVALID_ARG, "index is NULL");
+    Ctx *c = index->ix->ctx;
+    if (nq == 0) return PCR_OK;
+    if (!qx || !qy || !qz) return fail(c, PCR_ERR_INVALID_ARG, "null query pointer");
+    if (k == 0) {  // kdtree.rs:65
+        if (counts) memset(counts, 0, sizeof(uint32_t) * nq);
+        return PCR_OK;
+    }
+    if (!idx) return fail(c, PCR_ERR_INVALID_ARG, "idx is NULL");
+    if (k > PCR_MAX_K) return fail(c, PCR_ERR_UNSUPPORTED, "k = %zu exceeds PCR_MAX_K = %d", k, PCR_MAX_K);
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    float *dx, *dy, *dz;
+    PCR_TRY(stage_xyz(c, c->b_in2, qx, qy, qz, nq, &dx, &dy, &dz));
+    size_t rows = nq * k;
+    size_t bytes = rows * sizeof(uint32_t) + (dist ? rows * sizeof(float) : 0) + nq * sizeof(uint32_t) + 512;
+    PCR_TRY(ensure(c, c->b_out, bytes));
+    uint32_t *d_idx = (uint32_t *)c->b_out.p;
+    float *d_dist = dist ? (float *)(d_idx + rows) : nullptr;
+    uint32_t *d_cnt = (uint32_t *)((char *)c->b_out.p + rows * sizeof(uint32_t) + (dist ? rows * sizeof(float) : 0));
+    PCR_TRY(knn_queries_dev(index->ix, dx, dy, dz, nq, k, d_idx, d_dist, d_cnt));
+    PCR_CUDA(c, cudaMemcpyAsync(idx, d_idx, rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (dist) PCR_CUDA(c, cudaMemcpyAsync(dist, d_dist, rows * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (counts) PCR_CUDA(c, cudaMemcpyAsync(counts, d_cnt, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+int pcr_radius_count(pcr_index *index, const float *qx, const float *qy, const float *qz, size_t nq, float radius,
+                     uint32_t *counts) {
+    if (!index || !index->ix) return fail(nullptr, PCR_ERR_INVALID_ARG, "index is NULL");
+    Ctx *c = index->ix->ctx;
+    if (nq == 0) return PCR_OK;
+    if (!qx || !qy || !qz || !counts) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    float *dx, *dy, *dz;
+    PCR_TRY(stage_xyz(c, c->b_in2, qx, qy, qz, nq, &dx, &dy, &dz));
+    PCR_TRY(ensure(c, c->b_out, nq * sizeof(uint32_t)));
+    PCR_TRY(radius_count_dev(index->ix, dx, dy, dz, nq, radius, (uint32_t *)c->b_out.p));
+    PCR_CUDA(c, cudaMemcpyAsync(counts, c->b_out.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+int pcr_radius_search(pcr_index *index, const float *qx, const float *qy, const float *qz, size_t nq, float radius,
+                      uint64_t *offsets, uint32_t *idx, size_t cap, size_t *total) {
+    if (!index || !index->ix) return fail(nullptr, PCR_ERR_INVALID_ARG, "index is NULL");
+    Ctx *c = index->ix->ctx;
+    if (!offsets || !total) return fail(c, PCR_ERR_INVALID_ARG, "offsets/total is NULL");
+    *total = 0;
+    offsets[0] = 0;
+    if (nq == 0) return PCR_OK;
+    if (!qx || !qy || !qz) return fail(c, PCR_ERR_INVALID_ARG, "null query pointer");
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    float *dx, *dy, *dz;
+    PCR_TRY(stage_xyz(c, c->b_in2, qx, qy, qz, nq, &dx, &dy, &dz));
+    // counts (u32) | offsets (u64, nq+1)
+    size_t off_bytes = ((nq * sizeof(uint32_t) + 255) & ~(size_t)255);
+    PCR_TRY(ensure(c, c->b_out, off_bytes + (nq + 1) * sizeof(uint64_t)));
+    uint32_t *d_cnt = (uint32_t *)c->b_out.p;
+    uint64_t *d_off = (uint64_t *)((char *)c->b_out.p + off_bytes);
+    PCR_TRY(radius_count_dev(index->ix, dx, dy, dz, nq, radius, d_cnt));
+    PCR_TRY(exclusive_scan_u64_from_u32_dev(c, d_cnt, d_off, nq));
+    PCR_CUDA(c, cudaMemcpyAsync(offsets, d_off, (nq + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    *total = (size_t)offsets[nq];
+    if (*total > cap) return fail(c, PCR_ERR_CAPACITY, "radius_search needs room for %zu indices, cap is %zu", *total, cap);
+    if (*total == 0) return PCR_OK;
+    if (!idx) return fail(c, PCR_ERR_INVALID_ARG, "idx is NULL");
+    PCR_TRY(ensure(c, c->b_misc, *total * sizeof(uint32_t)));
+    PCR_TRY(radius_fill_dev(index->ix, dx, dy, dz, nq, radius, d_off, (uint32_t *)c->b_misc.p));
+    PCR_CUDA(c, cudaMemcpyAsync(idx, c->b_misc.p, *total * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+/* ---- SOR -------------------------------------------------------------------------------------- */
+// shared by the host- and device-pointer entry points; d_stats: 4 floats, d_kept: 1 u64
+static int sor_core(Ctx *c, const float *dx, const float *dy, const float *dz, size_t n, size_t k, float std_mul, uint8_t *d_keep,
+                    float *d_mean, float *d_stats, unsigned long long *d_kept) {
+    BuildOpts bo;
+    bo.k_hint = k + 1;
+    Index *ix = nullptr;
+    PCR_TRY(index_build_dev(c, dx, dy, dz, n, bo, &ix));
+    int s = sor_mean_dist_dev(ix, k, d_mean);
+    if (s == PCR_OK) s = sor_threshold_mask_dev(c, d_mean, nullptr, 1, n, std_mul, d_keep, d_stats, d_kept);
+    index_free(ix);
+    return s;
+}
+
+int pcr_sor_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n, size_t k, float std_mul,
+                uint8_t *d_keep, float *d_mean_d) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (n && (!d_x || !d_y || !d_z || !d_keep)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (!std::isfinite(std_mul) || std_mul < 0.f) return fail(c, PCR_ERR_INVALID_ARG, "std_mul must be >= 0 and finite");
+    if (k + 1 > PCR_MAX_K) return fail(c, PCR_ERR_UNSUPPORTED, "k = %zu exceeds PCR_MAX_K - 1", k);
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    if (n == 0) return PCR_OK;
+    if (k == 0) {  // statistical_outlier.rs:5-7
+        PCR_CUDA(c, cudaMemsetAsync(d_keep, 0, n, c->stream));
+        return PCR_OK;
+    }
+    if (n == 1) {  // statistical_outlier.rs:10-12
+        PCR_CUDA(c, cudaMemsetAsync(d_keep, 1, 1, c->stream));
+        return PCR_OK;
+    }
+    PCR_TRY(ensure(c, c->b_out, n * sizeof(float) + 1024));
+    float *d_mean = d_mean_d ? d_mean_d : (float *)c->b_out.p;
+    float *d_stats = (float *)((char *)c->b_out.p + ((n * sizeof(float) + 255) & ~(size_t)255));
+    unsigned long long *d_kept = (unsigned long long *)(d_stats + 8);
+    return sor_core(c, d_x, d_y, d_z, n, k, std_mul, d_keep, d_mean, d_stats, d_kept);
+    PCR_API_END(c)
+}
+
+int pcr_sor(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n, size_t k, float std_mul, uint8_t *keep,
+            size_t *n_kept, float *mean_d, float *stats) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (n_kept) *n_kept = 0;
+    if (n && (!x || !y || !z || !keep)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (!std::isfinite(std_mul) || std_mul < 0.f)  // crates/python/src/filters.rs:42-46
+        return fail(c, PCR_ERR_INVALID_ARG, "std_mul must be >= 0 and finite");
+    if (k + 1 > PCR_MAX_K) return fail(c, PCR_ERR_UNSUPPORTED, "k = %zu exceeds PCR_MAX_K - 1", k);
+    if (stats) stats[0] = stats[1] = stats[2] = NAN;
+    if (n == 0) return PCR_OK;
+    if (k == 0) {  // statistical_outlier.rs:5-7: empty result
+        memset(keep, 0, n);
+        if (mean_d) std::fill(mean_d, mean_d + n, INFINITY);
+        return PCR_OK;
+    }
+    if (n == 1) {  // statistical_outlier.rs:10-12: the cloud itself
+        keep[0] = 1;
+        if (n_kept) *n_kept = 1;
+        if (mean_d) mean_d[0] = INFINITY;
+        return PCR_OK;
+    }
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    float *dx, *dy, *dz;
+    PCR_TRY(stage_xyz(c, c->b_in, x, y, z, n, &dx, &dy, &dz));
+    // out: mean_d f32[n] | stats f32[8] | kept u64 | keep u8[n]
+    size_t o_stats = (n * sizeof(float) + 255) & ~(size_t)255;
+    size_t o_keep = o_stats + 256;
+    PCR_TRY(ensure(c, c->b_out, o_keep + n));
+    float *d_mean = (float *)c->b_out.p;
+    float *d_stats = (float *)((char *)c->b_out.p + o_stats);
+    unsigned long long *d_kept = (unsigned long long *)(d_stats + 8);
+    uint8_t *d_keep = (uint8_t *)c->b_out.p + o_keep;
+    PCR_TRY(sor_core(c, dx, dy, dz, n, k, std_mul, d_keep, d_mean, d_stats, d_kept));
+    struct {
+        float stats[8];
+        unsigned long long kept;
+    } *mail = (decltype(mail))c->pinned;
+    PCR_CUDA(c, cudaMemcpyAsync(keep, d_keep, n, cudaMemcpyDeviceToHost, c->stream));
+    if (mean_d) PCR_CUDA(c, cudaMemcpyAsync(mean_d, d_mean, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaMemcpyAsync(mail, d_stats, sizeof(*mail), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (n_kept) *n_kept = (size_t)mail->kept;
+    if (stats) {
+        stats[0] = mail->stats[0];
+        stats[1] = mail->stats[1];
+        stats[2] = mail->stats[2];
+    }
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+/* ---- radius outlier ------------------------------------------------------------------------------ */
+namespace pcr {
+__global__ void ror_mask_kernel(const uint32_t *__restrict__ counts, size_t n, uint64_t min_neighbors, uint8_t *__restrict__ keep,
+                                unsigned long long *__restrict__ kept) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned k = 0;
+    if (i < n) {
+        k = (uint64_t)counts[i] >= min_neighbors ? 1 : 0;  // radius_outlier.rs:13
+        keep[i] = (uint8_t)k;
+    }
+    k = __reduce_add_sync(PCR_FULL, k);
+    if ((threadIdx.x & 31) == 0 && k) atomicAdd(kept, (unsigned long long)k);
+}
+}  // namespace pcr
+
+int pcr_radius_outlier(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n, float radius, size_t min_neighbors,
+                       uint8_t *keep, size_t *n_kept) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (n_kept) *n_kept = 0;
+    if (n && (!x || !y || !z || !keep)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (n == 0) return PCR_OK;
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    float *dx, *dy, *dz;
+    PCR_TRY(stage_xyz(c, c->b_in, x, y, z, n, &dx, &dy, &dz));
+    // cell size = radius: the search box spans at most 3 cells per axis
+    const float saved = c->forced_cell;
+    if (saved == 0.f && radius > 0.f && std::isfinite(radius)) c->forced_cell = radius;
+    BuildOpts bo;
+    Index *ix = nullptr;
+    int s = index_build_dev(c, dx, dy, dz, n, bo, &ix);
+    c->forced_cell = saved;
+    PCR_TRY(s);
+    struct G {
+        Index *ix;
+        ~G() { index_free(ix); }
+    } g{ix};
+    size_t o_keep = (n * sizeof(uint32_t) + 255) & ~(size_t)255;
+    size_t o_kept = o_keep + ((n + 255) & ~(size_t)255);
+    PCR_TRY(ensure(c, c->b_out, o_kept + 64));
+    uint32_t *d_cnt = (uint32_t *)c->b_out.p;
+    uint8_t *d_keep = (uint8_t *)c->b_out.p + o_keep;
+    unsigned long long *d_kept = (unsigned long long *)((char *)c->b_out.p + o_kept);
+    PCR_TRY(radius_count_dev(ix, dx, dy, dz, n, radius, d_cnt));
+    PCR_CUDA(c, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long), c->stream));
+    ror_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_cnt, n, (uint64_t)min_neighbors, d_keep, d_kept);
+    PCR_LAUNCH_CHECK(c);
+    unsigned long long *mail = (unsigned long long *)c->pinned;
+    PCR_CUDA(c, cudaMemcpyAsync(keep, d_keep, n, cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaMemcpyAsync(mail, d_kept, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (n_kept) *n_kept = (size_t)*mail;
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+/* ---- normals -------------------------------------------------------------------------------------- */
+int pcr_estimate_normals_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n, size_t k,
+                             const float viewpoint[3], float *d_nx, float *d_ny, float *d_nz) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (n == 0 || k == 0) return PCR_OK;  // estimate.rs:25-31
+    if (!d_x || !d_y || !d_z || !d_nx || !d_ny || !d_nz || !viewpoint) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (k > PCR_MAX_K) return fail(c, PCR_ERR_UNSUPPORTED, "k = %zu exceeds PCR_MAX_K = %d", k, PCR_MAX_K);
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    BuildOpts bo;
+    bo.k_hint = k;
+    Index *ix = nullptr;
+    PCR_TRY(index_build_dev(c, d_x, d_y, d_z, n, bo, &ix));
+    int s = normals_dev(ix, k, viewpoint, d_nx, d_ny, d_nz, nullptr);
+    index_free(ix);
+    return s;
+    PCR_API_END(c)
+}
+
+int pcr_estimate_normals(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n, size_t k, const float viewpoint[3],
+                         float *nx, float *ny, float *nz) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (n == 0 || k == 0) return PCR_OK;  // estimate.rs:25-31: empty normals
+    if (!x || !y || !z || !nx || !ny || !nz || !viewpoint) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (k > PCR_MAX_K) return fail(c, PCR_ERR_UNSUPPORTED, "k = %zu exceeds PCR_MAX_K = %d", k, PCR_MAX_K);
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    float *dx, *dy, *dz;
+    PCR_TRY(stage_xyz(c, c->b_in, x, y, z, n, &dx, &dy, &dz));
+    size_t stride = (n + 63) & ~(size_t)63;
+    PCR_TRY(ensure(c, c->b_out, stride * 3 * sizeof(float)));
+    float *dnx = (float *)c->b_out.p, *dny = dnx + stride, *dnz = dny + stride;
+    BuildOpts bo;
+    bo.k_hint = k;
+    Index *ix = nullptr;
+    PCR_TRY(index_build_dev(c, dx, dy, dz, n, bo, &ix));
+    int s = normals_dev(ix, k, viewpoint, dnx, dny, dnz, nullptr);
+    index_free(ix);
+    PCR_TRY(s);
+    PCR_CUDA(c, cudaMemcpyAsync(nx, dnx, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaMemcpyAsync(ny, dny, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaMemcpyAsync(nz, dnz, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+/* ---- registration --------------------------------------------------------------------------------- */
+int pcr_find_correspondences(pcr_index *target, const float *sx, const float *sy, const float *sz, size_t ns, float max_distance,
+                             uint32_t *src_idx, uint32_t *tgt_idx, float *dist, size_t *count) {
+    if (!target || !target->ix) return fail(nullptr, PCR_ERR_INVALID_ARG, "target is NULL");
+    Ctx *c = target->ix->ctx;
+    if (!count) return fail(c, PCR_ERR_INVALID_ARG, "count is NULL");
+    *count = 0;
+    if (ns == 0) return PCR_OK;
+    if (!sx || !sy || !sz || !src_idx || !tgt_idx || !dist) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    float *dx, *dy, *dz;
+    PCR_TRY(stage_xyz(c, c->b_in2, sx, sy, sz, ns, &dx, &dy, &dz));
+    PCR_TRY(ensure(c, c->b_out, ns * 8));
+    uint32_t *d_t = (uint32_t *)c->b_out.p;
+    float *d_d = (float *)(d_t + ns);
+    PCR_TRY(find_correspondences_dev(target->ix, dx, dy, dz, ns, max_distance, d_t, d_d));
+    // compact on the host, in source order (correspondence.rs:23-36)
+    std::vector<uint32_t> ht(ns);
+    std::vector<float> hd(ns);
+    PCR_CUDA(c, cudaMemcpyAsync(ht.data(), d_t, ns * 4, cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaMemcpyAsync(hd.data(), d_d, ns * 4, cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    size_t m = 0;
+    for (size_t i = 0; i < ns; i++)
+        if (ht[i] != 0xffffffffu) {
+            src_idx[m] = (uint32_t)i;
+            tgt_idx[m] = ht[i];
+            dist[m] = hd[i];
+            m++;
+        }
+    *count = m;
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+int pcr_apply_transform(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n, const float rotation[9],
+                        const float translation[3], float *ox, float *oy, float *oz) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (n == 0) return PCR_OK;
+    if (!x || !y || !z || !ox || !oy || !oz || !rotation || !translation) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    float *dx, *dy, *dz;
+    PCR_TRY(stage_xyz(c, c->b_in, x, y, z, n, &dx, &dy, &dz));
+    size_t stride = (n + 63) & ~(size_t)63;
+    PCR_TRY(ensure(c, c->b_out, stride * 3 * sizeof(float)));
+    float *a = (float *)c->b_out.p, *b = a + stride, *d = b + stride;
+    PCR_TRY(apply_transform_dev(c, dx, dy, dz, n, rotation, translation, a, b, d));
+    PCR_CUDA(c, cudaMemcpyAsync(ox, a, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaMemcpyAsync(oy, b, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaMemcpyAsync(oz, d, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+static void icp_identity(pcr_icp_result *r) {
+    memset(r, 0, sizeof(*r));
+    r->rotation[0] = r->rotation[4] = r->rotation[8] = 1.f;
+}
+
+static int icp_common_dev(Ctx *c, const float *dsx, const float *dsy, const float *dsz, size_t ns, const float *dtx, const float *dty,
+                          const float *dtz, size_t nt, const float *dnx, const float *dny, const float *dnz,
+                          const pcr_icp_params *params, pcr_icp_result *result) {
+    IcpArgs a;
+    a.d_sx = dsx; a.d_sy = dsy; a.d_sz = dsz; a.ns = ns;
+    a.d_tx = dtx; a.d_ty = dty; a.d_tz = dtz; a.nt = nt;
+    a.d_nx = dnx; a.d_ny = dny; a.d_nz = dnz;
+    a.params = *params;
+    return icp_dev(c, a, result);
+}
+
+static int icp_check(Ctx *c, const pcr_icp_params *params, pcr_icp_result *result) {
+    if (!params || !result) return fail(c, PCR_ERR_INVALID_ARG, "params/result is NULL");
+    // crates/python/src/registration.rs:67-72: tolerance must not be NaN / negative
+    if (std::isnan(params->tolerance) || params->tolerance < 0.f) return fail(c, PCR_ERR_INVALID_ARG, "tolerance must be >= 0");
+    if (std::isnan(params->max_correspondence_distance) || params->max_correspondence_distance < 0.f)
+        return fail(c, PCR_ERR_INVALID_ARG, "max_correspondence_distance must be >= 0");
+    return PCR_OK;
+}
+
+static int icp_entry(pcr_ctx *ctx, bool dev, bool plane, const float *sx, const float *sy, const float *sz, size_t ns, const float *tx,
+                     const float *ty, const float *tz, size_t nt, const float *nx, const float *ny, const float *nz, size_t nn,
+                     const pcr_icp_params *params, pcr_icp_result *result) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    PCR_TRY(icp_check(c, params, result));
+    icp_identity(result);
+    if (plane && nn != nt)  // icp_plane.rs:27-32
+        return fail(c, PCR_ERR_NORMALS_MISMATCH, "target_normals length (%zu) does not match target cloud length (%zu)", nn, nt);
+    if (c->world == 1 && (ns == 0 || nt == 0)) {  // icp.rs:131-139
+        result->converged = (ns == 0 && nt == 0) ? 1 : 0;
+        return PCR_OK;
+    }
+    if (nt == 0) {
+        result->converged = 0;
+        return PCR_OK;
+    }
+    if ((ns && (!sx || !sy || !sz)) || !tx || !ty || !tz || (plane && (!nx || !ny || !nz))) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    if (dev) return icp_common_dev(c, sx, sy, sz, ns, tx, ty, tz, nt, plane ? nx : nullptr, ny, nz, params, result);
+    float *dsx, *dsy, *dsz, *dtx, *dty, *dtz, *dnx = nullptr, *dny = nullptr, *dnz = nullptr;
+    PCR_TRY(stage_xyz(c, c->b_in2, sx, sy, sz, ns, &dsx, &dsy, &dsz));
+    PCR_TRY(stage_xyz(c, c->b_in, tx, ty, tz, nt, &dtx, &dty, &dtz));
+    if (plane) PCR_TRY(stage_xyz(c, c->b_out, nx, ny, nz, nt, &dnx, &dny, &dnz));
+    return icp_common_dev(c, dsx, dsy, dsz, ns, dtx, dty, dtz, nt, dnx, dny, dnz, params, result);
+    PCR_API_END(c)
+}
+
+int pcr_icp_point_to_point(pcr_ctx *ctx, const float *sx, const float *sy, const float *sz, size_t ns, const float *tx,
+                           const float *ty, const float *tz, size_t nt, const pcr_icp_params *params, pcr_icp_result *result) {
+    return icp_entry(ctx, false, false, sx, sy, sz, ns, tx, ty, tz, nt, nullptr, nullptr, nullptr, nt, params, result);
+}
+int pcr_icp_point_to_plane(pcr_ctx *ctx, const float *sx, const float *sy, const float *sz, size_t ns, const float *tx,
+                           const float *ty, const float *tz, size_t nt, const float *nx, const float *ny, const float *nz,
+                           size_t n_normals, const pcr_icp_params *params, pcr_icp_result *result) {
+    return icp_entry(ctx, false, true, sx, sy, sz, ns, tx, ty, tz, nt, nx, ny, nz, n_normals, params, result);
+}
+int pcr_icp_point_to_point_dev(pcr_ctx *ctx, const float *sx, const float *sy, const float *sz, size_t ns, const float *tx,
+                               const float *ty, const float *tz, size_t nt, const pcr_icp_params *params, pcr_icp_result *result) {
+    return icp_entry(ctx, true, false, sx, sy, sz, ns, tx, ty, tz, nt, nullptr, nullptr, nullptr, nt, params, result);
+}
+int pcr_icp_point_to_plane_dev(pcr_ctx *ctx, const float *sx, const float *sy, const float *sz, size_t ns, const float *tx,
+                               const float *ty, const float *tz, size_t nt, const float *nx, const float *ny, const float *nz,
+                               size_t n_normals, const pcr_icp_params *params, pcr_icp_result *result) {
+    return icp_entry(ctx, true, true, sx, sy, sz, ns, tx, ty, tz, nt, nx, ny, nz, n_normals, params, result);
+}
+
+/* ---- multi-frame batch ---------------------------------------------------------------------------- */
+namespace pcr {
+// frames of exactly one point are returned unchanged by the reference (statistical_outlier.rs:10-12)
+__global__ void single_point_frames_kernel(const uint32_t *__restrict__ frame_off, int n_frames, uint8_t *__restrict__ keep,
+                                           unsigned long long *__restrict__ kept) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    if (frame_off[f + 1] - frame_off[f] == 1) {
+        keep[frame_off[f]] = 1;
+        kept[f] = 1;
+    }
+}
+}  // namespace pcr
+// One batched index over all frames for SOR, a second one over the kept points for the normals:
+// every kernel runs once for the whole batch (frames are an extra axis of the cell table).
+static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz, const uint64_t *frame_offsets, size_t n_frames,
+                      size_t n, size_t k_sor, float std_mul, size_t k_normals, const float vp[3], uint8_t *d_keep, float *d_nx,
+                      float *d_ny, float *d_nz, unsigned long long *d_kept /* n_frames */) {
+    const int F = (int)n_frames;
+    float *d_mean = nullptr, *d_stats = nullptr;
+    PCR_CUDA(c, cudaMallocAsync((void **)&d_mean, sizeof(float) * std::max<size_t>(n, 1), c->stream));
+    struct FreeLater {
+        void *p;
+        cudaStream_t s;
+        ~FreeLater() {
+            if (p) cudaFreeAsync(p, s);
+        }
+    } f1{d_mean, c->stream};
+    PCR_CUDA(c, cudaMallocAsync((void **)&d_stats, sizeof(float) * 4 * F, c->stream));
+    FreeLater f2{d_stats, c->stream};
+
+    BuildOpts bo;
+    bo.k_hint = k_sor + 1;
+    bo.n_frames = F;
+    bo.frame_offsets = frame_offsets;
+    Index *ix = nullptr;
+    PCR_TRY(index_build_dev(c, dx, dy, dz, n, bo, &ix));
+    int s = PCR_OK;
+    if (k_sor == 0) {
+        PCR_CUDA(c, cudaMemsetAsync(d_keep, 0, n, c->stream));
+        PCR_CUDA(c, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long) * F, c->stream));
+    } else {
+        s = sor_mean_dist_dev(ix, k_sor, d_mean);
+        if (s == PCR_OK) s = sor_threshold_mask_dev(c, d_mean, ix->frame_in_off, F, n, std_mul, d_keep, d_stats, d_kept);
+        if (s == PCR_OK && F > 1) {  // a one-point frame is returned as is, even if the point is not finite
+            single_point_frames_kernel<<<(F + 127) / 128, 128, 0, c->stream>>>(ix->frame_in_off, F, d_keep, d_kept);
+            c->launches++;
+        }
+    }
+    index_free(ix);
+    PCR_TRY(s);
+    if (k_normals == 0) return PCR_OK;
+    BuildOpts bn;
+    bn.k_hint = k_normals;
+    bn.n_frames = F;
+    bn.frame_offsets = frame_offsets;
+    bn.d_mask = d_keep;
+    Index *ixn = nullptr;
+    PCR_TRY(index_build_dev(c, dx, dy, dz, n, bn, &ixn));
+    // removed points get 0 and kept non-finite points (0,0,1) inside normals_dev
+    s = normals_dev(ixn, k_normals, vp, d_nx, d_ny, d_nz, d_keep);
+    index_free(ixn);
+    return s;
+}
+
+
+int pcr_sor_normals_batch_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, const uint64_t *frame_offsets,
+                              size_t n_frames, size_t k_sor, float std_mul, size_t k_normals, const float viewpoint[3],
+                              uint8_t *d_keep, float *d_nx, float *d_ny, float *d_nz) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (n_frames == 0) return PCR_OK;
+    if (!frame_offsets) return fail(c, PCR_ERR_INVALID_ARG, "frame_offsets is NULL");
+    const size_t n = (size_t)frame_offsets[n_frames];
+    if (n == 0) return PCR_OK;
+    if (!d_x || !d_y || !d_z || !d_keep || !viewpoint || (k_normals && (!d_nx || !d_ny || !d_nz)))
+        return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (!std::isfinite(std_mul) || std_mul < 0.f) return fail(c, PCR_ERR_INVALID_ARG, "std_mul must be >= 0 and finite");
+    if (k_sor + 1 > PCR_MAX_K || k_normals > PCR_MAX_K) return fail(c, PCR_ERR_UNSUPPORTED, "k exceeds PCR_MAX_K");
+    if (n_frames > 65535) return fail(c, PCR_ERR_UNSUPPORTED, "at most 65535 frames per batch");
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    unsigned long long *d_kept = nullptr;
+    PCR_CUDA(c, cudaMallocAsync((void **)&d_kept, sizeof(unsigned long long) * n_frames, c->stream));
+    int s = batch_core(c, d_x, d_y, d_z, frame_offsets, n_frames, n, k_sor, std_mul, k_normals, viewpoint, d_keep, d_nx, d_ny, d_nz,
+                       d_kept);
+    cudaFreeAsync(d_kept, c->stream);
+    return s;
+    PCR_API_END(c)
+}
+
+int pcr_sor_normals_batch(pcr_ctx *ctx, const float *x, const float *y, const float *z, const uint64_t *frame_offsets, size_t n_frames,
+                          size_t k_sor, float std_mul, size_t k_normals, const float viewpoint[3], uint8_t *keep, float *nx, float *ny,
+                          float *nz, uint64_t *n_kept_per_frame) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (n_frames == 0) return PCR_OK;
+    if (!frame_offsets) return fail(c, PCR_ERR_INVALID_ARG, "frame_offsets is NULL");
+    const size_t n = (size_t)frame_offsets[n_frames];
+    if (n_kept_per_frame) memset(n_kept_per_frame, 0, sizeof(uint64_t) * n_frames);
+    if (n == 0) return PCR_OK;
+    if (!x || !y || !z || !keep || !viewpoint || (k_normals && (!nx || !ny || !nz))) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (!std::isfinite(std_mul) || std_mul < 0.f) return fail(c, PCR_ERR_INVALID_ARG, "std_mul must be >= 0 and finite");
+    if (k_sor + 1 > PCR_MAX_K || k_normals > PCR_MAX_K) return fail(c, PCR_ERR_UNSUPPORTED, "k exceeds PCR_MAX_K");
+    if (n_frames > 65535) return fail(c, PCR_ERR_UNSUPPORTED, "at most 65535 frames per batch");
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    float *dx, *dy, *dz;
+    PCR_TRY(stage_xyz(c, c->b_in, x, y, z, n, &dx, &dy, &dz));
+    size_t stride = (n + 63) & ~(size_t)63;
+    size_t o_keep = stride * 3 * sizeof(float);
+    size_t o_kept = o_keep + ((n + 255) & ~(size_t)255);
+    PCR_TRY(ensure(c, c->b_out, o_kept + sizeof(unsigned long long) * n_frames));
+    float *dnx = (float *)c->b_out.p, *dny = dnx + stride, *dnz = dny + stride;
+    uint8_t *d_keep = (uint8_t *)c->b_out.p + o_keep;
+    unsigned long long *d_kept = (unsigned long long *)((char *)c->b_out.p + o_kept);
+    PCR_TRY(batch_core(c, dx, dy, dz, frame_offsets, n_frames, n, k_sor, std_mul, k_normals, viewpoint, d_keep, dnx, dny, dnz, d_kept));
+    PCR_CUDA(c, cudaMemcpyAsync(keep, d_keep, n, cudaMemcpyDeviceToHost, c->stream));
+    if (k_normals) {
+        PCR_CUDA(c, cudaMemcpyAsync(nx, dnx, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        PCR_CUDA(c, cudaMemcpyAsync(ny, dny, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        PCR_CUDA(c, cudaMemcpyAsync(nz, dnz, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    std::vector<unsigned long long> hk(n_frames);
+    PCR_CUDA(c, cudaMemcpyAsync(hk.data(), d_kept, sizeof(unsigned long long) * n_frames, cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (n_kept_per_frame)
+        for (size_t f = 0; f < n_frames; f++) n_kept_per_frame[f] = hk[f];
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+// comm.cu -- NCCL plumbing for the one exchange the path has: the per-iteration all-reduce of the
+// ICP normal equations (30 doubles) when the source cloud is sharded over GPUs.
+//
+// NCCL is resolved at run time with dlopen so that (a) the library has no link-time dependency on
+// it (single-GPU users never load it) and (b) inside a process that already carries a NCCL (e.g.
+// one that imported torch) the SAME copy is reused instead of a second one.
+#include "pcr_internal.cuh"
+
+#include <dlfcn.h>
+
+namespace pcr {
+
+namespace {
+
+typedef struct {
+    char internal[128];
+} ncclUniqueId_t;
+typedef void *ncclComm_t_;
+typedef int ncclResult_t_;
+enum { kNcclFloat64 = 8, kNcclSum = 0 };
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t_ (*GetUniqueId)(ncclUniqueId_t *) = nullptr;
+    ncclResult_t_ (*CommInitRank)(ncclComm_t_ *, int, ncclUniqueId_t, int) = nullptr;
+    ncclResult_t_ (*CommDestroy)(ncclComm_t_) = nullptr;
+    ncclResult_t_ (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t_, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t_) = nullptr;
+    bool ok = false;
+};
+
+NcclApi &api() {
+    static NcclApi a;
+    static bool tried = false;
+    if (tried) return a;
+    tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {  // a copy already mapped into the process wins
+        a.handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (a.handle) break;
+    }
+    if (!a.handle) {
+        const char *env = getenv("PCR_NCCL_LIBRARY");
+        if (env) a.handle = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    }
+    for (const char *n : names) {
+        if (a.handle) break;
+        a.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    }
+    if (!a.handle) return a;
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.handle, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.handle, "ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.handle, "ncclCommDestroy");
+    a.AllReduce = (decltype(a.AllReduce))dlsym(a.handle, "ncclAllReduce");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.handle, "ncclGetErrorString");
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce;
+    return a;
+}
+
+}  // namespace
+
+int comm_unique_id(void *out) {
+    static_assert(sizeof(ncclUniqueId_t) == PCR_UNIQUE_ID_BYTES, "id size");
+    NcclApi &a = api();
+    if (!a.ok) {
+        set_thread_error("NCCL library not found (set PCR_NCCL_LIBRARY)");
+        return PCR_ERR_NCCL;
+    }
+    ncclUniqueId_t id;
+    int r = a.GetUniqueId(&id);
+    if (r != 0) {
+        set_thread_error(a.GetErrorString ? a.GetErrorString(r) : "ncclGetUniqueId failed");
+        return PCR_ERR_NCCL;
+    }
+    memcpy(out, &id, sizeof(id));
+    return PCR_OK;
+}
+
+int comm_init(Ctx *ctx, const void *id, int rank, int world) {
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, PCR_ERR_INVALID_ARG, "bad rank/world");
+    comm_destroy(ctx);
+    ctx->rank = rank;
+    ctx->world = world;
+    if (world == 1) return PCR_OK;
+    NcclApi &a = api();
+    if (!a.ok) return fail(ctx, PCR_ERR_NCCL, "NCCL library not found (set PCR_NCCL_LIBRARY)");
+    ncclUniqueId_t uid;
+    memcpy(&uid, id, sizeof(uid));
+    PCR_CUDA(ctx, cudaSetDevice(ctx->device));
+    ncclComm_t_ comm = nullptr;
+    int r = a.CommInitRank(&comm, world, uid, rank);
+    if (r != 0) {
+        ctx->world = 1;
+        ctx->rank = 0;
+        return fail(ctx, PCR_ERR_NCCL, "ncclCommInitRank: %s", a.GetErrorString ? a.GetErrorString(r) : "error");
+    }
+    ctx->nccl_comm = comm;
+    return PCR_OK;
+}
+
+void comm_destroy(Ctx *ctx) {
+    if (ctx->nccl_comm) {
+        NcclApi &a = api();
+        if (a.ok) a.CommDestroy((ncclComm_t_)ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    ctx->world = 1;
+    ctx->rank = 0;
+}
+
+int comm_allreduce_f64(Ctx *ctx, double *d_buf, size_t count) {
+    if (ctx->world <= 1) return PCR_OK;
+    NcclApi &a = api();
+    if (!a.ok || !ctx->nccl_comm) return fail(ctx, PCR_ERR_NCCL, "communicator not initialised");
+    int r = a.AllReduce(d_buf, d_buf, count, kNcclFloat64, kNcclSum, (ncclComm_t_)ctx->nccl_comm, ctx->stream);
+    if (r != 0) return fail(ctx, PCR_ERR_NCCL, "ncclAllReduce: %s", a.GetErrorString ? a.GetErrorString(r) : "error");
+    return PCR_OK;
+}
+
+}  // namespace pcr

@@ -1,0 +1,625 @@
+// grid_build.cu -- uniform-grid spatial index build (replaces KdTree::build,
+// crates/spatial/src/kdtree.rs:25-44).
+//
+//   K0  bbox_kernel      finite-point bounding box + count per frame          (reads 12 B/pt)
+//   K1  count_kernel     cell id per point, per-cell counts (L2 atomics), AoS copy
+//                        (reads 12 B/pt, writes 16 B orig4 + 8 B cell id / rank)
+//   K1p stats_kernel     occupancy statistics used to choose the cell size     (probe only)
+//   K2  scan (2 kernels) exclusive prefix of the dense cell table              (8 B/cell)
+//   K3  scatter_kernel   single-pass counting (radix) sort by dense cell id -> cell-sorted float4
+//                        (reads 24 B/pt, writes 16 B/pt)
+//
+// The cell id is a dense linear key with the longest axis fastest, so a row of neighbouring cells
+// is ONE contiguous run of points; the order of points inside a cell is irrelevant because every
+// consumer ranks candidates by (d^2, original index).
+#include "pcr_internal.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace pcr {
+
+namespace {
+
+constexpr int kBuildThreads = 256;
+constexpr int kItems = 4;  // points per thread in the streaming kernels
+
+struct FrameStats {
+    unsigned mn[3], mx[3];  // order-preserving uint encoding of f32
+    unsigned count;
+    unsigned pad;
+};
+
+struct ProbeStats {
+    double sum_log_own, sum_log_super;
+};
+
+__device__ __forceinline__ unsigned f32_ordered(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static inline float ordered_f32(unsigned u) {
+    unsigned b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
+
+// ---- K0: bounding box of the finite (and, with a mask, kept) points of each frame -------------
+__global__ void __launch_bounds__(kBuildThreads) bbox_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                                                             const float *__restrict__ z,
+                                                             const uint32_t *__restrict__ frame_off, size_t n,
+                                                             const uint8_t *__restrict__ mask,
+                                                             FrameStats *__restrict__ stats) {
+    const int f = blockIdx.y;
+    const uint32_t b = frame_off ? frame_off[f] : 0u;
+    const uint32_t e = frame_off ? frame_off[f + 1] : (uint32_t)n;
+    unsigned mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u}, cnt = 0;
+    for (uint32_t i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) {
+        float px = x[i], py = y[i], pz = z[i];
+        if (finite3(px, py, pz) && (!mask || mask[i])) {
+            unsigned ux = f32_ordered(px), uy = f32_ordered(py), uz = f32_ordered(pz);
+            mn[0] = min(mn[0], ux); mx[0] = max(mx[0], ux);
+            mn[1] = min(mn[1], uy); mx[1] = max(mx[1], uy);
+            mn[2] = min(mn[2], uz); mx[2] = max(mx[2], uz);
+            cnt++;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        mn[a] = __reduce_min_sync(PCR_FULL, mn[a]);
+        mx[a] = __reduce_max_sync(PCR_FULL, mx[a]);
+    }
+    cnt = __reduce_add_sync(PCR_FULL, cnt);
+    __shared__ unsigned s_mn[3], s_mx[3], s_cnt;
+    if (threadIdx.x == 0) {
+        s_mn[0] = s_mn[1] = s_mn[2] = 0xffffffffu;
+        s_mx[0] = s_mx[1] = s_mx[2] = 0u;
+        s_cnt = 0;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && cnt) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            atomicMin(&s_mn[a], mn[a]);
+            atomicMax(&s_mx[a], mx[a]);
+        }
+        atomicAdd(&s_cnt, cnt);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            atomicMin(&stats[f].mn[a], s_mn[a]);
+            atomicMax(&stats[f].mx[a], s_mx[a]);
+        }
+        atomicAdd(&stats[f].count, s_cnt);
+    }
+}
+
+__global__ void init_stats_kernel(FrameStats *stats, int n_frames) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < n_frames) {
+        stats[f].mn[0] = stats[f].mn[1] = stats[f].mn[2] = 0xffffffffu;
+        stats[f].mx[0] = stats[f].mx[1] = stats[f].mx[2] = 0u;
+        stats[f].count = 0;
+        stats[f].pad = 0;
+    }
+}
+
+// ---- K1: cell id + per-cell count + rank inside the cell + AoS copy -----------------------------
+// rank = old value of the L2 atomic: the later scatter is then a plain store (no second atomic).
+__global__ void __launch_bounds__(kBuildThreads) count_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                                                              const float *__restrict__ z,
+                                                              const uint32_t *__restrict__ frame_off, size_t n,
+                                                              const uint8_t *__restrict__ mask,
+                                                              const GridDesc *__restrict__ grids,
+                                                              uint32_t *__restrict__ cell_count,
+                                                              uint32_t *__restrict__ cell_id, uint32_t *__restrict__ rank,
+                                                              float4 *__restrict__ orig4) {
+    const int f = blockIdx.y;
+    const uint32_t b = frame_off ? frame_off[f] : 0u;
+    const uint32_t e = frame_off ? frame_off[f + 1] : (uint32_t)n;
+    const GridDesc g = grids[f];
+    const uint32_t base = b + blockIdx.x * (kBuildThreads * kItems) + threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < kItems; it++) {
+        uint32_t i = base + it * kBuildThreads;
+        if (i >= e) break;
+        float px = x[i], py = y[i], pz = z[i];
+        if (orig4) orig4[i] = make_float4(px, py, pz, 0.f);
+        uint32_t cid = 0xffffffffu, r = 0;
+        if (finite3(px, py, pz) && (!mask || mask[i])) {
+            int c0 = cell_coord(g, 0, pick_axis(g.ax[0], px, py, pz), nullptr);
+            int c1 = cell_coord(g, 1, pick_axis(g.ax[1], px, py, pz), nullptr);
+            int c2 = cell_coord(g, 2, pick_axis(g.ax[2], px, py, pz), nullptr);
+            cid = cell_linear(g, c0, c1, c2);
+            r = atomicAdd(&cell_count[cid], 1u);
+        }
+        cell_id[i] = cid;
+        rank[i] = r;
+    }
+}
+
+// ---- K1p: occupancy statistics of a probe grid ---------------------------------------------------
+// For every indexed point: log2(points in its cell) and log2(points in its 2x2x2 super-cell).  The
+// two geometric means give the local occupancy m(h) and its scaling exponent D (m ~ h^D), from
+// which the host solves m(h*) = target for the final cell size.
+__global__ void __launch_bounds__(kBuildThreads) stats_kernel(const uint32_t *__restrict__ frame_off, size_t n,
+                                                              const GridDesc *__restrict__ grids,
+                                                              const uint32_t *__restrict__ cell_count,
+                                                              const uint32_t *__restrict__ cell_id,
+                                                              ProbeStats *__restrict__ out) {
+    const int f = blockIdx.y;
+    const uint32_t b = frame_off ? frame_off[f] : 0u;
+    const uint32_t e = frame_off ? frame_off[f + 1] : (uint32_t)n;
+    const GridDesc g = grids[f];
+    float s_own = 0.f, s_sup = 0.f;
+    for (uint32_t i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) {
+        uint32_t cid = cell_id[i];
+        if (cid == 0xffffffffu) continue;
+        uint32_t l = cid - g.cell_base;
+        int c2 = l % g.dims[2];
+        uint32_t t = l / g.dims[2];
+        int c1 = t % g.dims[1];
+        int c0 = t / g.dims[1];
+        uint32_t own = cell_count[cid], sup = 0;
+        int b0 = c0 & ~1, b1 = c1 & ~1, b2 = c2 & ~1;
+#pragma unroll
+        for (int d0 = 0; d0 < 2; d0++)
+#pragma unroll
+            for (int d1 = 0; d1 < 2; d1++)
+#pragma unroll
+                for (int d2 = 0; d2 < 2; d2++) {
+                    int a0 = b0 + d0, a1 = b1 + d1, a2 = b2 + d2;
+                    if (a0 < g.dims[0] && a1 < g.dims[1] && a2 < g.dims[2]) sup += cell_count[cell_linear(g, a0, a1, a2)];
+                }
+        s_own += log2f((float)own);
+        s_sup += log2f((float)sup);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s_own += __shfl_xor_sync(PCR_FULL, s_own, o);
+        s_sup += __shfl_xor_sync(PCR_FULL, s_sup, o);
+    }
+    __shared__ float sh[2][kBuildThreads / 32];
+    int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        sh[0][w] = s_own;
+        sh[1][w] = s_sup;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, c = 0;
+        for (int i = 0; i < kBuildThreads / 32; i++) {
+            a += sh[0][i];
+            c += sh[1][i];
+        }
+        atomicAdd(&out[f].sum_log_own, a);
+        atomicAdd(&out[f].sum_log_super, c);
+    }
+}
+
+// ---- K3: scatter into cell order --------------------------------------------------------------
+__global__ void __launch_bounds__(kBuildThreads) scatter_kernel(const float4 *__restrict__ orig4, size_t n,
+                                                                const uint32_t *__restrict__ cell_start,
+                                                                const uint32_t *__restrict__ cell_id,
+                                                                const uint32_t *__restrict__ rank,
+                                                                float4 *__restrict__ sorted) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t cid = cell_id[i];
+    if (cid == 0xffffffffu) return;
+    float4 p = orig4[i];
+    p.w = __uint_as_float(i);
+    sorted[cell_start[cid] + rank[i]] = p;
+}
+
+// ---- K2: exclusive scan of a u32 table (two kernels, no inter-block waiting) -------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *sh) {
+    v = __reduce_add_sync(PCR_FULL, v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t t = 0;
+    if (threadIdx.x < kScanThreads / 32) t = sh[threadIdx.x];
+    if (threadIdx.x < 32) t = __reduce_add_sync(PCR_FULL, t);
+    if (threadIdx.x == 0) sh[0] = t;
+    __syncthreads();
+    t = sh[0];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint32_t *__restrict__ data, size_t n,
+                                                                      uint32_t *__restrict__ tile_sums) {
+    __shared__ uint32_t sh[kScanThreads / 32];
+    size_t base = (size_t)blockIdx.x * kScanTile;
+    uint32_t s = 0;
+#pragma unroll
+    for (int it = 0; it < kScanItems; it++) {
+        size_t i = base + it * kScanThreads + threadIdx.x;
+        if (i < n) s += data[i];
+    }
+    s = block_sum_u32(s, sh);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = s;
+}
+
+// data[i] <- sum of data[0..i) ; each block first folds the sums of the tiles before it
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint32_t *__restrict__ data, size_t n,
+                                                                  const uint32_t *__restrict__ tile_sums) {
+    __shared__ uint32_t sh[kScanThreads / 32];
+    __shared__ uint32_t warp_off[kScanThreads / 32];
+    uint32_t pre = 0;
+    for (uint32_t t = threadIdx.x; t < blockIdx.x; t += kScanThreads) pre += tile_sums[t];
+    pre = block_sum_u32(pre, sh);
+    // thread-contiguous items: thread t owns [t*16, t*16+16) of the tile
+    size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int it = 0; it < kScanItems; it++) {
+        size_t i = base + it;
+        v[it] = i < n ? data[i] : 0u;
+        tsum += v[it];
+    }
+    // exclusive scan of the per-thread sums across the block
+    uint32_t incl = tsum;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t u = __shfl_up_sync(PCR_FULL, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) warp_off[w] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t ws = threadIdx.x < kScanThreads / 32 ? warp_off[threadIdx.x] : 0u;
+        uint32_t wi = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t u = __shfl_up_sync(PCR_FULL, wi, o);
+            if (lane >= o) wi += u;
+        }
+        if (threadIdx.x < kScanThreads / 32) warp_off[threadIdx.x] = wi - ws;
+    }
+    __syncthreads();
+    uint32_t run = pre + warp_off[w] + (incl - tsum);
+#pragma unroll
+    for (int it = 0; it < kScanItems; it++) {
+        size_t i = base + it;
+        if (i < n) data[i] = run;
+        run += v[it];
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_u64_kernel(const uint32_t *__restrict__ in,
+                                                                      uint64_t *__restrict__ out, size_t n,
+                                                                      const uint32_t *__restrict__ tile_sums) {
+    // same as scan_apply_kernel but widening to u64 and writing out[n] = total as well
+    __shared__ unsigned long long sh64[kScanThreads / 32];
+    __shared__ unsigned long long warp_off[kScanThreads / 32];
+    unsigned long long pre = 0;
+    for (uint32_t t = threadIdx.x; t < blockIdx.x; t += kScanThreads) pre += tile_sums[t];
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(PCR_FULL, pre, o);
+    if ((threadIdx.x & 31) == 0) sh64[threadIdx.x >> 5] = pre;
+    __syncthreads();
+    pre = 0;
+    for (int i = 0; i < kScanThreads / 32; i++) pre += sh64[i];
+    __syncthreads();
+    size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    unsigned long long tsum = 0;
+#pragma unroll
+    for (int it = 0; it < kScanItems; it++) {
+        size_t i = base + it;
+        v[it] = i < n ? in[i] : 0u;
+        tsum += v[it];
+    }
+    unsigned long long incl = tsum;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long u = __shfl_up_sync(PCR_FULL, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) warp_off[w] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (int i = 0; i < kScanThreads / 32; i++) {
+            unsigned long long t = warp_off[i];
+            warp_off[i] = acc;
+            acc += t;
+        }
+    }
+    __syncthreads();
+    unsigned long long run = pre + warp_off[w] + (incl - tsum);
+#pragma unroll
+    for (int it = 0; it < kScanItems; it++) {
+        size_t i = base + it;
+        if (i < n) out[i] = run;
+        run += v[it];
+        if (i + 1 == n) out[n] = run;
+    }
+}
+
+}  // namespace
+
+int exclusive_scan_u32_dev(Ctx *ctx, uint32_t *d_data, size_t n) {
+    if (n == 0) return PCR_OK;
+    size_t tiles = (n + kScanTile - 1) / kScanTile;
+    PCR_TRY(ensure(ctx, ctx->b_misc2, tiles * sizeof(uint32_t)));
+    uint32_t *tile_sums = (uint32_t *)ctx->b_misc2.p;
+    scan_tile_sums_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(d_data, n, tile_sums);
+    PCR_LAUNCH_CHECK(ctx);
+    scan_apply_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(d_data, n, tile_sums);
+    PCR_LAUNCH_CHECK(ctx);
+    return PCR_OK;
+}
+
+int exclusive_scan_u64_from_u32_dev(Ctx *ctx, const uint32_t *d_in, uint64_t *d_out, size_t n) {
+    if (n == 0) {
+        PCR_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(uint64_t), ctx->stream));
+        return PCR_OK;
+    }
+    size_t tiles = (n + kScanTile - 1) / kScanTile;
+    PCR_TRY(ensure(ctx, ctx->b_misc2, tiles * sizeof(uint32_t)));
+    uint32_t *tile_sums = (uint32_t *)ctx->b_misc2.p;
+    scan_tile_sums_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(d_in, n, tile_sums);
+    PCR_LAUNCH_CHECK(ctx);
+    scan_apply_u64_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(d_in, d_out, n, tile_sums);
+    PCR_LAUNCH_CHECK(ctx);
+    return PCR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: cell-size selection and build orchestration
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr uint64_t kMaxCellsPerFrame = 1ull << 24;
+constexpr uint64_t kMaxCellsTotal = 1ull << 27;
+
+struct FrameBox {
+    double mn[3], ext[3];
+    uint32_t count;
+};
+
+// occupancy target: points sharing a cell with a typical point.  Tuned with the scalar model
+// (oracle/orc_grid_knn_model) on the KITTI / aerial / uniform-cube shapes.
+double occupancy_target(size_t k_hint) {
+    double k = k_hint ? (double)k_hint : 10.0;
+    return std::min(64.0, std::max(2.0, 0.8 * k));
+}
+
+double initial_cell(const FrameBox &b, double target) {
+    if (b.count == 0) return 1.0;
+    double e[3] = {b.ext[0], b.ext[1], b.ext[2]};
+    std::sort(e, e + 3);
+    double tiny = std::max(e[2] * 1e-6, 1e-30);
+    double vol = std::max(e[0], tiny) * std::max(e[1], tiny) * std::max(e[2], tiny);
+    double area = std::max(e[1], tiny) * std::max(e[2], tiny);
+    double h3 = std::cbrt(vol * target / b.count);
+    double h2 = std::sqrt(area * target / b.count);
+    double h = std::sqrt(h2 * h3);
+    if (!(h > 0) || !std::isfinite(h)) h = 1.0;
+    return h;
+}
+
+// Fill dims / permutation for cell size h, growing h until the dense table fits the cap.
+void shape_grid(GridDesc &g, const FrameBox &b, double h, uint64_t cap) {
+    if (b.count == 0) h = 1.0;
+    int dims[3];
+    for (int iter = 0; iter < 64; iter++) {
+        double inv = 1.0 / h;
+        double cells = 1.0;
+        for (int a = 0; a < 3; a++) {
+            double d = std::floor(b.ext[a] * inv) + 1.0;
+            if (!(d >= 1.0)) d = 1.0;
+            cells *= d;
+            dims[a] = d > 2147483000.0 ? 2147483000 : (int)d;
+        }
+        if (cells <= (double)cap) break;
+        h *= std::cbrt(cells / (double)cap) * 1.02;
+    }
+    int order[3] = {0, 1, 2};
+    std::stable_sort(order, order + 3, [&](int p, int q) { return dims[p] < dims[q]; });
+    g.h = h;
+    g.inv_h = 1.0 / h;
+    for (int j = 0; j < 3; j++) {
+        g.ax[j] = order[j];
+        g.dims[j] = dims[order[j]];
+        g.o[j] = b.count ? b.mn[order[j]] : 0.0;
+    }
+    g.n_cells = (uint32_t)((uint64_t)g.dims[0] * g.dims[1] * g.dims[2]);
+}
+
+}  // namespace
+
+void index_free(Index *ix) {
+    if (!ix) return;
+    if (ix->owns_memory && ix->ctx) {
+        cudaStream_t s = ix->ctx->stream;
+        if (ix->grids) cudaFreeAsync(ix->grids, s);
+        if (ix->frame_in_off) cudaFreeAsync(ix->frame_in_off, s);
+        if (ix->sorted) cudaFreeAsync(ix->sorted, s);
+        if (ix->orig4) cudaFreeAsync(ix->orig4, s);
+        if (ix->cell_start) cudaFreeAsync(ix->cell_start, s);
+    }
+    delete ix;
+}
+
+int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz, size_t n, const BuildOpts &opts,
+                    Index **out) {
+    *out = nullptr;
+    if (n >= 0xfffffff0ull) return fail(ctx, PCR_ERR_UNSUPPORTED, "clouds above 2^32-16 points are not supported");
+    const int F = opts.n_frames > 0 ? opts.n_frames : 1;
+    if (F > 1 && !opts.frame_offsets) return fail(ctx, PCR_ERR_INVALID_ARG, "frame_offsets missing");
+    cudaStream_t st = ctx->stream;
+
+    Index *ix = new (std::nothrow) Index();
+    if (!ix) return fail(ctx, PCR_ERR_OOM, "host allocation failed");
+    ix->ctx = ctx;
+    ix->n = n;
+    ix->n_frames = F;
+    ix->grids_h.resize(F);
+    struct Guard {  // frees the half-built index on any early return
+        Index *ix;
+        ~Guard() {
+            if (ix) index_free(ix);
+        }
+    } guard{ix};
+
+    PCR_CUDA(ctx, cudaMallocAsync((void **)&ix->grids, sizeof(GridDesc) * F, st));
+    std::vector<uint32_t> off_h(F + 1);
+    if (F > 1) {
+        for (int f = 0; f <= F; f++) {
+            if (opts.frame_offsets[f] > n || (f && opts.frame_offsets[f] < opts.frame_offsets[f - 1]))
+                return fail(ctx, PCR_ERR_INVALID_ARG, "frame_offsets must be non-decreasing and end at n");
+            off_h[f] = (uint32_t)opts.frame_offsets[f];
+        }
+        if (off_h[0] != 0 || off_h[F] != n) return fail(ctx, PCR_ERR_INVALID_ARG, "frame_offsets must span [0, n]");
+        PCR_CUDA(ctx, cudaMallocAsync((void **)&ix->frame_in_off, sizeof(uint32_t) * (F + 1), st));
+        PCR_CUDA(ctx, cudaMemcpyAsync(ix->frame_in_off, off_h.data(), sizeof(uint32_t) * (F + 1), cudaMemcpyHostToDevice, st));
+    } else {
+        off_h[0] = 0;
+        off_h[1] = (uint32_t)n;
+    }
+    uint32_t max_frame = 0;
+    for (int f = 0; f < F; f++) max_frame = std::max(max_frame, off_h[f + 1] - off_h[f]);
+
+    if (n > 0) {
+        PCR_CUDA(ctx, cudaMallocAsync((void **)&ix->orig4, sizeof(float4) * n, st));
+        PCR_CUDA(ctx, cudaMallocAsync((void **)&ix->sorted, sizeof(float4) * n, st));
+    }
+
+    // ---- K0: bounding boxes -------------------------------------------------------------------
+    PCR_TRY(ensure(ctx, ctx->b_small, sizeof(FrameStats) * F + sizeof(ProbeStats) * F + 256));
+    PCR_TRY(ensure_pinned(ctx, sizeof(FrameStats) * F + sizeof(ProbeStats) * F + 256));
+    FrameStats *d_stats = (FrameStats *)ctx->b_small.p;
+    ProbeStats *d_probe = (ProbeStats *)((char *)ctx->b_small.p + sizeof(FrameStats) * F);
+    FrameStats *h_stats = (FrameStats *)ctx->pinned;
+    ProbeStats *h_probe = (ProbeStats *)((char *)ctx->pinned + sizeof(FrameStats) * F);
+    init_stats_kernel<<<(F + 255) / 256, 256, 0, st>>>(d_stats, F);
+    PCR_LAUNCH_CHECK(ctx);
+    if (n > 0) {
+        unsigned bx = (unsigned)std::min<size_t>((max_frame + kBuildThreads * 4 - 1) / (kBuildThreads * 4),
+                                                 F > 1 ? 64 : (size_t)ctx->sm_count * 4);
+        bx = std::max(bx, 1u);
+        bbox_kernel<<<dim3(bx, F), kBuildThreads, 0, st>>>(dx, dy, dz, ix->frame_in_off, n, opts.d_mask, d_stats);
+        PCR_LAUNCH_CHECK(ctx);
+    }
+    PCR_CUDA(ctx, cudaMemcpyAsync(h_stats, d_stats, sizeof(FrameStats) * F, cudaMemcpyDeviceToHost, st));
+    PCR_CUDA(ctx, cudaStreamSynchronize(st));
+
+    std::vector<FrameBox> box(F);
+    size_t n_indexed = 0;
+    for (int f = 0; f < F; f++) {
+        box[f].count = h_stats[f].count;
+        for (int a = 0; a < 3; a++) {
+            if (box[f].count) {
+                double lo = ordered_f32(h_stats[f].mn[a]), hi = ordered_f32(h_stats[f].mx[a]);
+                box[f].mn[a] = lo;
+                box[f].ext[a] = hi - lo;
+            } else {
+                box[f].mn[a] = 0;
+                box[f].ext[a] = 0;
+            }
+        }
+        n_indexed += box[f].count;
+    }
+    ix->n_indexed = n_indexed;
+
+    const double target = occupancy_target(opts.k_hint);
+    const uint64_t cap = std::max<uint64_t>(1, std::min<uint64_t>(kMaxCellsPerFrame, kMaxCellsTotal / (uint64_t)F));
+    std::vector<double> hsel(F);
+    const bool forced = ctx->forced_cell > 0.f;
+    for (int f = 0; f < F; f++) hsel[f] = forced ? (double)ctx->forced_cell : initial_cell(box[f], target);
+
+    PCR_TRY(ensure(ctx, ctx->b_misc, sizeof(uint32_t) * 2 * std::max<size_t>(n, 1)));
+    uint32_t *d_cell_id = (uint32_t *)ctx->b_misc.p;
+    uint32_t *d_rank = d_cell_id + std::max<size_t>(n, 1);
+
+    // lays the frames' tables back to back and uploads the descriptors
+    auto layout = [&](uint32_t *total_cells) -> int {
+        uint64_t base = 0;
+        uint32_t pt = 0;
+        for (int f = 0; f < F; f++) {
+            GridDesc &g = ix->grids_h[f];
+            shape_grid(g, box[f], hsel[f], cap);
+            g.cell_base = (uint32_t)base;
+            base += g.n_cells;
+            g.pt_begin = pt;
+            pt += box[f].count;
+            g.pt_end = pt;
+            g.in_begin = off_h[f];
+            g.in_end = off_h[f + 1];
+        }
+        if (base >= 0xffffffffull) return fail(ctx, PCR_ERR_UNSUPPORTED, "cell table too large");
+        *total_cells = (uint32_t)base;
+        PCR_CUDA(ctx, cudaMemcpyAsync(ix->grids, ix->grids_h.data(), sizeof(GridDesc) * F, cudaMemcpyHostToDevice, st));
+        return PCR_OK;
+    };
+    const unsigned count_bx = std::max(1u, (max_frame + kBuildThreads * kItems - 1) / (kBuildThreads * kItems));
+
+    // ---- probe rounds: measure occupancy, solve for the cell size ------------------------------
+    if (!forced && n_indexed > 0) {
+        for (int round = 0; round < 2; round++) {
+            uint32_t total = 0;
+            PCR_TRY(layout(&total));
+            PCR_TRY(ensure(ctx, ctx->b_table, sizeof(uint32_t) * ((size_t)total + 1)));
+            uint32_t *d_tab = (uint32_t *)ctx->b_table.p;
+            PCR_CUDA(ctx, cudaMemsetAsync(d_tab, 0, sizeof(uint32_t) * ((size_t)total + 1), st));
+            PCR_CUDA(ctx, cudaMemsetAsync(d_probe, 0, sizeof(ProbeStats) * F, st));
+            count_kernel<<<dim3(count_bx, F), kBuildThreads, 0, st>>>(dx, dy, dz, ix->frame_in_off, n, opts.d_mask, ix->grids,
+                                                                      d_tab, d_cell_id, d_rank, nullptr);
+            PCR_LAUNCH_CHECK(ctx);
+            unsigned sbx = (unsigned)std::min<size_t>((max_frame + kBuildThreads * 4 - 1) / (kBuildThreads * 4),
+                                                      F > 1 ? 64 : (size_t)ctx->sm_count * 4);
+            stats_kernel<<<dim3(std::max(sbx, 1u), F), kBuildThreads, 0, st>>>(ix->frame_in_off, n, ix->grids, d_tab,
+                                                                               d_cell_id, d_probe);
+            PCR_LAUNCH_CHECK(ctx);
+            PCR_CUDA(ctx, cudaMemcpyAsync(h_probe, d_probe, sizeof(ProbeStats) * F, cudaMemcpyDeviceToHost, st));
+            PCR_CUDA(ctx, cudaStreamSynchronize(st));
+            bool again = false;
+            for (int f = 0; f < F; f++) {
+                if (!box[f].count) continue;
+                double l1 = h_probe[f].sum_log_own / box[f].count;     // log2 m(h)
+                double l2 = h_probe[f].sum_log_super / box[f].count;   // log2 m(2h)
+                double D = std::min(3.0, std::max(1.0, l2 - l1));
+                double ratio = std::exp2((std::log2(target) - l1) / D);
+                ratio = std::min(6.0, std::max(1.0 / 6.0, ratio));
+                double hprobe = ix->grids_h[f].h;  // (may have been grown by the cell cap)
+                hsel[f] = hprobe * ratio;
+                if (ratio > 2.5 || ratio < 0.4) again = true;
+            }
+            if (!again) break;
+        }
+    }
+
+    // ---- final grid: count, scan, scatter ------------------------------------------------------
+    uint32_t total = 0;
+    PCR_TRY(layout(&total));
+    ix->total_cells = total;
+    PCR_CUDA(ctx, cudaMallocAsync((void **)&ix->cell_start, sizeof(uint32_t) * ((size_t)total + 1), st));
+    PCR_CUDA(ctx, cudaMemsetAsync(ix->cell_start, 0, sizeof(uint32_t) * ((size_t)total + 1), st));
+    if (n > 0) {
+        count_kernel<<<dim3(count_bx, F), kBuildThreads, 0, st>>>(dx, dy, dz, ix->frame_in_off, n, opts.d_mask, ix->grids,
+                                                                  ix->cell_start, d_cell_id, d_rank, ix->orig4);
+        PCR_LAUNCH_CHECK(ctx);
+    }
+    PCR_TRY(exclusive_scan_u32_dev(ctx, ix->cell_start, (size_t)total + 1));
+    if (n > 0) {
+        scatter_kernel<<<(unsigned)((n + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0, st>>>(
+            ix->orig4, n, ix->cell_start, d_cell_id, d_rank, ix->sorted);
+        PCR_LAUNCH_CHECK(ctx);
+    }
+    guard.ix = nullptr;
+    *out = ix;
+    return PCR_OK;
+}
+
+}  // namespace pcr

@@ -1,0 +1,538 @@
+// knn.cu -- batched KNN and the consumers fused onto it.
+//
+//   knn_queries_kernel   KdTree::knn / knn_indices for a batch of queries   kdtree.rs:64-96
+//   sor_mean_kernel      per-point mean neighbour distance                  statistical_outlier.rs:19-39
+//   normals_kernel       covariance + Cardano eigenvector + orientation     estimate.rs:42-109,139-238
+//   radius_*_kernel      radius_search[_unsorted]                           kdtree.rs:105-163
+//
+// Work layout: one warp per query for the search (lanes stream candidates, the top-k lives in
+// registers, one entry per lane); every warp takes 32 consecutive queries of the CELL-SORTED order
+// (neighbouring queries touch the same cells, so the runs they stream stay in L1), parks the 32
+// results in shared memory transposed, and then runs the per-query epilogue with one THREAD per
+// query -- the epilogues are sequential f32 folds in neighbour order (that order is part of the
+// reference's arithmetic), which would waste 31 lanes if done warp-wide.
+#include "knn_search.cuh"
+
+#include <algorithm>
+#include <type_traits>
+
+namespace pcr {
+
+namespace {
+
+constexpr int kWarps = 4;              // warps per block
+constexpr int kThreads = kWarps * 32;
+constexpr int kQPW = 32;               // queries per warp
+constexpr int kQPB = kWarps * kQPW;    // queries per block
+
+__device__ __forceinline__ int frame_of_sorted(const GridDesc *__restrict__ grids, int n_frames, uint32_t pos) {
+    if (n_frames <= 1) return 0;
+    int lo = 0, hi = n_frames - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (grids[mid].pt_begin <= pos) lo = mid;
+        else hi = mid - 1;
+    }
+    // skip empty frames that share pt_begin
+    while (lo + 1 < n_frames && grids[lo].pt_end <= pos) lo++;
+    return lo;
+}
+
+// ---- external queries -----------------------------------------------------------------------------
+template <class TopK>
+__device__ __forceinline__ void emit_row(const TopK &tk, int cnt, size_t k, size_t qi, uint32_t *__restrict__ idx,
+                                         float *__restrict__ dist);
+
+template <>
+__device__ __forceinline__ void emit_row<RegTopK>(const RegTopK &tk, int cnt, size_t k, size_t qi,
+                                                  uint32_t *__restrict__ idx, float *__restrict__ dist) {
+    if ((size_t)tk.lane < k) {
+        bool v = tk.lane < cnt;
+        idx[qi * k + tk.lane] = v ? key_idx(tk.K) : 0xffffffffu;
+        if (dist) dist[qi * k + tk.lane] = v ? __fsqrt_rn(key_d2(tk.K)) : INFINITY;  // kdtree.rs:76
+    }
+}
+template <>
+__device__ __forceinline__ void emit_row<SmemTopK>(const SmemTopK &tk, int cnt, size_t k, size_t qi,
+                                                   uint32_t *__restrict__ idx, float *__restrict__ dist) {
+    for (size_t j = tk.lane; j < k; j += 32) {
+        bool v = j < (size_t)cnt;
+        unsigned long long key = v ? tk.s[j] : 0ull;
+        idx[qi * k + j] = v ? key_idx(key) : 0xffffffffu;
+        if (dist) dist[qi * k + j] = v ? __fsqrt_rn(key_d2(key)) : INFINITY;
+    }
+}
+
+template <bool kSmem>
+__global__ void __launch_bounds__(kThreads) knn_queries_kernel(const GridDesc *__restrict__ grids,
+                                                               const uint32_t *__restrict__ cell_start,
+                                                               const float4 *__restrict__ sorted,
+                                                               const float *__restrict__ qx, const float *__restrict__ qy,
+                                                               const float *__restrict__ qz, size_t nq, int kk,
+                                                               uint32_t *__restrict__ idx, float *__restrict__ dist,
+                                                               uint32_t *__restrict__ counts) {
+    extern __shared__ unsigned long long smem_keys[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const GridDesc g = grids[0];
+    typename std::conditional<kSmem, SmemTopK, RegTopK>::type tk;
+    tk.kk = kk;
+    tk.lane = lane;
+    if constexpr (kSmem) tk.s = smem_keys + (size_t)w * kk;
+    const size_t q0 = ((size_t)blockIdx.x * kWarps + w) * kQPW;
+    for (int t = 0; t < kQPW; t++) {
+        size_t qi = q0 + t;
+        if (qi >= nq) break;
+        float x = __ldg(&qx[qi]), y = __ldg(&qy[qi]), z = __ldg(&qz[qi]);
+        int cnt = 0;
+        tk.reset(PCR_EMPTY_KEY);
+        if (finite3(x, y, z)) {  // kdtree.rs:65
+            warp_knn_search(tk, g, cell_start, sorted, x, y, z);
+            cnt = tk.count();
+        }
+        emit_row(tk, cnt, (size_t)kk, qi, idx, dist);
+        if (counts && lane == 0) counts[qi] = (uint32_t)cnt;
+        if constexpr (kSmem) __syncwarp();
+    }
+}
+
+// ---- SOR: mean distance to the k nearest neighbours (k+1 searched, self dropped) ----------------
+// smem per warp: dist[(kk)][33] f32 (transposed: neighbour-major) + cnt[32]
+template <bool kSmem>
+__global__ void __launch_bounds__(kThreads) sor_mean_kernel(const GridDesc *__restrict__ grids, int n_frames,
+                                                            const uint32_t *__restrict__ cell_start,
+                                                            const float4 *__restrict__ sorted, uint32_t n_sorted, int kk,
+                                                            float *__restrict__ mean_d) {
+    extern __shared__ unsigned long long smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t q0 = (blockIdx.x * kWarps + w) * kQPW;
+    if (q0 >= n_sorted) return;
+    if constexpr (!kSmem) {
+        float *sd = reinterpret_cast<float *>(smem_raw) + (size_t)w * (kk * 33 + 32);
+        int *scnt = reinterpret_cast<int *>(sd + kk * 33);
+        RegTopK tk;
+        tk.kk = kk;
+        tk.lane = lane;
+        int f = frame_of_sorted(grids, n_frames, q0);
+        GridDesc g = grids[f];
+        for (int t = 0; t < kQPW; t++) {
+            uint32_t qi = q0 + t;
+            if (qi >= n_sorted) break;
+            if (qi >= g.pt_end) {
+                f = frame_of_sorted(grids, n_frames, qi);
+                g = grids[f];
+            }
+            float4 q = __ldg(&sorted[qi]);
+            warp_knn_search(tk, g, cell_start, sorted, q.x, q.y, q.z);
+            int cnt = tk.count();
+            if (lane < kk) sd[lane * 33 + t] = __fsqrt_rn(key_d2(tk.K));  // kdtree.rs:76
+            if (lane == 0) scnt[t] = cnt;
+        }
+        __syncwarp();
+        uint32_t qi = q0 + lane;
+        if (qi < n_sorted) {
+            int cnt = scnt[lane];
+            // statistical_outlier.rs:28-37: drop the first (self) if there is more than one result,
+            // sequential f32 sum in ascending-distance order, divide by the count
+            int first = cnt > 1 ? 1 : 0;
+            float sum = 0.0f;
+            for (int j = first; j < cnt; j++) sum = __fadd_rn(sum, sd[j * 33 + lane]);
+            int m = cnt - first;
+            float md = m > 0 ? __fdiv_rn(sum, (float)m) : INFINITY;
+            mean_d[__float_as_uint(__ldg(&sorted[qi]).w)] = md;
+        }
+    } else {
+        SmemTopK tk;
+        tk.kk = kk;
+        tk.lane = lane;
+        tk.s = smem_raw + (size_t)w * kk;
+        for (int t = 0; t < kQPW; t++) {
+            uint32_t qi = q0 + t;
+            if (qi >= n_sorted) break;
+            int f = frame_of_sorted(grids, n_frames, qi);
+            const GridDesc g = grids[f];
+            float4 q = __ldg(&sorted[qi]);
+            warp_knn_search(tk, g, cell_start, sorted, q.x, q.y, q.z);
+            __syncwarp();
+            if (lane == 0) {
+                int cnt = tk.count();
+                int first = cnt > 1 ? 1 : 0;
+                float sum = 0.0f;
+                for (int j = first; j < cnt; j++) sum = __fadd_rn(sum, __fsqrt_rn(key_d2(tk.s[j])));
+                int m = cnt - first;
+                mean_d[__float_as_uint(q.w)] = m > 0 ? __fdiv_rn(sum, (float)m) : INFINITY;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---- normals ----------------------------------------------------------------------------------------
+// estimate.rs:139-238, f64 internally (compiled with -fmad=false: like the reference, no fusing)
+__device__ __forceinline__ void smallest_eigenvector_3x3(float fa00, float fa01, float fa02, float fa11, float fa12,
+                                                         float fa22, float &ox, float &oy, float &oz) {
+    const double a00 = fa00, a01 = fa01, a02 = fa02, a11 = fa11, a12 = fa12, a22 = fa22;
+    const double m = (a00 + a11 + a22) / 3.0;
+    const double b00 = a00 - m, b11 = a11 - m, b22 = a22 - m;
+    const double q = (b00 * (b11 * b22 - a12 * a12) - a01 * (a01 * b22 - a12 * a02) + a02 * (a01 * a12 - b11 * a02)) / 2.0;
+    const double p = (b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * (a01 * a01 + a02 * a02 + a12 * a12)) / 6.0;
+    const double pp = p > 0.0 ? p : 0.0;  // f64::max(0.0): NaN -> 0.0
+    ox = 0.f; oy = 0.f; oz = 1.f;
+    if (pp < 1e-30) return;
+    const double sqrt_p = sqrt(pp);
+    double det_ratio = q / (pp * sqrt_p);
+    det_ratio = det_ratio < -1.0 ? -1.0 : (det_ratio > 1.0 ? 1.0 : det_ratio);
+    const double phi = acos(det_ratio) / 3.0;
+    const double FRAC_PI_3 = 1.04719755119659774615421446109316763;
+    const double eig0 = m + 2.0 * sqrt_p * cos(phi + 2.0 * FRAC_PI_3);
+    const double eig2 = m + 2.0 * sqrt_p * cos(phi);
+    const double eig1 = 3.0 * m - eig0 - eig2;
+    double lambda;
+    if (fabs(eig0) <= fabs(eig1) && fabs(eig0) <= fabs(eig2)) lambda = eig0;
+    else if (fabs(eig1) <= fabs(eig2)) lambda = eig1;
+    else lambda = eig2;
+    const double r00 = a00 - lambda, r11 = a11 - lambda, r22 = a22 - lambda;
+    double ex = a01 * a12 - r11 * a02, ey = a02 * a01 - a12 * r00, ez = r00 * r11 - a01 * a01;
+    double len2 = ex * ex + ey * ey + ez * ez;
+    if (len2 < 1e-30) {
+        ex = a01 * r22 - a12 * a02; ey = a02 * a02 - r22 * r00; ez = r00 * a12 - a01 * a02;
+        len2 = ex * ex + ey * ey + ez * ez;
+        if (len2 < 1e-30) {
+            ex = r11 * r22 - a12 * a12; ey = a12 * a02 - r22 * a01; ez = a01 * a12 - r11 * a02;
+            len2 = ex * ex + ey * ey + ez * ez;
+            if (len2 < 1e-30) return;
+        }
+    }
+    const double inv = 1.0 / sqrt(len2);
+    ox = (float)(ex * inv);
+    oy = (float)(ey * inv);
+    oz = (float)(ez * inv);
+}
+
+// estimate.rs:47-109 for one point whose neighbours' coordinates are read through `nb(j, c)`
+template <class NB>
+__device__ __forceinline__ void normal_from_neighbours(int cnt, NB nb, float px, float py, float pz, float vx_, float vy_,
+                                                       float vz_, float &nx, float &ny, float &nz) {
+    if (cnt < 1) {
+        nx = 0.f; ny = 0.f; nz = 1.f;
+        return;
+    }
+    const float count = (float)cnt;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    for (int j = 0; j < cnt; j++) {
+        cx = __fadd_rn(cx, nb(j, 0));
+        cy = __fadd_rn(cy, nb(j, 1));
+        cz = __fadd_rn(cz, nb(j, 2));
+    }
+    cx = __fdiv_rn(cx, count);
+    cy = __fdiv_rn(cy, count);
+    cz = __fdiv_rn(cz, count);
+    float c00 = 0.f, c01 = 0.f, c02 = 0.f, c11 = 0.f, c12 = 0.f, c22 = 0.f;
+    for (int j = 0; j < cnt; j++) {
+        float dx = __fsub_rn(nb(j, 0), cx), dy = __fsub_rn(nb(j, 1), cy), dz = __fsub_rn(nb(j, 2), cz);
+        c00 = __fadd_rn(c00, __fmul_rn(dx, dx));
+        c01 = __fadd_rn(c01, __fmul_rn(dx, dy));
+        c02 = __fadd_rn(c02, __fmul_rn(dx, dz));
+        c11 = __fadd_rn(c11, __fmul_rn(dy, dy));
+        c12 = __fadd_rn(c12, __fmul_rn(dy, dz));
+        c22 = __fadd_rn(c22, __fmul_rn(dz, dz));
+    }
+    float ex, ey, ez;
+    smallest_eigenvector_3x3(c00, c01, c02, c11, c12, c22, ex, ey, ez);
+    float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
+    if (len > 1e-10f) {
+        ex = __fdiv_rn(ex, len);
+        ey = __fdiv_rn(ey, len);
+        ez = __fdiv_rn(ez, len);
+    }
+    float vx = __fsub_rn(vx_, px), vy = __fsub_rn(vy_, py), vz = __fsub_rn(vz_, pz);
+    float dot = __fadd_rn(__fadd_rn(__fmul_rn(ex, vx), __fmul_rn(ey, vy)), __fmul_rn(ez, vz));
+    if (dot < 0.0f) {
+        ex = -ex; ey = -ey; ez = -ez;
+    }
+    nx = ex; ny = ey; nz = ez;
+}
+
+// smem per warp (register path): coords[(kk*3)][33] f32 + cnt[32]
+template <bool kSmem>
+__global__ void __launch_bounds__(kThreads) normals_kernel(const GridDesc *__restrict__ grids, int n_frames,
+                                                           const uint32_t *__restrict__ cell_start,
+                                                           const float4 *__restrict__ sorted, uint32_t n_sorted,
+                                                           const float4 *__restrict__ orig4, int kk, float vx, float vy,
+                                                           float vz, float *__restrict__ nx, float *__restrict__ ny,
+                                                           float *__restrict__ nz) {
+    extern __shared__ unsigned long long smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t q0 = (blockIdx.x * kWarps + w) * kQPW;
+    if (q0 >= n_sorted) return;
+    if constexpr (!kSmem) {
+        float *sc = reinterpret_cast<float *>(smem_raw) + (size_t)w * (kk * 3 * 33 + 32);
+        int *scnt = reinterpret_cast<int *>(sc + kk * 3 * 33);
+        RegTopK tk;
+        tk.kk = kk;
+        tk.lane = lane;
+        int f = frame_of_sorted(grids, n_frames, q0);
+        GridDesc g = grids[f];
+        for (int t = 0; t < kQPW; t++) {
+            uint32_t qi = q0 + t;
+            if (qi >= n_sorted) break;
+            if (qi >= g.pt_end) {
+                f = frame_of_sorted(grids, n_frames, qi);
+                g = grids[f];
+            }
+            float4 q = __ldg(&sorted[qi]);
+            warp_knn_search(tk, g, cell_start, sorted, q.x, q.y, q.z);
+            int cnt = tk.count();
+            if (lane < cnt) {  // gather the neighbour's coordinates once (one 16 B load per lane)
+                float4 p = __ldg(&orig4[key_idx(tk.K)]);
+                sc[(lane * 3 + 0) * 33 + t] = p.x;
+                sc[(lane * 3 + 1) * 33 + t] = p.y;
+                sc[(lane * 3 + 2) * 33 + t] = p.z;
+            }
+            if (lane == 0) scnt[t] = cnt;
+        }
+        __syncwarp();
+        uint32_t qi = q0 + lane;
+        if (qi < n_sorted) {
+            float4 q = __ldg(&sorted[qi]);
+            float ox, oy, oz;
+            normal_from_neighbours(scnt[lane], [&](int j, int c) { return sc[(j * 3 + c) * 33 + lane]; }, q.x, q.y, q.z, vx, vy,
+                                   vz, ox, oy, oz);
+            uint32_t oi = __float_as_uint(q.w);
+            nx[oi] = ox;
+            ny[oi] = oy;
+            nz[oi] = oz;
+        }
+    } else {
+        SmemTopK tk;
+        tk.kk = kk;
+        tk.lane = lane;
+        tk.s = smem_raw + (size_t)w * kk;
+        for (int t = 0; t < kQPW; t++) {
+            uint32_t qi = q0 + t;
+            if (qi >= n_sorted) break;
+            int f = frame_of_sorted(grids, n_frames, qi);
+            const GridDesc g = grids[f];
+            float4 q = __ldg(&sorted[qi]);
+            warp_knn_search(tk, g, cell_start, sorted, q.x, q.y, q.z);
+            __syncwarp();
+            if (lane == 0) {
+                float ox, oy, oz;
+                const unsigned long long *s = tk.s;
+                normal_from_neighbours(tk.count(),
+                                       [&](int j, int c) {
+                                           float4 p = __ldg(&orig4[key_idx(s[j])]);
+                                           return c == 0 ? p.x : (c == 1 ? p.y : p.z);
+                                       },
+                                       q.x, q.y, q.z, vx, vy, vz, ox, oy, oz);
+                uint32_t oi = __float_as_uint(q.w);
+                nx[oi] = ox;
+                ny[oi] = oy;
+                nz[oi] = oz;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// value for points that are not in the index: non-finite points have no neighbours -> (0,0,1)
+// (estimate.rs:49-51); points removed by a mask (batch pipeline) -> 0.
+__global__ void fill_unindexed_normals_kernel(const float4 *__restrict__ orig4, const uint8_t *__restrict__ mask, size_t n,
+                                              float *__restrict__ nx, float *__restrict__ ny, float *__restrict__ nz) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = orig4[i];
+    bool removed = mask && !mask[i];
+    if (removed) {
+        nx[i] = 0.f; ny[i] = 0.f; nz[i] = 0.f;
+    } else if (!finite3(p.x, p.y, p.z)) {
+        nx[i] = 0.f; ny[i] = 0.f; nz[i] = 1.f;
+    }
+}
+
+__global__ void fill_f32_kernel(float *__restrict__ p, size_t n, float v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---- radius search (thread per query) ------------------------------------------------------------
+// d^2 <= r*r with r*r rounded in f32 (kdtree.rs:114,127).  Cells are taken from the box
+// [q - r', q + r'] with r' = sqrt(r2) * (1 + 1e-6): a point that passes the f32 test is at most a
+// few ulp further than sqrt(r2) on any axis.
+template <bool kFill>
+__global__ void __launch_bounds__(256) radius_kernel(const GridDesc *__restrict__ grids,
+                                                     const uint32_t *__restrict__ cell_start,
+                                                     const float4 *__restrict__ sorted, const float *__restrict__ qx,
+                                                     const float *__restrict__ qy, const float *__restrict__ qz, size_t nq,
+                                                     float radius, uint32_t *__restrict__ counts,
+                                                     const uint64_t *__restrict__ offsets, uint32_t *__restrict__ out_idx) {
+    size_t qi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    const GridDesc g = grids[0];
+    float x = qx[qi], y = qy[qi], z = qz[qi];
+    uint32_t cnt = 0;
+    uint32_t *dst = kFill ? out_idx + offsets[qi] : nullptr;
+    // kdtree.rs:106-112
+    if (g.pt_end > g.pt_begin && radius > 0.0f && isfinite(radius) && finite3(x, y, z)) {
+        const float r2 = __fmul_rn(radius, radius);
+        const double rr = sqrt((double)r2) * (1.0 + 1e-6) + 1e-300;
+        int lo[3], hi[3];
+        bool any = true;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double v = (double)pick_axis(g.ax[j], x, y, z);
+            double tl = floor((v - rr - g.o[j]) * g.inv_h), th = floor((v + rr - g.o[j]) * g.inv_h);
+            if (th < 0.0 || tl > (double)(g.dims[j] - 1)) any = false;
+            lo[j] = (int)fmin(fmax(tl, 0.0), (double)(g.dims[j] - 1));
+            hi[j] = (int)fmin(fmax(th, 0.0), (double)(g.dims[j] - 1));
+        }
+        if (any) {
+            for (int a0 = lo[0]; a0 <= hi[0]; a0++)
+                for (int a1 = lo[1]; a1 <= hi[1]; a1++) {
+                    uint32_t lin = cell_linear(g, a0, a1, lo[2]);
+                    uint32_t b = __ldg(&cell_start[lin]), e = __ldg(&cell_start[lin + (uint32_t)(hi[2] - lo[2]) + 1u]);
+                    for (uint32_t i = b; i < e; i++) {
+                        float4 p = __ldg(&sorted[i]);
+                        if (dist2_exact(x, y, z, p.x, p.y, p.z) <= r2) {
+                            if (kFill) dst[cnt] = __float_as_uint(p.w);
+                            cnt++;
+                        }
+                    }
+                }
+        }
+    }
+    if (!kFill) {
+        counts[qi] = cnt;
+    } else if (cnt > 1) {
+        // ascending index order (kdtree.rs:132): in-place heapsort of this query's slice
+        for (uint32_t start = cnt / 2; start-- > 0;) {
+            uint32_t root = start;
+            for (;;) {
+                uint32_t c = 2 * root + 1;
+                if (c >= cnt) break;
+                if (c + 1 < cnt && dst[c] < dst[c + 1]) c++;
+                if (dst[root] >= dst[c]) break;
+                uint32_t tmp = dst[root]; dst[root] = dst[c]; dst[c] = tmp;
+                root = c;
+            }
+        }
+        for (uint32_t end = cnt - 1; end > 0; end--) {
+            uint32_t tmp = dst[0]; dst[0] = dst[end]; dst[end] = tmp;
+            uint32_t root = 0;
+            for (;;) {
+                uint32_t c = 2 * root + 1;
+                if (c >= end) break;
+                if (c + 1 < end && dst[c] < dst[c + 1]) c++;
+                if (dst[root] >= dst[c]) break;
+                uint32_t t2 = dst[root]; dst[root] = dst[c]; dst[c] = t2;
+                root = c;
+            }
+        }
+    }
+}
+
+template <class Kern>
+int set_smem(Ctx *ctx, Kern kern, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        if (bytes > 200 * 1024) return fail(ctx, PCR_ERR_UNSUPPORTED, "k too large for shared memory");
+        PCR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    }
+    return PCR_OK;
+}
+
+}  // namespace
+
+int knn_queries_dev(Index *ix, const float *dqx, const float *dqy, const float *dqz, size_t nq, size_t k, uint32_t *d_idx,
+                    float *d_dist, uint32_t *d_counts) {
+    Ctx *ctx = ix->ctx;
+    if (nq == 0 || k == 0) return PCR_OK;
+    if (ix->n_frames != 1) return fail(ctx, PCR_ERR_UNSUPPORTED, "external queries need a single-frame index");
+    if (k > PCR_MAX_K) return fail(ctx, PCR_ERR_UNSUPPORTED, "k = %zu exceeds PCR_MAX_K = %d", k, PCR_MAX_K);
+    unsigned blocks = (unsigned)((nq + kQPB - 1) / kQPB);
+    if (k <= 32) {
+        knn_queries_kernel<false><<<blocks, kThreads, 0, ctx->stream>>>(ix->grids, ix->cell_start, ix->sorted, dqx, dqy, dqz, nq,
+                                                                        (int)k, d_idx, d_dist, d_counts);
+    } else {
+        size_t smem = sizeof(unsigned long long) * k * kWarps;
+        PCR_TRY(set_smem(ctx, knn_queries_kernel<true>, smem));
+        knn_queries_kernel<true><<<blocks, kThreads, smem, ctx->stream>>>(ix->grids, ix->cell_start, ix->sorted, dqx, dqy, dqz,
+                                                                          nq, (int)k, d_idx, d_dist, d_counts);
+    }
+    PCR_LAUNCH_CHECK(ctx);
+    return PCR_OK;
+}
+
+int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d) {
+    Ctx *ctx = ix->ctx;
+    if (ix->n == 0) return PCR_OK;
+    const size_t kk = k + 1;  // statistical_outlier.rs:25
+    if (kk > PCR_MAX_K) return fail(ctx, PCR_ERR_UNSUPPORTED, "k = %zu exceeds PCR_MAX_K - 1", k);
+    if (ix->n_indexed < ix->n) {  // statistical_outlier.rs:22-24: non-finite points -> INF
+        fill_f32_kernel<<<(unsigned)((ix->n + 255) / 256), 256, 0, ctx->stream>>>(d_mean_d, ix->n, INFINITY);
+        PCR_LAUNCH_CHECK(ctx);
+    }
+    if (ix->n_indexed == 0) return PCR_OK;
+    unsigned blocks = (unsigned)((ix->n_indexed + kQPB - 1) / kQPB);
+    if (kk <= 32) {
+        size_t smem = (kk * 33 + 32) * sizeof(float) * kWarps;
+        sor_mean_kernel<false><<<blocks, kThreads, smem, ctx->stream>>>(ix->grids, ix->n_frames, ix->cell_start, ix->sorted,
+                                                                        (uint32_t)ix->n_indexed, (int)kk, d_mean_d);
+    } else {
+        size_t smem = sizeof(unsigned long long) * kk * kWarps;
+        PCR_TRY(set_smem(ctx, sor_mean_kernel<true>, smem));
+        sor_mean_kernel<true><<<blocks, kThreads, smem, ctx->stream>>>(ix->grids, ix->n_frames, ix->cell_start, ix->sorted,
+                                                                       (uint32_t)ix->n_indexed, (int)kk, d_mean_d);
+    }
+    PCR_LAUNCH_CHECK(ctx);
+    return PCR_OK;
+}
+
+int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny, float *d_nz, const uint8_t *d_mask) {
+    Ctx *ctx = ix->ctx;
+    if (ix->n == 0 || k == 0) return PCR_OK;
+    if (k > PCR_MAX_K) return fail(ctx, PCR_ERR_UNSUPPORTED, "k = %zu exceeds PCR_MAX_K = %d", k, PCR_MAX_K);
+    if (ix->n_indexed < ix->n) {
+        fill_unindexed_normals_kernel<<<(unsigned)((ix->n + 255) / 256), 256, 0, ctx->stream>>>(ix->orig4, d_mask, ix->n, d_nx,
+                                                                                                d_ny, d_nz);
+        PCR_LAUNCH_CHECK(ctx);
+    }
+    if (ix->n_indexed == 0) return PCR_OK;
+    unsigned blocks = (unsigned)((ix->n_indexed + kQPB - 1) / kQPB);
+    if (k <= 32) {
+        size_t smem = (k * 3 * 33 + 32) * sizeof(float) * kWarps;
+        PCR_TRY(set_smem(ctx, normals_kernel<false>, smem));
+        normals_kernel<false><<<blocks, kThreads, smem, ctx->stream>>>(ix->grids, ix->n_frames, ix->cell_start, ix->sorted,
+                                                                       (uint32_t)ix->n_indexed, ix->orig4, (int)k, vp[0], vp[1],
+                                                                       vp[2], d_nx, d_ny, d_nz);
+    } else {
+        size_t smem = sizeof(unsigned long long) * k * kWarps;
+        PCR_TRY(set_smem(ctx, normals_kernel<true>, smem));
+        normals_kernel<true><<<blocks, kThreads, smem, ctx->stream>>>(ix->grids, ix->n_frames, ix->cell_start, ix->sorted,
+                                                                      (uint32_t)ix->n_indexed, ix->orig4, (int)k, vp[0], vp[1],
+                                                                      vp[2], d_nx, d_ny, d_nz);
+    }
+    PCR_LAUNCH_CHECK(ctx);
+    return PCR_OK;
+}
+
+int radius_count_dev(Index *ix, const float *dqx, const float *dqy, const float *dqz, size_t nq, float radius,
+                     uint32_t *d_counts) {
+    Ctx *ctx = ix->ctx;
+    if (nq == 0) return PCR_OK;
+    if (ix->n_frames != 1) return fail(ctx, PCR_ERR_UNSUPPORTED, "radius queries need a single-frame index");
+    radius_kernel<false><<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(ix->grids, ix->cell_start, ix->sorted, dqx, dqy,
+                                                                                dqz, nq, radius, d_counts, nullptr, nullptr);
+    PCR_LAUNCH_CHECK(ctx);
+    return PCR_OK;
+}
+
+int radius_fill_dev(Index *ix, const float *dqx, const float *dqy, const float *dqz, size_t nq, float radius,
+                    const uint64_t *d_offsets, uint32_t *d_idx) {
+    Ctx *ctx = ix->ctx;
+    if (nq == 0) return PCR_OK;
+    radius_kernel<true><<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(ix->grids, ix->cell_start, ix->sorted, dqx, dqy,
+                                                                               dqz, nq, radius, nullptr, d_offsets, d_idx);
+    PCR_LAUNCH_CHECK(ctx);
+    return PCR_OK;
+}
+
+}  // namespace pcr

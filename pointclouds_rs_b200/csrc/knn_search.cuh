@@ -1,0 +1,292 @@
+// knn_search.cuh -- the grid ring search shared by the KNN / SOR / normals kernels (warp per query)
+// and by the ICP 1-NN kernel (thread per query).  Replaces kiddo's nearest_n behind
+// KdTree::knn / knn_indices (crates/spatial/src/kdtree.rs:64-96).
+//
+// Search rule (mirrored on the CPU by oracle/orc_grid_knn_model, which is how it was validated):
+//   1. scan the 3x3x3 cells around the query's cell; every row of 3 cells along the fast axis is
+//      one contiguous run of the cell-sorted array;
+//   2. after shell R, everything not scanned lies beyond a face of the scanned cube; with f = the
+//      query's fractional position in its cell, the nearest such face is (R + min f) * h away.
+//      Stop iff the k-th best d^2 is STRICTLY below (that distance)^2 * (1 - 1e-6): the slack
+//      covers the rounding of f32 d^2 (<= 3 ulp) and of the f64 cell assignment, and strictness
+//      keeps an equal-distance, lower-index point outside the cube from being missed;
+//   3. otherwise scan shell R+1 (Chebyshev distance exactly R+1).  After kMaxRings shells the
+//      query falls back to scanning its whole frame (isolated outliers in huge sparse grids).
+// Candidates are ranked by the packed (d^2 bits, original index) key, so the result does not
+// depend on the scan order.
+#pragma once
+#include "pcr_internal.cuh"
+
+namespace pcr {
+
+constexpr int kMaxRings = 12;
+constexpr uint32_t kBruteFrame = 96;  // frames this small are scanned directly
+
+// ------------------------------------------------------------------------------------------------
+// Top-k containers.  Both keep the k best keys in ascending order.
+// ------------------------------------------------------------------------------------------------
+
+// k <= 32: lane j holds the j-th best key in a register; insertion = ballot + shuffle.
+struct RegTopK {
+    unsigned long long K;    // this lane's entry
+    unsigned long long thr;  // acceptance threshold (uniform): candidates with key < thr enter
+    unsigned long long cap;  // upper limit of thr (used by the whole-frame fallback)
+    int kk, lane;
+
+    __device__ __forceinline__ void reset(unsigned long long cap_) {
+        K = PCR_EMPTY_KEY;
+        cap = cap_;
+        thr = cap_;
+    }
+    __device__ __forceinline__ bool full() const { return __shfl_sync(PCR_FULL, K, kk - 1) != PCR_EMPTY_KEY; }
+    __device__ __forceinline__ unsigned long long kth() const { return __shfl_sync(PCR_FULL, K, kk - 1); }
+    __device__ __forceinline__ void insert(unsigned long long x) {
+        int pos = __popc(__ballot_sync(PCR_FULL, K < x));
+        unsigned long long up = __shfl_up_sync(PCR_FULL, K, 1);
+        if (lane > pos) K = up;
+        else if (lane == pos) K = x;
+        unsigned long long kth_ = __shfl_sync(PCR_FULL, K, kk - 1);
+        thr = kth_ < cap ? kth_ : cap;
+    }
+    __device__ __forceinline__ int count() const {
+        int c = __popc(__ballot_sync(PCR_FULL, K != PCR_EMPTY_KEY));
+        return c < kk ? c : kk;
+    }
+};
+
+// k <= PCR_MAX_K: sorted list in shared memory (one per warp), cooperative insertion.
+struct SmemTopK {
+    unsigned long long *s;  // kk entries
+    unsigned long long thr, cap;
+    int kk, lane, n;
+
+    __device__ __forceinline__ void reset(unsigned long long cap_) {
+        n = 0;
+        cap = cap_;
+        thr = cap_;
+    }
+    __device__ __forceinline__ bool full() const { return n == kk; }
+    __device__ __forceinline__ unsigned long long kth() const { return n == kk ? s[kk - 1] : PCR_EMPTY_KEY; }
+    __device__ __forceinline__ void insert(unsigned long long x) {
+        int c = 0;
+        for (int i = lane; i < n; i += 32) c += s[i] < x ? 1 : 0;
+        int pos = __reduce_add_sync(PCR_FULL, c);
+        int last = n < kk ? n : kk - 1;  // entries [pos, last) move up by one
+        for (int top = last; top > pos; top -= 32) {
+            int i = top - 1 - lane;
+            unsigned long long v = 0;
+            if (i >= pos) v = s[i];
+            __syncwarp();
+            if (i >= pos) s[i + 1] = v;
+            __syncwarp();
+        }
+        if (lane == 0) s[pos] = x;
+        __syncwarp();
+        if (n < kk) n++;
+        unsigned long long kth_ = n == kk ? s[kk - 1] : PCR_EMPTY_KEY;
+        thr = kth_ < cap ? kth_ : cap;
+    }
+    __device__ __forceinline__ int count() const { return n; }
+};
+
+// One contiguous run [b, e) of the cell-sorted array against the query, 32 candidates at a time.
+template <class TopK>
+__device__ __forceinline__ void scan_run(TopK &tk, const float4 *__restrict__ pts, uint32_t b, uint32_t e, float qx,
+                                         float qy, float qz) {
+    for (uint32_t base = b; base < e; base += 32) {
+        uint32_t i = base + tk.lane;
+        unsigned long long key = PCR_EMPTY_KEY;
+        if (i < e) {
+            float4 p = __ldg(&pts[i]);
+            key = make_key(dist2_exact(qx, qy, qz, p.x, p.y, p.z), __float_as_uint(p.w));
+        }
+        unsigned m = __ballot_sync(PCR_FULL, key < tk.thr);
+        while (m) {
+            int s = __ffs(m) - 1;
+            tk.insert(__shfl_sync(PCR_FULL, key, s));
+            // re-test the remaining lanes against the tightened threshold
+            m = __ballot_sync(PCR_FULL, key < tk.thr) & ~((2u << s) - 1u);
+        }
+    }
+}
+
+// lane-parallel lookup of up to 32 runs, then the warp streams the non-empty ones
+template <class TopK>
+__device__ __forceinline__ void scan_runs(TopK &tk, const float4 *__restrict__ pts, uint32_t b, uint32_t e,
+                                          unsigned first_mask, float qx, float qy, float qz) {
+    unsigned ne = __ballot_sync(PCR_FULL, e > b);
+    unsigned pri = ne & first_mask;  // runs to take first (the query's own row: tightens thr early)
+    ne &= ~first_mask;
+    while (pri) {
+        int s = __ffs(pri) - 1;
+        pri &= pri - 1;
+        scan_run(tk, pts, __shfl_sync(PCR_FULL, b, s), __shfl_sync(PCR_FULL, e, s), qx, qy, qz);
+    }
+    while (ne) {
+        int s = __ffs(ne) - 1;
+        ne &= ne - 1;
+        scan_run(tk, pts, __shfl_sync(PCR_FULL, b, s), __shfl_sync(PCR_FULL, e, s), qx, qy, qz);
+    }
+}
+
+// Warp-cooperative exact k-NN of (qx,qy,qz) in frame g.  All arguments are warp-uniform.
+template <class TopK>
+__device__ __forceinline__ void warp_knn_search(TopK &tk, const GridDesc &g, const uint32_t *__restrict__ cell_start,
+                                                const float4 *__restrict__ pts, float qx, float qy, float qz) {
+    tk.reset(PCR_EMPTY_KEY);
+    const uint32_t m = g.pt_end - g.pt_begin;
+    if (m == 0) return;
+    if (m <= kBruteFrame || m <= (uint32_t)tk.kk) {
+        scan_run(tk, pts, g.pt_begin, g.pt_end, qx, qy, qz);
+        return;
+    }
+    const int lane = tk.lane;
+    double f0, f1, f2;
+    const int c0 = cell_coord(g, 0, pick_axis(g.ax[0], qx, qy, qz), &f0);
+    const int c1 = cell_coord(g, 1, pick_axis(g.ax[1], qx, qy, qz), &f1);
+    const int c2 = cell_coord(g, 2, pick_axis(g.ax[2], qx, qy, qz), &f2);
+    const int d0n = g.dims[0], d1n = g.dims[1], d2n = g.dims[2];
+
+    {  // the 3x3x3 cube: 9 rows, one lane each
+        uint32_t b = 0, e = 0;
+        if (lane < 9) {
+            int a0 = c0 + lane / 3 - 1, a1 = c1 + lane % 3 - 1;
+            if (a0 >= 0 && a0 < d0n && a1 >= 0 && a1 < d1n) {
+                int z0 = max(c2 - 1, 0), z1 = min(c2 + 1, d2n - 1);
+                uint32_t lin = cell_linear(g, a0, a1, z0);
+                b = __ldg(&cell_start[lin]);
+                e = __ldg(&cell_start[lin + (uint32_t)(z1 - z0) + 1u]);
+            }
+        }
+        scan_runs(tk, pts, b, e, 1u << 4, qx, qy, qz);
+    }
+    for (int R = 1;; R++) {
+        // nearest face of the scanned cube that still has cells behind it
+        double mf = 1e300;
+        bool open = false;
+        if (c0 - R > 0) { open = true; mf = fmin(mf, f0); }
+        if (c0 + R < d0n - 1) { open = true; mf = fmin(mf, 1.0 - f0); }
+        if (c1 - R > 0) { open = true; mf = fmin(mf, f1); }
+        if (c1 + R < d1n - 1) { open = true; mf = fmin(mf, 1.0 - f1); }
+        if (c2 - R > 0) { open = true; mf = fmin(mf, f2); }
+        if (c2 + R < d2n - 1) { open = true; mf = fmin(mf, 1.0 - f2); }
+        if (!open) return;  // the whole grid has been scanned
+        const unsigned long long kth = tk.kth();
+        if (kth != PCR_EMPTY_KEY) {
+            double bound = ((double)R + mf) * g.h;
+            if (bound > 0.0 && (double)key_d2(kth) < bound * bound * (1.0 - 1e-6)) return;
+        }
+        if (R >= kMaxRings) {  // isolated query: rescan the frame, pruned by the k-th best so far
+            tk.reset(kth == PCR_EMPTY_KEY ? PCR_EMPTY_KEY : kth + 1ull);
+            scan_run(tk, pts, g.pt_begin, g.pt_end, qx, qy, qz);
+            return;
+        }
+        // shell R+1: rows (i0,i1) of the (2S+1)^2 square; border rows are full runs, interior rows
+        // contribute their two end cells (slot 0 = low end, slot 1 = high end)
+        const int S = R + 1, side = 2 * S + 1, T = 2 * side * side;
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            int t = t0 + lane;
+            uint32_t b = 0, e = 0;
+            if (t < T) {
+                int slot = t & 1, r = t >> 1;
+                int i0 = r / side, i1 = r - i0 * side;
+                int e0 = i0 - S, e1 = i1 - S;
+                int a0 = c0 + e0, a1 = c1 + e1;
+                if (a0 >= 0 && a0 < d0n && a1 >= 0 && a1 < d1n) {
+                    bool border = (e0 == S) || (e0 == -S) || (e1 == S) || (e1 == -S);
+                    int z0, z1;
+                    bool ok;
+                    if (border) {
+                        ok = slot == 0;
+                        z0 = max(c2 - S, 0);
+                        z1 = min(c2 + S, d2n - 1);
+                    } else {
+                        int z = slot == 0 ? c2 - S : c2 + S;
+                        ok = z >= 0 && z < d2n;
+                        z0 = z1 = z;
+                    }
+                    if (ok) {
+                        uint32_t lin = cell_linear(g, a0, a1, z0);
+                        b = __ldg(&cell_start[lin]);
+                        e = __ldg(&cell_start[lin + (uint32_t)(z1 - z0) + 1u]);
+                    }
+                }
+            }
+            scan_runs(tk, pts, b, e, 0u, qx, qy, qz);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Thread-per-query 1-NN (ICP correspondences): same rule, scalar best key.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void thread_scan_run(const float4 *__restrict__ pts, uint32_t b, uint32_t e, float qx, float qy,
+                                                float qz, unsigned long long &best) {
+    for (uint32_t i = b; i < e; i++) {
+        float4 p = __ldg(&pts[i]);
+        unsigned long long key = make_key(dist2_exact(qx, qy, qz, p.x, p.y, p.z), __float_as_uint(p.w));
+        best = key < best ? key : best;
+    }
+}
+
+__device__ __forceinline__ unsigned long long thread_nn_search(const GridDesc &g, const uint32_t *__restrict__ cell_start,
+                                                               const float4 *__restrict__ pts, float qx, float qy, float qz) {
+    unsigned long long best = PCR_EMPTY_KEY;
+    const uint32_t m = g.pt_end - g.pt_begin;
+    if (m == 0) return best;
+    if (m <= 32) {
+        thread_scan_run(pts, g.pt_begin, g.pt_end, qx, qy, qz, best);
+        return best;
+    }
+    double f0, f1, f2;
+    const int c0 = cell_coord(g, 0, pick_axis(g.ax[0], qx, qy, qz), &f0);
+    const int c1 = cell_coord(g, 1, pick_axis(g.ax[1], qx, qy, qz), &f1);
+    const int c2 = cell_coord(g, 2, pick_axis(g.ax[2], qx, qy, qz), &f2);
+    const int d0n = g.dims[0], d1n = g.dims[1], d2n = g.dims[2];
+    for (int S = 1;; S++) {
+        // shell S (S == 1 also takes the centre)
+        for (int e0 = -S; e0 <= S; e0++) {
+            int a0 = c0 + e0;
+            if (a0 < 0 || a0 >= d0n) continue;
+            for (int e1 = -S; e1 <= S; e1++) {
+                int a1 = c1 + e1;
+                if (a1 < 0 || a1 >= d1n) continue;
+                bool border = S == 1 || e0 == S || e0 == -S || e1 == S || e1 == -S;
+                if (border) {
+                    int z0 = max(c2 - S, 0), z1 = min(c2 + S, d2n - 1);
+                    uint32_t lin = cell_linear(g, a0, a1, z0);
+                    thread_scan_run(pts, __ldg(&cell_start[lin]), __ldg(&cell_start[lin + (uint32_t)(z1 - z0) + 1u]), qx, qy, qz, best);
+                } else {
+                    if (c2 - S >= 0) {
+                        uint32_t lin = cell_linear(g, a0, a1, c2 - S);
+                        thread_scan_run(pts, __ldg(&cell_start[lin]), __ldg(&cell_start[lin + 1u]), qx, qy, qz, best);
+                    }
+                    if (c2 + S < d2n) {
+                        uint32_t lin = cell_linear(g, a0, a1, c2 + S);
+                        thread_scan_run(pts, __ldg(&cell_start[lin]), __ldg(&cell_start[lin + 1u]), qx, qy, qz, best);
+                    }
+                }
+            }
+        }
+        const int R = S;
+        double mf = 1e300;
+        bool open = false;
+        if (c0 - R > 0) { open = true; mf = fmin(mf, f0); }
+        if (c0 + R < d0n - 1) { open = true; mf = fmin(mf, 1.0 - f0); }
+        if (c1 - R > 0) { open = true; mf = fmin(mf, f1); }
+        if (c1 + R < d1n - 1) { open = true; mf = fmin(mf, 1.0 - f1); }
+        if (c2 - R > 0) { open = true; mf = fmin(mf, f2); }
+        if (c2 + R < d2n - 1) { open = true; mf = fmin(mf, 1.0 - f2); }
+        if (!open) return best;
+        if (best != PCR_EMPTY_KEY) {
+            double bound = ((double)R + mf) * g.h;
+            if (bound > 0.0 && (double)key_d2(best) < bound * bound * (1.0 - 1e-6)) return best;
+        }
+        if (R >= kMaxRings) {
+            thread_scan_run(pts, g.pt_begin, g.pt_end, qx, qy, qz, best);
+            return best;
+        }
+    }
+}
+
+}  // namespace pcr

@@ -1,0 +1,229 @@
+// pcr_internal.cuh -- shared declarations of the sm_100a KNN engine (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pcr_b200.h"
+
+namespace pcr {
+
+// ------------------------------------------------------------------------------------------------
+// Grid description.  One per frame (a plain cloud is one frame).  Axes are PERMUTED so that the
+// axis with the most cells is the fastest-varying one: a row of cells along it is one contiguous
+// run of points in the cell-sorted array, which is what the query kernels stream.
+// ------------------------------------------------------------------------------------------------
+struct GridDesc {
+    double o[3];         // origin (bbox min) of permuted axis j
+    double h, inv_h;     // cell size and its reciprocal (f64: cell coordinates are computed in f64)
+    int32_t dims[3];     // cells along permuted axis j (j = 2 is the fastest)
+    int32_t ax[3];       // ax[j] = original axis (0 = x, 1 = y, 2 = z) behind permuted axis j
+    uint32_t cell_base;  // first entry of this frame in the cell table
+    uint32_t n_cells;    // dims[0] * dims[1] * dims[2]
+    uint32_t pt_begin;   // [pt_begin, pt_end): this frame's slice of the cell-sorted point array
+    uint32_t pt_end;
+    uint32_t in_begin;   // [in_begin, in_end): this frame's slice of the input (original order)
+    uint32_t in_end;
+};
+
+struct DevBuf {  // grow-only device scratch buffer
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct Ctx;
+
+// Device-resident index over one cloud or a batch of frames.
+struct Index {
+    Ctx *ctx = nullptr;
+    size_t n = 0;          // points of the cloud(s) (incl. non-finite ones)
+    size_t n_indexed = 0;  // finite points, i.e. entries of `sorted`
+    int n_frames = 1;
+    std::vector<GridDesc> grids_h;
+    GridDesc *grids = nullptr;       // device copy [n_frames]
+    uint32_t *frame_in_off = nullptr;  // device [n_frames + 1] input offsets (nullptr if n_frames == 1)
+    float4 *sorted = nullptr;        // [n_indexed] (x, y, z, original index as bits), cell order
+    float4 *orig4 = nullptr;         // [n] (x, y, z, -) in original order (gather target)
+    uint32_t *cell_start = nullptr;  // [total_cells + 1] exclusive prefix of the per-cell counts
+    uint32_t total_cells = 0;
+    bool owns_memory = true;
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 148;
+    std::string err;
+    uint64_t launches = 0;
+    float forced_cell = 0.f;
+    // scratch
+    DevBuf b_in;       // staged input x|y|z
+    DevBuf b_in2;      // second cloud (ICP source)
+    DevBuf b_out;      // staged outputs
+    DevBuf b_misc;     // per-point scratch (cell ids, ranks, mean distances ...)
+    DevBuf b_misc2;
+    DevBuf b_small;    // reductions, statistics, ICP state
+    DevBuf b_table;    // probe cell table
+    void *pinned = nullptr;  // small pinned host mailbox
+    size_t pinned_cap = 0;
+    // NCCL (loaded lazily with dlopen, see comm.cu)
+    void *nccl_comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing: nothing throws across the ABI
+// ------------------------------------------------------------------------------------------------
+int fail(Ctx *ctx, int code, const char *fmt, ...);
+void set_thread_error(const char *msg);
+
+#define PCR_CUDA(ctx, expr)                                                                       \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            cudaGetLastError();                                                                   \
+            return pcr::fail((ctx), _e == cudaErrorMemoryAllocation ? PCR_ERR_OOM : PCR_ERR_CUDA, \
+                             "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,    \
+                             __LINE__);                                                           \
+        }                                                                                         \
+    } while (0)
+
+#define PCR_TRY(expr)              \
+    do {                           \
+        int _s = (expr);           \
+        if (_s != PCR_OK) return _s; \
+    } while (0)
+
+#define PCR_LAUNCH_CHECK(ctx)                                                                   \
+    do {                                                                                        \
+        (ctx)->launches++;                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess)                                                                  \
+            return pcr::fail((ctx), PCR_ERR_CUDA, "kernel launch failed: %s (%s:%d)",           \
+                             cudaGetErrorString(_e), __FILE__, __LINE__);                       \
+    } while (0)
+
+int ensure(Ctx *ctx, DevBuf &b, size_t bytes);
+int ensure_pinned(Ctx *ctx, size_t bytes);
+
+// ------------------------------------------------------------------------------------------------
+// host entry points implemented across the .cu files (all asynchronous on ctx->stream)
+// ------------------------------------------------------------------------------------------------
+struct BuildOpts {
+    size_t k_hint = 0;
+    int n_frames = 1;
+    const uint64_t *frame_offsets = nullptr;  // host, n_frames + 1 (nullptr if n_frames == 1)
+    const uint8_t *d_mask = nullptr;          // optional device keep-mask: index only points with mask != 0
+};
+int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz, size_t n,
+                    const BuildOpts &opts, Index **out);
+void index_free(Index *ix);
+
+// KNN over external queries (n_frames == 1).  d_idx/d_dist row-major nq x k.
+int knn_queries_dev(Index *ix, const float *dqx, const float *dqy, const float *dqz, size_t nq,
+                    size_t k, uint32_t *d_idx, float *d_dist, uint32_t *d_counts);
+// mean neighbour distance of every point of the indexed cloud(s) (SOR, k+1 neighbours, drop self)
+int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d);
+// normals of every point of the indexed cloud(s); points not indexed get (0,0,1) (no neighbours)
+int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny, float *d_nz,
+                const uint8_t *d_mask);
+int radius_count_dev(Index *ix, const float *dqx, const float *dqy, const float *dqz, size_t nq,
+                     float radius, uint32_t *d_counts);
+int radius_fill_dev(Index *ix, const float *dqx, const float *dqy, const float *dqz, size_t nq,
+                    float radius, const uint64_t *d_offsets, uint32_t *d_idx);
+
+// SOR statistics + mask (statistical_outlier.rs:43-66), one segment per frame.  d_stats receives
+// per frame {mean, stddev, threshold, n_finite(as float bits)}; d_kept per-frame kept counts.
+int sor_threshold_mask_dev(Ctx *ctx, const float *d_mean_d, const uint32_t *d_frame_off /*dev, n_frames+1*/,
+                           int n_frames, size_t n, float std_mul, uint8_t *d_keep, float *d_stats,
+                           unsigned long long *d_kept);
+
+int exclusive_scan_u32_dev(Ctx *ctx, uint32_t *d_data, size_t n_plus_1);
+int exclusive_scan_u64_from_u32_dev(Ctx *ctx, const uint32_t *d_in, uint64_t *d_out, size_t n);
+
+struct IcpArgs {
+    const float *d_sx, *d_sy, *d_sz;
+    size_t ns;
+    const float *d_tx, *d_ty, *d_tz;
+    size_t nt;
+    const float *d_nx, *d_ny, *d_nz;  // nullptr for point-to-point
+    pcr_icp_params params;
+};
+int icp_dev(Ctx *ctx, const IcpArgs &a, pcr_icp_result *result);
+int find_correspondences_dev(Index *target, const float *dsx, const float *dsy, const float *dsz,
+                             size_t ns, float max_distance, uint32_t *d_tgt, float *d_dist);
+int apply_transform_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz, size_t n,
+                        const float R[9], const float t[3], float *ox, float *oy, float *oz);
+
+// NCCL plumbing (comm.cu)
+int comm_unique_id(void *out);
+int comm_init(Ctx *ctx, const void *id, int rank, int world);
+void comm_destroy(Ctx *ctx);
+int comm_allreduce_f64(Ctx *ctx, double *d_buf, size_t count);
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+#define PCR_FULL 0xffffffffu
+#define PCR_EMPTY_KEY 0xffffffffffffffffull
+
+// kiddo SquaredEuclidean on f32: ((dx*dx)+(dy*dy))+(dz*dz), every operation rounded, no FMA
+// (call sites crates/spatial/src/kdtree.rs:70,93,121-123).
+__device__ __forceinline__ float dist2_exact(float ax, float ay, float az, float bx, float by, float bz) {
+    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    float s = __fmul_rn(dx, dx);
+    s = __fadd_rn(s, __fmul_rn(dy, dy));
+    s = __fadd_rn(s, __fmul_rn(dz, dz));
+    return s;
+}
+
+// (d^2, index) total order in one u64: d^2 >= 0, so its bit pattern is monotone.
+__device__ __forceinline__ unsigned long long make_key(float d2, uint32_t idx) {
+    return ((unsigned long long)__float_as_uint(d2) << 32) | idx;
+}
+__device__ __forceinline__ float key_d2(unsigned long long k) { return __uint_as_float((uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t key_idx(unsigned long long k) { return (uint32_t)k; }
+
+__device__ __forceinline__ bool finite3(float a, float b, float c) { return isfinite(a) && isfinite(b) && isfinite(c); }
+
+__device__ __forceinline__ float pick_axis(int ax, float x, float y, float z) { return ax == 0 ? x : (ax == 1 ? y : z); }
+
+// Cell coordinate along permuted axis j and the fractional position inside that cell.  f64 on
+// purpose: the error of the cell assignment then is ~1e-16 relative, which the 1e-6 slack of the
+// ring-termination test (knn.cuh) covers with a wide margin.
+__device__ __forceinline__ int cell_coord(const GridDesc &g, int j, float v, double *frac) {
+    double t = ((double)v - g.o[j]) * g.inv_h;
+    double f = floor(t);
+    f = fmin(fmax(f, 0.0), (double)(g.dims[j] - 1));
+    if (frac) *frac = t - f;  // < 0 or > 1 for a query outside the grid (clamped cell)
+    return (int)f;
+}
+
+__device__ __forceinline__ uint32_t cell_linear(const GridDesc &g, int c0, int c1, int c2) {
+    return g.cell_base + ((uint32_t)c0 * (uint32_t)g.dims[1] + (uint32_t)c1) * (uint32_t)g.dims[2] + (uint32_t)c2;
+}
+
+// frame of input point i (binary search over the frame offsets); n_frames == 1 -> 0
+__device__ __forceinline__ int frame_of(const uint32_t *__restrict__ off, int n_frames, uint32_t i) {
+    if (n_frames <= 1) return 0;
+    int lo = 0, hi = n_frames - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (off[mid] <= i) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace pcr

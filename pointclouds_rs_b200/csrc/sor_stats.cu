@@ -1,0 +1,91 @@
+// sor_stats.cu -- global statistics and keep-mask of statistical_outlier_removal
+// (crates/filters/src/statistical_outlier.rs:43-66), one segment per frame.
+//
+//   mean  = (sequential f32 sum of the finite mean distances) / n_finite
+//   var   = (sequential f32 sum of (d - mean)^2) / n_finite      (population, two-pass)
+//   thr   = mean + std_mul * sqrt(var)
+//   keep  = mean_d <= thr
+#include "seq_fold.cuh"
+
+#include <algorithm>
+
+namespace pcr {
+
+namespace {
+
+struct SorFrameStats {
+    float mean, stddev, thr;
+    uint32_t n_finite;
+};
+
+// one block per frame; thread 0 walks the segment twice (left-to-right folds)
+__global__ void sor_stats_seq_kernel(const float *__restrict__ mean_d, const uint32_t *__restrict__ frame_off, size_t n,
+                                     float std_mul, SorFrameStats *__restrict__ stats) {
+    const int f = blockIdx.x;
+    const size_t b = frame_off ? frame_off[f] : 0, e = frame_off ? frame_off[f + 1] : n;
+    if (threadIdx.x != 0) return;
+    uint32_t nf = 0;
+    float sum = seq_fold_thread(mean_d, b, e, [](float v) { return v; }, &nf);
+    SorFrameStats s;
+    s.n_finite = nf;
+    if (nf == 0) {  // statistical_outlier.rs:49-51 -> empty result
+        s.mean = s.stddev = s.thr = __int_as_float(0x7fc00000);
+    } else {
+        const float nn = (float)nf;
+        const float gmean = __fdiv_rn(sum, nn);
+        float var = seq_fold_thread(
+            mean_d, b, e,
+            [gmean](float v) {
+                float d = __fsub_rn(v, gmean);
+                return __fmul_rn(d, d);
+            },
+            nullptr);
+        var = __fdiv_rn(var, nn);
+        const float sd = __fsqrt_rn(var);
+        s.mean = gmean;
+        s.stddev = sd;
+        s.thr = __fadd_rn(gmean, __fmul_rn(std_mul, sd));
+    }
+    stats[f] = s;
+}
+
+__global__ void __launch_bounds__(256) sor_mask_kernel(const float *__restrict__ mean_d, const uint32_t *__restrict__ frame_off,
+                                                       int n_frames, size_t n, const SorFrameStats *__restrict__ stats,
+                                                       uint8_t *__restrict__ keep, unsigned long long *__restrict__ kept) {
+    const int f = blockIdx.y;
+    const size_t b = frame_off ? frame_off[f] : 0, e = frame_off ? frame_off[f + 1] : n;
+    const SorFrameStats s = stats[f];
+    unsigned cnt = 0;
+    for (size_t i = b + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (size_t)gridDim.x * blockDim.x) {
+        // n_finite == 0 -> thr is NaN -> nothing is kept
+        uint8_t k = mean_d[i] <= s.thr ? 1 : 0;
+        keep[i] = k;
+        cnt += k;
+    }
+    cnt = __reduce_add_sync(PCR_FULL, cnt);
+    __shared__ unsigned sh;
+    if (threadIdx.x == 0) sh = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&sh, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0 && sh) atomicAdd(&kept[f], (unsigned long long)sh);
+}
+
+}  // namespace
+
+int sor_threshold_mask_dev(Ctx *ctx, const float *d_mean_d, const uint32_t *d_frame_off, int n_frames, size_t n, float std_mul,
+                           uint8_t *d_keep, float *d_stats, unsigned long long *d_kept) {
+    static_assert(sizeof(SorFrameStats) == 4 * sizeof(float), "stats layout");
+    if (n == 0) return PCR_OK;
+    sor_stats_seq_kernel<<<n_frames, 32, 0, ctx->stream>>>(d_mean_d, d_frame_off, n, std_mul, (SorFrameStats *)d_stats);
+    PCR_LAUNCH_CHECK(ctx);
+    PCR_CUDA(ctx, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long) * n_frames, ctx->stream));
+    size_t per = n / (size_t)n_frames + 1;
+    unsigned bx = (unsigned)std::min<size_t>((per + 255) / 256, (size_t)ctx->sm_count * 8);
+    sor_mask_kernel<<<dim3(bx ? bx : 1, n_frames), 256, 0, ctx->stream>>>(d_mean_d, d_frame_off, n_frames, n,
+                                                                          (const SorFrameStats *)d_stats, d_keep, d_kept);
+    PCR_LAUNCH_CHECK(ctx);
+    return PCR_OK;
+}
+
+}  // namespace pcr

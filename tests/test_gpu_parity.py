@@ -1,0 +1,344 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle -- the tests proper.
+
+Bars (BASELINE.json north_star): KNN index lists and distances bit-exact under (d^2, index);
+SOR mean distances, statistics and keep masks bit-exact; normals within 1e-4 rad; ICP transforms
+within 1e-4.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from pointclouds_rs_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+T = max(1, min(16, os.cpu_count() or 1))
+
+
+def _cloud(pcr, pts):
+    return pcr.PointCloud.from_numpy(np.ascontiguousarray(pts, dtype=np.float32))
+
+
+def lattice(n=10, spacing=1.0):
+    g = np.arange(n, dtype=np.float32) * np.float32(spacing)
+    return np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3).astype(np.float32)
+
+
+SCENES = {
+    "kitti20k": lambda: scenes.kitti_scene(3, (17_000, 850, 140, 1_160)),
+    "cube20k": lambda: scenes.uniform_cube(20_000, 5),
+    "lattice1000": lambda: lattice(10),
+    "dupes": lambda: np.repeat(scenes.uniform_cube(500, 9, 0, 10), 7, axis=0),
+    "line": lambda: np.stack([np.arange(300, dtype=np.float32), np.zeros(300, np.float32), np.zeros(300, np.float32)], 1),
+    "tiny5": lambda: scenes.uniform_cube(5, 1, 0, 1),
+    "plane_far_outlier": lambda: np.vstack([scenes.kitti_scene(4, (5_000, 10, 10, 10)), [[4000.0, -3000.0, 900.0]]]).astype(np.float32),
+}
+
+
+def _queries(pts, rng):
+    own = pts[rng.integers(0, len(pts), min(len(pts), 1500))]
+    lo, hi = pts.min(0), pts.max(0)
+    ext = rng.uniform(lo - 0.3 * (hi - lo) - 1, hi + 0.3 * (hi - lo) + 1, (400, 3)).astype(np.float32)
+    far = np.array([[1e6, 1e6, 1e6], [-5e4, 0, 0], [0, 0, 1e-30]], np.float32)
+    bad = np.array([[np.nan, 0, 0], [0, np.inf, 0], [0, 0, -np.inf]], np.float32)
+    return np.vstack([own, ext, far, bad]).astype(np.float32)
+
+
+@pytest.mark.parametrize("scene", list(SCENES))
+@pytest.mark.parametrize("k", [1, 2, 11, 20, 32, 33, 70])
+def test_knn_bit_exact(pcr, oracle, scene, k):
+    pts = SCENES[scene]()
+    rng = np.random.default_rng(11)
+    q = _queries(pts, rng)
+    tree = pcr.KdTree(_cloud(pcr, pts), k_hint=k)
+    idx, dist, cnt = tree.knn(q, k)
+    o_idx, o_dist, o_cnt = oracle.Tree(pts).knn_batch(q, k, threads=T)
+    assert np.array_equal(cnt, o_cnt)
+    assert np.array_equal(idx, o_idx), f"first diff row {np.nonzero((idx != o_idx).any(1))[0][:5]}"
+    assert np.array_equal(dist.view(np.uint32), o_dist.view(np.uint32))
+    idx2, cnt2 = tree.knn_indices(q, k)
+    assert np.array_equal(idx2, o_idx) and np.array_equal(cnt2, o_cnt)
+
+
+def test_knn_nonfinite_points_are_not_indexed(pcr, oracle):
+    pts = scenes.uniform_cube(3000, 2, 0, 10)
+    pts[::17, 0] = np.nan
+    pts[5::31, 2] = np.inf
+    q = scenes.uniform_cube(500, 3, 0, 10)
+    tree = pcr.KdTree(_cloud(pcr, pts), k_hint=8)
+    idx, dist, cnt = tree.knn(q, 8)
+    o_idx, o_dist, o_cnt = oracle.Tree(pts).knn_batch(q, 8)
+    assert np.array_equal(idx, o_idx) and np.array_equal(dist.view(np.uint32), o_dist.view(np.uint32))
+    assert tree.len() == 3000 and tree.info()["n_indexed"] == int(np.isfinite(pts).all(1).sum())
+
+
+def test_knn_edge_cases(pcr):
+    empty = pcr.KdTree(pcr.PointCloud())
+    idx, dist, cnt = empty.knn(np.zeros((3, 3), np.float32), 5)  # kdtree.rs:194-201
+    assert (cnt == 0).all() and (idx == 0xFFFFFFFF).all() and np.isinf(dist).all()
+    one = pcr.KdTree(_cloud(pcr, [[1, 2, 3]]))
+    idx, dist, cnt = one.knn(np.array([[0, 0, 0], [np.nan, 0, 0]], np.float32), 0)  # kdtree.rs:204-210
+    assert (cnt == 0).all()
+    idx, dist, cnt = one.knn(np.array([[0, 0, 0], [np.nan, 0, 0]], np.float32), 1)  # kdtree.rs:213-219
+    assert list(cnt) == [1, 0] and idx[0, 0] == 0
+    three = pcr.KdTree(_cloud(pcr, [[0, 0, 0], [1, 0, 0], [2, 0, 0]]))
+    idx, dist, cnt = three.knn(np.zeros((1, 3), np.float32), 100)  # kdtree.rs:238-243
+    assert cnt[0] == 3 and list(idx[0, :3]) == [0, 1, 2]
+    # kdtree.rs:173-183
+    col = pcr.KdTree(_cloud(pcr, [[0, 0, 0], [1, 0, 0], [2, 0, 0], [10, 0, 0]]))
+    idx, dist, cnt = col.knn(np.array([[0.2, 0, 0]], np.float32), 2)
+    assert list(idx[0]) == [0, 1] and dist[0, 0] <= dist[0, 1]
+
+
+@pytest.mark.parametrize("scene,k,std", [("kitti20k", 10, 1.0), ("kitti20k", 20, 2.0), ("cube20k", 10, 1.0),
+                                         ("lattice1000", 5, 3.0), ("dupes", 4, 1.0), ("plane_far_outlier", 10, 1.0),
+                                         ("kitti20k", 40, 1.0)])
+def test_sor_bit_exact(pcr, oracle, scene, k, std):
+    pts = SCENES[scene]()
+    keep, kept, mean_d, stats = pcr.sor_mask(_cloud(pcr, pts), k, std, want_mean=True)
+    o_keep, o_mean, o_stats = oracle.sor(pts, k, std, threads=T)
+    assert np.array_equal(mean_d.view(np.uint32), o_mean.view(np.uint32))
+    assert np.array_equal(stats.view(np.uint32), o_stats.view(np.uint32)), (stats, o_stats)
+    assert np.array_equal(keep, o_keep) and kept == int(o_keep.sum())
+
+
+def test_sor_full_frame_122k(pcr, oracle):
+    pts = scenes.kitti_scene()  # BASELINE config 2
+    assert len(pts) == 122_000
+    keep, kept, mean_d, stats = pcr.sor_mask(_cloud(pcr, pts), 10, 1.0, want_mean=True)
+    o_keep, o_mean, o_stats = oracle.sor(pts, 10, 1.0, threads=T)
+    assert np.array_equal(mean_d.view(np.uint32), o_mean.view(np.uint32))
+    assert np.array_equal(stats.view(np.uint32), o_stats.view(np.uint32))
+    assert np.array_equal(keep, o_keep)
+
+
+def test_sor_reference_known_answers(pcr):
+    # statistical_outlier.rs:78-101
+    v = [0.0, 0.1, -0.1, 0.05, -0.05, 100.0]
+    c = _cloud(pcr, np.stack([v, v, v], 1))
+    out = pcr.statistical_outlier_removal(c, 4, 1.0)
+    assert len(out) == 5 and np.abs(out.to_numpy()).max() <= 0.2
+    # :104-124
+    assert len(pcr.statistical_outlier_removal(_cloud(pcr, lattice(3)), 5, 3.0)) == 27
+    # :127-146
+    assert len(pcr.statistical_outlier_removal(pcr.PointCloud(), 5, 1.0)) == 0
+    single = pcr.statistical_outlier_removal(_cloud(pcr, [[1, 2, 3]]), 5, 1.0)
+    assert len(single) == 1 and list(single.to_numpy()[0]) == [1, 2, 3]
+    assert len(pcr.statistical_outlier_removal(_cloud(pcr, [[1, 3, 5], [2, 4, 6]]), 0, 1.0)) == 0
+    with pytest.raises(ValueError):
+        pcr.statistical_outlier_removal(_cloud(pcr, [[1, 3, 5], [2, 4, 6]]), 3, float("nan"))
+    with pytest.raises(ValueError):
+        pcr.statistical_outlier_removal(_cloud(pcr, [[1, 3, 5], [2, 4, 6]]), 3, -1.0)
+
+
+def test_sor_with_nonfinite_points(pcr, oracle):
+    pts = scenes.kitti_scene(8, (4_000, 200, 50, 100))
+    pts[10] = [np.nan, 0, 0]
+    pts[500] = [0, np.inf, 1]
+    keep, kept, mean_d, stats = pcr.sor_mask(_cloud(pcr, pts), 10, 1.0, want_mean=True)
+    o_keep, o_mean, o_stats = oracle.sor(pts, 10, 1.0)
+    assert np.array_equal(mean_d.view(np.uint32), o_mean.view(np.uint32))
+    assert np.array_equal(keep, o_keep) and keep[10] == 0 and keep[500] == 0
+
+
+def _angles(a, b):
+    c = np.clip(np.abs(np.sum(a.astype(np.float64) * b.astype(np.float64), axis=1)), 0.0, 1.0)
+    return np.arccos(c)
+
+
+@pytest.mark.parametrize("scene,k", [("kitti20k", 20), ("cube20k", 10), ("kitti20k", 15), ("cube20k", 40), ("dupes", 6)])
+def test_normals_parity(pcr, oracle, scene, k):
+    pts = SCENES[scene]()
+    nrm = pcr.normals_array(_cloud(pcr, pts), k)
+    o = oracle.normals(pts, k, threads=T)
+    assert nrm.shape == o.shape
+    ang = _angles(nrm, o)
+    # tolerance from north_star: 1e-4 rad (modulo sign only where the orientation dot is ~0)
+    assert np.nanmax(ang) < 1e-4, f"max angle {np.nanmax(ang)}, n>1e-4: {(ang > 1e-4).sum()}"
+    same_sign = np.sum(nrm * o, axis=1) > 0
+    assert same_sign.mean() > 0.9999
+    ln = np.linalg.norm(nrm, axis=1)
+    assert np.allclose(ln, 1.0, atol=1e-5)
+
+
+def test_normals_reference_known_answers(pcr):
+    # estimate.rs:307-350 planes, :401-453 degenerate, :456-492 viewpoint
+    idx = np.arange(100, dtype=np.float32)
+    i, j = np.divmod(np.arange(100), 10)
+    xy = np.stack([i.astype(np.float32), j.astype(np.float32), idx * np.float32(1e-7)], 1)
+    n = pcr.normals_array(_cloud(pcr, xy), 10)
+    assert (np.abs(n[:, 2]) > 0.9).all()
+    xz = np.stack([i.astype(np.float32), idx * np.float32(1e-7), j.astype(np.float32)], 1)
+    n = pcr.normals_array(_cloud(pcr, xz), 10)
+    assert (np.abs(n[:, 1]) > 0.9).all()
+    assert pcr.normals_array(pcr.PointCloud(), 10).shape == (0, 3)
+    assert pcr.normals_array(_cloud(pcr, [[1, 2, 3]]), 0).shape == (0, 3)
+    one = pcr.normals_array(_cloud(pcr, [[0, 0, 0]]), 20)  # data/bunny.pcd: exactly (0,0,1)
+    assert one.tolist() == [[0.0, 0.0, 1.0]]
+    two = pcr.normals_array(_cloud(pcr, [[1, 1, 1], [1, 1, 1]]), 5)  # test_adversarial.rs:197-211
+    assert np.isfinite(two).all()
+    up = np.stack([i.astype(np.float32), j.astype(np.float32), 5 + idx * np.float32(1e-7)], 1)
+    above = pcr.normals_array(_cloud(pcr, up), 10, (5.0, 5.0, 100.0))
+    below = pcr.normals_array(_cloud(pcr, up), 10, (5.0, 5.0, -100.0))
+    for t in (44, 45, 55, 54):
+        assert above[t, 2] > 0.9 and below[t, 2] < -0.9
+    withn = pcr.estimate_normals(_cloud(pcr, xy), 10)
+    assert withn.normals_to_numpy().shape == (100, 3) and len(withn) == 100
+
+
+def test_normals_nonfinite_points(pcr, oracle):
+    pts = scenes.uniform_cube(2000, 4, 0, 5)
+    pts[7] = [np.nan, 1, 1]
+    nrm = pcr.normals_array(_cloud(pcr, pts), 8)
+    o = oracle.normals(pts, 8)
+    assert nrm[7].tolist() == [0.0, 0.0, 1.0] == o[7].tolist()
+    ok = np.ones(len(pts), bool)
+    ok[7] = False
+    assert np.nanmax(_angles(nrm[ok], o[ok])) < 1e-4
+
+
+@pytest.mark.parametrize("radius", [0.05, 0.5, 2.0])
+def test_radius_parity(pcr, oracle, radius):
+    pts = scenes.kitti_scene(6, (8_000, 400, 60, 140))
+    rng = np.random.default_rng(5)
+    q = _queries(pts, rng)
+    tree = pcr.KdTree(_cloud(pcr, pts), k_hint=10)
+    cnt = tree.radius_count(q, radius)
+    otree = oracle.Tree(pts)
+    assert np.array_equal(cnt, otree.radius_count_batch(q, radius, threads=T))
+    off, idx = tree.radius_search(q, radius)
+    assert np.array_equal(np.diff(off).astype(np.uint32), cnt)
+    for j in list(range(0, 60)) + [len(q) - 1, len(q) - 4]:
+        assert np.array_equal(idx[off[j]:off[j + 1]], otree.radius_search(q[j], radius))
+    # kdtree.rs:106-112: r <= 0 / non-finite -> empty
+    assert (tree.radius_count(q, 0.0) == 0).all() and (tree.radius_count(q, -1.0) == 0).all()
+    assert (tree.radius_count(q, float("inf")) == 0).all()
+
+
+def test_radius_exact_boundary(pcr):
+    tree = pcr.KdTree(_cloud(pcr, [[1, 0, 0], [5, 0, 0]]))  # kdtree.rs:255-269
+    off, idx = tree.radius_search(np.zeros((1, 3), np.float32), 1.0)
+    assert list(idx) == [0]
+    tree = pcr.KdTree(_cloud(pcr, [[0, 0, 0], [0.5, 0, 0], [2, 0, 0]]))  # kdtree.rs:186-192
+    off, idx = tree.radius_search(np.zeros((1, 3), np.float32), 0.75)
+    assert list(idx) == [0, 1]
+
+
+def test_ror_parity(pcr, oracle):
+    pts = scenes.kitti_scene(6, (8_000, 400, 60, 140))
+    for r, mn in [(0.5, 5), (0.3, 2), (2.0, 40)]:
+        keep, kept = pcr.ror_mask(_cloud(pcr, pts), r, mn)
+        assert np.array_equal(keep, oracle.ror(pts, r, mn, threads=T)) and kept == int(keep.sum())
+    # radius_outlier.rs:26-61 and tests/test_adversarial.rs:185-193
+    c = _cloud(pcr, [[0, 0, 0], [0.1, 0, 0], [0.2, 0, 0], [100, 0, 0]])
+    assert len(pcr.radius_outlier_removal(c, 0.5, 2)) == 3
+    assert len(pcr.radius_outlier_removal(_cloud(pcr, [[0, 0, 0]]), 1.0, 2)) == 0
+    assert len(pcr.radius_outlier_removal(pcr.PointCloud(), 1.0, 2)) == 0
+    with pytest.raises(ValueError):
+        pcr.radius_outlier_removal(c, 0.0, 2)
+
+
+def test_apply_transform_bit_exact(pcr, oracle):
+    pts = scenes.uniform_cube(5000, 12, -50, 50)
+    R = scenes.rot_z(0.3)
+    t = [0.5, -1.25, 3.0]
+    out = pcr.apply_transform(_cloud(pcr, pts), R, t).to_numpy()
+    ref = oracle.apply_transform(pts, R, t)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+def test_find_correspondences(pcr, oracle):
+    tgt = scenes.hemisphere(3000, 3)
+    src = oracle.apply_transform(tgt, scenes.rot_z(0.03), [0.1, 0.0, -0.05])
+    tree = pcr.KdTree(_cloud(pcr, tgt), k_hint=1)
+    for md in (math.inf, 0.12):
+        si, ti, dd = tree.find_correspondences(_cloud(pcr, src), md)
+        osi, oti, odd = oracle.Tree(tgt).find_correspondences(src, md, threads=T)
+        assert np.array_equal(si, osi) and np.array_equal(ti, oti)
+        assert np.array_equal(dd.view(np.uint32), odd.view(np.uint32))
+
+
+def _check_icp(res, o, atol=1e-4):
+    assert res.num_iterations == o.num_iterations, (res.num_iterations, o.num_iterations)
+    assert res.converged == o.converged
+    assert np.allclose(np.array(res.rotation), o.rotation, atol=atol), (res.rotation, o.rotation)
+    assert np.allclose(np.array(res.translation), o.translation, atol=atol), (res.translation, o.translation)
+    assert abs(res.rmse - o.rmse) <= 1e-4 * max(1.0, abs(o.rmse))
+    assert abs(res.fitness - o.fitness) < 1e-6
+
+
+@pytest.mark.parametrize("n", [500, 6000])
+def test_icp_parity_hemisphere(pcr, oracle, n):
+    # tests/real_world_pipeline.rs:191-255 shape
+    tgt = scenes.hemisphere(n, 99, 5.0)
+    src = oracle.apply_transform(tgt, scenes.rot_z(0.05), [0.3, -0.2, 0.1])
+    s, t = _cloud(pcr, src), _cloud(pcr, tgt)
+    res = pcr.icp_point_to_point(s, t, max_iterations=100, tolerance=1e-6)
+    o = oracle.icp_point_to_point(src, tgt, 100, 1e-6, threads=T)
+    _check_icp(res, o)
+    assert res.converged and res.rmse < 0.5
+    tn = pcr.estimate_normals(t, 15)
+    res = pcr.icp_point_to_plane(s, tn, max_iterations=100, tolerance=1e-6)
+    o = oracle.icp_point_to_plane(src, tgt, oracle.normals(tgt, 15, threads=T), 100, 1e-6, threads=T)
+    _check_icp(res, o)
+    assert res.converged and res.rmse < 0.5
+
+
+def test_icp_fixed_iterations(pcr, oracle):
+    # BASELINE config 4 shape at reduced size: tolerance 0 -> exactly max_iterations iterations
+    tgt = scenes.aerial_scene(42, 0.01)
+    src = oracle.apply_transform(tgt, scenes.rot_z(0.05), [0.3, -0.2, 0.1])
+    nrm = oracle.normals(tgt, 20, threads=T)
+    t = _cloud(pcr, tgt)
+    t.normals = nrm
+    res = pcr.icp_point_to_plane(_cloud(pcr, src), t, max_iterations=30, tolerance=0.0)
+    o = oracle.icp_point_to_plane(src, tgt, nrm, 30, 0.0, threads=T)
+    assert res.num_iterations == 30 and not res.converged
+    _check_icp(res, o)
+
+
+def test_icp_reference_known_answers(pcr):
+    cube = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0], [0, 0, 1], [1, 0, 1], [0, 1, 1], [1, 1, 1]], np.float32)
+    c = _cloud(pcr, cube)
+    r = pcr.icp_point_to_point(c, c)  # icp.rs:326-344
+    assert np.allclose(r.rotation, np.eye(3), atol=1e-4) and np.allclose(r.translation, 0, atol=1e-4)
+    assert r.rmse < 1e-4 and abs(r.fitness - 1.0) < 1e-6 and r.converged
+    t = _cloud(pcr, cube + np.array([1, 0, 0], np.float32))  # icp.rs:347-371
+    r = pcr.icp_point_to_point(c, t, 100, 1e-8)
+    assert r.converged and r.rmse < 1e-3 and np.allclose(r.translation, [1, 0, 0], atol=0.05)
+    e = pcr.PointCloud()
+    r = pcr.icp_point_to_point(e, e)  # icp.rs:444-455
+    assert r.num_iterations == 0 and r.converged and np.allclose(r.rotation, np.eye(3))
+    r = pcr.icp_point_to_point(e, c)  # icp.rs:458-468
+    assert r.num_iterations == 0 and not r.converged
+    r = pcr.icp_point_to_point(c, c, max_iterations=0)  # tests/test_adversarial.rs:236-247
+    assert r.num_iterations == 0
+    with pytest.raises(ValueError):  # icp_plane.rs:27-32 / registration.rs:66-71
+        pcr.icp_point_to_plane(c, c)
+    bad = _cloud(pcr, cube)
+    bad.normals = np.zeros((3, 3), np.float32)
+    with pytest.raises(ValueError):
+        pcr.icp_point_to_plane(c, bad)
+
+
+def test_batch_matches_single_frames(pcr, oracle):
+    frames = [scenes.kitti_scene(s, (3_000 + 200 * s, 150, 30, 70 + s)) for s in range(5)]
+    frames.insert(2, np.array([[1, 2, 3]], np.float32))      # one-point frame
+    frames.insert(4, np.zeros((0, 3), np.float32))           # empty frame
+    off = np.concatenate([[0], np.cumsum([len(f) for f in frames])])
+    pts = np.vstack(frames)
+    keep, nrm, kept = pcr.sor_normals_batch(pts, off, 10, 1.0, 20)
+    for f, fr in enumerate(frames):
+        sl = slice(off[f], off[f + 1])
+        if len(fr) == 0:
+            continue
+        o_keep, _, _ = oracle.sor(fr, 10, 1.0, threads=T)
+        assert np.array_equal(keep[sl], o_keep), f"frame {f}"
+        assert kept[f] == o_keep.sum()
+        sel = np.nonzero(o_keep)[0]
+        o_n = oracle.normals(fr[sel], 20, threads=T)
+        got = nrm[sl][sel]
+        assert np.nanmax(_angles(got, o_n)) < 1e-4, f"frame {f}"
+        assert (nrm[sl][o_keep == 0] == 0).all()
