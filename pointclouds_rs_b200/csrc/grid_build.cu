@@ -141,6 +141,36 @@ __global__ void __launch_bounds__(kBuildThreads) count_kernel(const float *__res
     }
 }
 
+// same, for a coarser level of an existing index: reads the AoS copy (the caller's SoA may be gone)
+__global__ void __launch_bounds__(kBuildThreads) count4_kernel(const float4 *__restrict__ orig4,
+                                                               const uint32_t *__restrict__ frame_off, size_t n,
+                                                               const uint8_t *__restrict__ mask,
+                                                               const GridDesc *__restrict__ grids,
+                                                               uint32_t *__restrict__ cell_count,
+                                                               uint32_t *__restrict__ cell_id, uint32_t *__restrict__ rank) {
+    const int f = blockIdx.y;
+    const uint32_t b = frame_off ? frame_off[f] : 0u;
+    const uint32_t e = frame_off ? frame_off[f + 1] : (uint32_t)n;
+    const GridDesc g = grids[f];
+    const uint32_t base = b + blockIdx.x * (kBuildThreads * kItems) + threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < kItems; it++) {
+        uint32_t i = base + it * kBuildThreads;
+        if (i >= e) break;
+        float4 p = orig4[i];
+        uint32_t cid = 0xffffffffu, r = 0;
+        if (finite3(p.x, p.y, p.z) && (!mask || mask[i])) {
+            int c0 = cell_coord(g, 0, pick_axis(g.ax[0], p.x, p.y, p.z), nullptr);
+            int c1 = cell_coord(g, 1, pick_axis(g.ax[1], p.x, p.y, p.z), nullptr);
+            int c2 = cell_coord(g, 2, pick_axis(g.ax[2], p.x, p.y, p.z), nullptr);
+            cid = cell_linear(g, c0, c1, c2);
+            r = atomicAdd(&cell_count[cid], 1u);
+        }
+        cell_id[i] = cid;
+        rank[i] = r;
+    }
+}
+
 // ---- K1p: occupancy statistics of a probe grid ---------------------------------------------------
 // For every indexed point: log2(points in its cell) and log2(points in its 2x2x2 super-cell).  The
 // two geometric means give the local occupancy m(h) and its scaling exponent D (m ~ h^D), from
@@ -441,21 +471,102 @@ void shape_grid(GridDesc &g, const FrameBox &b, double h, uint64_t cap) {
 
 void index_free(Index *ix) {
     if (!ix) return;
+    if (ix->coarser) index_free(ix->coarser);
     if (ix->owns_memory && ix->ctx) {
         cudaStream_t s = ix->ctx->stream;
         if (ix->grids) cudaFreeAsync(ix->grids, s);
-        if (ix->frame_in_off) cudaFreeAsync(ix->frame_in_off, s);
         if (ix->sorted) cudaFreeAsync(ix->sorted, s);
-        if (ix->orig4) cudaFreeAsync(ix->orig4, s);
         if (ix->cell_start) cudaFreeAsync(ix->cell_start, s);
+        if (!ix->shares_orig4) {
+            if (ix->frame_in_off) cudaFreeAsync(ix->frame_in_off, s);
+            if (ix->orig4) cudaFreeAsync(ix->orig4, s);
+        }
     }
     delete ix;
+}
+
+// Next-coarser level: same points, same frames, cell size x kLevelFactor.  Reuses the bounding
+// boxes and the AoS copy of level 0, so it costs one count + scan + scatter (no host round trip).
+int index_coarser_level(Index *ix, Index **out) {
+    if (ix->coarser) {
+        *out = ix->coarser;
+        return PCR_OK;
+    }
+    Ctx *ctx = ix->ctx;
+    cudaStream_t st = ctx->stream;
+    const int F = ix->n_frames;
+    const size_t n = ix->n;
+    Index *c = new (std::nothrow) Index();
+    if (!c) return fail(ctx, PCR_ERR_OOM, "host allocation failed");
+    c->ctx = ctx;
+    c->n = n;
+    c->n_indexed = ix->n_indexed;
+    c->n_frames = F;
+    c->grids_h.resize(F);
+    c->box_min = ix->box_min;
+    c->box_ext = ix->box_ext;
+    c->box_count = ix->box_count;
+    c->d_mask = ix->d_mask;
+    c->orig4 = ix->orig4;
+    c->frame_in_off = ix->frame_in_off;
+    c->shares_orig4 = true;
+    struct Guard {
+        Index *ix;
+        ~Guard() {
+            if (ix) index_free(ix);
+        }
+    } guard{c};
+    PCR_CUDA(ctx, cudaMallocAsync((void **)&c->grids, sizeof(GridDesc) * F, st));
+    const uint64_t cap = std::max<uint64_t>(1, std::min<uint64_t>(kMaxCellsPerFrame, kMaxCellsTotal / (uint64_t)F));
+    uint64_t base = 0;
+    uint32_t max_frame = 0;
+    for (int f = 0; f < F; f++) {
+        FrameBox b;
+        for (int a = 0; a < 3; a++) {
+            b.mn[a] = ix->box_min[3 * f + a];
+            b.ext[a] = ix->box_ext[3 * f + a];
+        }
+        b.count = ix->box_count[f];
+        GridDesc &g = c->grids_h[f];
+        shape_grid(g, b, ix->grids_h[f].h * kLevelFactor, cap);
+        g.cell_base = (uint32_t)base;
+        base += g.n_cells;
+        g.pt_begin = ix->grids_h[f].pt_begin;
+        g.pt_end = ix->grids_h[f].pt_end;
+        g.in_begin = ix->grids_h[f].in_begin;
+        g.in_end = ix->grids_h[f].in_end;
+        max_frame = std::max(max_frame, g.in_end - g.in_begin);
+    }
+    c->total_cells = (uint32_t)base;
+    PCR_CUDA(ctx, cudaMemcpyAsync(c->grids, c->grids_h.data(), sizeof(GridDesc) * F, cudaMemcpyHostToDevice, st));
+    PCR_CUDA(ctx, cudaMallocAsync((void **)&c->cell_start, sizeof(uint32_t) * ((size_t)base + 1), st));
+    PCR_CUDA(ctx, cudaMemsetAsync(c->cell_start, 0, sizeof(uint32_t) * ((size_t)base + 1), st));
+    PCR_CUDA(ctx, cudaMallocAsync((void **)&c->sorted, sizeof(float4) * std::max<size_t>(n, 1), st));
+    PCR_TRY(ensure(ctx, ctx->b_misc, sizeof(uint32_t) * 2 * std::max<size_t>(n, 1)));
+    uint32_t *d_cell_id = (uint32_t *)ctx->b_misc.p;
+    uint32_t *d_rank = d_cell_id + std::max<size_t>(n, 1);
+    if (n > 0) {
+        const unsigned bx = std::max(1u, (max_frame + kBuildThreads * kItems - 1) / (kBuildThreads * kItems));
+        count4_kernel<<<dim3(bx, F), kBuildThreads, 0, st>>>(c->orig4, c->frame_in_off, n, c->d_mask, c->grids, c->cell_start,
+                                                             d_cell_id, d_rank);
+        PCR_LAUNCH_CHECK(ctx);
+    }
+    PCR_TRY(exclusive_scan_u32_dev(ctx, c->cell_start, (size_t)base + 1));
+    if (n > 0) {
+        scatter_kernel<<<(unsigned)((n + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0, st>>>(c->orig4, n, c->cell_start,
+                                                                                                      d_cell_id, d_rank, c->sorted);
+        PCR_LAUNCH_CHECK(ctx);
+    }
+    guard.ix = nullptr;
+    ix->coarser = c;
+    *out = c;
+    return PCR_OK;
 }
 
 int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz, size_t n, const BuildOpts &opts,
                     Index **out) {
     *out = nullptr;
-    if (n >= 0xfffffff0ull) return fail(ctx, PCR_ERR_UNSUPPORTED, "clouds above 2^32-16 points are not supported");
+    if (n > 0x7fffffffull) return fail(ctx, PCR_ERR_UNSUPPORTED, "clouds above 2^31 points are not supported");
     const int F = opts.n_frames > 0 ? opts.n_frames : 1;
     if (F > 1 && !opts.frame_offsets) return fail(ctx, PCR_ERR_INVALID_ARG, "frame_offsets missing");
     cudaStream_t st = ctx->stream;
@@ -532,6 +643,17 @@ int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz,
         n_indexed += box[f].count;
     }
     ix->n_indexed = n_indexed;
+    ix->d_mask = opts.d_mask;
+    ix->box_min.resize(3 * F);
+    ix->box_ext.resize(3 * F);
+    ix->box_count.resize(F);
+    for (int f = 0; f < F; f++) {
+        ix->box_count[f] = box[f].count;
+        for (int a = 0; a < 3; a++) {
+            ix->box_min[3 * f + a] = box[f].mn[a];
+            ix->box_ext[3 * f + a] = box[f].ext[a];
+        }
+    }
 
     const double target = occupancy_target(opts.k_hint);
     const uint64_t cap = std::max<uint64_t>(1, std::min<uint64_t>(kMaxCellsPerFrame, kMaxCellsTotal / (uint64_t)F));

@@ -22,8 +22,28 @@ namespace {
 
 constexpr int kWarps = 4;              // warps per block
 constexpr int kThreads = kWarps * 32;
-constexpr int kQPW = 32;               // queries per warp
-constexpr int kQPB = kWarps * kQPW;    // queries per block
+constexpr int kQPW0 = 32;              // queries per warp on level 0 (consecutive in cell order)
+constexpr int kQPWL = 1;               // queries per warp on the deferred lists (few, long queries)
+
+// One pass over one level of the grid.  Level 0 takes every query; level l > 0 takes the queries
+// the previous level deferred (qlist) and searches the 8x coarser grid of that level.
+struct LevelArgs {
+    const GridDesc *grids;
+    int n_frames;
+    const uint32_t *cell_start;
+    const float4 *pts;         // this level's cell-sorted points
+    const float4 *qpts;        // level-0 sorted points: where self-queries are read from
+    const uint32_t *qlist;     // nullptr on level 0 (query id == position)
+    uint32_t nq;
+    uint32_t *defer_list;      // queries this pass could not finish within max_rings shells
+    uint32_t *defer_count;
+    int max_rings;
+    int last_level;
+};
+
+__device__ __forceinline__ void defer_query(const LevelArgs &a, uint32_t qid, int lane) {
+    if (lane == 0) a.defer_list[atomicAdd(a.defer_count, 1u)] = qid;
+}
 
 __device__ __forceinline__ int frame_of_sorted(const GridDesc *__restrict__ grids, int n_frames, uint32_t pos) {
     if (n_frames <= 1) return 0;
@@ -63,33 +83,33 @@ __device__ __forceinline__ void emit_row<SmemTopK>(const SmemTopK &tk, int cnt, 
     }
 }
 
-template <bool kSmem>
-__global__ void __launch_bounds__(kThreads) knn_queries_kernel(const GridDesc *__restrict__ grids,
-                                                               const uint32_t *__restrict__ cell_start,
-                                                               const float4 *__restrict__ sorted,
-                                                               const float *__restrict__ qx, const float *__restrict__ qy,
-                                                               const float *__restrict__ qz, size_t nq, int kk,
-                                                               uint32_t *__restrict__ idx, float *__restrict__ dist,
+template <bool kSmem, int QPW>
+__global__ void __launch_bounds__(kThreads) knn_queries_kernel(LevelArgs a, const float *__restrict__ qx,
+                                                               const float *__restrict__ qy, const float *__restrict__ qz,
+                                                               int kk, uint32_t *__restrict__ idx, float *__restrict__ dist,
                                                                uint32_t *__restrict__ counts) {
     extern __shared__ unsigned long long smem_keys[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const GridDesc g = grids[0];
+    const GridDesc g = a.grids[0];
     typename std::conditional<kSmem, SmemTopK, RegTopK>::type tk;
     tk.kk = kk;
     tk.lane = lane;
     if constexpr (kSmem) tk.s = smem_keys + (size_t)w * kk;
-    const size_t q0 = ((size_t)blockIdx.x * kWarps + w) * kQPW;
-    for (int t = 0; t < kQPW; t++) {
-        size_t qi = q0 + t;
-        if (qi >= nq) break;
+    const uint32_t q0 = (blockIdx.x * kWarps + w) * QPW;
+    for (int t = 0; t < QPW; t++) {
+        if (q0 + t >= a.nq) break;
+        const uint32_t qi = a.qlist ? a.qlist[q0 + t] : q0 + t;
         float x = __ldg(&qx[qi]), y = __ldg(&qy[qi]), z = __ldg(&qz[qi]);
         int cnt = 0;
         tk.reset(PCR_EMPTY_KEY);
         if (finite3(x, y, z)) {  // kdtree.rs:65
-            warp_knn_search(tk, g, cell_start, sorted, x, y, z);
+            if (!warp_knn_search(tk, g, a.cell_start, a.pts, x, y, z, a.max_rings, a.last_level != 0)) {
+                defer_query(a, qi, lane);
+                continue;
+            }
             cnt = tk.count();
         }
-        emit_row(tk, cnt, (size_t)kk, qi, idx, dist);
+        emit_row(tk, cnt, (size_t)kk, (size_t)qi, idx, dist);
         if (counts && lane == 0) counts[qi] = (uint32_t)cnt;
         if constexpr (kSmem) __syncwarp();
     }
@@ -97,63 +117,71 @@ __global__ void __launch_bounds__(kThreads) knn_queries_kernel(const GridDesc *_
 
 // ---- SOR: mean distance to the k nearest neighbours (k+1 searched, self dropped) ----------------
 // smem per warp: dist[(kk)][33] f32 (transposed: neighbour-major) + cnt[32]
-template <bool kSmem>
-__global__ void __launch_bounds__(kThreads) sor_mean_kernel(const GridDesc *__restrict__ grids, int n_frames,
-                                                            const uint32_t *__restrict__ cell_start,
-                                                            const float4 *__restrict__ sorted, uint32_t n_sorted, int kk,
-                                                            float *__restrict__ mean_d) {
+template <bool kSmem, int QPW>
+__global__ void __launch_bounds__(kThreads) sor_mean_kernel(LevelArgs a, int kk, float *__restrict__ mean_d) {
     extern __shared__ unsigned long long smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t q0 = (blockIdx.x * kWarps + w) * kQPW;
-    if (q0 >= n_sorted) return;
+    const uint32_t q0 = (blockIdx.x * kWarps + w) * QPW;
+    if (q0 >= a.nq) return;
     if constexpr (!kSmem) {
-        float *sd = reinterpret_cast<float *>(smem_raw) + (size_t)w * (kk * 33 + 32);
+        float *sd = reinterpret_cast<float *>(smem_raw) + (size_t)w * (kk * 33 + 64);
         int *scnt = reinterpret_cast<int *>(sd + kk * 33);
+        uint32_t *spos = reinterpret_cast<uint32_t *>(scnt + 32);
         RegTopK tk;
         tk.kk = kk;
         tk.lane = lane;
-        int f = frame_of_sorted(grids, n_frames, q0);
-        GridDesc g = grids[f];
-        for (int t = 0; t < kQPW; t++) {
-            uint32_t qi = q0 + t;
-            if (qi >= n_sorted) break;
-            if (qi >= g.pt_end) {
-                f = frame_of_sorted(grids, n_frames, qi);
-                g = grids[f];
+        int f = -1;
+        GridDesc g;
+        for (int t = 0; t < QPW; t++) {
+            if (q0 + t >= a.nq) break;
+            const uint32_t pos = a.qlist ? a.qlist[q0 + t] : q0 + t;
+            if (f < 0 || pos >= g.pt_end || pos < g.pt_begin) {
+                f = frame_of_sorted(a.grids, a.n_frames, pos);
+                g = a.grids[f];
             }
-            float4 q = __ldg(&sorted[qi]);
-            warp_knn_search(tk, g, cell_start, sorted, q.x, q.y, q.z);
+            float4 q = __ldg(&a.qpts[pos]);
+            bool done = warp_knn_search(tk, g, a.cell_start, a.pts, q.x, q.y, q.z, a.max_rings, a.last_level != 0);
             int cnt = tk.count();
-            if (lane < kk) sd[lane * 33 + t] = __fsqrt_rn(key_d2(tk.K));  // kdtree.rs:76
-            if (lane == 0) scnt[t] = cnt;
+            if (!done) {
+                defer_query(a, pos, lane);
+                cnt = -1;
+            } else if (lane < kk) {
+                sd[lane * 33 + t] = __fsqrt_rn(key_d2(tk.K));  // kdtree.rs:76
+            }
+            if (lane == 0) {
+                scnt[t] = cnt;
+                spos[t] = pos;
+            }
         }
         __syncwarp();
-        uint32_t qi = q0 + lane;
-        if (qi < n_sorted) {
+        if (lane < QPW && q0 + lane < a.nq) {
             int cnt = scnt[lane];
-            // statistical_outlier.rs:28-37: drop the first (self) if there is more than one result,
-            // sequential f32 sum in ascending-distance order, divide by the count
-            int first = cnt > 1 ? 1 : 0;
-            float sum = 0.0f;
-            for (int j = first; j < cnt; j++) sum = __fadd_rn(sum, sd[j * 33 + lane]);
-            int m = cnt - first;
-            float md = m > 0 ? __fdiv_rn(sum, (float)m) : INFINITY;
-            mean_d[__float_as_uint(__ldg(&sorted[qi]).w)] = md;
+            if (cnt >= 0) {
+                // statistical_outlier.rs:28-37: drop the first (self) if there is more than one
+                // result, sequential f32 sum in ascending-distance order, divide by the count
+                int first = cnt > 1 ? 1 : 0;
+                float sum = 0.0f;
+                for (int j = first; j < cnt; j++) sum = __fadd_rn(sum, sd[j * 33 + lane]);
+                int m = cnt - first;
+                float md = m > 0 ? __fdiv_rn(sum, (float)m) : INFINITY;
+                mean_d[__float_as_uint(__ldg(&a.qpts[spos[lane]]).w)] = md;
+            }
         }
     } else {
         SmemTopK tk;
         tk.kk = kk;
         tk.lane = lane;
         tk.s = smem_raw + (size_t)w * kk;
-        for (int t = 0; t < kQPW; t++) {
-            uint32_t qi = q0 + t;
-            if (qi >= n_sorted) break;
-            int f = frame_of_sorted(grids, n_frames, qi);
-            const GridDesc g = grids[f];
-            float4 q = __ldg(&sorted[qi]);
-            warp_knn_search(tk, g, cell_start, sorted, q.x, q.y, q.z);
+        for (int t = 0; t < QPW; t++) {
+            if (q0 + t >= a.nq) break;
+            const uint32_t pos = a.qlist ? a.qlist[q0 + t] : q0 + t;
+            const GridDesc g = a.grids[frame_of_sorted(a.grids, a.n_frames, pos)];
+            float4 q = __ldg(&a.qpts[pos]);
+            bool done = warp_knn_search(tk, g, a.cell_start, a.pts, q.x, q.y, q.z, a.max_rings, a.last_level != 0);
             __syncwarp();
-            if (lane == 0) {
+            if (!done) {
+                defer_query(a, pos, lane);
+            } else if (lane == 0) {
                 int cnt = tk.count();
                 int first = cnt > 1 ? 1 : 0;
                 float sum = 0.0f;
@@ -252,48 +280,51 @@ __device__ __forceinline__ void normal_from_neighbours(int cnt, NB nb, float px,
     nx = ex; ny = ey; nz = ez;
 }
 
-// smem per warp (register path): coords[(kk*3)][33] f32 + cnt[32]
-template <bool kSmem>
-__global__ void __launch_bounds__(kThreads) normals_kernel(const GridDesc *__restrict__ grids, int n_frames,
-                                                           const uint32_t *__restrict__ cell_start,
-                                                           const float4 *__restrict__ sorted, uint32_t n_sorted,
-                                                           const float4 *__restrict__ orig4, int kk, float vx, float vy,
-                                                           float vz, float *__restrict__ nx, float *__restrict__ ny,
+// smem per warp (register path): coords[(kk*3)][33] f32 + cnt[32] + pos[32]
+template <bool kSmem, int QPW>
+__global__ void __launch_bounds__(kThreads) normals_kernel(LevelArgs a, const float4 *__restrict__ orig4, int kk, float vx,
+                                                           float vy, float vz, float *__restrict__ nx, float *__restrict__ ny,
                                                            float *__restrict__ nz) {
     extern __shared__ unsigned long long smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t q0 = (blockIdx.x * kWarps + w) * kQPW;
-    if (q0 >= n_sorted) return;
+    const uint32_t q0 = (blockIdx.x * kWarps + w) * QPW;
+    if (q0 >= a.nq) return;
     if constexpr (!kSmem) {
-        float *sc = reinterpret_cast<float *>(smem_raw) + (size_t)w * (kk * 3 * 33 + 32);
+        float *sc = reinterpret_cast<float *>(smem_raw) + (size_t)w * (kk * 3 * 33 + 64);
         int *scnt = reinterpret_cast<int *>(sc + kk * 3 * 33);
+        uint32_t *spos = reinterpret_cast<uint32_t *>(scnt + 32);
         RegTopK tk;
         tk.kk = kk;
         tk.lane = lane;
-        int f = frame_of_sorted(grids, n_frames, q0);
-        GridDesc g = grids[f];
-        for (int t = 0; t < kQPW; t++) {
-            uint32_t qi = q0 + t;
-            if (qi >= n_sorted) break;
-            if (qi >= g.pt_end) {
-                f = frame_of_sorted(grids, n_frames, qi);
-                g = grids[f];
+        int f = -1;
+        GridDesc g;
+        for (int t = 0; t < QPW; t++) {
+            if (q0 + t >= a.nq) break;
+            const uint32_t pos = a.qlist ? a.qlist[q0 + t] : q0 + t;
+            if (f < 0 || pos >= g.pt_end || pos < g.pt_begin) {
+                f = frame_of_sorted(a.grids, a.n_frames, pos);
+                g = a.grids[f];
             }
-            float4 q = __ldg(&sorted[qi]);
-            warp_knn_search(tk, g, cell_start, sorted, q.x, q.y, q.z);
+            float4 q = __ldg(&a.qpts[pos]);
+            bool done = warp_knn_search(tk, g, a.cell_start, a.pts, q.x, q.y, q.z, a.max_rings, a.last_level != 0);
             int cnt = tk.count();
-            if (lane < cnt) {  // gather the neighbour's coordinates once (one 16 B load per lane)
+            if (!done) {
+                defer_query(a, pos, lane);
+                cnt = -1;
+            } else if (lane < cnt) {  // gather the neighbour's coordinates once (one 16 B load per lane)
                 float4 p = __ldg(&orig4[key_idx(tk.K)]);
                 sc[(lane * 3 + 0) * 33 + t] = p.x;
                 sc[(lane * 3 + 1) * 33 + t] = p.y;
                 sc[(lane * 3 + 2) * 33 + t] = p.z;
             }
-            if (lane == 0) scnt[t] = cnt;
+            if (lane == 0) {
+                scnt[t] = cnt;
+                spos[t] = pos;
+            }
         }
         __syncwarp();
-        uint32_t qi = q0 + lane;
-        if (qi < n_sorted) {
-            float4 q = __ldg(&sorted[qi]);
+        if (lane < QPW && q0 + lane < a.nq && scnt[lane] >= 0) {
+            float4 q = __ldg(&a.qpts[spos[lane]]);
             float ox, oy, oz;
             normal_from_neighbours(scnt[lane], [&](int j, int c) { return sc[(j * 3 + c) * 33 + lane]; }, q.x, q.y, q.z, vx, vy,
                                    vz, ox, oy, oz);
@@ -307,15 +338,16 @@ __global__ void __launch_bounds__(kThreads) normals_kernel(const GridDesc *__res
         tk.kk = kk;
         tk.lane = lane;
         tk.s = smem_raw + (size_t)w * kk;
-        for (int t = 0; t < kQPW; t++) {
-            uint32_t qi = q0 + t;
-            if (qi >= n_sorted) break;
-            int f = frame_of_sorted(grids, n_frames, qi);
-            const GridDesc g = grids[f];
-            float4 q = __ldg(&sorted[qi]);
-            warp_knn_search(tk, g, cell_start, sorted, q.x, q.y, q.z);
+        for (int t = 0; t < QPW; t++) {
+            if (q0 + t >= a.nq) break;
+            const uint32_t pos = a.qlist ? a.qlist[q0 + t] : q0 + t;
+            const GridDesc g = a.grids[frame_of_sorted(a.grids, a.n_frames, pos)];
+            float4 q = __ldg(&a.qpts[pos]);
+            bool done = warp_knn_search(tk, g, a.cell_start, a.pts, q.x, q.y, q.z, a.max_rings, a.last_level != 0);
             __syncwarp();
-            if (lane == 0) {
+            if (!done) {
+                defer_query(a, pos, lane);
+            } else if (lane == 0) {
                 float ox, oy, oz;
                 const unsigned long long *s = tk.s;
                 normal_from_neighbours(tk.count(),
@@ -439,6 +471,53 @@ int set_smem(Ctx *ctx, Kern kern, size_t bytes) {
     return PCR_OK;
 }
 
+// Runs `launch(args, qpw)` level by level until no query is left deferred.  Reading the deferred
+// count costs one small D2H + sync per level that is actually needed (clouds without far outliers
+// finish on level 0 and pay exactly one).
+template <class Launch>
+int run_levels(Index *ix, uint32_t nq, Launch launch) {
+    Ctx *ctx = ix->ctx;
+    if (nq == 0) return PCR_OK;
+    PCR_TRY(ensure(ctx, ctx->b_list, (size_t)nq * 2 * sizeof(uint32_t) + 256));
+    uint32_t *counters = (uint32_t *)ctx->b_list.p;  // [2]
+    uint32_t *lists[2] = {counters + 64, counters + 64 + nq};
+    Index *cur = ix;
+    const uint32_t *qlist = nullptr;
+    uint32_t n_cur = nq;
+    for (int level = 0;; level++) {
+        const bool last = level == kMaxLevels - 1;
+        uint32_t *cnt = counters + (level & 1);
+        PCR_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(uint32_t), ctx->stream));
+        LevelArgs a;
+        a.grids = cur->grids;
+        a.n_frames = cur->n_frames;
+        a.cell_start = cur->cell_start;
+        a.pts = cur->sorted;
+        a.qpts = ix->sorted;
+        a.qlist = qlist;
+        a.nq = n_cur;
+        a.defer_list = lists[level & 1];
+        a.defer_count = cnt;
+        a.max_rings = last ? kMaxRings : kLevelRings;
+        a.last_level = last ? 1 : 0;
+        PCR_TRY(launch(a, level == 0 ? kQPW0 : kQPWL));
+        if (last) break;
+        uint32_t *mail = (uint32_t *)ctx->pinned + 32;
+        PCR_CUDA(ctx, cudaMemcpyAsync(mail, cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        PCR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        n_cur = *mail;
+        if (getenv("PCR_DEBUG")) fprintf(stderr, "[pcr] level %d: %u of %u queries deferred (cell %.4g)\n", level, n_cur, a.nq, cur->grids_h[0].h);
+        if (n_cur == 0) break;
+        Index *next = nullptr;
+        PCR_TRY(index_coarser_level(cur, &next));
+        cur = next;
+        qlist = lists[level & 1];
+    }
+    return PCR_OK;
+}
+
+inline unsigned blocks_for(uint32_t nq, int qpw) { return (nq + kWarps * qpw - 1) / (kWarps * qpw); }
+
 }  // namespace
 
 int knn_queries_dev(Index *ix, const float *dqx, const float *dqy, const float *dqz, size_t nq, size_t k, uint32_t *d_idx,
@@ -447,18 +526,23 @@ int knn_queries_dev(Index *ix, const float *dqx, const float *dqy, const float *
     if (nq == 0 || k == 0) return PCR_OK;
     if (ix->n_frames != 1) return fail(ctx, PCR_ERR_UNSUPPORTED, "external queries need a single-frame index");
     if (k > PCR_MAX_K) return fail(ctx, PCR_ERR_UNSUPPORTED, "k = %zu exceeds PCR_MAX_K = %d", k, PCR_MAX_K);
-    unsigned blocks = (unsigned)((nq + kQPB - 1) / kQPB);
-    if (k <= 32) {
-        knn_queries_kernel<false><<<blocks, kThreads, 0, ctx->stream>>>(ix->grids, ix->cell_start, ix->sorted, dqx, dqy, dqz, nq,
-                                                                        (int)k, d_idx, d_dist, d_counts);
-    } else {
-        size_t smem = sizeof(unsigned long long) * k * kWarps;
-        PCR_TRY(set_smem(ctx, knn_queries_kernel<true>, smem));
-        knn_queries_kernel<true><<<blocks, kThreads, smem, ctx->stream>>>(ix->grids, ix->cell_start, ix->sorted, dqx, dqy, dqz,
-                                                                          nq, (int)k, d_idx, d_dist, d_counts);
-    }
-    PCR_LAUNCH_CHECK(ctx);
-    return PCR_OK;
+    if (nq > 0xfffffff0ull) return fail(ctx, PCR_ERR_UNSUPPORTED, "too many queries");
+    const int kk = (int)k;
+    if (k > 32) PCR_TRY(set_smem(ctx, knn_queries_kernel<true, kQPW0>, sizeof(unsigned long long) * k * kWarps));
+    if (k > 32) PCR_TRY(set_smem(ctx, knn_queries_kernel<true, kQPWL>, sizeof(unsigned long long) * k * kWarps));
+    return run_levels(ix, (uint32_t)nq, [&](const LevelArgs &a, int qpw) -> int {
+        unsigned blocks = blocks_for(a.nq, qpw);
+        size_t smem = k <= 32 ? 0 : sizeof(unsigned long long) * k * kWarps;
+        if (k <= 32) {
+            if (qpw == kQPW0) knn_queries_kernel<false, kQPW0><<<blocks, kThreads, 0, ctx->stream>>>(a, dqx, dqy, dqz, kk, d_idx, d_dist, d_counts);
+            else knn_queries_kernel<false, kQPWL><<<blocks, kThreads, 0, ctx->stream>>>(a, dqx, dqy, dqz, kk, d_idx, d_dist, d_counts);
+        } else {
+            if (qpw == kQPW0) knn_queries_kernel<true, kQPW0><<<blocks, kThreads, smem, ctx->stream>>>(a, dqx, dqy, dqz, kk, d_idx, d_dist, d_counts);
+            else knn_queries_kernel<true, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, dqx, dqy, dqz, kk, d_idx, d_dist, d_counts);
+        }
+        PCR_LAUNCH_CHECK(ctx);
+        return PCR_OK;
+    });
 }
 
 int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d) {
@@ -471,19 +555,23 @@ int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d) {
         PCR_LAUNCH_CHECK(ctx);
     }
     if (ix->n_indexed == 0) return PCR_OK;
-    unsigned blocks = (unsigned)((ix->n_indexed + kQPB - 1) / kQPB);
-    if (kk <= 32) {
-        size_t smem = (kk * 33 + 32) * sizeof(float) * kWarps;
-        sor_mean_kernel<false><<<blocks, kThreads, smem, ctx->stream>>>(ix->grids, ix->n_frames, ix->cell_start, ix->sorted,
-                                                                        (uint32_t)ix->n_indexed, (int)kk, d_mean_d);
-    } else {
-        size_t smem = sizeof(unsigned long long) * kk * kWarps;
-        PCR_TRY(set_smem(ctx, sor_mean_kernel<true>, smem));
-        sor_mean_kernel<true><<<blocks, kThreads, smem, ctx->stream>>>(ix->grids, ix->n_frames, ix->cell_start, ix->sorted,
-                                                                       (uint32_t)ix->n_indexed, (int)kk, d_mean_d);
+    const size_t smem = kk <= 32 ? (kk * 33 + 64) * sizeof(float) * kWarps : sizeof(unsigned long long) * kk * kWarps;
+    if (kk > 32) {
+        PCR_TRY(set_smem(ctx, sor_mean_kernel<true, kQPW0>, smem));
+        PCR_TRY(set_smem(ctx, sor_mean_kernel<true, kQPWL>, smem));
     }
-    PCR_LAUNCH_CHECK(ctx);
-    return PCR_OK;
+    return run_levels(ix, (uint32_t)ix->n_indexed, [&](const LevelArgs &a, int qpw) -> int {
+        unsigned blocks = blocks_for(a.nq, qpw);
+        if (kk <= 32) {
+            if (qpw == kQPW0) sor_mean_kernel<false, kQPW0><<<blocks, kThreads, smem, ctx->stream>>>(a, (int)kk, d_mean_d);
+            else sor_mean_kernel<false, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, (int)kk, d_mean_d);
+        } else {
+            if (qpw == kQPW0) sor_mean_kernel<true, kQPW0><<<blocks, kThreads, smem, ctx->stream>>>(a, (int)kk, d_mean_d);
+            else sor_mean_kernel<true, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, (int)kk, d_mean_d);
+        }
+        PCR_LAUNCH_CHECK(ctx);
+        return PCR_OK;
+    });
 }
 
 int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny, float *d_nz, const uint8_t *d_mask) {
@@ -496,22 +584,27 @@ int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny
         PCR_LAUNCH_CHECK(ctx);
     }
     if (ix->n_indexed == 0) return PCR_OK;
-    unsigned blocks = (unsigned)((ix->n_indexed + kQPB - 1) / kQPB);
+    const size_t smem = k <= 32 ? (k * 3 * 33 + 64) * sizeof(float) * kWarps : sizeof(unsigned long long) * k * kWarps;
     if (k <= 32) {
-        size_t smem = (k * 3 * 33 + 32) * sizeof(float) * kWarps;
-        PCR_TRY(set_smem(ctx, normals_kernel<false>, smem));
-        normals_kernel<false><<<blocks, kThreads, smem, ctx->stream>>>(ix->grids, ix->n_frames, ix->cell_start, ix->sorted,
-                                                                       (uint32_t)ix->n_indexed, ix->orig4, (int)k, vp[0], vp[1],
-                                                                       vp[2], d_nx, d_ny, d_nz);
+        PCR_TRY(set_smem(ctx, normals_kernel<false, kQPW0>, smem));
+        PCR_TRY(set_smem(ctx, normals_kernel<false, kQPWL>, smem));
     } else {
-        size_t smem = sizeof(unsigned long long) * k * kWarps;
-        PCR_TRY(set_smem(ctx, normals_kernel<true>, smem));
-        normals_kernel<true><<<blocks, kThreads, smem, ctx->stream>>>(ix->grids, ix->n_frames, ix->cell_start, ix->sorted,
-                                                                      (uint32_t)ix->n_indexed, ix->orig4, (int)k, vp[0], vp[1],
-                                                                      vp[2], d_nx, d_ny, d_nz);
+        PCR_TRY(set_smem(ctx, normals_kernel<true, kQPW0>, smem));
+        PCR_TRY(set_smem(ctx, normals_kernel<true, kQPWL>, smem));
     }
-    PCR_LAUNCH_CHECK(ctx);
-    return PCR_OK;
+    const float v0 = vp[0], v1 = vp[1], v2 = vp[2];
+    return run_levels(ix, (uint32_t)ix->n_indexed, [&](const LevelArgs &a, int qpw) -> int {
+        unsigned blocks = blocks_for(a.nq, qpw);
+        if (k <= 32) {
+            if (qpw == kQPW0) normals_kernel<false, kQPW0><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);
+            else normals_kernel<false, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);
+        } else {
+            if (qpw == kQPW0) normals_kernel<true, kQPW0><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);
+            else normals_kernel<true, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);
+        }
+        PCR_LAUNCH_CHECK(ctx);
+        return PCR_OK;
+    });
 }
 
 int radius_count_dev(Index *ix, const float *dqx, const float *dqy, const float *dqz, size_t nq, float radius,

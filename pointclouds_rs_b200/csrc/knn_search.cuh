@@ -10,8 +10,11 @@
 //      Stop iff the k-th best d^2 is STRICTLY below (that distance)^2 * (1 - 1e-6): the slack
 //      covers the rounding of f32 d^2 (<= 3 ulp) and of the f64 cell assignment, and strictness
 //      keeps an equal-distance, lower-index point outside the cube from being missed;
-//   3. otherwise scan shell R+1 (Chebyshev distance exactly R+1).  After kMaxRings shells the
-//      query falls back to scanning its whole frame (isolated outliers in huge sparse grids).
+//   3. otherwise scan shell R+1 (Chebyshev distance exactly R+1).  After `max_rings` shells the
+//      query is DEFERRED (returns false): the caller re-runs it on a coarser level of the grid
+//      (knn.cu: level l+1 has 8x the cell size), so isolated outliers -- the very points SOR exists
+//      to find -- never walk hundreds of empty shells.  Only on the coarsest level does a query
+//      fall back to scanning its whole frame, pruned by the k-th best found so far.
 // Candidates are ranked by the packed (d^2 bits, original index) key, so the result does not
 // depend on the scan order.
 #pragma once
@@ -19,7 +22,9 @@
 
 namespace pcr {
 
-constexpr int kMaxRings = 12;
+constexpr int kMaxRings = 12;         // thread-per-query search (ICP) and the coarsest level
+constexpr int kLevelRings = 4;        // shells scanned per grid level before a query is deferred
+constexpr int kMaxLevels = 4;
 constexpr uint32_t kBruteFrame = 96;  // frames this small are scanned directly
 
 // ------------------------------------------------------------------------------------------------
@@ -89,24 +94,41 @@ struct SmemTopK {
     __device__ __forceinline__ int count() const { return n; }
 };
 
-// One contiguous run [b, e) of the cell-sorted array against the query, 32 candidates at a time.
+// offer one batch (one candidate key per lane, EMPTY for idle lanes) to the top-k
+template <class TopK>
+__device__ __forceinline__ void offer_batch(TopK &tk, unsigned long long key) {
+    unsigned m = __ballot_sync(PCR_FULL, key < tk.thr);
+    while (m) {
+        int s = __ffs(m) - 1;
+        tk.insert(__shfl_sync(PCR_FULL, key, s));
+        // re-test the remaining lanes against the tightened threshold
+        m = __ballot_sync(PCR_FULL, key < tk.thr) & ~((2u << s) - 1u);
+    }
+}
+
+// One contiguous run [b, e) of the cell-sorted array against the query, 32 candidates per batch.
+// Long runs are taken four batches at a time with all four loads issued up front (the insertion
+// loop is data dependent, so without this a warp has a single load in flight).
 template <class TopK>
 __device__ __forceinline__ void scan_run(TopK &tk, const float4 *__restrict__ pts, uint32_t b, uint32_t e, float qx,
                                          float qy, float qz) {
-    for (uint32_t base = b; base < e; base += 32) {
+    uint32_t base = b;
+    for (; base + 128 <= e; base += 128) {
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) p[u] = __ldg(&pts[base + u * 32 + tk.lane]);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            offer_batch(tk, make_key(dist2_exact(qx, qy, qz, p[u].x, p[u].y, p[u].z), __float_as_uint(p[u].w)));
+    }
+    for (; base < e; base += 32) {
         uint32_t i = base + tk.lane;
         unsigned long long key = PCR_EMPTY_KEY;
         if (i < e) {
             float4 p = __ldg(&pts[i]);
             key = make_key(dist2_exact(qx, qy, qz, p.x, p.y, p.z), __float_as_uint(p.w));
         }
-        unsigned m = __ballot_sync(PCR_FULL, key < tk.thr);
-        while (m) {
-            int s = __ffs(m) - 1;
-            tk.insert(__shfl_sync(PCR_FULL, key, s));
-            // re-test the remaining lanes against the tightened threshold
-            m = __ballot_sync(PCR_FULL, key < tk.thr) & ~((2u << s) - 1u);
-        }
+        offer_batch(tk, key);
     }
 }
 
@@ -130,15 +152,17 @@ __device__ __forceinline__ void scan_runs(TopK &tk, const float4 *__restrict__ p
 }
 
 // Warp-cooperative exact k-NN of (qx,qy,qz) in frame g.  All arguments are warp-uniform.
+// Returns false if the query has to be re-run on a coarser level (only when !last_level).
 template <class TopK>
-__device__ __forceinline__ void warp_knn_search(TopK &tk, const GridDesc &g, const uint32_t *__restrict__ cell_start,
-                                                const float4 *__restrict__ pts, float qx, float qy, float qz) {
+__device__ __forceinline__ bool warp_knn_search(TopK &tk, const GridDesc &g, const uint32_t *__restrict__ cell_start,
+                                                const float4 *__restrict__ pts, float qx, float qy, float qz,
+                                                int max_rings, bool last_level) {
     tk.reset(PCR_EMPTY_KEY);
     const uint32_t m = g.pt_end - g.pt_begin;
-    if (m == 0) return;
+    if (m == 0) return true;
     if (m <= kBruteFrame || m <= (uint32_t)tk.kk) {
         scan_run(tk, pts, g.pt_begin, g.pt_end, qx, qy, qz);
-        return;
+        return true;
     }
     const int lane = tk.lane;
     double f0, f1, f2;
@@ -170,16 +194,18 @@ __device__ __forceinline__ void warp_knn_search(TopK &tk, const GridDesc &g, con
         if (c1 + R < d1n - 1) { open = true; mf = fmin(mf, 1.0 - f1); }
         if (c2 - R > 0) { open = true; mf = fmin(mf, f2); }
         if (c2 + R < d2n - 1) { open = true; mf = fmin(mf, 1.0 - f2); }
-        if (!open) return;  // the whole grid has been scanned
+        if (!open) return true;  // the whole grid has been scanned
         const unsigned long long kth = tk.kth();
         if (kth != PCR_EMPTY_KEY) {
             double bound = ((double)R + mf) * g.h;
-            if (bound > 0.0 && (double)key_d2(kth) < bound * bound * (1.0 - 1e-6)) return;
+            if (bound > 0.0 && (double)key_d2(kth) < bound * bound * (1.0 - 1e-6)) return true;
         }
-        if (R >= kMaxRings) {  // isolated query: rescan the frame, pruned by the k-th best so far
+        if (R >= max_rings) {
+            if (!last_level) return false;  // deferred to the next (coarser) level
+            // coarsest level: rescan the frame, pruned by the k-th best so far
             tk.reset(kth == PCR_EMPTY_KEY ? PCR_EMPTY_KEY : kth + 1ull);
             scan_run(tk, pts, g.pt_begin, g.pt_end, qx, qy, qz);
-            return;
+            return true;
         }
         // shell R+1: rows (i0,i1) of the (2S+1)^2 square; border rows are full runs, interior rows
         // contribute their two end cells (slot 0 = low end, slot 1 = high end)

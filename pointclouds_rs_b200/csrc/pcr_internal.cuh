@@ -32,6 +32,8 @@ struct GridDesc {
     uint32_t in_end;
 };
 
+constexpr int kLevelFactor = 8;  // cell-size ratio between consecutive grid levels (knn_search.cuh)
+
 struct DevBuf {  // grow-only device scratch buffer
     void *p = nullptr;
     size_t cap = 0;
@@ -53,6 +55,12 @@ struct Index {
     uint32_t *cell_start = nullptr;  // [total_cells + 1] exclusive prefix of the per-cell counts
     uint32_t total_cells = 0;
     bool owns_memory = true;
+    // bounding boxes (original axis order, 3 doubles per frame: min and extent) and finite counts
+    std::vector<double> box_min, box_ext;
+    std::vector<uint32_t> box_count;
+    const uint8_t *d_mask = nullptr;  // keep-mask the index was built with (caller memory)
+    Index *coarser = nullptr;         // next grid level (8x the cell size), built on demand
+    bool shares_orig4 = false;        // coarser levels borrow orig4 / grids layout from level 0
 };
 
 struct Ctx {
@@ -71,6 +79,7 @@ struct Ctx {
     DevBuf b_misc2;
     DevBuf b_small;    // reductions, statistics, ICP state
     DevBuf b_table;    // probe cell table
+    DevBuf b_list;     // deferred-query lists of the level loop
     void *pinned = nullptr;  // small pinned host mailbox
     size_t pinned_cap = 0;
     // NCCL (loaded lazily with dlopen, see comm.cu)
@@ -125,6 +134,8 @@ struct BuildOpts {
 int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz, size_t n,
                     const BuildOpts &opts, Index **out);
 void index_free(Index *ix);
+// The next-coarser level of `ix` (cell size x kLevelFactor), built on first use and owned by `ix`.
+int index_coarser_level(Index *ix, Index **out);
 
 // KNN over external queries (n_frames == 1).  d_idx/d_dist row-major nq x k.
 int knn_queries_dev(Index *ix, const float *dqx, const float *dqy, const float *dqz, size_t nq,

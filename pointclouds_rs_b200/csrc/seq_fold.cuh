@@ -1,43 +1,264 @@
-// seq_fold.cuh -- sequential-order f32 folds.
+// seq_fold.cuh -- EXACT parallel evaluation of a sequential f32 fold of non-negative values.
 //
 // The reference sums with `iter().sum::<f32>()`: a strictly left-to-right f32 fold
 // (statistical_outlier.rs:54-59, icp.rs:277-280).  Its rounding error at N = 1e5..1e6 is ~1e-5..1e-4
 // relative, i.e. larger than the band the SOR mask is allowed to differ in, so the fold ORDER is
-// part of the result and has to be reproduced, not just the mathematical sum.
+// part of the result and has to be reproduced bit for bit -- but a 122 K-long dependent FADD chain
+// on one GPU thread costs milliseconds.  This file evaluates the same chain in parallel:
+//
+//   While the running sum s stays inside one binade [2^E, 2^(E+1)), its ulp u = 2^(E-23) is fixed
+//   and s = S*u with a 24-bit integer S.  Adding x >= 0 then is integer arithmetic: with
+//   x = (q + r)*u, 0 <= r < 1,   fl(s + x) = (S + q + [r > 1/2] + [r == 1/2 and S+q odd]) * u
+//   (round-to-nearest-even).  The only dependence on the running value is the PARITY of S in the
+//   tie case, so every element is a map  S -> S + a[S & 1]  with two increments (a0, a1); such maps
+//   compose associatively (the output parity is determined by the input parity), hence a block
+//   SCAN gives every prefix exactly.  When a prefix reaches 2^24 the sum leaves the binade: that one
+//   addition is done with a real FADD and the remainder of the tile is rescanned in the new
+//   binade.  Sums double between such crossings, so there are only ~log2(N) of them, and the first
+//   ones (short prefixes) are taken by a plain sequential head.
+//
+// Validated against numpy's sequential float32 accumulation (denormals, ties, overflow) before it
+// was ported; on the GPU the SOR statistics are compared bit for bit with the CPU oracle.
 #pragma once
 #include "pcr_internal.cuh"
 
 namespace pcr {
 
-// Plain left-to-right fold by one thread over v[b, e): sum of the elements for which
-// `pred(v)` holds, mapped through `fn`.  Loads are independent of the add chain, so the loop runs
-// at one dependent FADD (4 cycles) per element.
+constexpr int kFoldThreads = 1024;
+constexpr int kFoldItems = 8;
+constexpr int kFoldTile = kFoldThreads * kFoldItems;
+constexpr int kFoldHead = 1024;        // elements folded sequentially by thread 0 first (<= kFoldThreads)
+constexpr uint32_t kFoldSat = 1u << 25;  // increments saturate here (anything >= 2^24 is a crossing)
+constexpr uint32_t kFoldLimit = 1u << 24;
+
+struct FoldMap {
+    uint32_t a0, a1;  // increment of S (in ulps) for incoming parity 0 / 1
+};
+
+__device__ __forceinline__ uint32_t fold_sat_add(uint32_t a, uint32_t b) {
+    uint32_t c = a + b;
+    return c > kFoldSat ? kFoldSat : c;
+}
+
+// apply f first, then g
+__device__ __forceinline__ FoldMap fold_compose(FoldMap f, FoldMap g) {
+    FoldMap h;
+    h.a0 = fold_sat_add(f.a0, (f.a0 & 1u) ? g.a1 : g.a0);
+    h.a1 = fold_sat_add(f.a1, ((f.a1 + 1u) & 1u) ? g.a1 : g.a0);
+    return h;
+}
+
+// effective exponent (>= -126) and integer mantissa of s >= 0:  s = S * 2^(E - 23)
+__device__ __forceinline__ void fold_split(float s, int &E, uint32_t &S) {
+    uint32_t b = __float_as_uint(s);
+    uint32_t ex = (b >> 23) & 0xffu, m = b & 0x7fffffu;
+    if (ex == 0) {
+        E = -126;
+        S = m;
+    } else {
+        E = (int)ex - 127;
+        S = m | 0x800000u;
+    }
+}
+__device__ __forceinline__ float fold_join(int E, uint32_t S) {
+    if (E == -126) return __uint_as_float(S);  // denormal or the first normal binade: bits == S
+    return __uint_as_float(((uint32_t)(E + 127) << 23) | (S & 0x7fffffu));
+}
+
+// x = (q + r) * 2^(E-23): q (saturated) and kind = 0: r < 1/2 (or exact), 1: r > 1/2, 2: r == 1/2.
+// Done in f64, where x / u is exact (a 24-bit mantissa times a power of two): floor and the
+// remainder are exact as well.  inv_u = 2^(23-E) is uniform per pass.
+__device__ __forceinline__ double fold_inv_ulp(int E) {  // 2^(23-E), E in [-126, 128]
+    return __longlong_as_double((long long)(1023 + 23 - E) << 52);
+}
+__device__ __forceinline__ void fold_decompose(float x, double inv_u, uint32_t &q, int &kind) {
+    double y = (double)x * inv_u;  // +inf stays +inf -> saturates
+    double fl = floor(y);
+    double r = y - fl;
+    q = fl >= (double)kFoldSat ? kFoldSat : (uint32_t)fl;
+    kind = r > 0.5 ? 1 : (r == 0.5 ? 2 : 0);
+}
+
+__device__ __forceinline__ FoldMap fold_element_map(float x, double inv_u) {
+    uint32_t q;
+    int kind;
+    fold_decompose(x, inv_u, q, kind);
+    FoldMap m;
+    if (kind == 2) {
+        m.a0 = fold_sat_add(q, q & 1u);
+        m.a1 = fold_sat_add(q, (q + 1u) & 1u);
+    } else {
+        m.a0 = m.a1 = fold_sat_add(q, kind == 1 ? 1u : 0u);
+    }
+    return m;
+}
+
+// S after adding x in binade E, exact (valid while the result stays below 2^24)
+__device__ __forceinline__ uint32_t fold_step(uint32_t S, float x, double inv_u) {
+    uint32_t q;
+    int kind;
+    fold_decompose(x, inv_u, q, kind);
+    uint32_t t = fold_sat_add(S, q);
+    if (kind == 1 || (kind == 2 && (t & 1u))) t = fold_sat_add(t, 1u);
+    return t;
+}
+
+struct FoldShared {
+    FoldMap warp_tot[32];
+    uint32_t cross_idx;   // tile-local index of the first crossing element
+    uint32_t s_before;    // S just before it
+    float x_cross;
+    uint32_t s_last;      // S after the last element of the tile (no crossing)
+    float s;              // running sum (broadcast)
+    uint32_t done_upto;   // tile-local: elements below this index are already folded
+    uint32_t cnt[32];
+    float head[kFoldHead];
+};
+
+// Left-to-right f32 sum of fn(v[i]) over the finite v[i], i in [b, e), evaluated by the whole block
+// (kFoldThreads threads).  fn must return a non-negative value.  Returns the sum in every thread;
+// *n_used (if not null) receives the number of finite elements.
 template <class Fn>
-__device__ __forceinline__ float seq_fold_thread(const float *__restrict__ v, size_t b, size_t e, Fn fn, uint32_t *n_used) {
-    float s = 0.0f;
-    uint32_t cnt = 0;
-    size_t i = b;
-    for (; i + 8 <= e; i += 8) {
-        float t[8];
+__device__ float block_exact_fold(const float *__restrict__ v, size_t b, size_t e, Fn fn, FoldShared &sh, uint32_t *n_used) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    uint32_t my_cnt = 0;
+    // ---- sequential head: the first crossings come after 1, 2, 4, ... elements ------------------
+    size_t head_end = b + kFoldHead < e ? b + kFoldHead : e;
+    if (tid < kFoldHead) {  // stage through shared memory so that thread 0 never waits on DRAM
+        float t = b + tid < head_end ? v[b + tid] : INFINITY;
+        bool ok = isfinite(t);
+        sh.head[tid] = ok ? fn(t) : -1.0f;  // fn >= 0: a negative entry marks "skip"
+        my_cnt += ok ? 1u : 0u;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.0f;
+        const int nh = (int)(head_end - b);
+        for (int i = 0; i < nh; i++) {
+            float t = sh.head[i];
+            if (t >= 0.0f) s = __fadd_rn(s, t);
+        }
+        sh.s = s;
+    }
+    __syncthreads();
+    // ---- tiles ------------------------------------------------------------------------------------
+    for (size_t tile = head_end; tile < e; tile += kFoldTile) {
+        float x[kFoldItems];
+        bool use[kFoldItems];
+        const size_t base = tile + (size_t)tid * kFoldItems;  // thread-contiguous items
 #pragma unroll
-        for (int j = 0; j < 8; j++) t[j] = v[i + j];
+        for (int j = 0; j < kFoldItems; j++) {
+            size_t i = base + j;
+            float t = i < e ? v[i] : INFINITY;
+            use[j] = isfinite(t);
+            x[j] = use[j] ? fn(t) : 0.0f;
+            my_cnt += use[j] ? 1u : 0u;
+        }
+        if (tid == 0) sh.done_upto = 0;
+        __syncthreads();
+        for (;;) {
+            const float s = sh.s;
+            if (!isfinite(s)) break;  // overflowed to +inf: stays there (all terms are >= 0)
+            const uint32_t done = sh.done_upto;
+            int E;
+            uint32_t S_in;
+            fold_split(s, E, S_in);
+            const double inv_u = fold_inv_ulp(E);
+            // 1. per-thread aggregate map over the pending items
+            FoldMap agg = {0u, 0u};
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (isfinite(t[j])) {
-                s = __fadd_rn(s, fn(t[j]));
-                cnt++;
+            for (int j = 0; j < kFoldItems; j++) {
+                uint32_t li = (uint32_t)tid * kFoldItems + j;
+                if (use[j] && li >= done) agg = fold_compose(agg, fold_element_map(x[j], inv_u));
             }
+            // 2. block exclusive scan of the aggregates
+            FoldMap inc = agg;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                FoldMap u;
+                u.a0 = __shfl_up_sync(PCR_FULL, inc.a0, o);
+                u.a1 = __shfl_up_sync(PCR_FULL, inc.a1, o);
+                if (lane >= o) inc = fold_compose(u, inc);
+            }
+            if (lane == 31) sh.warp_tot[w] = inc;
+            if (tid == 0) {
+                sh.cross_idx = 0xffffffffu;
+            }
+            __syncthreads();
+            if (w == 0) {
+                FoldMap t = sh.warp_tot[lane], ti = t;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    FoldMap u;
+                    u.a0 = __shfl_up_sync(PCR_FULL, ti.a0, o);
+                    u.a1 = __shfl_up_sync(PCR_FULL, ti.a1, o);
+                    if (lane >= o) ti = fold_compose(u, ti);
+                }
+                // exclusive
+                FoldMap ex;
+                ex.a0 = __shfl_up_sync(PCR_FULL, ti.a0, 1);
+                ex.a1 = __shfl_up_sync(PCR_FULL, ti.a1, 1);
+                if (lane == 0) ex = FoldMap{0u, 0u};
+                sh.warp_tot[lane] = ex;
+            }
+            __syncthreads();
+            FoldMap lane_ex;
+            lane_ex.a0 = __shfl_up_sync(PCR_FULL, inc.a0, 1);
+            lane_ex.a1 = __shfl_up_sync(PCR_FULL, inc.a1, 1);
+            if (lane == 0) lane_ex = FoldMap{0u, 0u};
+            const FoldMap pre = fold_compose(sh.warp_tot[w], lane_ex);
+            // 3. walk the own items with the actual running value; find the first crossing
+            uint32_t S = fold_sat_add(S_in, (S_in & 1u) ? pre.a1 : pre.a0);
+            uint32_t my_cross = 0xffffffffu, S_before = 0;
+            float xc = 0.f;
+            if (S < kFoldLimit) {
+#pragma unroll
+                for (int j = 0; j < kFoldItems; j++) {
+                    uint32_t li = (uint32_t)tid * kFoldItems + j;
+                    if (use[j] && li >= done && my_cross == 0xffffffffu) {
+                        uint32_t S2 = fold_step(S, x[j], inv_u);
+                        if (S2 >= kFoldLimit) {
+                            my_cross = li;
+                            S_before = S;
+                            xc = x[j];
+                        } else {
+                            S = S2;
+                        }
+                    }
+                }
+            }
+            if (my_cross != 0xffffffffu) atomicMin(&sh.cross_idx, my_cross);
+            if (tid == kFoldThreads - 1) sh.s_last = S;
+            __syncthreads();
+            const uint32_t c = sh.cross_idx;
+            if (c == 0xffffffffu) {
+                if (tid == 0) sh.s = fold_join(E, sh.s_last);
+                __syncthreads();
+                break;
+            }
+            if (my_cross == c) {  // exactly one thread owns the crossing element
+                sh.s = __fadd_rn(fold_join(E, S_before), xc);
+                sh.done_upto = c + 1u;
+            }
+            __syncthreads();
         }
+        __syncthreads();
     }
-    for (; i < e; i++) {
-        float t = v[i];
-        if (isfinite(t)) {
-            s = __fadd_rn(s, fn(t));
-            cnt++;
+    // ---- count of finite elements ------------------------------------------------------------------
+    if (n_used) {
+        uint32_t c = __reduce_add_sync(PCR_FULL, my_cnt);
+        if (lane == 0) sh.cnt[w] = c;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t t = __reduce_add_sync(PCR_FULL, sh.cnt[lane]);
+            if (lane == 0) sh.cnt[0] = t;
         }
+        __syncthreads();
+        *n_used = sh.cnt[0];
     }
-    if (n_used) *n_used = cnt;
-    return s;
+    const float r = sh.s;
+    __syncthreads();
+    return r;
 }
 
 }  // namespace pcr

@@ -18,35 +18,36 @@ struct SorFrameStats {
     uint32_t n_finite;
 };
 
-// one block per frame; thread 0 walks the segment twice (left-to-right folds)
-__global__ void sor_stats_seq_kernel(const float *__restrict__ mean_d, const uint32_t *__restrict__ frame_off, size_t n,
-                                     float std_mul, SorFrameStats *__restrict__ stats) {
+// one block per frame: two exact left-to-right folds (seq_fold.cuh), then the threshold
+__global__ void __launch_bounds__(kFoldThreads) sor_stats_kernel(const float *__restrict__ mean_d,
+                                                                  const uint32_t *__restrict__ frame_off, size_t n,
+                                                                  float std_mul, SorFrameStats *__restrict__ stats) {
+    __shared__ FoldShared sh;
     const int f = blockIdx.x;
     const size_t b = frame_off ? frame_off[f] : 0, e = frame_off ? frame_off[f + 1] : n;
-    if (threadIdx.x != 0) return;
     uint32_t nf = 0;
-    float sum = seq_fold_thread(mean_d, b, e, [](float v) { return v; }, &nf);
+    const float sum = block_exact_fold(mean_d, b, e, [](float v) { return v; }, sh, &nf);
     SorFrameStats s;
     s.n_finite = nf;
-    if (nf == 0) {  // statistical_outlier.rs:49-51 -> empty result
+    if (nf == 0) {  // statistical_outlier.rs:49-51 -> empty result (NaN threshold keeps nothing)
         s.mean = s.stddev = s.thr = __int_as_float(0x7fc00000);
     } else {
         const float nn = (float)nf;
         const float gmean = __fdiv_rn(sum, nn);
-        float var = seq_fold_thread(
+        float var = block_exact_fold(
             mean_d, b, e,
             [gmean](float v) {
                 float d = __fsub_rn(v, gmean);
-                return __fmul_rn(d, d);
+                return __fmul_rn(d, d);  // powi(2)
             },
-            nullptr);
+            sh, nullptr);
         var = __fdiv_rn(var, nn);
         const float sd = __fsqrt_rn(var);
         s.mean = gmean;
         s.stddev = sd;
         s.thr = __fadd_rn(gmean, __fmul_rn(std_mul, sd));
     }
-    stats[f] = s;
+    if (threadIdx.x == 0) stats[f] = s;
 }
 
 __global__ void __launch_bounds__(256) sor_mask_kernel(const float *__restrict__ mean_d, const uint32_t *__restrict__ frame_off,
@@ -77,7 +78,7 @@ int sor_threshold_mask_dev(Ctx *ctx, const float *d_mean_d, const uint32_t *d_fr
                            uint8_t *d_keep, float *d_stats, unsigned long long *d_kept) {
     static_assert(sizeof(SorFrameStats) == 4 * sizeof(float), "stats layout");
     if (n == 0) return PCR_OK;
-    sor_stats_seq_kernel<<<n_frames, 32, 0, ctx->stream>>>(d_mean_d, d_frame_off, n, std_mul, (SorFrameStats *)d_stats);
+    sor_stats_kernel<<<n_frames, kFoldThreads, 0, ctx->stream>>>(d_mean_d, d_frame_off, n, std_mul, (SorFrameStats *)d_stats);
     PCR_LAUNCH_CHECK(ctx);
     PCR_CUDA(ctx, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long) * n_frames, ctx->stream));
     size_t per = n / (size_t)n_frames + 1;

@@ -1,0 +1,18 @@
+"""One warm-up + one measured call of each consumer (for `ncu --metrics gpu__time_duration.sum`)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import pointclouds_rs_b200 as pcr
+from pointclouds_rs_b200 import scenes
+which = sys.argv[1] if len(sys.argv) > 1 else "sor"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+if which in ("sor", "normals", "knn"):
+    c = pcr.PointCloud.from_numpy(scenes.kitti_scene())
+elif which == "aerial":
+    c = pcr.PointCloud.from_numpy(scenes.aerial_scene())
+for _ in range(reps):
+    if which == "sor":
+        pcr.sor_mask(c, 10, 1.0)
+    elif which in ("normals", "aerial"):
+        pcr.normals_array(c, 20)
+print("done", pcr.default_context().launch_count)
