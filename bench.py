@@ -1,0 +1,398 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline benchmark of the B200 KNN engine (driver contract: ONE JSON line).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): SOR + normals points/sec, k = 10 / 20.
+Workload at every N (weak scaling, one process per GPU, no data-path collective): BASELINE
+configs[1] -- a KITTI-shaped synthetic frame of 122 000 points (numpy PCG64, seed 42 + rank),
+voxel_downsample(0.05) as untimed input preparation, then per step
+
+    statistical_outlier_removal(k = 10, std_mul = 1.0)  ->  estimate_normals(k = 20) on the kept points
+
+A step is one pass of that hot path over one frame.
+  value : points/s, inputs resident in HBM (pcr_sor_normals_batch_dev), CUDA events on the stream
+          the kernels run on, max over ranks, L2 flushed between steps.
+  e2e   : the same through the host-pointer C-ABI call (pcr_sor_normals_batch) from PINNED host
+          buffers: H2D of x/y/z and D2H of mask + normals inside the timed region (wall clock).
+  roofline     : the dominant kernel (KNN + fused normals, grid level 0), algorithmic bytes / its
+                 device time measured live with cudaEvents inside the library (pcr_ctx_get_timing).
+  cpu_baseline : the CPU oracle (C port of the reference path) timed on this box's host cores on a
+                 bounded sample, rank 0, N = 1 only.
+--impl reference times that CPU port as the reference arm (the Rust reference cannot be built in
+this image: no cargo/rustc).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_SOR, STD_MUL, K_NORMALS = 10, 1.0, 20
+VOXEL = 0.05
+METRIC = "sor_normals_points_per_sec"
+UNIT = "points/s"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_frame(rank: int):
+    from pointclouds_rs_b200 import scenes
+
+    raw = scenes.kitti_scene(seed=42 + rank)
+    pts = scenes.voxel_downsample_np(raw, VOXEL)  # untimed input preparation (not on the KNN path)
+    return raw, np.ascontiguousarray(pts, np.float32)
+
+
+def workload_config(n_raw: int, n_in: int, world: int):
+    return {
+        "workload": "BASELINE configs[1]: KITTI-shaped synthetic frame 122K pts: voxel 0.05 -> SOR k=10 -> normals",
+        "points_raw_per_frame": n_raw,
+        "points_per_step_per_gpu": n_in,
+        "k_sor": K_SOR,
+        "std_mul": STD_MUL,
+        "k_normals": K_NORMALS,
+        "frames_per_step_per_gpu": 1,
+        "sharding": f"frames: one independent frame per GPU per step x {world} GPU(s), no data-path collective",
+        "l2": "256 MiB buffer overwritten between timed steps (outside the events); the frame itself is L2-sized",
+        "seed": "numpy PCG64, 42 + rank",
+    }
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)),
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2.0)
+        return {
+            "sm_mhz": float(np.median(self.samples)) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+def cpu_reference_run(pts: np.ndarray, reps: int, threads_normals: int):
+    """The CPU port of the reference path, threaded the way the reference is: SOR is a serial loop
+    (statistical_outlier.rs:19), normals run on all cores (rayon par_iter, estimate.rs:42-44)."""
+    from oracle import oracle as O  # the checker, used here only as the timed CPU baseline
+
+    O.lib()
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        keep, _, _ = O.sor(pts, K_SOR, STD_MUL, threads=1)
+        kept = pts[keep.astype(bool)]
+        O.normals(kept, K_NORMALS, threads=threads_normals)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def cpu_reference_all_threads(pts: np.ndarray, threads: int):
+    from oracle import oracle as O
+
+    t0 = time.perf_counter()
+    keep, _, _ = O.sor(pts, K_SOR, STD_MUL, threads=threads)
+    O.normals(pts[keep.astype(bool)], K_NORMALS, threads=threads)
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0  # the CPU arm runs on rank 0 only
+    raw, pts = make_frame(0)
+    cores = os.cpu_count() or 1
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_reference_run(pts, 1, cores)
+    steps = max(1, min(args.steps, 8))  # bounded: each step is ~0.5 s of CPU work
+    times = cpu_reference_run(pts, steps, cores)
+    t = float(np.mean(times))
+    value = len(pts) / t
+    t_all = cpu_reference_all_threads(pts, cores)
+    sample = (f"{steps} step(s) of the full workload (one {len(pts)}-point frame per step); SOR on 1 thread (the reference's "
+              f"loop is serial), normals on {cores} threads (reference: rayon); C port of the reference path (oracle/)")
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(len(raw), len(pts), 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "all_threads_value": len(pts) / t_all},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-icp", action="store_true", help="skip the secondary ICP measurement")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    distributed = world > 1
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import pointclouds_rs_b200 as pcr
+    from pointclouds_rs_b200 import dist as pdist
+
+    stream = torch.cuda.current_stream()
+    ctx = pcr.Context(device=local_rank, stream=stream.cuda_stream)
+
+    raw, pts = make_frame(rank)
+    n = len(pts)
+    offsets = np.array([0, n], np.uint64)
+    vp = np.zeros(3, np.float32)
+
+    # device-resident inputs / outputs (torch only provides the memory and the stream)
+    d_xyz = torch.from_numpy(np.ascontiguousarray(pts.T)).cuda()  # (3, n): x | y | z
+    d_keep = torch.empty(n, dtype=torch.uint8, device="cuda")
+    d_nrm = torch.empty((3, n), dtype=torch.float32, device="cuda")
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    # pinned host buffers for the end-to-end arm
+    h_xyz = torch.from_numpy(np.ascontiguousarray(pts.T)).pin_memory()
+    h_keep = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_nrm = torch.empty((3, n), dtype=torch.float32).pin_memory()
+    h_kept = np.zeros(1, np.uint64)
+
+    def step_device():
+        pcr.sor_normals_batch_raw(ctx, d_xyz[0].data_ptr(), d_xyz[1].data_ptr(), d_xyz[2].data_ptr(), n, offsets, K_SOR, STD_MUL,
+                                  K_NORMALS, vp, d_keep.data_ptr(), d_nrm[0].data_ptr(), d_nrm[1].data_ptr(), d_nrm[2].data_ptr(),
+                                  device=True)
+
+    def step_e2e():
+        pcr.sor_normals_batch_raw(ctx, h_xyz[0].data_ptr(), h_xyz[1].data_ptr(), h_xyz[2].data_ptr(), n, offsets, K_SOR, STD_MUL,
+                                  K_NORMALS, vp, h_keep.data_ptr(), h_nrm[0].data_ptr(), h_nrm[1].data_ptr(), h_nrm[2].data_ptr(),
+                                  kept=h_kept, device=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also grows every scratch buffer to its final size) -------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+        step_e2e()
+    torch.cuda.synchronize()
+    n_kept = int(d_keep.sum().item())
+
+    # ---- timed region 1: device-resident ------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    ctx.set_timing(True)
+    ctx.get_timing()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = ctx.launch_count
+    barrier()
+    sampler.start()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)  # evict L2 (outside the timed events)
+        starts[i].record(stream)
+        step_device()
+        stops[i].record(stream)
+    barrier()
+    launches = ctx.launch_count - launches0
+    stage = ctx.get_timing()
+    ctx.set_timing(False)
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+
+    # ---- timed region 2: end to end through the host-pointer C ABI --------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop()
+
+    dev_ms_max = pdist.max_over_ranks(dist if distributed else None, dev_ms, "cuda")
+    e2e_s_max = pdist.max_over_ranks(dist if distributed else None, e2e_s, "cuda")
+    n_total = pdist.sum_over_ranks(dist if distributed else None, float(n), "cuda")
+
+    # parity spot check of the timed configuration against the e2e arm (same inputs, same results)
+    same = bool(torch.equal(d_keep.cpu(), h_keep)) and bool(torch.equal(d_nrm.cpu(), h_nrm))
+
+    value = n_total * args.steps / (dev_ms_max * 1e-3)
+    e2e_value = n_total * args.steps / e2e_s_max
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------
+    peak, peak_src = load_peaks()
+    knn_n_ms, knn_n_cnt = stage["knn_normals"]
+    knn_s_ms, knn_s_cnt = stage["knn"]
+    # algorithmic bytes per launch: read one cell-sorted float4 per query, write 3 f32
+    bytes_normals = n_kept * (16 + 12)
+    dur_normals = knn_n_ms / max(knn_n_cnt, 1) * 1e-3
+    achieved = bytes_normals / dur_normals / 1e9 if dur_normals > 0 else 0.0
+    roofline = {
+        "bound": "hbm", "kernel": "normals_kernel<false,32> (grid KNN k=20 + covariance + Cardano, level 0)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        "traffic": None,
+        "algorithmic_bytes_per_launch": bytes_normals, "avg_launch_ms": dur_normals * 1e3,
+        "note": "a 119 K-point frame is L2-resident: the kernel is bound by FP32/integer issue, not by HBM (DESIGN.md)",
+        "stage_ms_per_step": {k: v[0] / args.steps for k, v in stage.items() if v[1]},
+        "sor_knn_kernel": {"avg_launch_ms": knn_s_ms / max(knn_s_cnt, 1), "algorithmic_bytes_per_launch": n * (16 + 4)},
+    }
+    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                roofline["traffic"] = json.load(f).get("normals_kernel_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_icp:
+        try:
+            extra["icp"] = icp_measurement(pcr, ctx)
+        except Exception as ex:  # the headline must not die on the secondary measurement
+            extra["icp"] = {"error": str(ex)}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        times = cpu_reference_run(pts, 3, cores)
+        t_all = cpu_reference_all_threads(pts, cores)
+        cpu_baseline = {
+            "value": n / float(np.mean(times)), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": (f"3 steps of the same frame ({n} points): SOR on 1 thread (reference loop is serial), normals on {cores} "
+                       "threads (reference: rayon); C port of the reference (oracle/), not the Rust build"),
+            "all_threads_value": n / t_all,
+        }
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(len(raw), n, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * 4 * n, "d2h_bytes_per_step": n + 3 * 4 * n + 8,
+                    "ms_per_step": e2e_s_max / args.steps * 1e3, "timer": "wall clock around the synchronous C-ABI call, pinned host buffers"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "kept_points": n_kept,
+            "device_and_e2e_results_identical": same,
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def icp_measurement(pcr, ctx):
+    """BASELINE configs[3] at N = 1: point-to-plane ICP, two synthetic scans of 1 M points, 30 iterations."""
+    from pointclouds_rs_b200 import scenes
+
+    tgt_np = scenes.aerial_scene(42, 0.415)
+    R = scenes.rot_z(0.05)
+    src_np = (tgt_np @ R.T + np.array([0.3, -0.2, 0.1], np.float32)).astype(np.float32)
+    tgt = pcr.estimate_normals(pcr.PointCloud.from_numpy(tgt_np), 20, ctx)
+    src = pcr.PointCloud.from_numpy(np.ascontiguousarray(src_np))
+    pcr.icp_point_to_plane(src, tgt, 30, 0.0, ctx=ctx)  # warm-up
+    ctx.set_timing(True)
+    ctx.get_timing()
+    t0 = time.perf_counter()
+    res = pcr.icp_point_to_plane(src, tgt, 30, 0.0, ctx=ctx)
+    wall = time.perf_counter() - t0
+    stage = ctx.get_timing()
+    ctx.set_timing(False)
+    step_ms, step_cnt = stage["icp_step"]
+    return {
+        "workload": "BASELINE configs[3]: point-to-plane ICP, two synthetic scans, 30 iterations, tolerance 0",
+        "points": len(src), "iterations": res.num_iterations,
+        "ms_per_iter_e2e": wall * 1e3 / max(res.num_iterations, 1),
+        "ms_per_iter_step_kernel": step_ms / max(step_cnt, 1),
+        "rmse": res.rmse, "translation": res.translation,
+    }
+
+
+if __name__ == "__main__":
+    sys.exit(main())

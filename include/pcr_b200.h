@@ -83,6 +83,16 @@ int pcr_ctx_synchronize(pcr_ctx *ctx);
 const char *pcr_last_error(const pcr_ctx *ctx);
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 uint64_t pcr_ctx_launch_count(const pcr_ctx *ctx);
+/* Per-stage device timing for benchmarks: when enabled, every stage is bracketed by a cudaEvent
+ * pair on the context's stream.  pcr_ctx_get_timing synchronises, adds the elapsed milliseconds of
+ * all spans since the previous call per tag, and resets.  Tags: 0 index build, 1 KNN kernel on grid
+ * level 0 (with its fused consumer), 2 deferred queries on coarser levels (their builds included),
+ * 3 SOR statistics + mask, 4 ICP step kernel, 5 ICP reduce/solve, 6 KNN + normals kernel on grid
+ * level 0, 7 other.  (Tag 1 is the KNN kernel of pcr_knn and of SOR.) */
+#define PCR_NUM_TIMING_TAGS 8
+int pcr_ctx_set_timing(pcr_ctx *ctx, int enable);
+int pcr_ctx_get_timing(pcr_ctx *ctx, double *ms_per_tag /* [PCR_NUM_TIMING_TAGS] */,
+                       uint64_t *spans_per_tag /* [PCR_NUM_TIMING_TAGS] or NULL */);
 /* Tuning: force the grid cell size (metres) for subsequent index builds; 0 = automatic. */
 int pcr_ctx_set_cell_size(pcr_ctx *ctx, float cell_size);
 

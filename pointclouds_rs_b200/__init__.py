@@ -75,6 +75,16 @@ class Context:
     def launch_count(self) -> int:
         return int(_ffi.load().pcr_ctx_launch_count(self._h))
 
+    def set_timing(self, enable: bool):
+        _ffi.check(_ffi.load().pcr_ctx_set_timing(self._h, 1 if enable else 0), self._h)
+
+    def get_timing(self):
+        """-> {tag: (milliseconds, spans)} accumulated since the previous call (synchronises)."""
+        ms = (C.c_double * _ffi.PCR_NUM_TIMING_TAGS)()
+        cnt = (C.c_uint64 * _ffi.PCR_NUM_TIMING_TAGS)()
+        _ffi.check(_ffi.load().pcr_ctx_get_timing(self._h, ms, cnt), self._h)
+        return {_ffi.TIMING_TAGS[i]: (ms[i], int(cnt[i])) for i in range(_ffi.PCR_NUM_TIMING_TAGS)}
+
     def set_cell_size(self, cell: float):
         _ffi.check(_ffi.load().pcr_ctx_set_cell_size(self._h, float(cell)), self._h)
 
@@ -446,3 +456,21 @@ def sor_normals_batch(points: np.ndarray, frame_offsets: Sequence[int], k_sor: i
                                            _p(nx, _ffi.f32p), _p(ny, _ffi.f32p), _p(nz, _ffi.f32p), _p(kept, _ffi.u64p))
     _ffi.check(st, ctx._h)
     return keep[:n], np.stack([nx[:n], ny[:n], nz[:n]], axis=1), kept[:nf]
+
+
+def sor_normals_batch_raw(ctx: Context, x, y, z, n: int, frame_offsets: np.ndarray, k_sor: int, std_mul: float,
+                          k_normals: int, viewpoint: np.ndarray, keep, nx, ny, nz, kept=None, device: bool = False):
+    """Thin call for benchmarks: x..nz are raw addresses (ints).  device=True -> *_dev entry point
+    (device pointers, nothing copied, asynchronous on the context's stream)."""
+    lib = _ffi.load()
+    nf = len(frame_offsets) - 1
+    if device:
+        st = lib.pcr_sor_normals_batch_dev(ctx._h, x, y, z, _p(frame_offsets, _ffi.u64p), nf, k_sor, float(std_mul), k_normals,
+                                           _p(viewpoint, _ffi.f32p), keep, nx, ny, nz)
+    else:
+        cast = lambda a, t: C.cast(C.c_void_p(a), t)
+        st = lib.pcr_sor_normals_batch(ctx._h, cast(x, _ffi.f32p), cast(y, _ffi.f32p), cast(z, _ffi.f32p),
+                                       _p(frame_offsets, _ffi.u64p), nf, k_sor, float(std_mul), k_normals,
+                                       _p(viewpoint, _ffi.f32p), cast(keep, _ffi.u8p), cast(nx, _ffi.f32p), cast(ny, _ffi.f32p),
+                                       cast(nz, _ffi.f32p), _p(kept, _ffi.u64p) if kept is not None else None)
+    _ffi.check(st, ctx._h)

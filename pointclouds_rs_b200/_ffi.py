@@ -22,6 +22,8 @@ PCR_ERR_UNSUPPORTED = 7
 PCR_ERR_CAPACITY = 8
 PCR_MAX_K = 1024
 PCR_UNIQUE_ID_BYTES = 128
+PCR_NUM_TIMING_TAGS = 8
+TIMING_TAGS = ("build", "knn", "knn_deferred", "sor_stats", "icp_step", "icp_solve", "knn_normals", "other")
 
 f32p = C.POINTER(C.c_float)
 u32p = C.POINTER(C.c_uint32)
@@ -65,6 +67,8 @@ SIGNATURES = {
     "pcr_last_error": (C.c_char_p, [vp]),
     "pcr_ctx_launch_count": (C.c_uint64, [vp]),
     "pcr_ctx_set_cell_size": (C.c_int, [vp, C.c_float]),
+    "pcr_ctx_set_timing": (C.c_int, [vp, C.c_int]),
+    "pcr_ctx_get_timing": (C.c_int, [vp, C.POINTER(C.c_double), u64p]),
     "pcr_comm_unique_id": (C.c_int, [vp]),
     "pcr_ctx_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
     "pcr_ctx_comm_rank": (C.c_int, [vp]),

@@ -25,6 +25,27 @@ int fail(Ctx *ctx, int code, const char *fmt, ...) {
     return code;
 }
 
+TimeScope::TimeScope(Ctx *ctx, int tag) : c(ctx) {
+    if (!c->timing) return;
+    Ctx::TimedSpan sp;
+    sp.tag = tag;
+    for (cudaEvent_t *e : {&sp.a, &sp.b}) {
+        if (!c->event_pool.empty()) {
+            *e = c->event_pool.back();
+            c->event_pool.pop_back();
+        } else if (cudaEventCreate(e) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+    }
+    cudaEventRecord(sp.a, c->stream);
+    idx = (int)c->spans.size();
+    c->spans.push_back(sp);
+}
+TimeScope::~TimeScope() {
+    if (idx >= 0) cudaEventRecord(c->spans[idx].b, c->stream);
+}
+
 int ensure(Ctx *ctx, DevBuf &b, size_t bytes) {
     if (bytes <= b.cap) return PCR_OK;
     size_t want = std::max(bytes, b.cap + b.cap / 2);
@@ -206,6 +227,11 @@ void pcr_ctx_destroy(pcr_ctx *ctx) {
     free_buf(c, c->b_small);
     free_buf(c, c->b_table);
     cudaStreamSynchronize(c->stream);
+    for (auto &sp : c->spans) {
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->owns_stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
@@ -220,6 +246,35 @@ int pcr_ctx_synchronize(pcr_ctx *ctx) {
 }
 
 uint64_t pcr_ctx_launch_count(const pcr_ctx *ctx) { return ctx ? ctx->c.launches : 0; }
+
+int pcr_ctx_set_timing(pcr_ctx *ctx, int enable) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    ctx->c.timing = enable != 0;
+    return PCR_OK;
+}
+
+int pcr_ctx_get_timing(pcr_ctx *ctx, double *ms_per_tag, uint64_t *spans_per_tag) {
+    if (!ctx || !ms_per_tag) return fail(nullptr, PCR_ERR_INVALID_ARG, "null pointer");
+    Ctx *c = &ctx->c;
+    DevSetter ds(c);
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int t = 0; t < PCR_NUM_TIMING_TAGS; t++) {
+        ms_per_tag[t] = 0.0;
+        if (spans_per_tag) spans_per_tag[t] = 0;
+    }
+    for (auto &sp : c->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess && sp.tag >= 0 && sp.tag < PCR_NUM_TIMING_TAGS) {
+            ms_per_tag[sp.tag] += ms;
+            if (spans_per_tag) spans_per_tag[sp.tag]++;
+        }
+        c->event_pool.push_back(sp.a);
+        c->event_pool.push_back(sp.b);
+    }
+    cudaGetLastError();
+    c->spans.clear();
+    return PCR_OK;
+}
 
 int pcr_ctx_set_cell_size(pcr_ctx *ctx, float cell_size) {
     if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");

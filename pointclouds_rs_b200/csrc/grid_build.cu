@@ -567,6 +567,7 @@ int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz,
                     Index **out) {
     *out = nullptr;
     if (n > 0x7fffffffull) return fail(ctx, PCR_ERR_UNSUPPORTED, "clouds above 2^31 points are not supported");
+    TimeScope ts(ctx, kTagBuild);
     const int F = opts.n_frames > 0 ? opts.n_frames : 1;
     if (F > 1 && !opts.frame_offsets) return fail(ctx, PCR_ERR_INVALID_ARG, "frame_offsets missing");
     cudaStream_t st = ctx->stream;

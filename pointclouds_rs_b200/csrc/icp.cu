@@ -63,31 +63,16 @@ __global__ void apply_transform_kernel(const float *__restrict__ x, const float 
     oz[i] = c;
 }
 
-// ---- plain correspondences (C ABI pcr_find_correspondences) --------------------------------------
-__global__ void __launch_bounds__(kIcpThreads) correspond_kernel(const GridDesc *__restrict__ grids,
-                                                                 const uint32_t *__restrict__ cell_start,
-                                                                 const float4 *__restrict__ sorted,
-                                                                 const float *__restrict__ sx, const float *__restrict__ sy,
-                                                                 const float *__restrict__ sz, size_t ns, float max_distance,
-                                                                 uint32_t *__restrict__ tgt, float *__restrict__ dist) {
+// ---- plain correspondences (C ABI pcr_find_correspondences): k = 1 KNN + the distance test ------
+__global__ void correspond_filter_kernel(size_t ns, float max_distance, uint32_t *__restrict__ tgt, float *__restrict__ dist,
+                                         const uint32_t *__restrict__ counts) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ns) return;
-    const GridDesc g = grids[0];
-    float x = sx[i], y = sy[i], z = sz[i];
-    uint32_t t = 0xffffffffu;
-    float d = INFINITY;
-    if (finite3(x, y, z)) {
-        unsigned long long best = thread_nn_search(g, cell_start, sorted, x, y, z);
-        if (best != PCR_EMPTY_KEY) {
-            float dd = __fsqrt_rn(key_d2(best));
-            if (dd <= max_distance) {  // correspondence.rs:28
-                t = key_idx(best);
-                d = dd;
-            }
-        }
+    bool ok = counts[i] > 0 && dist[i] <= max_distance;  // correspondence.rs:27-28
+    if (!ok) {
+        tgt[i] = 0xffffffffu;
+        dist[i] = INFINITY;
     }
-    tgt[i] = t;
-    dist[i] = d;
 }
 
 // ---- binning of the source by target cell ---------------------------------------------------------
@@ -120,49 +105,92 @@ __global__ void __launch_bounds__(256) src_scatter_kernel(const float *__restric
     cur[table[cell_id[i]] + rank[i]] = make_float4(sx[i], sy[i], sz[i], __uint_as_float((uint32_t)i));
 }
 
-// ---- the per-iteration streaming kernel -----------------------------------------------------------
-template <bool kPlane>
-__global__ void __launch_bounds__(kIcpThreads) icp_step_kernel(const GridDesc *__restrict__ grids,
-                                                               const uint32_t *__restrict__ cell_start,
-                                                               const float4 *__restrict__ sorted,
-                                                               const float4 *__restrict__ tgt4,
-                                                               const float4 *__restrict__ nrm4, float4 *__restrict__ cur,
-                                                               size_t ns, float max_distance,
-                                                               const IcpState *__restrict__ state,
-                                                               double *__restrict__ partials) {
+// ---- per-iteration kernels ---------------------------------------------------------------------------
+// (A) transform + 1-NN on grid level 0, one thread per source point.  A point whose 27 cells are
+//     empty (a source that pokes out of the target, e.g. two scans that only partly overlap) is
+//     deferred to the coarser levels instead of walking shells of empty fine cells.
+__global__ void __launch_bounds__(kIcpThreads) icp_search_kernel(const GridDesc *__restrict__ grids,
+                                                                 const uint32_t *__restrict__ cell_start,
+                                                                 const float4 *__restrict__ sorted, float4 *__restrict__ cur,
+                                                                 size_t ns, const IcpState *__restrict__ state,
+                                                                 unsigned long long *__restrict__ nn,
+                                                                 uint32_t *__restrict__ defer_list,
+                                                                 uint32_t *__restrict__ defer_count, int last_level) {
     if (state->done) return;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
     const GridDesc g = grids[0];
-    float R[9], tr[3];
-    const bool has_inc = state->has_inc != 0;
-    if (has_inc) {
-#pragma unroll
-        for (int j = 0; j < 9; j++) R[j] = state->inc_R[j];
-#pragma unroll
-        for (int j = 0; j < 3; j++) tr[j] = state->inc_t[j];
+    float4 p = cur[i];
+    if (state->has_inc) {  // icp.rs:186 / icp_plane.rs:78: current = apply_transform(current, incremental)
+        float a, b, c;
+        apply_point(state->inc_R, state->inc_t, p.x, p.y, p.z, a, b, c);
+        p.x = a; p.y = b; p.z = c;
+        cur[i] = p;
     }
+    unsigned long long best = PCR_EMPTY_KEY;
+    if (finite3(p.x, p.y, p.z)) {  // kdtree.rs:65: a non-finite query has no neighbour
+        ThreadBest1 acc;
+        if (thread_grid_search(acc, g, cell_start, sorted, p.x, p.y, p.z, 1, last_level ? kMaxRings : kLevelRings, last_level != 0)) {
+            best = acc.best;
+        } else {
+            defer_list[atomicAdd(defer_count, 1u)] = (uint32_t)i;
+        }
+    }
+    nn[i] = best;
+}
+
+// (A') deferred source points on a coarser level: one warp per point, persistent over the list
+__global__ void __launch_bounds__(128) icp_deferred_kernel(const GridDesc *__restrict__ grids,
+                                                           const uint32_t *__restrict__ cell_start,
+                                                           const float4 *__restrict__ pts, const float4 *__restrict__ cur,
+                                                           const IcpState *__restrict__ state,
+                                                           const uint32_t *__restrict__ in_list,
+                                                           const uint32_t *__restrict__ in_count,
+                                                           unsigned long long *__restrict__ nn, uint32_t *__restrict__ out_list,
+                                                           uint32_t *__restrict__ out_count, int last_level) {
+    if (state->done) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = *in_count;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    const GridDesc g = grids[0];
+    RegTopK tk;
+    tk.kk = 1;
+    tk.lane = lane;
+    for (uint32_t j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += warps) {
+        const uint32_t i = in_list[j];
+        const float4 p = cur[i];
+        if (warp_knn_search(tk, g, cell_start, pts, p.x, p.y, p.z, last_level ? kMaxRings : kLevelRings, last_level != 0)) {
+            unsigned long long best = __shfl_sync(PCR_FULL, tk.K, 0);
+            if (lane == 0) nn[i] = best;
+        } else if (lane == 0) {
+            out_list[atomicAdd(out_count, 1u)] = i;
+        }
+    }
+}
+
+// (B) residuals and normal equations from the correspondences, per-block partials in a fixed order
+template <bool kPlane>
+__global__ void __launch_bounds__(kIcpThreads) icp_accum_kernel(const float4 *__restrict__ tgt4, const float4 *__restrict__ nrm4,
+                                                                const float4 *__restrict__ cur,
+                                                                const unsigned long long *__restrict__ nn, size_t ns,
+                                                                float max_distance, const IcpState *__restrict__ state,
+                                                                double *__restrict__ partials) {
+    if (state->done) return;
     double acc[NP];
 #pragma unroll
     for (int j = 0; j < NP; j++) acc[j] = 0.0;
-
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += (size_t)gridDim.x * blockDim.x) {
-        float4 p = cur[i];
-        if (has_inc) {  // icp.rs:186 / icp_plane.rs:78: current = apply_transform(current, incremental)
-            float a, b, c;
-            apply_point(R, tr, p.x, p.y, p.z, a, b, c);
-            p.x = a; p.y = b; p.z = c;
-            cur[i] = p;
-        }
-        if (!finite3(p.x, p.y, p.z)) continue;  // kdtree.rs:65 -> no correspondence
-        unsigned long long best = thread_nn_search(g, cell_start, sorted, p.x, p.y, p.z);
+        const unsigned long long best = nn[i];
         if (best == PCR_EMPTY_KEY) continue;
         const float d = __fsqrt_rn(key_d2(best));
         if (!(d <= max_distance)) continue;  // correspondence.rs:28
+        const float4 p = cur[i];
         const float4 t = __ldg(&tgt4[key_idx(best)]);
         acc[kSumSq] += (double)__fmul_rn(d, d);  // icp.rs:279
         acc[kCount] += 1.0;
         if (kPlane) {  // icp_plane.rs:152-179
-            const float4 nn = __ldg(&nrm4[key_idx(best)]);
-            const double sx = p.x, sy = p.y, sz = p.z, n0 = nn.x, n1 = nn.y, n2 = nn.z;
+            const float4 nn4 = __ldg(&nrm4[key_idx(best)]);
+            const double sx = p.x, sy = p.y, sz = p.z, n0 = nn4.x, n1 = nn4.y, n2 = nn4.z;
             double a[6] = {sy * n2 - sz * n1, sz * n0 - sx * n2, sx * n1 - sy * n0, n0, n1, n2};
             const double b = ((double)t.x - sx) * n0 + ((double)t.y - sy) * n1 + ((double)t.z - sz) * n2;
             int o = 0;
@@ -576,8 +604,11 @@ int find_correspondences_dev(Index *target, const float *dsx, const float *dsy, 
                              float max_distance, uint32_t *d_tgt, float *d_dist) {
     Ctx *ctx = target->ctx;
     if (ns == 0) return PCR_OK;
-    correspond_kernel<<<(unsigned)((ns + kIcpThreads - 1) / kIcpThreads), kIcpThreads, 0, ctx->stream>>>(
-        target->grids, target->cell_start, target->sorted, dsx, dsy, dsz, ns, max_distance, d_tgt, d_dist);
+    PCR_TRY(ensure(ctx, ctx->b_misc2, ns * sizeof(uint32_t)));
+    uint32_t *d_cnt = (uint32_t *)ctx->b_misc2.p;
+    PCR_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, ns * sizeof(uint32_t), ctx->stream));
+    PCR_TRY(knn_queries_dev(target, dsx, dsy, dsz, ns, 1, d_tgt, d_dist, d_cnt));  // correspondence.rs:25
+    correspond_filter_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, ctx->stream>>>(ns, max_distance, d_tgt, d_dist, d_cnt);
     PCR_LAUNCH_CHECK(ctx);
     return PCR_OK;
 }
@@ -627,6 +658,18 @@ int icp_dev(Ctx *ctx, const IcpArgs &a, pcr_icp_result *result) {
         PCR_LAUNCH_CHECK(ctx);
     }
 
+    // coarser levels of the target grid for deferred source points (built once, reused every iteration)
+    Index *levels[kMaxLevels] = {tgt, nullptr, nullptr, nullptr};
+    for (int l = 1; l < kMaxLevels; l++) PCR_TRY(index_coarser_level(levels[l - 1], &levels[l]));
+    unsigned long long *nn = nullptr;
+    uint32_t *dlist = nullptr;  // 2 ping-pong lists of ns entries + counters
+    PCR_CUDA(ctx, cudaMallocAsync((void **)&nn, sizeof(unsigned long long) * std::max<size_t>(ns, 1), st));
+    FreeLater f3{nn, st};
+    PCR_CUDA(ctx, cudaMallocAsync((void **)&dlist, sizeof(uint32_t) * (2 * std::max<size_t>(ns, 1) + 64), st));
+    FreeLater f4{dlist, st};
+    uint32_t *dcount = dlist;  // [kMaxLevels]
+    uint32_t *dl[2] = {dlist + 64, dlist + 64 + std::max<size_t>(ns, 1)};
+
     const int n_blocks = (int)std::max<size_t>(1, std::min<size_t>((ns + kIcpThreads - 1) / kIcpThreads, (size_t)ctx->sm_count * 8));
     PCR_TRY(ensure(ctx, ctx->b_small, 8192 + sizeof(IcpState)));
     PCR_TRY(ensure(ctx, ctx->b_misc2, sizeof(double) * NP * (size_t)n_blocks));
@@ -640,14 +683,29 @@ int icp_dev(Ctx *ctx, const IcpArgs &a, pcr_icp_result *result) {
     PCR_LAUNCH_CHECK(ctx);
 
     auto one_pass = [&](int metrics_only) -> int {
-        if (plane)
-            icp_step_kernel<true><<<n_blocks, kIcpThreads, 0, st>>>(tgt->grids, tgt->cell_start, tgt->sorted, tgt->orig4, nrm4, cur,
-                                                                    ns, a.params.max_correspondence_distance, d_state, partials);
-        else
-            icp_step_kernel<false><<<n_blocks, kIcpThreads, 0, st>>>(tgt->grids, tgt->cell_start, tgt->sorted, tgt->orig4, nullptr,
-                                                                     cur, ns, a.params.max_correspondence_distance, d_state,
-                                                                     partials);
-        PCR_LAUNCH_CHECK(ctx);
+        {
+            TimeScope ts(ctx, kTagIcpStep);
+            PCR_CUDA(ctx, cudaMemsetAsync(dcount, 0, sizeof(uint32_t) * kMaxLevels, st));
+            if (ns > 0) {
+                icp_search_kernel<<<(unsigned)((ns + kIcpThreads - 1) / kIcpThreads), kIcpThreads, 0, st>>>(
+                    tgt->grids, tgt->cell_start, tgt->sorted, cur, ns, d_state, nn, dl[0], dcount + 0, 0);
+                PCR_LAUNCH_CHECK(ctx);
+                for (int l = 1; l < kMaxLevels; l++) {  // no host round trip: the list length stays on the device
+                    icp_deferred_kernel<<<ctx->sm_count * 2, 128, 0, st>>>(levels[l]->grids, levels[l]->cell_start, levels[l]->sorted,
+                                                                          cur, d_state, dl[(l - 1) & 1], dcount + (l - 1), nn,
+                                                                          dl[l & 1], dcount + l, l == kMaxLevels - 1 ? 1 : 0);
+                    PCR_LAUNCH_CHECK(ctx);
+                }
+            }
+            if (plane)
+                icp_accum_kernel<true><<<n_blocks, kIcpThreads, 0, st>>>(tgt->orig4, nrm4, cur, nn, ns,
+                                                                         a.params.max_correspondence_distance, d_state, partials);
+            else
+                icp_accum_kernel<false><<<n_blocks, kIcpThreads, 0, st>>>(tgt->orig4, nullptr, cur, nn, ns,
+                                                                          a.params.max_correspondence_distance, d_state, partials);
+            PCR_LAUNCH_CHECK(ctx);
+        }
+        TimeScope ts2(ctx, kTagIcpSolve);
         icp_reduce_kernel<<<1, 32, 0, st>>>(partials, n_blocks, ns, d_state);
         PCR_LAUNCH_CHECK(ctx);
         if (ctx->world > 1) PCR_TRY(comm_allreduce_f64(ctx, d_state->sums, NP));

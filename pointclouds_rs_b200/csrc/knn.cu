@@ -366,6 +366,161 @@ __global__ void __launch_bounds__(kThreads) normals_kernel(LevelArgs a, const fl
     }
 }
 
+// ---- level 0, k <= 32: one THREAD per query, top-k in registers -----------------------------------
+struct ThreadArgs {
+    // MODE 0: external queries
+    const float *qx, *qy, *qz;
+    uint32_t *idx;
+    float *dist;
+    uint32_t *counts;
+    // MODE 1: SOR
+    float *mean_d;
+    // MODE 2: normals
+    const float4 *orig4;
+    float vx, vy, vz;
+    float *nx, *ny, *nz;
+    int kk;
+};
+
+constexpr int kTQThreads = 128;
+
+// estimate.rs:47-109 with the neighbour list in registers (static indexing: no local memory)
+template <int KC>
+__device__ __forceinline__ void normal_from_topk(const ThreadTopK<KC> &acc, int cnt, const float4 *__restrict__ orig4, float px,
+                                                 float py, float pz, float vx_, float vy_, float vz_, float &nx, float &ny,
+                                                 float &nz) {
+    if (cnt < 1) {
+        nx = 0.f; ny = 0.f; nz = 1.f;
+        return;
+    }
+    const float count = (float)cnt;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+#pragma unroll
+    for (int j = 0; j < KC; j++)
+        if (j < cnt) {
+            float4 p = __ldg(&orig4[key_idx(acc.K[j])]);
+            cx = __fadd_rn(cx, p.x);
+            cy = __fadd_rn(cy, p.y);
+            cz = __fadd_rn(cz, p.z);
+        }
+    cx = __fdiv_rn(cx, count);
+    cy = __fdiv_rn(cy, count);
+    cz = __fdiv_rn(cz, count);
+    float c00 = 0.f, c01 = 0.f, c02 = 0.f, c11 = 0.f, c12 = 0.f, c22 = 0.f;
+#pragma unroll
+    for (int j = 0; j < KC; j++)
+        if (j < cnt) {
+            float4 p = __ldg(&orig4[key_idx(acc.K[j])]);  // second pass: L1 hits
+            float dx = __fsub_rn(p.x, cx), dy = __fsub_rn(p.y, cy), dz = __fsub_rn(p.z, cz);
+            c00 = __fadd_rn(c00, __fmul_rn(dx, dx));
+            c01 = __fadd_rn(c01, __fmul_rn(dx, dy));
+            c02 = __fadd_rn(c02, __fmul_rn(dx, dz));
+            c11 = __fadd_rn(c11, __fmul_rn(dy, dy));
+            c12 = __fadd_rn(c12, __fmul_rn(dy, dz));
+            c22 = __fadd_rn(c22, __fmul_rn(dz, dz));
+        }
+    float ex, ey, ez;
+    smallest_eigenvector_3x3(c00, c01, c02, c11, c12, c22, ex, ey, ez);
+    float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
+    if (len > 1e-10f) {
+        ex = __fdiv_rn(ex, len);
+        ey = __fdiv_rn(ey, len);
+        ez = __fdiv_rn(ez, len);
+    }
+    float vx = __fsub_rn(vx_, px), vy = __fsub_rn(vy_, py), vz = __fsub_rn(vz_, pz);
+    float dot = __fadd_rn(__fadd_rn(__fmul_rn(ex, vx), __fmul_rn(ey, vy)), __fmul_rn(ez, vz));
+    if (dot < 0.0f) {
+        ex = -ex; ey = -ey; ez = -ez;
+    }
+    nx = ex; ny = ey; nz = ez;
+}
+
+template <int KC, int MODE>
+__global__ void __launch_bounds__(kTQThreads) knn_thread_kernel(LevelArgs a, ThreadArgs t) {
+    const uint32_t q = blockIdx.x * kTQThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool active = q < a.nq;
+    ThreadTopK<KC> acc;
+    acc.kk = t.kk;
+    bool resolved = true;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    uint32_t out = q;
+    int cnt = 0;
+    if (active) {
+        bool searchable = true;
+        int f = 0;
+        if (MODE == 0) {
+            px = __ldg(&t.qx[q]);
+            py = __ldg(&t.qy[q]);
+            pz = __ldg(&t.qz[q]);
+            searchable = finite3(px, py, pz);  // kdtree.rs:65
+        } else {
+            float4 p = __ldg(&a.qpts[q]);
+            px = p.x; py = p.y; pz = p.z;
+            out = __float_as_uint(p.w);
+            f = frame_of_sorted(a.grids, a.n_frames, q);
+        }
+        acc.reset();
+        if (searchable) {
+            const GridDesc g = a.grids[f];
+            resolved = thread_grid_search(acc, g, a.cell_start, a.pts, px, py, pz, t.kk, a.max_rings, a.last_level != 0);
+            cnt = acc.count();
+        }
+    }
+    // deferred queries: one atomic per warp
+    const unsigned dmask = __ballot_sync(PCR_FULL, active && !resolved);
+    if (dmask) {
+        uint32_t base = 0;
+        if (lane == __ffs(dmask) - 1) base = atomicAdd(a.defer_count, (uint32_t)__popc(dmask));
+        base = __shfl_sync(PCR_FULL, base, __ffs(dmask) - 1);
+        if (active && !resolved) a.defer_list[base + __popc(dmask & ((1u << lane) - 1u))] = q;
+    }
+    if (!active || !resolved) return;
+    if (MODE == 0) {
+        uint32_t *ri = t.idx + (size_t)q * t.kk;
+        float *rd = t.dist ? t.dist + (size_t)q * t.kk : nullptr;
+#pragma unroll
+        for (int j = 0; j < KC; j++)
+            if (j < t.kk) {
+                bool v = j < cnt;
+                ri[j] = v ? key_idx(acc.K[j]) : 0xffffffffu;
+                if (rd) rd[j] = v ? __fsqrt_rn(key_d2(acc.K[j])) : INFINITY;  // kdtree.rs:76
+            }
+        if (t.counts) t.counts[q] = (uint32_t)cnt;
+    } else if (MODE == 1) {
+        // statistical_outlier.rs:28-37: drop the first (self) if there is more than one result,
+        // sequential f32 sum in ascending-distance order, divide by the count
+        const int first = cnt > 1 ? 1 : 0;
+        float sum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < KC; j++)
+            if (j >= first && j < cnt) sum = __fadd_rn(sum, __fsqrt_rn(key_d2(acc.K[j])));
+        const int m = cnt - first;
+        t.mean_d[out] = m > 0 ? __fdiv_rn(sum, (float)m) : INFINITY;
+    } else {
+        float ox, oy, oz;
+        normal_from_topk<KC>(acc, cnt, t.orig4, px, py, pz, t.vx, t.vy, t.vz, ox, oy, oz);
+        t.nx[out] = ox;
+        t.ny[out] = oy;
+        t.nz[out] = oz;
+    }
+}
+
+template <int MODE>
+int launch_thread_kernel(Ctx *ctx, const LevelArgs &a, const ThreadArgs &t) {
+    const unsigned blocks = (a.nq + kTQThreads - 1) / kTQThreads;
+    const int kk = t.kk;
+#define PCR_TQ(KC)                                                                          \
+    if (kk <= KC) {                                                                         \
+        knn_thread_kernel<KC, MODE><<<blocks, kTQThreads, 0, ctx->stream>>>(a, t);          \
+        PCR_LAUNCH_CHECK(ctx);                                                              \
+        return PCR_OK;                                                                      \
+    }
+    PCR_TQ(2) PCR_TQ(4) PCR_TQ(8) PCR_TQ(11) PCR_TQ(12) PCR_TQ(16) PCR_TQ(20) PCR_TQ(21) PCR_TQ(24) PCR_TQ(32)
+#undef PCR_TQ
+    return fail(ctx, PCR_ERR_UNSUPPORTED, "thread kernel: k too large");
+}
+
 // value for points that are not in the index: non-finite points have no neighbours -> (0,0,1)
 // (estimate.rs:49-51); points removed by a mask (batch pipeline) -> 0.
 __global__ void fill_unindexed_normals_kernel(const float4 *__restrict__ orig4, const uint8_t *__restrict__ mask, size_t n,
@@ -475,7 +630,7 @@ int set_smem(Ctx *ctx, Kern kern, size_t bytes) {
 // count costs one small D2H + sync per level that is actually needed (clouds without far outliers
 // finish on level 0 and pay exactly one).
 template <class Launch>
-int run_levels(Index *ix, uint32_t nq, Launch launch) {
+int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch) {
     Ctx *ctx = ix->ctx;
     if (nq == 0) return PCR_OK;
     PCR_TRY(ensure(ctx, ctx->b_list, (size_t)nq * 2 * sizeof(uint32_t) + 256));
@@ -500,7 +655,10 @@ int run_levels(Index *ix, uint32_t nq, Launch launch) {
         a.defer_count = cnt;
         a.max_rings = last ? kMaxRings : kLevelRings;
         a.last_level = last ? 1 : 0;
-        PCR_TRY(launch(a, level == 0 ? kQPW0 : kQPWL));
+        {
+            TimeScope ts(ctx, level == 0 ? tag0 : kTagKnnDeferred);
+            PCR_TRY(launch(a, level == 0 ? kQPW0 : kQPWL));
+        }
         if (last) break;
         uint32_t *mail = (uint32_t *)ctx->pinned + 32;
         PCR_CUDA(ctx, cudaMemcpyAsync(mail, cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -509,7 +667,10 @@ int run_levels(Index *ix, uint32_t nq, Launch launch) {
         if (getenv("PCR_DEBUG")) fprintf(stderr, "[pcr] level %d: %u of %u queries deferred (cell %.4g)\n", level, n_cur, a.nq, cur->grids_h[0].h);
         if (n_cur == 0) break;
         Index *next = nullptr;
-        PCR_TRY(index_coarser_level(cur, &next));
+        {
+            TimeScope ts(ctx, kTagKnnDeferred);
+            PCR_TRY(index_coarser_level(cur, &next));
+        }
         cur = next;
         qlist = lists[level & 1];
     }
@@ -530,7 +691,12 @@ int knn_queries_dev(Index *ix, const float *dqx, const float *dqy, const float *
     const int kk = (int)k;
     if (k > 32) PCR_TRY(set_smem(ctx, knn_queries_kernel<true, kQPW0>, sizeof(unsigned long long) * k * kWarps));
     if (k > 32) PCR_TRY(set_smem(ctx, knn_queries_kernel<true, kQPWL>, sizeof(unsigned long long) * k * kWarps));
-    return run_levels(ix, (uint32_t)nq, [&](const LevelArgs &a, int qpw) -> int {
+    ThreadArgs ta = {};
+    ta.qx = dqx; ta.qy = dqy; ta.qz = dqz;
+    ta.idx = d_idx; ta.dist = d_dist; ta.counts = d_counts;
+    ta.kk = kk;
+    return run_levels(ix, (uint32_t)nq, kTagKnn, [&](const LevelArgs &a, int qpw) -> int {
+        if (qpw == kQPW0 && k <= 32) return launch_thread_kernel<0>(ctx, a, ta);
         unsigned blocks = blocks_for(a.nq, qpw);
         size_t smem = k <= 32 ? 0 : sizeof(unsigned long long) * k * kWarps;
         if (k <= 32) {
@@ -560,7 +726,11 @@ int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d) {
         PCR_TRY(set_smem(ctx, sor_mean_kernel<true, kQPW0>, smem));
         PCR_TRY(set_smem(ctx, sor_mean_kernel<true, kQPWL>, smem));
     }
-    return run_levels(ix, (uint32_t)ix->n_indexed, [&](const LevelArgs &a, int qpw) -> int {
+    ThreadArgs ta = {};
+    ta.mean_d = d_mean_d;
+    ta.kk = (int)kk;
+    return run_levels(ix, (uint32_t)ix->n_indexed, kTagKnn, [&](const LevelArgs &a, int qpw) -> int {
+        if (qpw == kQPW0 && kk <= 32) return launch_thread_kernel<1>(ctx, a, ta);
         unsigned blocks = blocks_for(a.nq, qpw);
         if (kk <= 32) {
             if (qpw == kQPW0) sor_mean_kernel<false, kQPW0><<<blocks, kThreads, smem, ctx->stream>>>(a, (int)kk, d_mean_d);
@@ -593,7 +763,13 @@ int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny
         PCR_TRY(set_smem(ctx, normals_kernel<true, kQPWL>, smem));
     }
     const float v0 = vp[0], v1 = vp[1], v2 = vp[2];
-    return run_levels(ix, (uint32_t)ix->n_indexed, [&](const LevelArgs &a, int qpw) -> int {
+    ThreadArgs ta = {};
+    ta.orig4 = ix->orig4;
+    ta.vx = v0; ta.vy = v1; ta.vz = v2;
+    ta.nx = d_nx; ta.ny = d_ny; ta.nz = d_nz;
+    ta.kk = (int)k;
+    return run_levels(ix, (uint32_t)ix->n_indexed, kTagKnnNormals, [&](const LevelArgs &a, int qpw) -> int {
+        if (qpw == kQPW0 && k <= 32) return launch_thread_kernel<2>(ctx, a, ta);
         unsigned blocks = blocks_for(a.nq, qpw);
         if (k <= 32) {
             if (qpw == kQPW0) normals_kernel<false, kQPW0><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);

@@ -244,56 +244,135 @@ __device__ __forceinline__ bool warp_knn_search(TopK &tk, const GridDesc &g, con
 }
 
 // ------------------------------------------------------------------------------------------------
-// Thread-per-query 1-NN (ICP correspondences): same rule, scalar best key.
+// Thread-per-query search (level 0 of the KNN / SOR / normals kernels with k <= 32, and the ICP
+// 1-NN): same rule, but every THREAD owns one query and keeps its k best keys in registers.
+// Neighbouring threads hold neighbouring queries of the cell-sorted order, so a warp walks (almost)
+// the same runs in lock step: loads are warp-broadcast L1 hits, no lane idles on a short run, and
+// an insertion costs ~6 instructions per slot instead of a ~30-instruction shuffle round.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void thread_scan_run(const float4 *__restrict__ pts, uint32_t b, uint32_t e, float qx, float qy,
-                                                float qz, unsigned long long &best) {
-    for (uint32_t i = b; i < e; i++) {
+
+// k best keys, ascending, capacity KC (compile time).  With kk < KC the list simply keeps KC
+// entries (the threshold is a little looser than needed); only the first kk are reported.
+template <int KC>
+struct ThreadTopK {
+    unsigned long long K[KC];
+    int kk;
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int j = 0; j < KC; j++) K[j] = PCR_EMPTY_KEY;
+    }
+    __device__ __forceinline__ void offer(unsigned long long x) {
+        if (x < K[KC - 1]) {
+#pragma unroll
+            for (int j = KC - 1; j > 0; --j) {
+                bool up = x < K[j - 1];
+                K[j] = up ? K[j - 1] : (x < K[j] ? x : K[j]);
+            }
+            K[0] = x < K[0] ? x : K[0];
+        }
+    }
+    __device__ __forceinline__ unsigned long long kth() const {  // kk-th best, EMPTY if not there yet
+        unsigned long long r = K[KC - 1];
+#pragma unroll
+        for (int j = 0; j < KC - 1; j++) r = (j == kk - 1) ? K[j] : r;
+        return r;
+    }
+    __device__ __forceinline__ int count() const {
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < KC; j++) c += (K[j] != PCR_EMPTY_KEY && j < kk) ? 1 : 0;
+        return c;
+    }
+};
+
+struct ThreadBest1 {  // k = 1
+    unsigned long long best;
+    __device__ __forceinline__ void reset() { best = PCR_EMPTY_KEY; }
+    __device__ __forceinline__ void offer(unsigned long long x) { best = x < best ? x : best; }
+    __device__ __forceinline__ unsigned long long kth() const { return best; }
+    __device__ __forceinline__ int count() const { return best != PCR_EMPTY_KEY ? 1 : 0; }
+};
+
+template <class Acc>
+__device__ __forceinline__ void thread_scan_run(Acc &acc, const float4 *__restrict__ pts, uint32_t b, uint32_t e, float qx,
+                                                float qy, float qz) {
+    uint32_t i = b;
+    for (; i + 2 <= e; i += 2) {  // two loads in flight
+        float4 p0 = __ldg(&pts[i]), p1 = __ldg(&pts[i + 1]);
+        acc.offer(make_key(dist2_exact(qx, qy, qz, p0.x, p0.y, p0.z), __float_as_uint(p0.w)));
+        acc.offer(make_key(dist2_exact(qx, qy, qz, p1.x, p1.y, p1.z), __float_as_uint(p1.w)));
+    }
+    if (i < e) {
         float4 p = __ldg(&pts[i]);
-        unsigned long long key = make_key(dist2_exact(qx, qy, qz, p.x, p.y, p.z), __float_as_uint(p.w));
-        best = key < best ? key : best;
+        acc.offer(make_key(dist2_exact(qx, qy, qz, p.x, p.y, p.z), __float_as_uint(p.w)));
     }
 }
 
-__device__ __forceinline__ unsigned long long thread_nn_search(const GridDesc &g, const uint32_t *__restrict__ cell_start,
-                                                               const float4 *__restrict__ pts, float qx, float qy, float qz) {
-    unsigned long long best = PCR_EMPTY_KEY;
+// Returns false if the query is deferred to the next (coarser) grid level.  `kk` = neighbours wanted
+// (for the early-deferral rule): a query that has found less than kk/4 candidates in its 27 cells,
+// or is still short of kk after two shells, sits in (near-)empty space -- walking more shells of
+// this fine grid is the expensive way to find its neighbours.
+// The run scan has ONE call site (the top-k insertion is unrolled and large): shells and the
+// whole-frame pass are both expressed as "a list of runs".
+template <class Acc>
+__device__ __forceinline__ bool thread_grid_search(Acc &acc, const GridDesc &g, const uint32_t *__restrict__ cell_start,
+                                                   const float4 *__restrict__ pts, float qx, float qy, float qz, int kk,
+                                                   int max_rings, bool last_level) {
+    acc.reset();
     const uint32_t m = g.pt_end - g.pt_begin;
-    if (m == 0) return best;
-    if (m <= 32) {
-        thread_scan_run(pts, g.pt_begin, g.pt_end, qx, qy, qz, best);
-        return best;
+    if (m == 0) return true;
+    bool whole = m <= kBruteFrame || m <= (uint32_t)kk;  // tiny frame: one run = everything
+    double f0 = 0, f1 = 0, f2 = 0;
+    int c0 = 0, c1 = 0, c2 = 0;
+    if (!whole) {
+        c0 = cell_coord(g, 0, pick_axis(g.ax[0], qx, qy, qz), &f0);
+        c1 = cell_coord(g, 1, pick_axis(g.ax[1], qx, qy, qz), &f1);
+        c2 = cell_coord(g, 2, pick_axis(g.ax[2], qx, qy, qz), &f2);
     }
-    double f0, f1, f2;
-    const int c0 = cell_coord(g, 0, pick_axis(g.ax[0], qx, qy, qz), &f0);
-    const int c1 = cell_coord(g, 1, pick_axis(g.ax[1], qx, qy, qz), &f1);
-    const int c2 = cell_coord(g, 2, pick_axis(g.ax[2], qx, qy, qz), &f2);
     const int d0n = g.dims[0], d1n = g.dims[1], d2n = g.dims[2];
     for (int S = 1;; S++) {
-        // shell S (S == 1 also takes the centre)
-        for (int e0 = -S; e0 <= S; e0++) {
-            int a0 = c0 + e0;
-            if (a0 < 0 || a0 >= d0n) continue;
-            for (int e1 = -S; e1 <= S; e1++) {
-                int a1 = c1 + e1;
-                if (a1 < 0 || a1 >= d1n) continue;
-                bool border = S == 1 || e0 == S || e0 == -S || e1 == S || e1 == -S;
-                if (border) {
-                    int z0 = max(c2 - S, 0), z1 = min(c2 + S, d2n - 1);
-                    uint32_t lin = cell_linear(g, a0, a1, z0);
-                    thread_scan_run(pts, __ldg(&cell_start[lin]), __ldg(&cell_start[lin + (uint32_t)(z1 - z0) + 1u]), qx, qy, qz, best);
-                } else {
-                    if (c2 - S >= 0) {
-                        uint32_t lin = cell_linear(g, a0, a1, c2 - S);
-                        thread_scan_run(pts, __ldg(&cell_start[lin]), __ldg(&cell_start[lin + 1u]), qx, qy, qz, best);
+        // shell S (S == 1 also takes the centre): rows (e0, e1) of the (2S+1)^2 square; border rows
+        // are full runs (slot 0), interior rows contribute their two end cells (slot 0 / 1)
+        int e0 = -S, e1 = -S, slot = 0;
+        const int T = whole ? 1 : 2 * (2 * S + 1) * (2 * S + 1);
+        for (int t = 0; t < T; t++) {
+            uint32_t b = 0, e = 0;
+            if (whole) {
+                b = g.pt_begin;
+                e = g.pt_end;
+            } else {
+                const int a0 = c0 + e0, a1 = c1 + e1;
+                if (a0 >= 0 && a0 < d0n && a1 >= 0 && a1 < d1n) {
+                    const bool border = S == 1 || e0 == S || e0 == -S || e1 == S || e1 == -S;
+                    int z0, z1;
+                    bool ok;
+                    if (border) {
+                        ok = slot == 0;
+                        z0 = max(c2 - S, 0);
+                        z1 = min(c2 + S, d2n - 1);
+                    } else {
+                        const int z = slot == 0 ? c2 - S : c2 + S;
+                        ok = z >= 0 && z < d2n;
+                        z0 = z1 = z;
                     }
-                    if (c2 + S < d2n) {
-                        uint32_t lin = cell_linear(g, a0, a1, c2 + S);
-                        thread_scan_run(pts, __ldg(&cell_start[lin]), __ldg(&cell_start[lin + 1u]), qx, qy, qz, best);
+                    if (ok) {
+                        const uint32_t lin = cell_linear(g, a0, a1, z0);
+                        b = __ldg(&cell_start[lin]);
+                        e = __ldg(&cell_start[lin + (uint32_t)(z1 - z0) + 1u]);
+                    }
+                }
+                slot ^= 1;
+                if (!slot) {
+                    e1++;
+                    if (e1 > S) {
+                        e1 = -S;
+                        e0++;
                     }
                 }
             }
+            thread_scan_run(acc, pts, b, e, qx, qy, qz);
         }
+        if (whole) return true;
         const int R = S;
         double mf = 1e300;
         bool open = false;
@@ -303,14 +382,19 @@ __device__ __forceinline__ unsigned long long thread_nn_search(const GridDesc &g
         if (c1 + R < d1n - 1) { open = true; mf = fmin(mf, 1.0 - f1); }
         if (c2 - R > 0) { open = true; mf = fmin(mf, f2); }
         if (c2 + R < d2n - 1) { open = true; mf = fmin(mf, 1.0 - f2); }
-        if (!open) return best;
-        if (best != PCR_EMPTY_KEY) {
+        if (!open) return true;
+        const unsigned long long kth = acc.kth();
+        if (kth != PCR_EMPTY_KEY) {
             double bound = ((double)R + mf) * g.h;
-            if (bound > 0.0 && (double)key_d2(best) < bound * bound * (1.0 - 1e-6)) return best;
+            if (bound > 0.0 && (double)key_d2(kth) < bound * bound * (1.0 - 1e-6)) return true;
         }
-        if (R >= kMaxRings) {
-            thread_scan_run(pts, g.pt_begin, g.pt_end, qx, qy, qz, best);
-            return best;
+        if (!last_level) {
+            if (R >= max_rings) return false;
+            const int cnt = acc.count();
+            if ((R == 1 && cnt * 4 < kk) || (R >= 2 && cnt < kk)) return false;
+        } else if (R >= max_rings) {
+            acc.reset();  // restart with a whole-frame pass (re-offering a listed key would duplicate it)
+            whole = true;
         }
     }
 }

@@ -82,6 +82,14 @@ struct Ctx {
     DevBuf b_list;     // deferred-query lists of the level loop
     void *pinned = nullptr;  // small pinned host mailbox
     size_t pinned_cap = 0;
+    // optional per-stage device timing (cudaEvents on the context's stream; bench.py's roofline)
+    bool timing = false;
+    struct TimedSpan {
+        cudaEvent_t a, b;
+        int tag;
+    };
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> event_pool;
     // NCCL (loaded lazily with dlopen, see comm.cu)
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
@@ -118,6 +126,16 @@ void set_thread_error(const char *msg);
             return pcr::fail((ctx), PCR_ERR_CUDA, "kernel launch failed: %s (%s:%d)",           \
                              cudaGetErrorString(_e), __FILE__, __LINE__);                       \
     } while (0)
+
+// stage tags of the timing spans (pcr_ctx_get_timing)
+enum TimeTag { kTagBuild = 0, kTagKnn = 1, kTagKnnDeferred = 2, kTagSorStats = 3, kTagIcpStep = 4, kTagIcpSolve = 5, kTagKnnNormals = 6, kTagOther = 7, kNumTags = 8 };
+
+struct TimeScope {  // records an event pair around a stage when timing is enabled
+    Ctx *c;
+    int idx = -1;
+    TimeScope(Ctx *ctx, int tag);
+    ~TimeScope();
+};
 
 int ensure(Ctx *ctx, DevBuf &b, size_t bytes);
 int ensure_pinned(Ctx *ctx, size_t bytes);

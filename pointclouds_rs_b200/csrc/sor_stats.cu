@@ -78,6 +78,7 @@ int sor_threshold_mask_dev(Ctx *ctx, const float *d_mean_d, const uint32_t *d_fr
                            uint8_t *d_keep, float *d_stats, unsigned long long *d_kept) {
     static_assert(sizeof(SorFrameStats) == 4 * sizeof(float), "stats layout");
     if (n == 0) return PCR_OK;
+    TimeScope ts(ctx, kTagSorStats);
     sor_stats_kernel<<<n_frames, kFoldThreads, 0, ctx->stream>>>(d_mean_d, d_frame_off, n, std_mul, (SorFrameStats *)d_stats);
     PCR_LAUNCH_CHECK(ctx);
     PCR_CUDA(ctx, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long) * n_frames, ctx->stream));

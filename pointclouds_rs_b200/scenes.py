@@ -148,3 +148,26 @@ def uniform_cube(n: int, seed: int = 42, lo: float = 0.0, hi: float = 100.0) -> 
 def rot_z(angle: float) -> np.ndarray:
     c, s = np.float32(np.cos(np.float32(angle))), np.float32(np.sin(np.float32(angle)))
     return np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]], np.float32)
+
+
+def voxel_downsample_np(pts: np.ndarray, voxel_size: float) -> np.ndarray:
+    """numpy restatement of voxel_downsample (crates/filters/src/voxel_downsample.rs:12-65): input
+    preparation for BASELINE config 2 (it is not on the KNN path).  key = floor(p / voxel) as i32,
+    per-voxel f32 sums in input order, mean = sum / count, output sorted by key."""
+    if not np.isfinite(voxel_size) or voxel_size <= 0:
+        raise ValueError("voxel_size must be > 0 and finite")
+    pts = np.asarray(pts, np.float32).reshape(-1, 3)
+    ok = np.isfinite(pts).all(axis=1)
+    p = pts[ok]
+    if len(p) == 0:
+        return np.zeros((0, 3), np.float32)
+    key = np.floor(p / np.float32(voxel_size)).astype(np.int64).clip(-2**31, 2**31 - 1)
+    order = np.lexsort((np.arange(len(p)), key[:, 2], key[:, 1], key[:, 0]))  # key order, then input order
+    ks = key[order]
+    new = np.ones(len(p), bool)
+    new[1:] = (ks[1:] != ks[:-1]).any(axis=1)
+    seg = np.cumsum(new) - 1
+    sums = np.zeros((seg[-1] + 1, 3), np.float32)
+    np.add.at(sums, seg, p[order])  # unbuffered: sequential f32 adds in input order
+    cnt = np.bincount(seg).astype(np.float32)
+    return (sums / cnt[:, None]).astype(np.float32)
