@@ -1,0 +1,93 @@
+"""The C-ABI library loads on a machine without a GPU, exports every symbol include/pcr_b200.h
+declares, and fails loudly (no CPU fallback) when asked to compute without a device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pcr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pcr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from pointclouds_rs_b200 import _ffi
+
+    lib = _ffi.load()
+    names = declared_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in pcr_b200.h but not exported"
+    assert set(names) == set(_ffi.SIGNATURES), set(names) ^ set(_ffi.SIGNATURES)
+    assert lib.pcr_version() == 100
+
+
+def test_no_torch_in_library_dependencies():
+    import subprocess
+
+    from pointclouds_rs_b200 import _ffi
+
+    out = subprocess.run(["ldd", _ffi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "libc10" not in out and "nccl" not in out  # NCCL is dlopen'ed on demand
+
+
+def test_fails_loudly_without_device():
+    from pointclouds_rs_b200 import _ffi
+
+    lib = _ffi.load()
+    if lib.pcr_device_count() > 0:
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    st = lib.pcr_ctx_create(0, C.byref(h))
+    assert st == _ffi.PCR_ERR_NO_DEVICE and not h.value
+    assert b"no CPU fallback" in lib.pcr_last_error(None)
+    import pointclouds_rs_b200 as pcr
+
+    with pytest.raises(pcr.PcrError):
+        pcr.statistical_outlier_removal(pcr.PointCloud.from_numpy(__import__("numpy").zeros((4, 3), "float32")), 2, 1.0)
+
+
+def test_null_arguments_are_rejected_not_crashing():
+    from pointclouds_rs_b200 import _ffi
+
+    lib = _ffi.load()
+    assert lib.pcr_ctx_create(0, None) == _ffi.PCR_ERR_INVALID_ARG
+    assert lib.pcr_ctx_synchronize(None) == _ffi.PCR_ERR_INVALID_ARG
+    assert lib.pcr_index_len(None) == 0
+    lib.pcr_index_free(None)
+    lib.pcr_ctx_destroy(None)
+    assert lib.pcr_comm_unique_id(None) == _ffi.PCR_ERR_INVALID_ARG
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "pointclouds_rs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "pcr_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_python_surface_mirrors_reference_names():
+    import pointclouds_rs_b200 as pcr
+
+    for name in ("PointCloud", "statistical_outlier_removal", "radius_outlier_removal", "estimate_normals", "IcpResult",
+                 "icp_point_to_point", "icp_point_to_plane", "apply_transform"):
+        assert hasattr(pcr, name)
+    pc = pcr.PointCloud.from_numpy(__import__("numpy").arange(12, dtype="float64").reshape(4, 3))
+    assert pc.len() == 4 and len(pc) == 4 and not pc.is_empty() and repr(pc) == "PointCloud(n=4)"
+    assert pc.select([0, 2]).to_numpy().tolist() == [[0, 1, 2], [6, 7, 8]]
+    assert pc.select_inverse([0, 2]).to_numpy().tolist() == [[3, 4, 5], [9, 10, 11]]
+    with pytest.raises(IndexError):
+        pc.select([7])
+    with pytest.raises(TypeError):
+        pcr.PointCloud.from_numpy(__import__("numpy").zeros((3, 3), "int32"))
+    with pytest.raises(ValueError):
+        pcr.PointCloud.from_numpy(__import__("numpy").zeros((3, 4), "float32"))
+    with pytest.raises(ValueError):
+        pcr.PointCloud.from_numpy(__import__("numpy").asfortranarray(__import__("numpy").zeros((3, 3), "float32")))

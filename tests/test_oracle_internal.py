@@ -1,0 +1,111 @@
+"""The oracle checked against itself: kd-tree == brute force == grid-search model == scipy (f64)."""
+import numpy as np
+import pytest
+
+from pointclouds_rs_b200 import scenes
+
+
+def _scene():
+    pts = scenes.kitti_scene(11, (2500, 120, 20, 60))
+    return pts
+
+
+@pytest.mark.parametrize("k", [1, 3, 11, 40])
+def test_tree_equals_brute_force(oracle, k):
+    pts = _scene()
+    rng = np.random.default_rng(0)
+    q = np.vstack([pts[rng.integers(0, len(pts), 120)], rng.uniform(-45, 45, (40, 3)).astype(np.float32)])
+    idx, dist, cnt = oracle.Tree(pts).knn_batch(q, k)
+    for j in range(len(q)):
+        bi, bd = oracle.knn_brute(pts, q[j], k)
+        assert np.array_equal(idx[j, :len(bi)], bi) and np.array_equal(dist[j, :len(bi)].view(np.uint32), bd.view(np.uint32))
+
+
+def test_ties_are_broken_by_index(oracle):
+    g = np.arange(6, dtype=np.float32)
+    pts = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    idx, dist, _ = oracle.Tree(pts).knn_batch(pts, 7)
+    for j in range(len(pts)):
+        bi, bd = oracle.knn_brute(pts, pts[j], 7)
+        assert np.array_equal(idx[j], bi)
+        same = np.nonzero(np.diff(dist[j]) == 0)[0]
+        assert (idx[j][same] < idx[j][same + 1]).all()  # equal distances -> ascending index
+
+
+@pytest.mark.parametrize("cell", [0.07, 0.5, 3.0, 500.0])
+def test_grid_model_is_exact(oracle, cell):
+    """The ring-termination rule of the CUDA engine, restated in scalar C, for cell sizes from
+    far-too-small (dozens of rings) to one-cell-holds-everything."""
+    pts = _scene()
+    rng = np.random.default_rng(1)
+    q = np.vstack([pts[rng.integers(0, len(pts), 150)], rng.uniform(-60, 60, (50, 3)).astype(np.float32),
+                   np.array([[1e4, -1e4, 0]], np.float32)])
+    for k in (1, 11, 21):
+        ti, td, tc = oracle.Tree(pts).knn_batch(q, k)
+        gi, gd, gc, stats = oracle.grid_knn_model(pts, q, k, cell)
+        assert np.array_equal(gi, ti) and np.array_equal(gd.view(np.uint32), td.view(np.uint32)) and np.array_equal(gc, tc)
+
+
+def test_grid_model_boundary_points(oracle):
+    # points exactly on cell faces and queries exactly on faces / corners
+    cell = 0.25
+    g = np.arange(0, 3.01, cell, dtype=np.float32)
+    pts = np.stack(np.meshgrid(g, g, g[:4], indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    q = pts[::7] + np.float32(0.0)
+    ti, td, tc = oracle.Tree(pts).knn_batch(q, 9)
+    gi, gd, gc, _ = oracle.grid_knn_model(pts, q, 9, cell)
+    assert np.array_equal(gi, ti) and np.array_equal(gd.view(np.uint32), td.view(np.uint32))
+
+
+def test_scipy_cross_check(oracle):
+    from scipy.spatial import cKDTree
+
+    pts = scenes.uniform_cube(4000, 3)
+    q = scenes.uniform_cube(300, 4)
+    idx, dist, _ = oracle.Tree(pts).knn_batch(q, 10)
+    d64, i64 = cKDTree(pts.astype(np.float64)).query(q.astype(np.float64), k=10)
+    assert all(set(a) == set(b) for a, b in zip(idx, i64))  # no exact ties in random data
+    assert np.allclose(dist, d64, rtol=1e-5)
+
+
+def test_radius_matches_definition(oracle):
+    pts = _scene()
+    t = oracle.Tree(pts)
+    q = pts[5]
+    for r in (0.3, 1.0):
+        r2 = np.float32(r) * np.float32(r)
+        d = pts - q
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        assert np.array_equal(t.radius_search(q, r), np.nonzero(d2 <= r2)[0].astype(np.uint32))
+
+
+def test_sor_matches_numpy_restatement(oracle):
+    pts = _scene()
+    keep, mean, stats = oracle.sor(pts, 10, 1.0)
+    idx, dist, cnt = oracle.Tree(pts).knn_batch(pts, 11)
+    md = np.empty(len(pts), np.float32)
+    for i in range(len(pts)):
+        s = np.float32(0)
+        for v in dist[i, 1:cnt[i]]:
+            s = np.float32(s + v)
+        md[i] = s / np.float32(cnt[i] - 1)
+    assert np.array_equal(md.view(np.uint32), mean.view(np.uint32))
+    s = np.float32(0)
+    for v in md:
+        s = np.float32(s + v)
+    gm = s / np.float32(len(md))
+    v = np.float32(0)
+    for x in md:
+        d = np.float32(x - gm)
+        v = np.float32(v + np.float32(d * d))
+    sd = np.sqrt(np.float32(v / np.float32(len(md))))
+    thr = np.float32(gm + np.float32(np.float32(1.0) * sd))
+    assert np.float32(stats[0]) == gm and np.float32(stats[2]) == thr
+    assert np.array_equal(keep, (md <= thr).astype(np.uint8))
+
+
+def test_scene_shapes():
+    assert scenes.kitti_scene().shape == (122_000, 3)
+    assert scenes.kitti_scene(0, scenes.KITTI_COUNTS["frame80k"]).shape == (80_000, 3)
+    assert scenes.kitti_scene(0, scenes.KITTI_COUNTS["demo68k"]).shape == (68_000, 3)
+    assert scenes.aerial_scene(42, 0.1).shape == (241_000, 3)
