@@ -794,12 +794,13 @@ int pcr_icp_point_to_plane_dev(pcr_ctx *ctx, const float *sx, const float *sy, c
 /* ---- multi-frame batch ---------------------------------------------------------------------------- */
 namespace pcr {
 // frames of exactly one point are returned unchanged by the reference (statistical_outlier.rs:10-12)
-__global__ void single_point_frames_kernel(const uint32_t *__restrict__ frame_off, int n_frames, uint8_t *__restrict__ keep,
-                                           unsigned long long *__restrict__ kept) {
+__global__ void single_point_frames_kernel(const uint32_t *__restrict__ frame_off, int n_frames, size_t n,
+                                           uint8_t *__restrict__ keep, unsigned long long *__restrict__ kept) {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
-    if (frame_off[f + 1] - frame_off[f] == 1) {
-        keep[frame_off[f]] = 1;
+    const size_t b = frame_off ? frame_off[f] : 0, e = frame_off ? frame_off[f + 1] : n;
+    if (e - b == 1) {
+        keep[b] = 1;
         kept[f] = 1;
     }
 }
@@ -822,38 +823,34 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
     PCR_CUDA(c, cudaMallocAsync((void **)&d_stats, sizeof(float) * 4 * F, c->stream));
     FreeLater f2{d_stats, c->stream};
 
+    // ONE index serves both stages: built for the larger k, then the points SOR removes are
+    // tombstoned in place (NaN coordinates) and the normals of the kept points run on the same grid.
     BuildOpts bo;
-    bo.k_hint = k_sor + 1;
+    bo.k_hint = std::max(k_sor + 1, k_normals);
+    if (const char *e = getenv("PCR_BATCH_KHINT")) bo.k_hint = (size_t)atoi(e);
     bo.n_frames = F;
     bo.frame_offsets = frame_offsets;
     Index *ix = nullptr;
     PCR_TRY(index_build_dev(c, dx, dy, dz, n, bo, &ix));
-    int s = PCR_OK;
-    if (k_sor == 0) {
+    struct IxGuard {
+        Index *ix;
+        ~IxGuard() { index_free(ix); }
+    } g{ix};
+    if (k_sor == 0) {  // statistical_outlier.rs:5-7: empty result
         PCR_CUDA(c, cudaMemsetAsync(d_keep, 0, n, c->stream));
         PCR_CUDA(c, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long) * F, c->stream));
     } else {
-        s = sor_mean_dist_dev(ix, k_sor, d_mean);
-        if (s == PCR_OK) s = sor_threshold_mask_dev(c, d_mean, ix->frame_in_off, F, n, std_mul, d_keep, d_stats, d_kept);
-        if (s == PCR_OK && F > 1) {  // a one-point frame is returned as is, even if the point is not finite
-            single_point_frames_kernel<<<(F + 127) / 128, 128, 0, c->stream>>>(ix->frame_in_off, F, d_keep, d_kept);
-            c->launches++;
+        PCR_TRY(sor_mean_dist_dev(ix, k_sor, d_mean));
+        PCR_TRY(sor_threshold_mask_dev(c, d_mean, ix->frame_in_off, F, n, std_mul, d_keep, d_stats, d_kept));
+        if (F > 1 || n == 1) {  // a one-point frame is returned as is, even if the point is not finite
+            single_point_frames_kernel<<<(F + 127) / 128, 128, 0, c->stream>>>(ix->frame_in_off, F, n, d_keep, d_kept);
+            PCR_LAUNCH_CHECK(c);
         }
     }
-    index_free(ix);
-    PCR_TRY(s);
     if (k_normals == 0) return PCR_OK;
-    BuildOpts bn;
-    bn.k_hint = k_normals;
-    bn.n_frames = F;
-    bn.frame_offsets = frame_offsets;
-    bn.d_mask = d_keep;
-    Index *ixn = nullptr;
-    PCR_TRY(index_build_dev(c, dx, dy, dz, n, bn, &ixn));
+    PCR_TRY(index_apply_mask_dev(ix, d_keep));
     // removed points get 0 and kept non-finite points (0,0,1) inside normals_dev
-    s = normals_dev(ixn, k_normals, vp, d_nx, d_ny, d_nz, d_keep);
-    index_free(ixn);
-    return s;
+    return normals_dev(ix, k_normals, vp, d_nx, d_ny, d_nz, d_keep);
 }
 
 

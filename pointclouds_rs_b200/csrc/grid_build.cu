@@ -244,6 +244,19 @@ __global__ void __launch_bounds__(kBuildThreads) scatter_kernel(const float4 *__
     sorted[cell_start[cid] + rank[i]] = p;
 }
 
+// ---- tombstones: drop masked-out points from a built level without rebuilding it ------------------
+__global__ void __launch_bounds__(256) tombstone_kernel(float4 *__restrict__ sorted, uint32_t n_sorted,
+                                                        const uint8_t *__restrict__ keep) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sorted) return;
+    float4 p = sorted[i];
+    if (!keep[__float_as_uint(p.w)]) {
+        const float qnan = __int_as_float(0x7fc00000);
+        p.x = p.y = p.z = qnan;  // every distance to it is NaN: its key can never enter a top-k
+        sorted[i] = p;
+    }
+}
+
 // ---- K2: exclusive scan of a u32 table (two kernels, no inter-block waiting) -------------------
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 16;
@@ -422,7 +435,9 @@ struct FrameBox {
 // (oracle/orc_grid_knn_model) on the KITTI / aerial / uniform-cube shapes.
 double occupancy_target(size_t k_hint) {
     double k = k_hint ? (double)k_hint : 10.0;
-    return std::min(64.0, std::max(2.0, 0.8 * k));
+    double scale = 0.25;
+    if (const char *e = getenv("PCR_OCC_SCALE")) scale = atof(e);  // tuning hook
+    return std::min(64.0, std::max(2.0, scale * k));
 }
 
 double initial_cell(const FrameBox &b, double target) {
@@ -483,6 +498,18 @@ void index_free(Index *ix) {
         }
     }
     delete ix;
+}
+
+int index_apply_mask_dev(Index *ix, const uint8_t *d_keep) {
+    Ctx *ctx = ix->ctx;
+    for (Index *l = ix; l; l = l->coarser) {
+        l->d_mask = d_keep;  // levels built from now on leave the removed points out
+        if (l->n_indexed) {
+            tombstone_kernel<<<(unsigned)((l->n_indexed + 255) / 256), 256, 0, ctx->stream>>>(l->sorted, (uint32_t)l->n_indexed, d_keep);
+            PCR_LAUNCH_CHECK(ctx);
+        }
+    }
+    return PCR_OK;
 }
 
 // Next-coarser level: same points, same frames, cell size x kLevelFactor.  Reuses the bounding

@@ -140,6 +140,10 @@ __global__ void __launch_bounds__(kThreads) sor_mean_kernel(LevelArgs a, int kk,
                 g = a.grids[f];
             }
             float4 q = __ldg(&a.qpts[pos]);
+            if (q.x != q.x) {  // tombstoned point: not a query
+                if (lane == 0) scnt[t] = -1;
+                continue;
+            }
             bool done = warp_knn_search(tk, g, a.cell_start, a.pts, q.x, q.y, q.z, a.max_rings, a.last_level != 0);
             int cnt = tk.count();
             if (!done) {
@@ -177,6 +181,7 @@ __global__ void __launch_bounds__(kThreads) sor_mean_kernel(LevelArgs a, int kk,
             const uint32_t pos = a.qlist ? a.qlist[q0 + t] : q0 + t;
             const GridDesc g = a.grids[frame_of_sorted(a.grids, a.n_frames, pos)];
             float4 q = __ldg(&a.qpts[pos]);
+            if (q.x != q.x) continue;  // tombstoned point: not a query
             bool done = warp_knn_search(tk, g, a.cell_start, a.pts, q.x, q.y, q.z, a.max_rings, a.last_level != 0);
             __syncwarp();
             if (!done) {
@@ -306,6 +311,10 @@ __global__ void __launch_bounds__(kThreads) normals_kernel(LevelArgs a, const fl
                 g = a.grids[f];
             }
             float4 q = __ldg(&a.qpts[pos]);
+            if (q.x != q.x) {  // tombstoned point: not a query
+                if (lane == 0) scnt[t] = -1;
+                continue;
+            }
             bool done = warp_knn_search(tk, g, a.cell_start, a.pts, q.x, q.y, q.z, a.max_rings, a.last_level != 0);
             int cnt = tk.count();
             if (!done) {
@@ -343,6 +352,7 @@ __global__ void __launch_bounds__(kThreads) normals_kernel(LevelArgs a, const fl
             const uint32_t pos = a.qlist ? a.qlist[q0 + t] : q0 + t;
             const GridDesc g = a.grids[frame_of_sorted(a.grids, a.n_frames, pos)];
             float4 q = __ldg(&a.qpts[pos]);
+            if (q.x != q.x) continue;  // tombstoned point: not a query
             bool done = warp_knn_search(tk, g, a.cell_start, a.pts, q.x, q.y, q.z, a.max_rings, a.last_level != 0);
             __syncwarp();
             if (!done) {
@@ -442,7 +452,7 @@ __global__ void __launch_bounds__(kTQThreads) knn_thread_kernel(LevelArgs a, Thr
     const bool active = q < a.nq;
     ThreadTopK<KC> acc;
     acc.kk = t.kk;
-    bool resolved = true;
+    bool resolved = true, skip = false;
     float px = 0.f, py = 0.f, pz = 0.f;
     uint32_t out = q;
     int cnt = 0;
@@ -459,6 +469,8 @@ __global__ void __launch_bounds__(kTQThreads) knn_thread_kernel(LevelArgs a, Thr
             px = p.x; py = p.y; pz = p.z;
             out = __float_as_uint(p.w);
             f = frame_of_sorted(a.grids, a.n_frames, q);
+            searchable = px == px;  // a tombstoned point (index_apply_mask_dev) is not a query either
+            skip = !searchable;
         }
         acc.reset();
         if (searchable) {
@@ -475,7 +487,7 @@ __global__ void __launch_bounds__(kTQThreads) knn_thread_kernel(LevelArgs a, Thr
         base = __shfl_sync(PCR_FULL, base, __ffs(dmask) - 1);
         if (active && !resolved) a.defer_list[base + __popc(dmask & ((1u << lane) - 1u))] = q;
     }
-    if (!active || !resolved) return;
+    if (!active || !resolved || skip) return;
     if (MODE == 0) {
         uint32_t *ri = t.idx + (size_t)q * t.kk;
         float *rd = t.dist ? t.dist + (size_t)q * t.kk : nullptr;
@@ -748,7 +760,7 @@ int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny
     Ctx *ctx = ix->ctx;
     if (ix->n == 0 || k == 0) return PCR_OK;
     if (k > PCR_MAX_K) return fail(ctx, PCR_ERR_UNSUPPORTED, "k = %zu exceeds PCR_MAX_K = %d", k, PCR_MAX_K);
-    if (ix->n_indexed < ix->n) {
+    if (d_mask || ix->n_indexed < ix->n) {
         fill_unindexed_normals_kernel<<<(unsigned)((ix->n + 255) / 256), 256, 0, ctx->stream>>>(ix->orig4, d_mask, ix->n, d_nx,
                                                                                                 d_ny, d_nz);
         PCR_LAUNCH_CHECK(ctx);

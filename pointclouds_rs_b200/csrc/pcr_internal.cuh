@@ -163,6 +163,10 @@ int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d);
 // normals of every point of the indexed cloud(s); points not indexed get (0,0,1) (no neighbours)
 int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny, float *d_nz,
                 const uint8_t *d_mask);
+// Removes the points with keep[idx] == 0 from every built level of the index IN PLACE (their
+// coordinates become NaN) and makes later-built levels skip them: the index of the SOR pass is
+// reused for the normals of the kept points without a rebuild.
+int index_apply_mask_dev(Index *ix, const uint8_t *d_keep);
 int radius_count_dev(Index *ix, const float *dqx, const float *dqy, const float *dqz, size_t nq,
                      float radius, uint32_t *d_counts);
 int radius_fill_dev(Index *ix, const float *dqx, const float *dqy, const float *dqz, size_t nq,
@@ -203,7 +207,10 @@ int comm_allreduce_f64(Ctx *ctx, double *d_buf, size_t count);
 #ifdef __CUDACC__
 
 #define PCR_FULL 0xffffffffu
-#define PCR_EMPTY_KEY 0xffffffffffffffffull
+// "no entry" sentinel: just above every real key (d^2 bits <= 0x7f800000 = +inf).  A candidate whose
+// d^2 is NaN -- a tombstoned point, see tombstone_kernel -- has a key >= the sentinel and can
+// therefore never pass `key < threshold`, even while a list is not full yet.
+#define PCR_EMPTY_KEY 0x7f80000100000000ull
 
 // kiddo SquaredEuclidean on f32: ((dx*dx)+(dy*dy))+(dz*dz), every operation rounded, no FMA
 // (call sites crates/spatial/src/kdtree.rs:70,93,121-123).

@@ -384,3 +384,16 @@ def test_batch_matches_single_frames(pcr, oracle):
         got = nrm[sl][sel]
         assert np.nanmax(_angles(got, o_n)) < 1e-4, f"frame {f}"
         assert (nrm[sl][o_keep == 0] == 0).all()
+
+
+def test_batch_large_k_generic_path(pcr, oracle):
+    # k > 32 runs the shared-memory top-k kernels on every level, with the tombstoned shared index
+    frames = [scenes.kitti_scene(20 + s, (2_000, 100, 20, 40)) for s in range(2)]
+    off = np.concatenate([[0], np.cumsum([len(f) for f in frames])])
+    keep, nrm, kept = pcr.sor_normals_batch(np.vstack(frames), off, 35, 1.0, 40)
+    for f, fr in enumerate(frames):
+        sl = slice(off[f], off[f + 1])
+        o_keep, _, _ = oracle.sor(fr, 35, 1.0, threads=T)
+        assert np.array_equal(keep[sl], o_keep)
+        sel = np.nonzero(o_keep)[0]
+        assert np.nanmax(_angles(nrm[sl][sel], oracle.normals(fr[sel], 40, threads=T))) < 1e-4
