@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpcr_b200.so")
+LIB_PATH = os.environ.get("PCR_LIB_OVERRIDE") or os.path.join(_HERE, "lib", "libpcr_b200.so")  # override: A/B builds
 
 PCR_OK = 0
 PCR_ERR_INVALID_ARG = 1

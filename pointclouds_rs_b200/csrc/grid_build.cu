@@ -141,34 +141,63 @@ __global__ void __launch_bounds__(kBuildThreads) count_kernel(const float *__res
     }
 }
 
-// same, for a coarser level of an existing index: reads the AoS copy (the caller's SoA may be gone)
-__global__ void __launch_bounds__(kBuildThreads) count4_kernel(const float4 *__restrict__ orig4,
-                                                               const uint32_t *__restrict__ frame_off, size_t n,
-                                                               const uint8_t *__restrict__ mask,
-                                                               const GridDesc *__restrict__ grids,
-                                                               uint32_t *__restrict__ cell_count,
-                                                               uint32_t *__restrict__ cell_id, uint32_t *__restrict__ rank) {
-    const int f = blockIdx.y;
-    const uint32_t b = frame_off ? frame_off[f] : 0u;
-    const uint32_t e = frame_off ? frame_off[f + 1] : (uint32_t)n;
-    const GridDesc g = grids[f];
-    const uint32_t base = b + blockIdx.x * (kBuildThreads * kItems) + threadIdx.x;
-#pragma unroll
-    for (int it = 0; it < kItems; it++) {
-        uint32_t i = base + it * kBuildThreads;
-        if (i >= e) break;
-        float4 p = orig4[i];
-        uint32_t cid = 0xffffffffu, r = 0;
-        if (finite3(p.x, p.y, p.z) && (!mask || mask[i])) {
+// same, for a coarser level of an existing index: reads the finer level's CELL-SORTED points, so
+// neighbouring threads fall into the same coarse cell and one warp-aggregated atomic per distinct
+// cell replaces up to 32 same-address atomics.  Tombstoned (NaN) entries are skipped.
+__global__ void __launch_bounds__(kBuildThreads) count_sorted_kernel(const float4 *__restrict__ fine_sorted, uint32_t n_sorted,
+                                                                     const GridDesc *__restrict__ grids, int n_frames,
+                                                                     uint32_t *__restrict__ cell_count,
+                                                                     uint32_t *__restrict__ cell_id, uint32_t *__restrict__ rank) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t cid = 0xffffffffu;
+    if (i < n_sorted) {
+        const float4 p = fine_sorted[i];
+        if (p.x == p.x) {
+            int f = 0;
+            if (n_frames > 1) {  // frames own contiguous slices of the sorted array
+                int lo = 0, hi = n_frames - 1;
+                while (lo < hi) {
+                    int mid = (lo + hi + 1) >> 1;
+                    if (grids[mid].pt_begin <= i) lo = mid;
+                    else hi = mid - 1;
+                }
+                while (lo + 1 < n_frames && grids[lo].pt_end <= i) lo++;
+                f = lo;
+            }
+            const GridDesc g = grids[f];
             int c0 = cell_coord(g, 0, pick_axis(g.ax[0], p.x, p.y, p.z), nullptr);
             int c1 = cell_coord(g, 1, pick_axis(g.ax[1], p.x, p.y, p.z), nullptr);
             int c2 = cell_coord(g, 2, pick_axis(g.ax[2], p.x, p.y, p.z), nullptr);
             cid = cell_linear(g, c0, c1, c2);
-            r = atomicAdd(&cell_count[cid], 1u);
         }
+    }
+    // warp-aggregated atomic: one leader per distinct cell id
+    const unsigned peers = __match_any_sync(PCR_FULL, cid);
+    uint32_t r = 0;
+    if (cid != 0xffffffffu) {
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&cell_count[cid], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        r = base + __popc(peers & ((1u << lane) - 1u));
+    }
+    if (i < n_sorted) {
         cell_id[i] = cid;
         rank[i] = r;
     }
+}
+
+__global__ void __launch_bounds__(kBuildThreads) scatter_sorted_kernel(const float4 *__restrict__ fine_sorted, uint32_t n_sorted,
+                                                                       const uint32_t *__restrict__ cell_start,
+                                                                       const uint32_t *__restrict__ cell_id,
+                                                                       const uint32_t *__restrict__ rank,
+                                                                       float4 *__restrict__ sorted) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sorted) return;
+    uint32_t cid = cell_id[i];
+    if (cid == 0xffffffffu) return;
+    sorted[cell_start[cid] + rank[i]] = fine_sorted[i];
 }
 
 // ---- K1p: occupancy statistics of a probe grid ---------------------------------------------------
@@ -555,7 +584,9 @@ int index_coarser_level(Index *ix, Index **out) {
         }
         b.count = ix->box_count[f];
         GridDesc &g = c->grids_h[f];
-        shape_grid(g, b, ix->grids_h[f].h * kLevelFactor, cap);
+        double factor = kLevelFactor;
+        if (const char *ev = getenv("PCR_LEVEL_FACTOR")) factor = atof(ev);  // tuning hook
+        shape_grid(g, b, ix->grids_h[f].h * factor, cap);
         g.cell_base = (uint32_t)base;
         base += g.n_cells;
         g.pt_begin = ix->grids_h[f].pt_begin;
@@ -572,16 +603,16 @@ int index_coarser_level(Index *ix, Index **out) {
     PCR_TRY(ensure(ctx, ctx->b_misc, sizeof(uint32_t) * 2 * std::max<size_t>(n, 1)));
     uint32_t *d_cell_id = (uint32_t *)ctx->b_misc.p;
     uint32_t *d_rank = d_cell_id + std::max<size_t>(n, 1);
-    if (n > 0) {
-        const unsigned bx = std::max(1u, (max_frame + kBuildThreads * kItems - 1) / (kBuildThreads * kItems));
-        count4_kernel<<<dim3(bx, F), kBuildThreads, 0, st>>>(c->orig4, c->frame_in_off, n, c->d_mask, c->grids, c->cell_start,
-                                                             d_cell_id, d_rank);
+    const uint32_t ns = (uint32_t)ix->n_indexed;
+    if (ns > 0) {
+        count_sorted_kernel<<<(ns + kBuildThreads - 1) / kBuildThreads, kBuildThreads, 0, st>>>(ix->sorted, ns, c->grids, F, c->cell_start,
+                                                                                               d_cell_id, d_rank);
         PCR_LAUNCH_CHECK(ctx);
     }
     PCR_TRY(exclusive_scan_u32_dev(ctx, c->cell_start, (size_t)base + 1));
-    if (n > 0) {
-        scatter_kernel<<<(unsigned)((n + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0, st>>>(c->orig4, n, c->cell_start,
-                                                                                                      d_cell_id, d_rank, c->sorted);
+    if (ns > 0) {
+        scatter_sorted_kernel<<<(ns + kBuildThreads - 1) / kBuildThreads, kBuildThreads, 0, st>>>(ix->sorted, ns, c->cell_start, d_cell_id,
+                                                                                                 d_rank, c->sorted);
         PCR_LAUNCH_CHECK(ctx);
     }
     guard.ix = nullptr;

@@ -341,7 +341,10 @@ __device__ __forceinline__ bool thread_grid_search(Acc &acc, const GridDesc &g, 
                 b = g.pt_begin;
                 e = g.pt_end;
             } else {
-                const int a0 = c0 + e0, a1 = c1 + e1;
+                // S == 1: take the query's own row first (the threshold tightens early)
+                const int m0 = S == 1 ? (e0 == -1 ? 0 : (e0 == 0 ? -1 : 1)) : e0;
+                const int m1 = S == 1 ? (e1 == -1 ? 0 : (e1 == 0 ? -1 : 1)) : e1;
+                const int a0 = c0 + m0, a1 = c1 + m1;
                 if (a0 >= 0 && a0 < d0n && a1 >= 0 && a1 < d1n) {
                     const bool border = S == 1 || e0 == S || e0 == -S || e1 == S || e1 == -S;
                     int z0, z1;

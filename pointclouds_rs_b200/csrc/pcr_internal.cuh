@@ -32,7 +32,7 @@ struct GridDesc {
     uint32_t in_end;
 };
 
-constexpr int kLevelFactor = 8;  // cell-size ratio between consecutive grid levels (knn_search.cuh)
+constexpr int kLevelFactor = 6;  // cell-size ratio between consecutive grid levels (knn_search.cuh)
 
 struct DevBuf {  // grow-only device scratch buffer
     void *p = nullptr;

@@ -20,12 +20,14 @@
 // Validated against numpy's sequential float32 accumulation (denormals, ties, overflow) before it
 // was ported; on the GPU the SOR statistics are compared bit for bit with the CPU oracle.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "pcr_internal.cuh"
 
 namespace pcr {
 
 constexpr int kFoldThreads = 1024;
-constexpr int kFoldItems = 8;
+constexpr int kFoldItems = 4;
 constexpr int kFoldTile = kFoldThreads * kFoldItems;
 constexpr int kFoldHead = 1024;        // elements folded sequentially by thread 0 first (<= kFoldThreads)
 constexpr uint32_t kFoldSat = 1u << 25;  // increments saturate here (anything >= 2^24 is a crossing)
@@ -105,30 +107,38 @@ __device__ __forceinline__ uint32_t fold_step(uint32_t S, float x, double inv_u)
 
 struct FoldShared {
     FoldMap warp_tot[32];
-    uint32_t cross_idx;   // tile-local index of the first crossing element
+    FoldMap cta_total;    // composed map of this CTA's sub-tile (read by the other CTAs of the cluster)
+    FoldMap cta_prefix;   // composition of the totals of the lower-ranked CTAs
+    uint32_t cross_idx;   // cluster-tile-local index of this CTA's first crossing element
     uint32_t s_before;    // S just before it
     float x_cross;
-    uint32_t s_last;      // S after the last element of the tile (no crossing)
-    float s;              // running sum (broadcast)
-    uint32_t done_upto;   // tile-local: elements below this index are already folded
+    uint32_t s_last;      // S after this CTA's last element (valid if nothing crossed before it)
+    float s;              // running sum (every CTA of the cluster holds the same value)
+    uint32_t done_upto;   // cluster-tile-local: elements below this index are already folded
     uint32_t cnt[32];
     float head[kFoldHead];
 };
 
-// Left-to-right f32 sum of fn(v[i]) over the finite v[i], i in [b, e), evaluated by the whole block
-// (kFoldThreads threads).  fn must return a non-negative value.  Returns the sum in every thread;
-// *n_used (if not null) receives the number of finite elements.
+// Left-to-right f32 sum of fn(v[i]) over the finite v[i], i in [b, e), evaluated by a whole thread
+// block CLUSTER (kFoldThreads threads per CTA; a cluster of one CTA works too).  Each CTA scans its
+// own sub-tile; the CTAs exchange their composed maps and their first crossing through distributed
+// shared memory, so one pass covers cluster_size * kFoldTile elements.  fn must return a
+// non-negative value.  Returns the sum in every thread of every CTA; *n_used (if not null) receives
+// the number of finite elements.
 template <class Fn>
-__device__ float block_exact_fold(const float *__restrict__ v, size_t b, size_t e, Fn fn, FoldShared &sh, uint32_t *n_used) {
+__device__ float cluster_exact_fold(const float *__restrict__ v, size_t b, size_t e, Fn fn, FoldShared &sh, uint32_t *n_used) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank(), CS = cluster.num_blocks();
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     uint32_t my_cnt = 0;
-    // ---- sequential head: the first crossings come after 1, 2, 4, ... elements ------------------
+    // ---- sequential head (every CTA computes it redundantly: no communication) ---------------------
     size_t head_end = b + kFoldHead < e ? b + kFoldHead : e;
     if (tid < kFoldHead) {  // stage through shared memory so that thread 0 never waits on DRAM
         float t = b + tid < head_end ? v[b + tid] : INFINITY;
         bool ok = isfinite(t);
         sh.head[tid] = ok ? fn(t) : -1.0f;  // fn >= 0: a negative entry marks "skip"
-        my_cnt += ok ? 1u : 0u;
+        my_cnt += (ok && rank == 0) ? 1u : 0u;
     }
     __syncthreads();
     if (tid == 0) {
@@ -142,10 +152,12 @@ __device__ float block_exact_fold(const float *__restrict__ v, size_t b, size_t 
     }
     __syncthreads();
     // ---- tiles ------------------------------------------------------------------------------------
-    for (size_t tile = head_end; tile < e; tile += kFoldTile) {
+    const size_t ctile = (size_t)CS * kFoldTile;
+    for (size_t tile = head_end; tile < e; tile += ctile) {
         float x[kFoldItems];
         bool use[kFoldItems];
-        const size_t base = tile + (size_t)tid * kFoldItems;  // thread-contiguous items
+        const uint32_t li0 = rank * kFoldTile + (uint32_t)tid * kFoldItems;  // cluster-tile-local index of item 0
+        const size_t base = tile + li0;                                       // thread-contiguous items
 #pragma unroll
         for (int j = 0; j < kFoldItems; j++) {
             size_t i = base + j;
@@ -158,7 +170,7 @@ __device__ float block_exact_fold(const float *__restrict__ v, size_t b, size_t 
         __syncthreads();
         for (;;) {
             const float s = sh.s;
-            if (!isfinite(s)) break;  // overflowed to +inf: stays there (all terms are >= 0)
+            if (!isfinite(s)) break;  // overflowed to +inf: stays there (all terms are >= 0); uniform across the cluster
             const uint32_t done = sh.done_upto;
             int E;
             uint32_t S_in;
@@ -167,11 +179,9 @@ __device__ float block_exact_fold(const float *__restrict__ v, size_t b, size_t 
             // 1. per-thread aggregate map over the pending items
             FoldMap agg = {0u, 0u};
 #pragma unroll
-            for (int j = 0; j < kFoldItems; j++) {
-                uint32_t li = (uint32_t)tid * kFoldItems + j;
-                if (use[j] && li >= done) agg = fold_compose(agg, fold_element_map(x[j], inv_u));
-            }
-            // 2. block exclusive scan of the aggregates
+            for (int j = 0; j < kFoldItems; j++)
+                if (use[j] && li0 + j >= done) agg = fold_compose(agg, fold_element_map(x[j], inv_u));
+            // 2. block scan of the aggregates
             FoldMap inc = agg;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -181,9 +191,7 @@ __device__ float block_exact_fold(const float *__restrict__ v, size_t b, size_t 
                 if (lane >= o) inc = fold_compose(u, inc);
             }
             if (lane == 31) sh.warp_tot[w] = inc;
-            if (tid == 0) {
-                sh.cross_idx = 0xffffffffu;
-            }
+            if (tid == 0) sh.cross_idx = 0xffffffffu;
             __syncthreads();
             if (w == 0) {
                 FoldMap t = sh.warp_tot[lane], ti = t;
@@ -194,31 +202,49 @@ __device__ float block_exact_fold(const float *__restrict__ v, size_t b, size_t 
                     u.a1 = __shfl_up_sync(PCR_FULL, ti.a1, o);
                     if (lane >= o) ti = fold_compose(u, ti);
                 }
-                // exclusive
+                if (lane == 31) sh.cta_total = ti;
                 FoldMap ex;
                 ex.a0 = __shfl_up_sync(PCR_FULL, ti.a0, 1);
                 ex.a1 = __shfl_up_sync(PCR_FULL, ti.a1, 1);
                 if (lane == 0) ex = FoldMap{0u, 0u};
                 sh.warp_tot[lane] = ex;
             }
+            cluster.sync();  // every CTA's total is visible
+            // 3. prefix over the lower-ranked CTAs (warp 0: one lane per CTA, then a shuffle scan)
+            if (w == 0) {
+                FoldMap t = {0u, 0u};
+                if ((unsigned)lane < CS) t = cluster.map_shared_rank(&sh, lane)->cta_total;
+                FoldMap ti = t;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    FoldMap u;
+                    u.a0 = __shfl_up_sync(PCR_FULL, ti.a0, o);
+                    u.a1 = __shfl_up_sync(PCR_FULL, ti.a1, o);
+                    if (lane >= o) ti = fold_compose(u, ti);
+                }
+                FoldMap ex;
+                ex.a0 = __shfl_up_sync(PCR_FULL, ti.a0, 1);
+                ex.a1 = __shfl_up_sync(PCR_FULL, ti.a1, 1);
+                if (lane == 0) ex = FoldMap{0u, 0u};
+                if ((unsigned)lane == rank) sh.cta_prefix = ex;
+            }
             __syncthreads();
             FoldMap lane_ex;
             lane_ex.a0 = __shfl_up_sync(PCR_FULL, inc.a0, 1);
             lane_ex.a1 = __shfl_up_sync(PCR_FULL, inc.a1, 1);
             if (lane == 0) lane_ex = FoldMap{0u, 0u};
-            const FoldMap pre = fold_compose(sh.warp_tot[w], lane_ex);
-            // 3. walk the own items with the actual running value; find the first crossing
+            const FoldMap pre = fold_compose(sh.cta_prefix, fold_compose(sh.warp_tot[w], lane_ex));
+            // 4. walk the own items with the actual running value; find the first crossing
             uint32_t S = fold_sat_add(S_in, (S_in & 1u) ? pre.a1 : pre.a0);
             uint32_t my_cross = 0xffffffffu, S_before = 0;
             float xc = 0.f;
             if (S < kFoldLimit) {
 #pragma unroll
                 for (int j = 0; j < kFoldItems; j++) {
-                    uint32_t li = (uint32_t)tid * kFoldItems + j;
-                    if (use[j] && li >= done && my_cross == 0xffffffffu) {
+                    if (use[j] && li0 + j >= done && my_cross == 0xffffffffu) {
                         uint32_t S2 = fold_step(S, x[j], inv_u);
                         if (S2 >= kFoldLimit) {
-                            my_cross = li;
+                            my_cross = li0 + j;
                             S_before = S;
                             xc = x[j];
                         } else {
@@ -230,17 +256,34 @@ __device__ float block_exact_fold(const float *__restrict__ v, size_t b, size_t 
             if (my_cross != 0xffffffffu) atomicMin(&sh.cross_idx, my_cross);
             if (tid == kFoldThreads - 1) sh.s_last = S;
             __syncthreads();
-            const uint32_t c = sh.cross_idx;
-            if (c == 0xffffffffu) {
-                if (tid == 0) sh.s = fold_join(E, sh.s_last);
-                __syncthreads();
-                break;
+            if (my_cross != 0xffffffffu && my_cross == sh.cross_idx) {  // this CTA's first crossing
+                sh.s_before = S_before;
+                sh.x_cross = xc;
             }
-            if (my_cross == c) {  // exactly one thread owns the crossing element
-                sh.s = __fadd_rn(fold_join(E, S_before), xc);
-                sh.done_upto = c + 1u;
+            cluster.sync();  // every CTA's crossing record is visible
+            // 5. the cluster-wide first crossing decides the new state (every CTA computes the same)
+            if (w == 0) {
+                uint32_t c = 0xffffffffu;
+                if ((unsigned)lane < CS) c = cluster.map_shared_rank(&sh, lane)->cross_idx;
+                const uint32_t cmin = __reduce_min_sync(PCR_FULL, c);
+                float ns;
+                uint32_t nd = 0;
+                if (cmin == 0xffffffffu) {
+                    ns = fold_join(E, cluster.map_shared_rank(&sh, CS - 1)->s_last);
+                } else {
+                    const unsigned owner = __ffs(__ballot_sync(PCR_FULL, c == cmin)) - 1;
+                    const FoldShared *o = cluster.map_shared_rank(&sh, owner);
+                    ns = __fadd_rn(fold_join(E, o->s_before), o->x_cross);
+                    nd = cmin + 1u;
+                }
+                if (lane == 0) {
+                    sh.warp_tot[0].a0 = cmin;  // scratch: lets the other warps see whether to loop
+                    sh.s = ns;
+                    sh.done_upto = nd;
+                }
             }
-            __syncthreads();
+            cluster.sync();  // all remote reads of this pass are done before anything is overwritten
+            if (sh.warp_tot[0].a0 == 0xffffffffu) break;
         }
         __syncthreads();
     }
@@ -253,8 +296,11 @@ __device__ float block_exact_fold(const float *__restrict__ v, size_t b, size_t 
             uint32_t t = __reduce_add_sync(PCR_FULL, sh.cnt[lane]);
             if (lane == 0) sh.cnt[0] = t;
         }
-        __syncthreads();
-        *n_used = sh.cnt[0];
+        cluster.sync();
+        uint32_t tot = 0;
+        for (unsigned r = 0; r < CS; r++) tot += cluster.map_shared_rank(&sh, r)->cnt[0];
+        cluster.sync();
+        *n_used = tot;
     }
     const float r = sh.s;
     __syncthreads();

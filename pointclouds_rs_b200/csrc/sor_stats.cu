@@ -18,15 +18,15 @@ struct SorFrameStats {
     uint32_t n_finite;
 };
 
-// one block per frame: two exact left-to-right folds (seq_fold.cuh), then the threshold
+// one block CLUSTER per frame: two exact left-to-right folds (seq_fold.cuh), then the threshold
 __global__ void __launch_bounds__(kFoldThreads) sor_stats_kernel(const float *__restrict__ mean_d,
                                                                   const uint32_t *__restrict__ frame_off, size_t n,
                                                                   float std_mul, SorFrameStats *__restrict__ stats) {
     __shared__ FoldShared sh;
-    const int f = blockIdx.x;
+    const int f = blockIdx.x / cooperative_groups::this_cluster().num_blocks();
     const size_t b = frame_off ? frame_off[f] : 0, e = frame_off ? frame_off[f + 1] : n;
     uint32_t nf = 0;
-    const float sum = block_exact_fold(mean_d, b, e, [](float v) { return v; }, sh, &nf);
+    const float sum = cluster_exact_fold(mean_d, b, e, [](float v) { return v; }, sh, &nf);
     SorFrameStats s;
     s.n_finite = nf;
     if (nf == 0) {  // statistical_outlier.rs:49-51 -> empty result (NaN threshold keeps nothing)
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(kFoldThreads) sor_stats_kernel(const float *__
     } else {
         const float nn = (float)nf;
         const float gmean = __fdiv_rn(sum, nn);
-        float var = block_exact_fold(
+        float var = cluster_exact_fold(
             mean_d, b, e,
             [gmean](float v) {
                 float d = __fsub_rn(v, gmean);
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kFoldThreads) sor_stats_kernel(const float *__
         s.stddev = sd;
         s.thr = __fadd_rn(gmean, __fmul_rn(std_mul, sd));
     }
-    if (threadIdx.x == 0) stats[f] = s;
+    if (threadIdx.x == 0 && cooperative_groups::this_cluster().block_rank() == 0) stats[f] = s;
 }
 
 __global__ void __launch_bounds__(256) sor_mask_kernel(const float *__restrict__ mean_d, const uint32_t *__restrict__ frame_off,
@@ -79,8 +79,23 @@ int sor_threshold_mask_dev(Ctx *ctx, const float *d_mean_d, const uint32_t *d_fr
     static_assert(sizeof(SorFrameStats) == 4 * sizeof(float), "stats layout");
     if (n == 0) return PCR_OK;
     TimeScope ts(ctx, kTagSorStats);
-    sor_stats_kernel<<<n_frames, kFoldThreads, 0, ctx->stream>>>(d_mean_d, d_frame_off, n, std_mul, (SorFrameStats *)d_stats);
-    PCR_LAUNCH_CHECK(ctx);
+    {
+        // a cluster of 8 CTAs per frame (one CTA for small frames: fewer cluster barriers)
+        const unsigned cs = n / (size_t)n_frames > 4 * (size_t)kFoldTile ? 8u : 1u;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)n_frames * cs);
+        cfg.blockDim = dim3(kFoldThreads);
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        PCR_CUDA(ctx, cudaLaunchKernelEx(&cfg, sor_stats_kernel, d_mean_d, d_frame_off, n, std_mul, (SorFrameStats *)d_stats));
+        ctx->launches++;
+    }
     PCR_CUDA(ctx, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long) * n_frames, ctx->stream));
     size_t per = n / (size_t)n_frames + 1;
     unsigned bx = (unsigned)std::min<size_t>((per + 255) / 256, (size_t)ctx->sm_count * 8);

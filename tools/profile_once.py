@@ -6,6 +6,14 @@ import pointclouds_rs_b200 as pcr
 from pointclouds_rs_b200 import scenes
 which = sys.argv[1] if len(sys.argv) > 1 else "sor"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+if which == "batch":
+    from pointclouds_rs_b200 import scenes as _s
+    pts = _s.voxel_downsample_np(_s.kitti_scene(), 0.05)
+    off = np.array([0, len(pts)], np.uint64)
+    for _ in range(reps):
+        pcr.sor_normals_batch(pts, off, 10, 1.0, 20)
+    print("done", pcr.default_context().launch_count)
+    sys.exit(0)
 if which in ("sor", "normals", "knn"):
     c = pcr.PointCloud.from_numpy(scenes.kitti_scene())
 elif which == "aerial":
