@@ -1322,24 +1322,34 @@ void orc_grid_knn_model(const float *x, const float *y, const float *z, size_t n
                         }
                     }
                 }
-                /* termination: lower bound on the distance to anything not yet scanned */
-                double bound = INFINITY;
+                /* termination: lower bound on the distance to anything not yet scanned.  Beyond an
+                 * open face of axis a everything is at least dist_a away along a AND at least gap_b
+                 * away along every other axis b on which the query lies outside the grid. */
+                double gap[3], g2 = 0.0;
+                for (int a = 0; a < 3; a++) {
+                    double lo_ext = g.o[a], hi_ext = g.o[a] + (double)g.dims[a] * g.h;
+                    gap[a] = (double)q[a] < lo_ext ? lo_ext - (double)q[a] : ((double)q[a] > hi_ext ? (double)q[a] - hi_ext : 0.0);
+                    g2 += gap[a] * gap[a];
+                }
+                double bound2 = INFINITY;
                 int open = 0;
                 for (int a = 0; a < 3; a++) {
                     int lo = c[a] - R, hi = c[a] + R;
                     if (lo > 0) {
                         open = 1;
                         double d = (double)q[a] - (g.o[a] + (double)lo * g.h);
-                        if (d < bound) bound = d;
+                        double b2 = d > 0.0 ? d * d + (g2 - gap[a] * gap[a]) : 0.0;
+                        if (b2 < bound2) bound2 = b2;
                     }
                     if (hi < g.dims[a] - 1) {
                         open = 1;
                         double d = (g.o[a] + (double)(hi + 1) * g.h) - (double)q[a];
-                        if (d < bound) bound = d;
+                        double b2 = d > 0.0 ? d * d + (g2 - gap[a] * gap[a]) : 0.0;
+                        if (b2 < bound2) bound2 = b2;
                     }
                 }
                 if (!open) break;
-                if (h.n == h.cap && bound > 0.0 && (double)key_d2(h.a[0]) < bound * bound * (1.0 - 1e-6)) break;
+                if (h.n == h.cap && bound2 > 0.0 && (double)key_d2(h.a[0]) < bound2 * (1.0 - 1e-6)) break;
             }
             r = heap_emit(&h, ri, rd);
         }

@@ -139,7 +139,10 @@ __global__ void __launch_bounds__(kIcpThreads) icp_search_kernel(const GridDesc 
     nn[i] = best;
 }
 
-// (A') deferred source points on a coarser level: one warp per point, persistent over the list
+// (A') deferred source points on a coarser level, persistent over the device-side list: one warp
+//      per point (measured faster than thread-per-point here: a coarse cell holds ~70 points, so the
+//      lanes are busy; kThreadPerPoint is kept for experiments).
+template <bool kThreadPerPoint>
 __global__ void __launch_bounds__(128) icp_deferred_kernel(const GridDesc *__restrict__ grids,
                                                            const uint32_t *__restrict__ cell_start,
                                                            const float4 *__restrict__ pts, const float4 *__restrict__ cur,
@@ -149,21 +152,34 @@ __global__ void __launch_bounds__(128) icp_deferred_kernel(const GridDesc *__res
                                                            unsigned long long *__restrict__ nn, uint32_t *__restrict__ out_list,
                                                            uint32_t *__restrict__ out_count, int last_level) {
     if (state->done) return;
-    const int lane = threadIdx.x & 31;
     const uint32_t n = *in_count;
-    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
     const GridDesc g = grids[0];
-    RegTopK tk;
-    tk.kk = 1;
-    tk.lane = lane;
-    for (uint32_t j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += warps) {
-        const uint32_t i = in_list[j];
-        const float4 p = cur[i];
-        if (warp_knn_search(tk, g, cell_start, pts, p.x, p.y, p.z, last_level ? kMaxRings : kLevelRings, last_level != 0)) {
-            unsigned long long best = __shfl_sync(PCR_FULL, tk.K, 0);
-            if (lane == 0) nn[i] = best;
-        } else if (lane == 0) {
-            out_list[atomicAdd(out_count, 1u)] = i;
+    if (kThreadPerPoint) {
+        const uint32_t threads = gridDim.x * blockDim.x;
+        for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += threads) {
+            const uint32_t i = in_list[j];
+            const float4 p = cur[i];
+            ThreadBest1 acc;
+            if (thread_grid_search(acc, g, cell_start, pts, p.x, p.y, p.z, 1, last_level ? kMaxRings : kLevelRings, last_level != 0))
+                nn[i] = acc.best;
+            else
+                out_list[atomicAdd(out_count, 1u)] = i;
+        }
+    } else {
+        const int lane = threadIdx.x & 31;
+        const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+        RegTopK tk;
+        tk.kk = 1;
+        tk.lane = lane;
+        for (uint32_t j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += warps) {
+            const uint32_t i = in_list[j];
+            const float4 p = cur[i];
+            if (warp_knn_search(tk, g, cell_start, pts, p.x, p.y, p.z, last_level ? kMaxRings : kLevelRings, last_level != 0)) {
+                unsigned long long best = __shfl_sync(PCR_FULL, tk.K, 0);
+                if (lane == 0) nn[i] = best;
+            } else if (lane == 0) {
+                out_list[atomicAdd(out_count, 1u)] = i;
+            }
         }
     }
 }
@@ -230,15 +246,17 @@ __global__ void __launch_bounds__(kIcpThreads) icp_accum_kernel(const float4 *__
     }
 }
 
-__global__ void icp_reduce_kernel(const double *__restrict__ partials, int n_blocks, size_t ns_local, IcpState *state) {
+// Folds the per-block partials in a fixed order: 32 lanes per value take strided subsets, then a
+// shuffle tree -- deterministic for a given launch configuration.
+__global__ void __launch_bounds__(NP * 32) icp_reduce_kernel(const double *__restrict__ partials, int n_blocks, size_t ns_local,
+                                                             IcpState *state) {
     if (state->done) return;
-    int j = threadIdx.x;
-    if (j < NP) {
-        double v = 0.0;
-        for (int b = 0; b < n_blocks; b++) v += partials[(size_t)b * NP + j];
-        if (j == kSrcN) v = (double)ns_local;
-        state->sums[j] = v;
-    }
+    const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double v = 0.0;
+    for (int b = lane; b < n_blocks; b += 32) v += partials[(size_t)b * NP + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PCR_FULL, v, o);
+    if (lane == 0) state->sums[j] = j == kSrcN ? (double)ns_local : v;
 }
 
 // ---- device-side solves ----------------------------------------------------------------------------
@@ -670,7 +688,7 @@ int icp_dev(Ctx *ctx, const IcpArgs &a, pcr_icp_result *result) {
     uint32_t *dcount = dlist;  // [kMaxLevels]
     uint32_t *dl[2] = {dlist + 64, dlist + 64 + std::max<size_t>(ns, 1)};
 
-    const int n_blocks = (int)std::max<size_t>(1, std::min<size_t>((ns + kIcpThreads - 1) / kIcpThreads, (size_t)ctx->sm_count * 8));
+    const int n_blocks = (int)std::max<size_t>(1, std::min<size_t>((ns + kIcpThreads - 1) / kIcpThreads, (size_t)ctx->sm_count * 4));
     PCR_TRY(ensure(ctx, ctx->b_small, 8192 + sizeof(IcpState)));
     PCR_TRY(ensure(ctx, ctx->b_misc2, sizeof(double) * NP * (size_t)n_blocks));
     PCR_TRY(ensure_pinned(ctx, 8192 + sizeof(IcpState)));
@@ -691,9 +709,11 @@ int icp_dev(Ctx *ctx, const IcpArgs &a, pcr_icp_result *result) {
                     tgt->grids, tgt->cell_start, tgt->sorted, cur, ns, d_state, nn, dl[0], dcount + 0, 0);
                 PCR_LAUNCH_CHECK(ctx);
                 for (int l = 1; l < kMaxLevels; l++) {  // no host round trip: the list length stays on the device
-                    icp_deferred_kernel<<<ctx->sm_count * 2, 128, 0, st>>>(levels[l]->grids, levels[l]->cell_start, levels[l]->sorted,
-                                                                          cur, d_state, dl[(l - 1) & 1], dcount + (l - 1), nn,
-                                                                          dl[l & 1], dcount + l, l == kMaxLevels - 1 ? 1 : 0);
+                    const bool last = l == kMaxLevels - 1;
+                    // level 1 may hold 10-20 % of a badly aligned source: give it more resident warps
+                    icp_deferred_kernel<false><<<ctx->sm_count * (l == 1 ? 8 : 2), 128, 0, st>>>(
+                        levels[l]->grids, levels[l]->cell_start, levels[l]->sorted, cur, d_state, dl[(l - 1) & 1], dcount + (l - 1), nn,
+                        dl[l & 1], dcount + l, last ? 1 : 0);
                     PCR_LAUNCH_CHECK(ctx);
                 }
             }
@@ -705,8 +725,15 @@ int icp_dev(Ctx *ctx, const IcpArgs &a, pcr_icp_result *result) {
                                                                           a.params.max_correspondence_distance, d_state, partials);
             PCR_LAUNCH_CHECK(ctx);
         }
+        if (getenv("PCR_DEBUG")) {
+            uint32_t hc[kMaxLevels];
+            cudaMemcpyAsync(hc, dcount, sizeof(hc), cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            fprintf(stderr, "[pcr] icp pass: deferred per level %u %u %u %u of %zu (cells %.3g / %.3g)\n", hc[0], hc[1], hc[2], hc[3], ns,
+                    levels[0]->grids_h[0].h, levels[1]->grids_h[0].h);
+        }
         TimeScope ts2(ctx, kTagIcpSolve);
-        icp_reduce_kernel<<<1, 32, 0, st>>>(partials, n_blocks, ns, d_state);
+        icp_reduce_kernel<<<1, NP * 32, 0, st>>>(partials, n_blocks, ns, d_state);
         PCR_LAUNCH_CHECK(ctx);
         if (ctx->world > 1) PCR_TRY(comm_allreduce_f64(ctx, d_state->sums, NP));
         if (plane) icp_solve_kernel<true><<<1, 32, 0, st>>>(d_state, metrics_only, a.params.tolerance, (int *)h_done);

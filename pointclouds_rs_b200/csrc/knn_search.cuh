@@ -27,6 +27,32 @@ constexpr int kLevelRings = 4;        // shells scanned per grid level before a 
 constexpr int kMaxLevels = 4;
 constexpr uint32_t kBruteFrame = 96;  // frames this small are scanned directly
 
+// Squared lower bound (metres^2) on the distance from the query to anything outside the scanned cube
+// of radius R cells around cell (c0,c1,c2); f = fractional position of the query in that cell
+// (< 0 or >= 1 when the query lies outside the grid and the cell was clamped).  Beyond an open face
+// of axis a a point is at least (R + f)h away along a AND at least gap_b away along every other axis
+// b on which the query is outside the grid -- without the gap term a query 20 m outside the cloud
+// would need 20 m worth of rings to prove its neighbour optimal.  Returns false if no face is open
+// (the whole grid has been scanned).
+__device__ __forceinline__ bool ring_bound2(const GridDesc &g, int c0, int c1, int c2, double f0, double f1, double f2, int R,
+                                            double &bound2) {
+    const double gp0 = f0 < 0.0 ? -f0 : (f0 > 1.0 ? f0 - 1.0 : 0.0);
+    const double gp1 = f1 < 0.0 ? -f1 : (f1 > 1.0 ? f1 - 1.0 : 0.0);
+    const double gp2 = f2 < 0.0 ? -f2 : (f2 > 1.0 ? f2 - 1.0 : 0.0);
+    const double o0 = gp1 * gp1 + gp2 * gp2, o1 = gp0 * gp0 + gp2 * gp2, o2 = gp0 * gp0 + gp1 * gp1;
+    const double r = (double)R;
+    double b = 1e300;
+    bool open = false;
+    if (c0 - R > 0) { open = true; double d = r + f0; b = fmin(b, d * d + o0); }
+    if (c0 + R < g.dims[0] - 1) { open = true; double d = r + 1.0 - f0; b = fmin(b, d * d + o0); }
+    if (c1 - R > 0) { open = true; double d = r + f1; b = fmin(b, d * d + o1); }
+    if (c1 + R < g.dims[1] - 1) { open = true; double d = r + 1.0 - f1; b = fmin(b, d * d + o1); }
+    if (c2 - R > 0) { open = true; double d = r + f2; b = fmin(b, d * d + o2); }
+    if (c2 + R < g.dims[2] - 1) { open = true; double d = r + 1.0 - f2; b = fmin(b, d * d + o2); }
+    bound2 = b * g.h * g.h;
+    return open;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Top-k containers.  Both keep the k best keys in ascending order.
 // ------------------------------------------------------------------------------------------------
@@ -186,20 +212,10 @@ __device__ __forceinline__ bool warp_knn_search(TopK &tk, const GridDesc &g, con
     }
     for (int R = 1;; R++) {
         // nearest face of the scanned cube that still has cells behind it
-        double mf = 1e300;
-        bool open = false;
-        if (c0 - R > 0) { open = true; mf = fmin(mf, f0); }
-        if (c0 + R < d0n - 1) { open = true; mf = fmin(mf, 1.0 - f0); }
-        if (c1 - R > 0) { open = true; mf = fmin(mf, f1); }
-        if (c1 + R < d1n - 1) { open = true; mf = fmin(mf, 1.0 - f1); }
-        if (c2 - R > 0) { open = true; mf = fmin(mf, f2); }
-        if (c2 + R < d2n - 1) { open = true; mf = fmin(mf, 1.0 - f2); }
-        if (!open) return true;  // the whole grid has been scanned
+        double bound2;
+        if (!ring_bound2(g, c0, c1, c2, f0, f1, f2, R, bound2)) return true;  // the whole grid has been scanned
         const unsigned long long kth = tk.kth();
-        if (kth != PCR_EMPTY_KEY) {
-            double bound = ((double)R + mf) * g.h;
-            if (bound > 0.0 && (double)key_d2(kth) < bound * bound * (1.0 - 1e-6)) return true;
-        }
+        if (kth != PCR_EMPTY_KEY && (double)key_d2(kth) < bound2 * (1.0 - 1e-6)) return true;
         if (R >= max_rings) {
             if (!last_level) return false;  // deferred to the next (coarser) level
             // coarsest level: rescan the frame, pruned by the k-th best so far
@@ -377,20 +393,10 @@ __device__ __forceinline__ bool thread_grid_search(Acc &acc, const GridDesc &g, 
         }
         if (whole) return true;
         const int R = S;
-        double mf = 1e300;
-        bool open = false;
-        if (c0 - R > 0) { open = true; mf = fmin(mf, f0); }
-        if (c0 + R < d0n - 1) { open = true; mf = fmin(mf, 1.0 - f0); }
-        if (c1 - R > 0) { open = true; mf = fmin(mf, f1); }
-        if (c1 + R < d1n - 1) { open = true; mf = fmin(mf, 1.0 - f1); }
-        if (c2 - R > 0) { open = true; mf = fmin(mf, f2); }
-        if (c2 + R < d2n - 1) { open = true; mf = fmin(mf, 1.0 - f2); }
-        if (!open) return true;
+        double bound2;
+        if (!ring_bound2(g, c0, c1, c2, f0, f1, f2, R, bound2)) return true;
         const unsigned long long kth = acc.kth();
-        if (kth != PCR_EMPTY_KEY) {
-            double bound = ((double)R + mf) * g.h;
-            if (bound > 0.0 && (double)key_d2(kth) < bound * bound * (1.0 - 1e-6)) return true;
-        }
+        if (kth != PCR_EMPTY_KEY && (double)key_d2(kth) < bound2 * (1.0 - 1e-6)) return true;
         if (!last_level) {
             if (R >= max_rings) return false;
             const int cnt = acc.count();
