@@ -195,6 +195,20 @@ int pcr_icp_point_to_plane_dev(pcr_ctx *ctx, const float *d_sx, const float *d_s
                                size_t nt, const float *d_nx, const float *d_ny, const float *d_nz,
                                size_t n_normals, const pcr_icp_params *params, pcr_icp_result *result);
 
+/* ---- segmentation ------------------------------------------------------------------
+ * euclidean_cluster (crates/segmentation/src/euclidean_cluster.rs:96-101): connected components of
+ * "d^2 <= r^2 between points of key-adjacent cells", clusters with min_size <= size <= max_size,
+ * size descending then first index ascending, indices ascending inside a cluster.  CSR output:
+ * cluster c = indices[offsets[c] .. offsets[c+1]); the caller sizes offsets n + 1 and indices n.
+ * Empty cloud, threshold <= 0 or min_size == 0 -> 0 clusters (:102-104).  Non-finite points are
+ * singleton components. */
+int pcr_euclidean_cluster(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n,
+                          float distance_threshold, size_t min_size, size_t max_size,
+                          uint32_t *offsets, uint32_t *indices, size_t *n_clusters);
+/* Device form: d_labels[i] = smallest index of the component of point i (before the size filter). */
+int pcr_cluster_labels_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z,
+                           size_t n, float distance_threshold, uint32_t *d_labels);
+
 /* ---- multi-frame batch (BASELINE config 5) ------------------------------------------------------
  * Frames are independent clouds stored back to back: frame f = points [frame_offsets[f],
  * frame_offsets[f+1]).  Per frame: SOR(k_sor, std_mul) then normals(k_normals, viewpoint) on the

@@ -91,6 +91,9 @@ def lib():
         L.orc_icp_point_to_point.argtypes = [_f32p] * 3 + [C.c_size_t] + [_f32p] * 3 + [C.c_size_t, C.POINTER(_IcpParams), C.POINTER(_IcpResult), C.c_int]
         L.orc_icp_point_to_plane.restype = C.c_int
         L.orc_icp_point_to_plane.argtypes = [_f32p] * 3 + [C.c_size_t] + [_f32p] * 3 + [C.c_size_t] + [_f32p] * 3 + [C.c_size_t, C.POINTER(_IcpParams), C.POINTER(_IcpResult), C.c_int]
+        for fn in (L.orc_euclidean_cluster, L.orc_euclidean_cluster_brute):
+            fn.restype = C.c_size_t
+            fn.argtypes = [_f32p, _f32p, _f32p, C.c_size_t, C.c_float, C.c_size_t, C.c_size_t, _u32p, _u32p]
         L.orc_voxel_downsample.restype = C.c_size_t
         L.orc_voxel_downsample.argtypes = [_f32p, _f32p, _f32p, C.c_size_t, C.c_float, _f32p, _f32p, _f32p]
         L.orc_read_pcd_ascii.restype = C.c_long
@@ -307,6 +310,18 @@ def icp_point_to_plane(source, target, target_normals, max_iterations=50, tolera
             f"target_normals length ({len(nx)}) does not match target cloud length ({len(tx)})"
         )
     return _icp_out(res)
+
+
+def euclidean_cluster(pts, distance_threshold, min_size, max_size, brute=False):
+    """euclidean_cluster.rs:96-187 -> list of index arrays (reference order).  brute=True: the O(n^2)
+    checker of tests/cluster_differential.rs."""
+    x, y, z = _xyz(pts)
+    n = len(x)
+    off = np.zeros(n + 1, np.uint32)
+    idx = np.zeros(max(n, 1), np.uint32)
+    fn = lib().orc_euclidean_cluster_brute if brute else lib().orc_euclidean_cluster
+    nc = fn(_p(x, _f32p), _p(y, _f32p), _p(z, _f32p), n, float(distance_threshold), int(min_size), int(max_size), _p(off, _u32p), _p(idx, _u32p))
+    return [idx[off[c]:off[c + 1]].copy() for c in range(nc)]
 
 
 def voxel_downsample(pts, voxel_size):

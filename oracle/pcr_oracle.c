@@ -1177,6 +1177,165 @@ size_t orc_voxel_downsample(const float *x, const float *y, const float *z, size
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* euclidean_cluster  (crates/segmentation/src/euclidean_cluster.rs:96-187)                   */
+/* ------------------------------------------------------------------------------------------ */
+
+typedef struct {
+    uint32_t *parent;
+    uint8_t *rank;
+} orc_uf;
+
+static uint32_t uf_find(orc_uf *u, uint32_t x) { /* :20-28, path splitting */
+    while (u->parent[x] != x) {
+        uint32_t p = u->parent[x];
+        u->parent[x] = u->parent[p];
+        x = u->parent[x];
+    }
+    return x;
+}
+
+static void uf_union(orc_uf *u, uint32_t a, uint32_t b) { /* :30-46, union by rank */
+    uint32_t ra = uf_find(u, a), rb = uf_find(u, b);
+    if (ra == rb) return;
+    if (u->rank[ra] < u->rank[rb]) u->parent[ra] = rb;
+    else if (u->rank[ra] > u->rank[rb]) u->parent[rb] = ra;
+    else {
+        u->parent[rb] = ra;
+        u->rank[ra]++;
+    }
+}
+
+static int cmp_key3(const int32_t *a, const int32_t *b) {
+    for (int c = 0; c < 3; c++)
+        if (a[c] != b[c]) return a[c] < b[c] ? -1 : 1;
+    return 0;
+}
+
+/* first entry of `keys` (sorted) whose key equals k, or -1 */
+static long find_cell(const vox_key *keys, size_t m, const int32_t k[3]) {
+    size_t lo = 0, hi = m;
+    while (lo < hi) {
+        size_t mid = (lo + hi) / 2;
+        if (cmp_key3(keys[mid].k, k) < 0) lo = mid + 1;
+        else hi = mid;
+    }
+    return (lo < m && cmp_key3(keys[lo].k, k) == 0) ? (long)lo : -1;
+}
+
+typedef struct {
+    uint32_t root, size, first;
+} orc_comp;
+
+static int cmp_comp(const void *a, const void *b) { /* :183-185: size descending, then lexicographic */
+    const orc_comp *p = (const orc_comp *)a, *q = (const orc_comp *)b;
+    if (p->size != q->size) return p->size > q->size ? -1 : 1;
+    return p->first < q->first ? -1 : (p->first > q->first ? 1 : 0);
+}
+
+/* components of `parent` -> CSR in the reference's output order; returns the cluster count */
+static size_t emit_clusters(orc_uf *u, size_t n, size_t min_size, size_t max_size, uint32_t *offsets, uint32_t *indices) {
+    uint32_t *root = (uint32_t *)malloc(sizeof(uint32_t) * n), *size = (uint32_t *)calloc(n, sizeof(uint32_t));
+    uint32_t *first = (uint32_t *)malloc(sizeof(uint32_t) * n), *slot = (uint32_t *)malloc(sizeof(uint32_t) * n);
+    for (size_t i = 0; i < n; i++) {
+        root[i] = uf_find(u, (uint32_t)i); /* :164-168 */
+        if (size[root[i]]++ == 0) first[root[i]] = (uint32_t)i;
+    }
+    orc_comp *comps = (orc_comp *)malloc(sizeof(orc_comp) * n);
+    size_t nc = 0;
+    for (size_t r = 0; r < n; r++)
+        if (size[r] && size[r] >= min_size && size[r] <= max_size) { /* :172-175 */
+            comps[nc].root = (uint32_t)r;
+            comps[nc].size = size[r];
+            comps[nc].first = first[r];
+            nc++;
+        }
+    qsort(comps, nc, sizeof(orc_comp), cmp_comp);
+    for (size_t r = 0; r < n; r++) slot[r] = UINT32_MAX;
+    offsets[0] = 0;
+    for (size_t c = 0; c < nc; c++) {
+        slot[comps[c].root] = offsets[c];
+        offsets[c + 1] = offsets[c] + comps[c].size;
+    }
+    for (size_t i = 0; i < n; i++) /* ascending i => indices inside a cluster ascending (:177) */
+        if (slot[root[i]] != UINT32_MAX) indices[slot[root[i]]++] = (uint32_t)i;
+    free(root); free(size); free(first); free(slot); free(comps);
+    return nc;
+}
+
+size_t orc_euclidean_cluster(const float *x, const float *y, const float *z, size_t n, float distance_threshold,
+                             size_t min_size, size_t max_size, uint32_t *offsets, uint32_t *indices) {
+    offsets[0] = 0;
+    if (n == 0 || distance_threshold <= 0.0f || min_size == 0) return 0; /* :102-104 */
+    const float inv_r = 1.0f / distance_threshold;               /* :107 */
+    const float r2 = distance_threshold * distance_threshold;    /* :108 */
+    vox_key *keys = (vox_key *)malloc(sizeof(vox_key) * n);
+    size_t m = 0;
+    for (size_t i = 0; i < n; i++) { /* :112-119, cell_key :55-61 */
+        if (!finite3(x[i], y[i], z[i])) continue;
+        keys[m].k[0] = sat_i32(floorf(x[i] * inv_r));
+        keys[m].k[1] = sat_i32(floorf(y[i] * inv_r));
+        keys[m].k[2] = sat_i32(floorf(z[i] * inv_r));
+        keys[m].i = (uint32_t)i;
+        m++;
+    }
+    qsort(keys, m, sizeof(vox_key), cmp_vox); /* cells = runs of equal keys, input order inside a cell */
+    orc_uf u;
+    u.parent = (uint32_t *)malloc(sizeof(uint32_t) * n);
+    u.rank = (uint8_t *)calloc(n, 1);
+    for (size_t i = 0; i < n; i++) u.parent[i] = (uint32_t)i;
+    static const int half[14][3] = {{0, 0, 0},  {1, 0, 0},  {1, 1, 0},   {1, -1, 0}, {1, 0, 1}, {1, 0, -1}, {1, 1, 1},
+                                    {1, 1, -1}, {1, -1, 1}, {1, -1, -1}, {0, 1, 0},  {0, 1, 1}, {0, 1, -1}, {0, 0, 1}}; /* :65-82 */
+    size_t a0 = 0;
+    while (a0 < m) {
+        size_t a1 = a0;
+        while (a1 < m && cmp_key3(keys[a1].k, keys[a0].k) == 0) a1++;
+        for (int o = 0; o < 14; o++) { /* :131-157 */
+            /* i32 wrap-around of cx + dx is a panic in debug Rust / wraps in release; never reached by finite data */
+            int32_t nk[3] = {(int32_t)((int64_t)keys[a0].k[0] + half[o][0]), (int32_t)((int64_t)keys[a0].k[1] + half[o][1]),
+                             (int32_t)((int64_t)keys[a0].k[2] + half[o][2])};
+            long b0 = o == 0 ? (long)a0 : find_cell(keys, m, nk);
+            if (b0 < 0) continue;
+            size_t b1 = (size_t)b0;
+            while (b1 < m && cmp_key3(keys[b1].k, nk) == 0) b1++;
+            for (size_t ai = a0; ai < a1; ai++) {
+                const uint32_t ia = keys[ai].i;
+                size_t start = o == 0 ? ai + 1 : (size_t)b0; /* :145 */
+                for (size_t bi = start; bi < b1; bi++) {
+                    const uint32_t ib = keys[bi].i;
+                    if (dist2(x[ia], y[ia], z[ia], x[ib], y[ib], z[ib]) <= r2) uf_union(&u, ia, ib); /* :147-151, :160-165 */
+                }
+            }
+        }
+        a0 = a1;
+    }
+    size_t nc = emit_clusters(&u, n, min_size, max_size, offsets, indices);
+    free(keys); free(u.parent); free(u.rank);
+    return nc;
+}
+
+/* tests/cluster_differential.rs:13-82: the reference's own O(n^2) checker */
+size_t orc_euclidean_cluster_brute(const float *x, const float *y, const float *z, size_t n, float distance_threshold,
+                                   size_t min_size, size_t max_size, uint32_t *offsets, uint32_t *indices) {
+    offsets[0] = 0;
+    if (n == 0 || distance_threshold <= 0.0f || min_size == 0) return 0;
+    const float r2 = distance_threshold * distance_threshold;
+    orc_uf u;
+    u.parent = (uint32_t *)malloc(sizeof(uint32_t) * n);
+    u.rank = (uint8_t *)calloc(n, 1);
+    for (size_t i = 0; i < n; i++) u.parent[i] = (uint32_t)i;
+    for (size_t i = 0; i < n; i++) {
+        if (!finite3(x[i], y[i], z[i])) continue;
+        for (size_t j = i + 1; j < n; j++) {
+            if (!finite3(x[j], y[j], z[j])) continue;
+            if (dist2(x[i], y[i], z[i], x[j], y[j], z[j]) <= r2) uf_union(&u, (uint32_t)i, (uint32_t)j);
+        }
+    }
+    size_t nc = emit_clusters(&u, n, min_size, max_size, offsets, indices);
+    free(u.parent); free(u.rank);
+    return nc;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* ASCII PCD body reader (crates/io/src/pcd.rs:202-234)                                       */
 /* ------------------------------------------------------------------------------------------ */
 

@@ -116,6 +116,17 @@ int orc_icp_point_to_plane(const float *sx, const float *sy, const float *sz, si
                            const float *nx, const float *ny, const float *nz, size_t nn,
                            const orc_icp_params *p, orc_icp_result *out, int threads);
 
+/* crates/segmentation/src/euclidean_cluster.rs:96-187.  CSR output in the reference's order (size
+ * descending, then smallest index ascending; indices ascending inside a cluster): offsets needs
+ * n + 1 entries, indices n.  Returns the number of clusters.  Non-finite points are singleton
+ * components (:112-119 leaves them out of the grid, :164-168 still lists them).  The dx*dx+dy*dy+dz*dz
+ * of :147-150 is the same left-to-right f32 expression as kiddo's d^2. */
+size_t orc_euclidean_cluster(const float *x, const float *y, const float *z, size_t n, float distance_threshold,
+                             size_t min_size, size_t max_size, uint32_t *offsets, uint32_t *indices);
+/* tests/cluster_differential.rs:13-82 (the reference's own brute-force checker), same output form */
+size_t orc_euclidean_cluster_brute(const float *x, const float *y, const float *z, size_t n, float distance_threshold,
+                                   size_t min_size, size_t max_size, uint32_t *offsets, uint32_t *indices);
+
 /* crates/filters/src/voxel_downsample.rs:12-65.  Outputs sized n; returns voxel count,
  * or (size_t)-1 if voxel_size is not finite / <= 0 (the reference panics, :13-16). */
 size_t orc_voxel_downsample(const float *x, const float *y, const float *z, size_t n,

@@ -20,7 +20,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
-from typing import Optional, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 
@@ -31,7 +31,7 @@ __all__ = [
     "PointCloud", "KdTree", "IcpResult", "Context",
     "statistical_outlier_removal", "radius_outlier_removal", "estimate_normals",
     "icp_point_to_point", "icp_point_to_plane", "apply_transform", "find_correspondences",
-    "sor_normals_batch", "default_context", "PcrError",
+    "sor_normals_batch", "default_context", "PcrError", "euclidean_cluster",
 ]
 
 
@@ -333,6 +333,40 @@ def ror_mask(cloud: PointCloud, radius: float, min_neighbors: int, ctx: Optional
 def radius_outlier_removal(cloud: PointCloud, radius: float, min_neighbors: int, ctx: Optional[Context] = None) -> PointCloud:
     keep, _ = ror_mask(cloud, radius, min_neighbors, ctx)
     return cloud.select(np.nonzero(keep)[0])
+
+
+# ---------------------------------------------------------------------------------------------------
+# segmentation
+# ---------------------------------------------------------------------------------------------------
+
+def euclidean_cluster(cloud: PointCloud, distance_threshold: float, min_size: int, max_size: int,
+                      ctx: Optional[Context] = None) -> List[List[int]]:
+    """crates/python/src/segmentation.rs:4-17 -> list of index lists (largest cluster first)."""
+    ctx = ctx or default_context()
+    n = len(cloud)
+    off = np.zeros(n + 1, np.uint32)
+    idx = np.zeros(max(n, 1), np.uint32)
+    nc = C.c_size_t()
+    st = _ffi.load().pcr_euclidean_cluster(ctx._h, _p(cloud.x, _ffi.f32p), _p(cloud.y, _ffi.f32p), _p(cloud.z, _ffi.f32p), n,
+                                           float(distance_threshold), int(min_size), int(max_size), _p(off, _ffi.u32p),
+                                           _p(idx, _ffi.u32p), C.byref(nc))
+    _ffi.check(st, ctx._h)
+    return [idx[off[c]:off[c + 1]].tolist() for c in range(int(nc.value))]
+
+
+def cluster_arrays(cloud: PointCloud, distance_threshold: float, min_size: int, max_size: int, ctx: Optional[Context] = None):
+    """Same call, CSR form (offsets, indices) without building Python lists."""
+    ctx = ctx or default_context()
+    n = len(cloud)
+    off = np.zeros(n + 1, np.uint32)
+    idx = np.zeros(max(n, 1), np.uint32)
+    nc = C.c_size_t()
+    st = _ffi.load().pcr_euclidean_cluster(ctx._h, _p(cloud.x, _ffi.f32p), _p(cloud.y, _ffi.f32p), _p(cloud.z, _ffi.f32p), n,
+                                           float(distance_threshold), int(min_size), int(max_size), _p(off, _ffi.u32p),
+                                           _p(idx, _ffi.u32p), C.byref(nc))
+    _ffi.check(st, ctx._h)
+    k = int(nc.value)
+    return off[:k + 1].copy(), idx[:int(off[k])].copy()
 
 
 # ---------------------------------------------------------------------------------------------------

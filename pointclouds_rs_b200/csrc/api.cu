@@ -611,6 +611,44 @@ int pcr_radius_outlier(pcr_ctx *ctx, const float *x, const float *y, const float
     PCR_API_END(c)
 }
 
+/* ---- segmentation ---------------------------------------------------------------------------------- */
+int pcr_cluster_labels_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n, float distance_threshold,
+                           uint32_t *d_labels) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (n && (!d_x || !d_y || !d_z || !d_labels)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (distance_threshold <= 0.0f) return fail(c, PCR_ERR_INVALID_ARG, "distance_threshold must be > 0");
+    if (n == 0) return PCR_OK;
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    return cluster_labels_dev(c, d_x, d_y, d_z, n, distance_threshold, d_labels);
+    PCR_API_END(c)
+}
+
+int pcr_euclidean_cluster(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n, float distance_threshold,
+                          size_t min_size, size_t max_size, uint32_t *offsets, uint32_t *indices, size_t *n_clusters) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (n_clusters) *n_clusters = 0;
+    if (!offsets || !n_clusters) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    offsets[0] = 0;
+    if (n && (!x || !y || !z || !indices)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (n == 0 || distance_threshold <= 0.0f || min_size == 0) return PCR_OK;  // euclidean_cluster.rs:102-104
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    float *dx, *dy, *dz;
+    PCR_TRY(stage_xyz(c, c->b_in, x, y, z, n, &dx, &dy, &dz));
+    PCR_TRY(ensure(c, c->b_out, n * sizeof(uint32_t)));
+    uint32_t *d_labels = (uint32_t *)c->b_out.p;
+    PCR_TRY(cluster_labels_dev(c, dx, dy, dz, n, distance_threshold, d_labels));
+    std::vector<uint32_t> labels(n), scratch;
+    PCR_CUDA(c, cudaMemcpyAsync(labels.data(), d_labels, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    *n_clusters = clusters_from_labels(labels.data(), n, min_size, max_size, offsets, indices, scratch);
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
 /* ---- normals -------------------------------------------------------------------------------------- */
 int pcr_estimate_normals_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n, size_t k,
                              const float viewpoint[3], float *d_nx, float *d_ny, float *d_nz) {

@@ -195,6 +195,11 @@ int find_correspondences_dev(Index *target, const float *dsx, const float *dsy, 
 int apply_transform_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz, size_t n,
                         const float R[9], const float t[3], float *ox, float *oy, float *oz);
 
+// euclidean_cluster (cluster.cu): labels[i] = smallest index of the component of point i
+int cluster_labels_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz, size_t n, float threshold, uint32_t *d_labels);
+size_t clusters_from_labels(const uint32_t *labels, size_t n, size_t min_size, size_t max_size, uint32_t *offsets, uint32_t *indices,
+                            std::vector<uint32_t> &scratch);
+
 // NCCL plumbing (comm.cu)
 int comm_unique_id(void *out);
 int comm_init(Ctx *ctx, const void *id, int rank, int world);
