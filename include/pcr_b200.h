@@ -195,6 +195,17 @@ int pcr_icp_point_to_plane_dev(pcr_ctx *ctx, const float *d_sx, const float *d_s
                                size_t nt, const float *d_nx, const float *d_ny, const float *d_nz,
                                size_t n_normals, const pcr_icp_params *params, pcr_icp_result *result);
 
+/* ---- voxel grid filter ---------------------------------------------------------------
+ * voxel_downsample (crates/filters/src/voxel_downsample.rs:12-65): one point per occupied voxel
+ * (key = floor(p / voxel_size) as i32), the mean of the voxel's points summed in input order, voxels
+ * in ascending key order.  Outputs sized n; *n_out = number of voxels.  voxel_size not finite or <= 0
+ * -> PCR_ERR_INVALID_ARG (the reference panics, :13-16; its Python layer raises ValueError). */
+int pcr_voxel_downsample(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n,
+                         float voxel_size, float *ox, float *oy, float *oz, size_t *n_out);
+int pcr_voxel_downsample_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z,
+                             size_t n, float voxel_size, float *d_ox, float *d_oy, float *d_oz,
+                             size_t *n_out);
+
 /* ---- segmentation ------------------------------------------------------------------
  * euclidean_cluster (crates/segmentation/src/euclidean_cluster.rs:96-101): connected components of
  * "d^2 <= r^2 between points of key-adjacent cells", clusters with min_size <= size <= max_size,

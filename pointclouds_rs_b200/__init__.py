@@ -31,7 +31,7 @@ __all__ = [
     "PointCloud", "KdTree", "IcpResult", "Context",
     "statistical_outlier_removal", "radius_outlier_removal", "estimate_normals",
     "icp_point_to_point", "icp_point_to_plane", "apply_transform", "find_correspondences",
-    "sor_normals_batch", "default_context", "PcrError", "euclidean_cluster",
+    "sor_normals_batch", "default_context", "PcrError", "euclidean_cluster", "voxel_downsample",
 ]
 
 
@@ -315,6 +315,21 @@ def sor_mask(cloud: PointCloud, k: int, std_mul: float, ctx: Optional[Context] =
 def statistical_outlier_removal(cloud: PointCloud, k: int, std_mul: float, ctx: Optional[Context] = None) -> PointCloud:
     keep, _, _, _ = sor_mask(cloud, k, std_mul, ctx)
     return cloud.select(np.nonzero(keep)[0])  # statistical_outlier.rs:68
+
+
+def voxel_downsample(cloud: PointCloud, voxel_size: float, ctx: Optional[Context] = None) -> PointCloud:
+    """crates/python/src/filters.rs:4-13 (ValueError unless voxel_size > 0 and finite)."""
+    ctx = ctx or default_context()
+    if not math.isfinite(voxel_size) or voxel_size <= 0.0:
+        raise ValueError("voxel_size must be > 0 and finite")
+    n = len(cloud)
+    ox, oy, oz = (np.zeros(max(n, 1), np.float32) for _ in range(3))
+    m = C.c_size_t()
+    st = _ffi.load().pcr_voxel_downsample(ctx._h, _p(cloud.x, _ffi.f32p), _p(cloud.y, _ffi.f32p), _p(cloud.z, _ffi.f32p), n,
+                                          float(voxel_size), _p(ox, _ffi.f32p), _p(oy, _ffi.f32p), _p(oz, _ffi.f32p), C.byref(m))
+    _ffi.check(st, ctx._h)
+    k = int(m.value)
+    return PointCloud._from_xyz(ox[:k].copy(), oy[:k].copy(), oz[:k].copy())
 
 
 def ror_mask(cloud: PointCloud, radius: float, min_neighbors: int, ctx: Optional[Context] = None):

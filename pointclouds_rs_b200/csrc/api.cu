@@ -611,6 +611,50 @@ int pcr_radius_outlier(pcr_ctx *ctx, const float *x, const float *y, const float
     PCR_API_END(c)
 }
 
+/* ---- voxel grid filter ------------------------------------------------------------------------------ */
+int pcr_voxel_downsample_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n, float voxel_size,
+                             float *d_ox, float *d_oy, float *d_oz, size_t *n_out) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (!n_out) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    *n_out = 0;
+    if (!std::isfinite(voxel_size) || !(voxel_size > 0.f)) return fail(c, PCR_ERR_INVALID_ARG, "voxel_size must be > 0 and finite");
+    if (n && (!d_x || !d_y || !d_z || !d_ox || !d_oy || !d_oz)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    return voxel_downsample_dev(c, d_x, d_y, d_z, n, voxel_size, d_ox, d_oy, d_oz, n_out);
+    PCR_API_END(c)
+}
+
+int pcr_voxel_downsample(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n, float voxel_size, float *ox,
+                         float *oy, float *oz, size_t *n_out) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (!n_out) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    *n_out = 0;
+    if (!std::isfinite(voxel_size) || !(voxel_size > 0.f)) return fail(c, PCR_ERR_INVALID_ARG, "voxel_size must be > 0 and finite");
+    if (n && (!x || !y || !z || !ox || !oy || !oz)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (n == 0) return PCR_OK;
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    float *dx, *dy, *dz;
+    PCR_TRY(stage_xyz(c, c->b_in, x, y, z, n, &dx, &dy, &dz));
+    const size_t stride = (n + 63) & ~(size_t)63;
+    PCR_TRY(ensure(c, c->b_out, sizeof(float) * 3 * stride));
+    float *o0 = (float *)c->b_out.p, *o1 = o0 + stride, *o2 = o1 + stride;
+    size_t m = 0;
+    PCR_TRY(voxel_downsample_dev(c, dx, dy, dz, n, voxel_size, o0, o1, o2, &m));
+    if (m) {
+        PCR_CUDA(c, cudaMemcpyAsync(ox, o0, m * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        PCR_CUDA(c, cudaMemcpyAsync(oy, o1, m * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        PCR_CUDA(c, cudaMemcpyAsync(oz, o2, m * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    *n_out = m;
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
 /* ---- segmentation ---------------------------------------------------------------------------------- */
 int pcr_cluster_labels_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n, float distance_threshold,
                            uint32_t *d_labels) {

@@ -170,8 +170,8 @@ int cluster_labels_dev(Ctx *ctx, const float *dx, const float *dy, const float *
     while (T < 2u * (uint32_t)n) T <<= 1;
     // scratch: cpts[n] | rep[T] | count[T+1] | slot_of[n] | rank_of[n] | cslot[n] | parent[n]
     const size_t need = sizeof(float4) * n + sizeof(uint32_t) * (2 * (size_t)T + 1 + 4 * n) + 256;
-    PCR_TRY(ensure(ctx, ctx->b_misc2, need));
-    char *p = (char *)ctx->b_misc2.p;
+    PCR_TRY(ensure(ctx, ctx->b_table, need));  // (b_misc2 is the scan's own scratch)
+    char *p = (char *)ctx->b_table.p;
     float4 *cpts = (float4 *)p;
     p += sizeof(float4) * n;
     uint32_t *rep = (uint32_t *)p;

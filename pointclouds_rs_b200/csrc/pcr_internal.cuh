@@ -200,6 +200,12 @@ int cluster_labels_dev(Ctx *ctx, const float *dx, const float *dy, const float *
 size_t clusters_from_labels(const uint32_t *labels, size_t n, size_t min_size, size_t max_size, uint32_t *offsets, uint32_t *indices,
                             std::vector<uint32_t> &scratch);
 
+// voxel_downsample + the stable radix sort it uses (voxel.cu)
+int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz, size_t n, float voxel, float *d_ox, float *d_oy,
+                         float *d_oz, size_t *n_out);
+int radix_sort_pairs_dev(Ctx *ctx, unsigned long long **keys, uint32_t **vals, unsigned long long **keys_alt, uint32_t **vals_alt,
+                         size_t n, int bits, uint32_t *d_hist);
+
 // NCCL plumbing (comm.cu)
 int comm_unique_id(void *out);
 int comm_init(Ctx *ctx, const void *id, int rank, int world);

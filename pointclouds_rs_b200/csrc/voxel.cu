@@ -1,0 +1,328 @@
+// voxel.cu -- voxel_downsample (crates/filters/src/voxel_downsample.rs:12-65) on the GPU, and the
+// stable LSD radix sort it is built on.
+//
+// The reference accumulates, per voxel key (floor(p / voxel) as i32, :32-36), the f32 sums of x, y, z
+// in INPUT order (:38-42: sequential f32 additions, so the order is part of the result), divides by the
+// count and emits the voxels in ascending key order (:49-50).  One stable sort of (packed key, index)
+// pairs gives both orders at once: equal keys keep their input order, and the runs come out in key
+// order.
+//
+//   vox_range_kernel   key range of the finite points (warp redux + atomics)             12 B/pt
+//   vox_pack_kernel    packed u64 key per point (non-finite points sort last)            12 + 12 B/pt
+//   radix passes       8 bits per pass over the significant bits only (KITTI frame at 5 cm: 29 bits,
+//                      4 passes); one WARP owns a tile of 1024 consecutive pairs and walks it in order,
+//                      __match_any_sync ranks equal digits inside a round of 32, running per-digit
+//                      offsets in shared memory carry the order across rounds: stable by construction
+//   vox_heads_kernel   run heads -> voxel ids (exclusive scan) -> run starts
+//   vox_mean_kernel    one thread per voxel: the reference's sequential f32 sums, then / count
+// If the key box needs more than 63 bits (a far outlier with a tiny voxel) the same sort runs three
+// times on 32-bit axis keys (z, then y, then x): stable LSD over the axes.
+#include "pcr_internal.cuh"
+
+#include <algorithm>
+
+namespace pcr {
+
+namespace {
+
+constexpr int kSortRounds = 32;                  // rounds of 32 pairs per warp tile
+constexpr int kSortTile = 32 * kSortRounds;      // 1024 pairs
+constexpr int kSortWarps = 4;                    // warps (tiles) per block
+
+struct VoxRange {
+    int mn[3];
+    int mx[3];
+    unsigned finite;
+};
+
+// voxel_downsample.rs:32-36: (p / voxel).floor() as i32 -- IEEE division, round down, saturate, NaN -> 0
+__device__ __forceinline__ int vox_cell(float v, float voxel) { return __float2int_rd(__fdiv_rn(v, voxel)); }
+
+__global__ void vox_init_kernel(VoxRange *r) {
+    for (int a = 0; a < 3; a++) {
+        r->mn[a] = 2147483647;
+        r->mx[a] = -2147483647 - 1;
+    }
+    r->finite = 0;
+}
+
+__global__ void __launch_bounds__(256) vox_range_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                                                        const float *__restrict__ z, size_t n, float voxel, VoxRange *r) {
+    int mn[3] = {2147483647, 2147483647, 2147483647}, mx[3] = {-2147483647 - 1, -2147483647 - 1, -2147483647 - 1};
+    unsigned cnt = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float px = x[i], py = y[i], pz = z[i];
+        if (!finite3(px, py, pz)) continue;  // :28-30
+        const int k[3] = {vox_cell(px, voxel), vox_cell(py, voxel), vox_cell(pz, voxel)};
+        for (int a = 0; a < 3; a++) {
+            mn[a] = min(mn[a], k[a]);
+            mx[a] = max(mx[a], k[a]);
+        }
+        cnt++;
+    }
+    for (int a = 0; a < 3; a++) {
+        mn[a] = __reduce_min_sync(PCR_FULL, mn[a]);
+        mx[a] = __reduce_max_sync(PCR_FULL, mx[a]);
+    }
+    cnt = __reduce_add_sync(PCR_FULL, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        for (int a = 0; a < 3; a++) {
+            atomicMin(&r->mn[a], mn[a]);
+            atomicMax(&r->mx[a], mx[a]);
+        }
+        atomicAdd(&r->finite, cnt);
+    }
+}
+
+// axis < 0: packed key ((kx - mn0) << s0) | ((ky - mn1) << s1) | (kz - mn2); axis 0..2: that axis alone
+// (biased to unsigned).  Non-finite points get `last`, above every real key.
+__global__ void __launch_bounds__(256) vox_pack_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                                                       const float *__restrict__ z, const uint32_t *order, size_t n,
+                                                       float voxel, int axis, int mn0, int mn1, int mn2, int s0, int s1,
+                                                       unsigned long long last, unsigned long long *__restrict__ keys,
+                                                       uint32_t *vals /* may alias order */) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t i = order ? order[t] : (uint32_t)t;
+    const float px = x[i], py = y[i], pz = z[i];
+    unsigned long long key = last;
+    if (finite3(px, py, pz)) {
+        const int kx = vox_cell(px, voxel), ky = vox_cell(py, voxel), kz = vox_cell(pz, voxel);
+        if (axis < 0)
+            key = ((unsigned long long)(uint32_t)(kx - mn0) << s0) | ((unsigned long long)(uint32_t)(ky - mn1) << s1) |
+                  (unsigned long long)(uint32_t)(kz - mn2);
+        else
+            key = (unsigned long long)((uint32_t)(axis == 0 ? kx : (axis == 1 ? ky : kz)) ^ 0x80000000u);
+    }
+    keys[t] = key;
+    vals[t] = i;
+}
+
+// ---- stable LSD radix sort, 8 bits per pass -----------------------------------------------------------
+// hist[digit * n_tiles + tile] = number of pairs of `tile` with that digit
+__global__ void __launch_bounds__(32 * kSortWarps) sort_hist_kernel(const unsigned long long *__restrict__ keys, size_t n, int shift,
+                                                                    uint32_t n_tiles, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t cnt[kSortWarps][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x * kSortWarps + w;
+    for (int d = lane; d < 256; d += 32) cnt[w][d] = 0;
+    __syncwarp();
+    if (tile < n_tiles) {
+        const size_t base = (size_t)tile * kSortTile;
+        for (int r = 0; r < kSortRounds; r++) {
+            const size_t i = base + (size_t)r * 32 + lane;
+            const bool valid = i < n;
+            const unsigned vmask = __ballot_sync(PCR_FULL, valid);
+            if (valid) {
+                const unsigned d = (unsigned)(keys[i] >> shift) & 255u;
+                const unsigned peers = __match_any_sync(vmask, d);
+                if (lane == __ffs(peers) - 1) cnt[w][d] += __popc(peers);
+            }
+            __syncwarp();
+        }
+        for (int d = lane; d < 256; d += 32) hist[(size_t)d * n_tiles + tile] = cnt[w][d];
+    }
+}
+
+__global__ void __launch_bounds__(32 * kSortWarps) sort_scatter_kernel(const unsigned long long *__restrict__ keys,
+                                                                       const uint32_t *__restrict__ vals, size_t n, int shift,
+                                                                       uint32_t n_tiles, const uint32_t *__restrict__ offs,
+                                                                       unsigned long long *__restrict__ keys_out,
+                                                                       uint32_t *__restrict__ vals_out) {
+    __shared__ uint32_t pos[kSortWarps][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x * kSortWarps + w;
+    if (tile >= n_tiles) return;
+    for (int d = lane; d < 256; d += 32) pos[w][d] = offs[(size_t)d * n_tiles + tile];
+    __syncwarp();
+    const size_t base = (size_t)tile * kSortTile;
+    for (int r = 0; r < kSortRounds; r++) {
+        const size_t i = base + (size_t)r * 32 + lane;
+        const bool valid = i < n;
+        const unsigned vmask = __ballot_sync(PCR_FULL, valid);
+        unsigned long long key = 0;
+        uint32_t val = 0, dst = 0;
+        unsigned d = 0, peers = 0;
+        if (valid) {
+            key = keys[i];
+            val = vals[i];
+            d = (unsigned)(key >> shift) & 255u;
+            peers = __match_any_sync(vmask, d);
+            dst = pos[w][d] + __popc(peers & ((1u << lane) - 1u));  // earlier lanes = earlier input positions
+        }
+        __syncwarp();
+        if (valid && lane == __ffs(peers) - 1) pos[w][d] += __popc(peers);
+        __syncwarp();
+        if (valid) {
+            keys_out[dst] = key;
+            vals_out[dst] = val;
+        }
+    }
+}
+
+// ---- runs -> voxels -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vox_heads_kernel(const unsigned long long *__restrict__ keys, uint32_t m, uint32_t *__restrict__ flag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > m) return;
+    flag[i] = (i < m && (i == 0 || keys[i] != keys[i - 1])) ? 1u : 0u;  // flag[m] = 0: slot of the total
+}
+
+// the three-pass (z, y, x) fallback has no packed key: heads are compared on the recomputed triple
+__global__ void __launch_bounds__(256) vox_heads_triple_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                                                               const float *__restrict__ z, const uint32_t *__restrict__ vals, uint32_t m,
+                                                               float voxel, uint32_t *__restrict__ flag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > m) return;
+    uint32_t f = 0;
+    if (i < m) {
+        f = 1;
+        if (i > 0) {
+            const uint32_t a = vals[i], b = vals[i - 1];
+            f = (vox_cell(x[a], voxel) != vox_cell(x[b], voxel) || vox_cell(y[a], voxel) != vox_cell(y[b], voxel) ||
+                 vox_cell(z[a], voxel) != vox_cell(z[b], voxel))
+                    ? 1u
+                    : 0u;
+        }
+    }
+    flag[i] = f;
+}
+
+// vid = exclusive scan of the head flags (m + 1 entries, vid[m] = number of voxels): position i is a
+// head iff vid[i + 1] != vid[i], and then it starts voxel vid[i]
+__global__ void __launch_bounds__(256) vox_starts_kernel(const uint32_t *__restrict__ vid, uint32_t m, uint32_t *__restrict__ start) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > m) return;
+    if (i == m) {
+        start[vid[m]] = m;  // end sentinel of the last voxel
+        return;
+    }
+    if (vid[i + 1] != vid[i]) start[vid[i]] = i;
+}
+
+__global__ void __launch_bounds__(128) vox_mean_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
+                                                       const uint32_t *__restrict__ vals, const uint32_t *__restrict__ start,
+                                                       const uint32_t *__restrict__ n_vox_dev, float *__restrict__ ox,
+                                                       float *__restrict__ oy, float *__restrict__ oz) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= *n_vox_dev) return;
+    const uint32_t b = start[v], e = start[v + 1];
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (uint32_t i = b; i < e; i++) {  // :38-42, input order (the sort is stable)
+        const uint32_t p = vals[i];
+        sx = __fadd_rn(sx, x[p]);
+        sy = __fadd_rn(sy, y[p]);
+        sz = __fadd_rn(sz, z[p]);
+    }
+    const float denom = (float)(e - b);  // :56
+    ox[v] = __fdiv_rn(sx, denom);
+    oy[v] = __fdiv_rn(sy, denom);
+    oz[v] = __fdiv_rn(sz, denom);
+}
+
+int bits_for(uint64_t range) {  // smallest b with 2^b >= range
+    int b = 0;
+    while (b < 64 && (1ull << b) < range) b++;
+    return b;
+}
+
+}  // namespace
+
+// Sorts the n (key, val) pairs by the low `bits` bits of the key, stably.  The result is in
+// (*keys, *vals): the pointers are swapped with the alternate buffers after every pass.
+int radix_sort_pairs_dev(Ctx *ctx, unsigned long long **keys, uint32_t **vals, unsigned long long **keys_alt, uint32_t **vals_alt,
+                         size_t n, int bits, uint32_t *d_hist /* 256 * n_tiles + 1 */) {
+    if (n == 0) return PCR_OK;
+    const uint32_t n_tiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
+    const unsigned blocks = (n_tiles + kSortWarps - 1) / kSortWarps;
+    for (int shift = 0; shift < bits; shift += 8) {
+        sort_hist_kernel<<<blocks, 32 * kSortWarps, 0, ctx->stream>>>(*keys, n, shift, n_tiles, d_hist);
+        PCR_LAUNCH_CHECK(ctx);
+        PCR_TRY(exclusive_scan_u32_dev(ctx, d_hist, (size_t)256 * n_tiles + 1));
+        sort_scatter_kernel<<<blocks, 32 * kSortWarps, 0, ctx->stream>>>(*keys, *vals, n, shift, n_tiles, d_hist, *keys_alt, *vals_alt);
+        PCR_LAUNCH_CHECK(ctx);
+        std::swap(*keys, *keys_alt);
+        std::swap(*vals, *vals_alt);
+    }
+    return PCR_OK;
+}
+
+// voxel_downsample on device arrays.  Outputs sized n; *n_out = number of voxels.  One host round trip
+// (key range), one more for the count.
+int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz, size_t n, float voxel, float *d_ox, float *d_oy,
+                         float *d_oz, size_t *n_out) {
+    *n_out = 0;
+    if (n == 0) return PCR_OK;  // :18-20
+    if (n > 0x7fffffffull) return fail(ctx, PCR_ERR_UNSUPPORTED, "clouds above 2^31 points are not supported");
+    cudaStream_t st = ctx->stream;
+    TimeScope ts(ctx, kTagOther);
+    PCR_TRY(ensure(ctx, ctx->b_small, 4096));
+    PCR_TRY(ensure_pinned(ctx, 4096));
+    VoxRange *d_range = (VoxRange *)ctx->b_small.p;
+    uint32_t *d_nvox = (uint32_t *)((char *)ctx->b_small.p + 256);
+    VoxRange *h_range = (VoxRange *)ctx->pinned;
+    vox_init_kernel<<<1, 1, 0, st>>>(d_range);
+    PCR_LAUNCH_CHECK(ctx);
+    const unsigned bx = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
+    vox_range_kernel<<<bx, 256, 0, st>>>(dx, dy, dz, n, voxel, d_range);
+    PCR_LAUNCH_CHECK(ctx);
+    PCR_CUDA(ctx, cudaMemcpyAsync(h_range, d_range, sizeof(VoxRange), cudaMemcpyDeviceToHost, st));
+    PCR_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t m = h_range->finite;
+    if (m == 0) return PCR_OK;  // :45-47
+    int bits[3];
+    for (int a = 0; a < 3; a++) bits[a] = bits_for((uint64_t)((int64_t)h_range->mx[a] - (int64_t)h_range->mn[a]) + 1);
+    const int total_bits = bits[0] + bits[1] + bits[2];
+    const bool packed = total_bits <= 63;
+
+    // scratch (b_table): keys A/B u64[n] | vals A/B u32[n] | hist u32[256 * tiles + 1] | flag/vid u32[n + 1] | start u32[n + 1]
+    const size_t n_tiles = (n + kSortTile - 1) / kSortTile;
+    const size_t need = 2 * sizeof(unsigned long long) * n + sizeof(uint32_t) * (2 * n + 256 * n_tiles + 1 + 2 * (n + 1)) + 1024;
+    PCR_TRY(ensure(ctx, ctx->b_table, need));
+    char *p = (char *)ctx->b_table.p;
+    unsigned long long *kA = (unsigned long long *)p;
+    p += sizeof(unsigned long long) * n;
+    unsigned long long *kB = (unsigned long long *)p;
+    p += sizeof(unsigned long long) * n;
+    uint32_t *vA = (uint32_t *)p;
+    p += sizeof(uint32_t) * n;
+    uint32_t *vB = (uint32_t *)p;
+    p += sizeof(uint32_t) * n;
+    uint32_t *hist = (uint32_t *)p;
+    p += sizeof(uint32_t) * (256 * n_tiles + 1);
+    uint32_t *vid = (uint32_t *)p;
+    p += sizeof(uint32_t) * (n + 1);
+    uint32_t *start = (uint32_t *)p;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (packed) {
+        const unsigned long long last = 1ull << total_bits;  // non-finite points: above every real key
+        vox_pack_kernel<<<nb, 256, 0, st>>>(dx, dy, dz, nullptr, n, voxel, -1, h_range->mn[0], h_range->mn[1], h_range->mn[2],
+                                            bits[1] + bits[2], bits[2], last, kA, vA);
+        PCR_LAUNCH_CHECK(ctx);
+        PCR_TRY(radix_sort_pairs_dev(ctx, &kA, &vA, &kB, &vB, n, total_bits + 1, hist));
+        vox_heads_kernel<<<(m + 1 + 255) / 256, 256, 0, st>>>(kA, m, vid);
+        PCR_LAUNCH_CHECK(ctx);
+    } else {
+        const unsigned long long last = 1ull << 32;
+        for (int axis = 2; axis >= 0; axis--) {  // LSD over the axes: z, y, x
+            // after the first pass vA holds the order so far; the pack kernel reads and rewrites it in place
+            vox_pack_kernel<<<nb, 256, 0, st>>>(dx, dy, dz, axis == 2 ? nullptr : vA, n, voxel, axis, 0, 0, 0, 0, 0, last, kA, vA);
+            PCR_LAUNCH_CHECK(ctx);
+            PCR_TRY(radix_sort_pairs_dev(ctx, &kA, &vA, &kB, &vB, n, 33, hist));
+        }
+        vox_heads_triple_kernel<<<(m + 1 + 255) / 256, 256, 0, st>>>(dx, dy, dz, vA, m, voxel, vid);
+        PCR_LAUNCH_CHECK(ctx);
+    }
+    PCR_TRY(exclusive_scan_u32_dev(ctx, vid, (size_t)m + 1));  // vid[m] = number of voxels
+    vox_starts_kernel<<<(m + 1 + 255) / 256, 256, 0, st>>>(vid, m, start);
+    PCR_LAUNCH_CHECK(ctx);
+    PCR_CUDA(ctx, cudaMemcpyAsync(d_nvox, vid + m, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    vox_mean_kernel<<<(m + 127) / 128, 128, 0, st>>>(dx, dy, dz, vA, start, d_nvox, d_ox, d_oy, d_oz);
+    PCR_LAUNCH_CHECK(ctx);
+    uint32_t *mail = (uint32_t *)ctx->pinned + 64;
+    PCR_CUDA(ctx, cudaMemcpyAsync(mail, d_nvox, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PCR_CUDA(ctx, cudaStreamSynchronize(st));
+    *n_out = *mail;
+    return PCR_OK;
+}
+
+}  // namespace pcr
