@@ -147,6 +147,9 @@ int pcr_sor_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d
 int pcr_radius_outlier(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n,
                        float radius, size_t min_neighbors, uint8_t *keep, size_t *n_kept);
 
+int pcr_radius_outlier_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n,
+                           float radius, size_t min_neighbors, uint8_t *d_keep);
+
 /* ---- normals ----------------------------------------------------------------------------------- */
 int pcr_estimate_normals(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n,
                          size_t k, const float viewpoint[3], float *nx, float *ny, float *nz);
@@ -234,6 +237,41 @@ int pcr_sor_normals_batch_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, 
                               size_t k_sor, float std_mul, size_t k_normals,
                               const float viewpoint[3], uint8_t *d_keep, float *d_nx, float *d_ny,
                               float *d_nz);
+
+/* ---- device-resident clouds ---------------------------------------------------------
+ * PointCloud (crates/core/src/cloud.rs:4-18) kept in HBM between the steps of a pipeline: one upload,
+ * one download, `select` (cloud.rs:103-140) as a device compaction that carries the normals along.
+ * Every function that returns a cloud allocates a new handle (free it with pcr_cloud_free); inputs
+ * are never modified.  Edge cases follow the reference functions named on each line. */
+typedef struct pcr_cloud pcr_cloud;
+int pcr_cloud_upload(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n, pcr_cloud **out);
+void pcr_cloud_free(pcr_cloud *cloud);
+size_t pcr_cloud_len(const pcr_cloud *cloud);
+int pcr_cloud_has_normals(const pcr_cloud *cloud);
+int pcr_cloud_download(const pcr_cloud *cloud, float *x, float *y, float *z);            /* arrays of pcr_cloud_len */
+int pcr_cloud_download_normals(const pcr_cloud *cloud, float *nx, float *ny, float *nz);
+/* device pointers of the SoA arrays (valid until the cloud is freed; normals NULL if absent) */
+int pcr_cloud_device_pointers(const pcr_cloud *cloud, const float **d_x, const float **d_y, const float **d_z,
+                              const float **d_nx, const float **d_ny, const float **d_nz);
+/* cloud.rs:103-140; an index >= len -> PCR_ERR_INVALID_ARG (the reference panics, :109) */
+int pcr_cloud_select(const pcr_cloud *cloud, const uint32_t *indices, size_t m, pcr_cloud **out);
+int pcr_cloud_voxel_downsample(const pcr_cloud *cloud, float voxel_size, pcr_cloud **out);           /* voxel_downsample.rs:12 */
+int pcr_cloud_statistical_outlier_removal(const pcr_cloud *cloud, size_t k, float std_mul,
+                                          pcr_cloud **out);                                           /* statistical_outlier.rs:4 */
+int pcr_cloud_radius_outlier_removal(const pcr_cloud *cloud, float radius, size_t min_neighbors,
+                                     pcr_cloud **out);                                                /* radius_outlier.rs:4 */
+/* estimate.rs:19: a copy of the cloud with normals attached (viewpoint NULL = origin, :13-15) */
+int pcr_cloud_estimate_normals(const pcr_cloud *cloud, size_t k, const float viewpoint[3], pcr_cloud **out);
+int pcr_cloud_euclidean_cluster(const pcr_cloud *cloud, float distance_threshold, size_t min_size,
+                                size_t max_size, uint32_t *offsets, uint32_t *indices,
+                                size_t *n_clusters);                                                  /* euclidean_cluster.rs:96 */
+int pcr_cloud_apply_transform(const pcr_cloud *cloud, const float rotation[9], const float translation[3],
+                              pcr_cloud **out);                                                       /* icp.rs:77-92 */
+int pcr_cloud_icp_point_to_point(const pcr_cloud *source, const pcr_cloud *target,
+                                 const pcr_icp_params *params, pcr_icp_result *result);              /* icp.rs:125 */
+/* the target must carry normals (crates/python/src/registration.rs:80-86) */
+int pcr_cloud_icp_point_to_plane(const pcr_cloud *source, const pcr_cloud *target,
+                                 const pcr_icp_params *params, pcr_icp_result *result);              /* icp_plane.rs:20 */
 
 #ifdef __cplusplus
 }

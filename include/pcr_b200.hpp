@@ -11,6 +11,9 @@
 //   pcr::find_correspondences            crates/registration/src/correspondence.rs:16
 //   pcr::apply_transform, RigidTransform crates/registration/src/icp.rs:8-92
 //   pcr::icp_point_to_point / _plane     crates/registration/src/icp.rs:125, icp_plane.rs:20
+//   pcr::voxel_downsample                crates/filters/src/voxel_downsample.rs:12
+//   pcr::euclidean_cluster               crates/segmentation/src/euclidean_cluster.rs:96
+//   pcr::DeviceCloud                     the same calls on a cloud that stays in HBM between steps
 #pragma once
 
 #include <cmath>
@@ -266,5 +269,117 @@ inline IcpResult icp_point_to_plane(const PointCloud &source, const PointCloud &
                                      target_normals.nz.data(), target_normals.nx.size(), &cp, &r));
     return detail::to_result(r);
 }
+
+// crates/filters/src/voxel_downsample.rs:12-65 (the reference asserts on a bad voxel size: std::invalid_argument here)
+inline PointCloud voxel_downsample(const PointCloud &cloud, float voxel_size, Context &ctx = default_context()) {
+    if (!std::isfinite(voxel_size) || !(voxel_size > 0.f)) throw std::invalid_argument("voxel_size must be > 0 and finite");
+    const size_t n = cloud.len();
+    std::vector<float> ox(n ? n : 1), oy(n ? n : 1), oz(n ? n : 1);
+    size_t m = 0;
+    ctx.check(pcr_voxel_downsample(ctx.get(), cloud.x.data(), cloud.y.data(), cloud.z.data(), n, voxel_size, ox.data(), oy.data(), oz.data(), &m));
+    ox.resize(m);
+    oy.resize(m);
+    oz.resize(m);
+    return PointCloud::from_xyz(std::move(ox), std::move(oy), std::move(oz));
+}
+
+// crates/segmentation/src/euclidean_cluster.rs:96-187
+inline std::vector<std::vector<size_t>> euclidean_cluster(const PointCloud &cloud, float distance_threshold, size_t min_size,
+                                                          size_t max_size, Context &ctx = default_context()) {
+    const size_t n = cloud.len();
+    std::vector<uint32_t> off(n + 1), idx(n ? n : 1);
+    size_t nc = 0;
+    ctx.check(pcr_euclidean_cluster(ctx.get(), cloud.x.data(), cloud.y.data(), cloud.z.data(), n, distance_threshold, min_size, max_size,
+                                    off.data(), idx.data(), &nc));
+    std::vector<std::vector<size_t>> out(nc);
+    for (size_t c = 0; c < nc; c++) out[c].assign(idx.begin() + off[c], idx.begin() + off[c + 1]);
+    return out;
+}
+
+// A PointCloud that stays in HBM between the steps of a pipeline (one upload, one download).
+class DeviceCloud {
+  public:
+    static DeviceCloud upload(const PointCloud &cloud, Context &ctx = default_context()) {
+        pcr_cloud *h = nullptr;
+        ctx.check(pcr_cloud_upload(ctx.get(), cloud.x.data(), cloud.y.data(), cloud.z.data(), cloud.len(), &h));
+        return DeviceCloud(h, &ctx);
+    }
+    ~DeviceCloud() { pcr_cloud_free(h_); }
+    DeviceCloud(DeviceCloud &&o) noexcept : h_(o.h_), ctx_(o.ctx_) { o.h_ = nullptr; }
+    DeviceCloud &operator=(DeviceCloud &&o) noexcept {
+        if (this != &o) {
+            pcr_cloud_free(h_);
+            h_ = o.h_;
+            ctx_ = o.ctx_;
+            o.h_ = nullptr;
+        }
+        return *this;
+    }
+    DeviceCloud(const DeviceCloud &) = delete;
+    DeviceCloud &operator=(const DeviceCloud &) = delete;
+
+    size_t len() const { return pcr_cloud_len(h_); }
+    bool is_empty() const { return len() == 0; }
+    bool has_normals() const { return pcr_cloud_has_normals(h_) != 0; }
+    PointCloud download() const {
+        const size_t n = len();
+        PointCloud c;
+        c.x.resize(n);
+        c.y.resize(n);
+        c.z.resize(n);
+        ctx_->check(pcr_cloud_download(h_, c.x.data(), c.y.data(), c.z.data()));
+        if (has_normals()) {
+            Normals nr;
+            nr.nx.resize(n);
+            nr.ny.resize(n);
+            nr.nz.resize(n);
+            ctx_->check(pcr_cloud_download_normals(h_, nr.nx.data(), nr.ny.data(), nr.nz.data()));
+            c.normals = std::move(nr);
+        }
+        return c;
+    }
+    DeviceCloud select(const std::vector<uint32_t> &indices) const { return make(&pcr_cloud_select, indices.data(), indices.size()); }
+    DeviceCloud voxel_downsample(float voxel_size) const { return make(&pcr_cloud_voxel_downsample, voxel_size); }
+    DeviceCloud statistical_outlier_removal(size_t k, float std_mul) const { return make(&pcr_cloud_statistical_outlier_removal, k, std_mul); }
+    DeviceCloud radius_outlier_removal(float radius, size_t min_neighbors) const {
+        return make(&pcr_cloud_radius_outlier_removal, radius, min_neighbors);
+    }
+    DeviceCloud estimate_normals(size_t k) const { return make(&pcr_cloud_estimate_normals, k, (const float *)nullptr); }
+    DeviceCloud apply_transform(const RigidTransform &t) const {
+        return make(&pcr_cloud_apply_transform, &t.rotation[0][0], (const float *)t.translation);
+    }
+    std::vector<std::vector<size_t>> euclidean_cluster(float distance_threshold, size_t min_size, size_t max_size) const {
+        const size_t n = len();
+        std::vector<uint32_t> off(n + 1), idx(n ? n : 1);
+        size_t nc = 0;
+        ctx_->check(pcr_cloud_euclidean_cluster(h_, distance_threshold, min_size, max_size, off.data(), idx.data(), &nc));
+        std::vector<std::vector<size_t>> out(nc);
+        for (size_t c = 0; c < nc; c++) out[c].assign(idx.begin() + off[c], idx.begin() + off[c + 1]);
+        return out;
+    }
+    IcpResult icp_point_to_point(const DeviceCloud &target, const IcpParams &p) const {
+        pcr_icp_params cp{p.max_iterations, p.tolerance, p.max_correspondence_distance};
+        pcr_icp_result r;
+        ctx_->check(pcr_cloud_icp_point_to_point(h_, target.h_, &cp, &r));
+        return detail::to_result(r);
+    }
+    IcpResult icp_point_to_plane(const DeviceCloud &target, const IcpParams &p) const {
+        pcr_icp_params cp{p.max_iterations, p.tolerance, p.max_correspondence_distance};
+        pcr_icp_result r;
+        ctx_->check(pcr_cloud_icp_point_to_plane(h_, target.h_, &cp, &r));
+        return detail::to_result(r);
+    }
+
+  private:
+    DeviceCloud(pcr_cloud *h, Context *c) : h_(h), ctx_(c) {}
+    template <class Fn, class... A>
+    DeviceCloud make(Fn fn, A... args) const {
+        pcr_cloud *o = nullptr;
+        ctx_->check(fn(h_, args..., &o));
+        return DeviceCloud(o, ctx_);
+    }
+    pcr_cloud *h_ = nullptr;
+    Context *ctx_ = nullptr;
+};
 
 }  // namespace pcr

@@ -31,7 +31,7 @@ __all__ = [
     "PointCloud", "KdTree", "IcpResult", "Context",
     "statistical_outlier_removal", "radius_outlier_removal", "estimate_normals",
     "icp_point_to_point", "icp_point_to_plane", "apply_transform", "find_correspondences",
-    "sor_normals_batch", "default_context", "PcrError", "euclidean_cluster", "voxel_downsample",
+    "sor_normals_batch", "default_context", "PcrError", "euclidean_cluster", "voxel_downsample", "DeviceCloud",
 ]
 
 
@@ -480,6 +480,135 @@ def apply_transform(cloud: PointCloud, rotation, translation, ctx: Optional[Cont
     _ffi.check(st, ctx._h)
     return PointCloud._from_xyz(ox, oy, oz)
 
+
+
+# ---------------------------------------------------------------------------------------------------
+# device-resident clouds (superset of the reference surface: the same calls without the PCIe round
+# trips between the steps of a pipeline)
+# ---------------------------------------------------------------------------------------------------
+
+class DeviceCloud:
+    """A PointCloud that lives in HBM.  Every filter returns a new DeviceCloud; nothing crosses PCIe
+    until to_numpy() / normals_to_numpy() / the cluster index lists / the ICP result."""
+
+    def __init__(self, handle, ctx: Context):
+        self._h = handle
+        self._ctx = ctx
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _ffi.load().pcr_cloud_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def from_numpy(array, ctx: Optional[Context] = None) -> "DeviceCloud":
+        return DeviceCloud.from_cloud(PointCloud.from_numpy(array), ctx)
+
+    @staticmethod
+    def from_cloud(cloud: PointCloud, ctx: Optional[Context] = None) -> "DeviceCloud":
+        ctx = ctx or default_context()
+        h = C.c_void_p()
+        st = _ffi.load().pcr_cloud_upload(ctx._h, _p(cloud.x, _ffi.f32p), _p(cloud.y, _ffi.f32p), _p(cloud.z, _ffi.f32p), len(cloud),
+                                          C.byref(h))
+        _ffi.check(st, ctx._h)
+        return DeviceCloud(h, ctx)
+
+    def _new(self, fn, *args) -> "DeviceCloud":
+        h = C.c_void_p()
+        _ffi.check(fn(self._h, *args, C.byref(h)), self._ctx._h)
+        return DeviceCloud(h, self._ctx)
+
+    def len(self) -> int:
+        return int(_ffi.load().pcr_cloud_len(self._h))
+
+    __len__ = len
+
+    def is_empty(self) -> bool:
+        return self.len() == 0
+
+    def has_normals(self) -> bool:
+        return bool(_ffi.load().pcr_cloud_has_normals(self._h))
+
+    def __repr__(self) -> str:
+        return f"DeviceCloud(n={self.len()}, normals={self.has_normals()})"
+
+    def to_numpy(self) -> np.ndarray:
+        n = self.len()
+        x, y, z = (np.zeros(max(n, 1), np.float32) for _ in range(3))
+        _ffi.check(_ffi.load().pcr_cloud_download(self._h, _p(x, _ffi.f32p), _p(y, _ffi.f32p), _p(z, _ffi.f32p)), self._ctx._h)
+        return np.stack([x[:n], y[:n], z[:n]], axis=1)
+
+    def normals_to_numpy(self) -> Optional[np.ndarray]:
+        if not self.has_normals():
+            return None
+        n = self.len()
+        x, y, z = (np.zeros(max(n, 1), np.float32) for _ in range(3))
+        _ffi.check(_ffi.load().pcr_cloud_download_normals(self._h, _p(x, _ffi.f32p), _p(y, _ffi.f32p), _p(z, _ffi.f32p)), self._ctx._h)
+        return np.stack([x[:n], y[:n], z[:n]], axis=1)
+
+    def to_cloud(self) -> PointCloud:
+        a = self.to_numpy()
+        return PointCloud._from_xyz(*_soa(a), self.normals_to_numpy())
+
+    def select(self, indices: Sequence[int]) -> "DeviceCloud":
+        idx = np.asarray(indices, dtype=np.int64).reshape(-1)
+        n = self.len()
+        bad = idx[(idx >= n) | (idx < 0)]
+        if len(bad):
+            raise IndexError(f"index {int(bad[0])} out of bounds for cloud with {n} points")
+        i32 = np.ascontiguousarray(idx, np.uint32)
+        return self._new(_ffi.load().pcr_cloud_select, _p(i32, _ffi.u32p), len(i32))
+
+    def voxel_downsample(self, voxel_size: float) -> "DeviceCloud":
+        if not math.isfinite(voxel_size) or voxel_size <= 0.0:
+            raise ValueError("voxel_size must be > 0 and finite")
+        return self._new(_ffi.load().pcr_cloud_voxel_downsample, float(voxel_size))
+
+    def statistical_outlier_removal(self, k: int, std_mul: float) -> "DeviceCloud":
+        if not math.isfinite(std_mul) or std_mul < 0.0:  # crates/python/src/filters.rs:42-46
+            raise ValueError("std_mul must be >= 0 and finite")
+        return self._new(_ffi.load().pcr_cloud_statistical_outlier_removal, int(k), float(std_mul))
+
+    def radius_outlier_removal(self, radius: float, min_neighbors: int) -> "DeviceCloud":
+        if not math.isfinite(radius) or radius <= 0.0:
+            raise ValueError("radius must be > 0 and finite")
+        return self._new(_ffi.load().pcr_cloud_radius_outlier_removal, float(radius), int(min_neighbors))
+
+    def estimate_normals(self, k: int, viewpoint=(0.0, 0.0, 0.0)) -> "DeviceCloud":
+        vp = np.asarray(viewpoint, np.float32)
+        return self._new(_ffi.load().pcr_cloud_estimate_normals, int(k), _p(vp, _ffi.f32p))
+
+    def euclidean_cluster(self, distance_threshold: float, min_size: int, max_size: int) -> List[List[int]]:
+        n = self.len()
+        off = np.zeros(n + 1, np.uint32)
+        idx = np.zeros(max(n, 1), np.uint32)
+        nc = C.c_size_t()
+        st = _ffi.load().pcr_cloud_euclidean_cluster(self._h, float(distance_threshold), int(min_size), int(max_size), _p(off, _ffi.u32p),
+                                                     _p(idx, _ffi.u32p), C.byref(nc))
+        _ffi.check(st, self._ctx._h)
+        return [idx[off[c]:off[c + 1]].tolist() for c in range(int(nc.value))]
+
+    def apply_transform(self, rotation, translation) -> "DeviceCloud":
+        r = np.ascontiguousarray(np.asarray(rotation, np.float32).reshape(9))
+        t = np.ascontiguousarray(np.asarray(translation, np.float32).reshape(3))
+        return self._new(_ffi.load().pcr_cloud_apply_transform, _p(r, _ffi.f32p), _p(t, _ffi.f32p))
+
+    def icp_point_to_point(self, target: "DeviceCloud", max_iterations: int = 50, tolerance: float = 1e-5,
+                           max_correspondence_distance: float = math.inf) -> "IcpResult":
+        prm = _icp_params(max_iterations, tolerance, max_correspondence_distance)
+        res = _ffi.IcpResultC()
+        _ffi.check(_ffi.load().pcr_cloud_icp_point_to_point(self._h, target._h, C.byref(prm), C.byref(res)), self._ctx._h)
+        return IcpResult(res)
+
+    def icp_point_to_plane(self, target: "DeviceCloud", max_iterations: int = 50, tolerance: float = 1e-5,
+                           max_correspondence_distance: float = math.inf) -> "IcpResult":
+        prm = _icp_params(max_iterations, tolerance, max_correspondence_distance)
+        res = _ffi.IcpResultC()
+        _ffi.check(_ffi.load().pcr_cloud_icp_point_to_plane(self._h, target._h, C.byref(prm), C.byref(res)), self._ctx._h)
+        return IcpResult(res)
 
 # ---------------------------------------------------------------------------------------------------
 # multi-frame batch (BASELINE config 5)

@@ -166,13 +166,7 @@ int stage_xyz(Ctx *ctx, DevBuf &buf, const float *x, const float *y, const float
 
 using namespace pcr;
 
-struct pcr_ctx {
-    Ctx c;
-};
-struct pcr_index {
-    Index *ix;
-    pcr_ctx *owner;
-};
+// struct pcr_ctx / pcr_index: pcr_internal.cuh
 
 extern "C" {
 
@@ -569,17 +563,9 @@ __global__ void ror_mask_kernel(const uint32_t *__restrict__ counts, size_t n, u
 }
 }  // namespace pcr
 
-int pcr_radius_outlier(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n, float radius, size_t min_neighbors,
-                       uint8_t *keep, size_t *n_kept) {
-    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
-    Ctx *c = &ctx->c;
-    if (n_kept) *n_kept = 0;
-    if (n && (!x || !y || !z || !keep)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
-    if (n == 0) return PCR_OK;
-    PCR_API_BEGIN
-    DevSetter ds(c);
-    float *dx, *dy, *dz;
-    PCR_TRY(stage_xyz(c, c->b_in, x, y, z, n, &dx, &dy, &dz));
+// keep mask + kept count of radius_outlier_removal on device arrays (radius_outlier.rs:4-18)
+static int ror_core(Ctx *c, const float *dx, const float *dy, const float *dz, size_t n, float radius, size_t min_neighbors,
+                    uint8_t *d_keep, unsigned long long *d_kept) {
     // cell size = radius: the search box spans at most 3 cells per axis
     const float saved = c->forced_cell;
     if (saved == 0.f && radius > 0.f && std::isfinite(radius)) c->forced_cell = radius;
@@ -592,16 +578,44 @@ int pcr_radius_outlier(pcr_ctx *ctx, const float *x, const float *y, const float
         Index *ix;
         ~G() { index_free(ix); }
     } g{ix};
-    size_t o_keep = (n * sizeof(uint32_t) + 255) & ~(size_t)255;
-    size_t o_kept = o_keep + ((n + 255) & ~(size_t)255);
-    PCR_TRY(ensure(c, c->b_out, o_kept + 64));
-    uint32_t *d_cnt = (uint32_t *)c->b_out.p;
-    uint8_t *d_keep = (uint8_t *)c->b_out.p + o_keep;
-    unsigned long long *d_kept = (unsigned long long *)((char *)c->b_out.p + o_kept);
+    PCR_TRY(ensure(c, c->b_misc, n * sizeof(uint32_t)));
+    uint32_t *d_cnt = (uint32_t *)c->b_misc.p;
     PCR_TRY(radius_count_dev(ix, dx, dy, dz, n, radius, d_cnt));
     PCR_CUDA(c, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long), c->stream));
     ror_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_cnt, n, (uint64_t)min_neighbors, d_keep, d_kept);
     PCR_LAUNCH_CHECK(c);
+    return PCR_OK;
+}
+
+int pcr_radius_outlier_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n, float radius,
+                           size_t min_neighbors, uint8_t *d_keep) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (n && (!d_x || !d_y || !d_z || !d_keep)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (n == 0) return PCR_OK;
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    PCR_TRY(ensure(c, c->b_small, 4096));
+    return ror_core(c, d_x, d_y, d_z, n, radius, min_neighbors, d_keep, (unsigned long long *)((char *)c->b_small.p + 1024));
+    PCR_API_END(c)
+}
+
+int pcr_radius_outlier(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n, float radius, size_t min_neighbors,
+                       uint8_t *keep, size_t *n_kept) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (n_kept) *n_kept = 0;
+    if (n && (!x || !y || !z || !keep)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (n == 0) return PCR_OK;
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    float *dx, *dy, *dz;
+    PCR_TRY(stage_xyz(c, c->b_in, x, y, z, n, &dx, &dy, &dz));
+    size_t o_kept = (n + 255) & ~(size_t)255;
+    PCR_TRY(ensure(c, c->b_out, o_kept + 64));
+    uint8_t *d_keep = (uint8_t *)c->b_out.p;
+    unsigned long long *d_kept = (unsigned long long *)((char *)c->b_out.p + o_kept);
+    PCR_TRY(ror_core(c, dx, dy, dz, n, radius, min_neighbors, d_keep, d_kept));
     unsigned long long *mail = (unsigned long long *)c->pinned;
     PCR_CUDA(c, cudaMemcpyAsync(keep, d_keep, n, cudaMemcpyDeviceToHost, c->stream));
     PCR_CUDA(c, cudaMemcpyAsync(mail, d_kept, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
@@ -1000,6 +1014,344 @@ int pcr_sor_normals_batch(pcr_ctx *ctx, const float *x, const float *y, const fl
         for (size_t f = 0; f < n_frames; f++) n_kept_per_frame[f] = hk[f];
     return PCR_OK;
     PCR_API_END(c)
+}
+
+}  // extern "C"
+
+/* ---- device-resident clouds -------------------------------------------------------------
+ * PointCloud (crates/core/src/cloud.rs:4-18) kept in HBM between the steps of a pipeline
+ * (voxel -> SOR -> normals -> cluster / ICP): one upload, one download, `select` as a device
+ * compaction.  Layout: one allocation, x | y | z | (nx | ny | nz), every array 256 B aligned. */
+struct pcr_cloud {
+    pcr_ctx *owner;
+    size_t n, stride;
+    float *base;
+    bool has_normals;
+    float *x() const { return base; }
+    float *y() const { return base + stride; }
+    float *z() const { return base + 2 * stride; }
+    float *nx() const { return base + 3 * stride; }
+    float *ny() const { return base + 4 * stride; }
+    float *nz() const { return base + 5 * stride; }
+};
+
+namespace pcr {
+namespace {
+
+int cloud_alloc(pcr_ctx *ctx, size_t n, bool normals, pcr_cloud **out) {
+    Ctx *c = &ctx->c;
+    pcr_cloud *cl = new (std::nothrow) pcr_cloud();
+    if (!cl) return fail(c, PCR_ERR_OOM, "host allocation failed");
+    cl->owner = ctx;
+    cl->n = n;
+    cl->stride = std::max<size_t>((n + 63) & ~(size_t)63, 64);
+    cl->has_normals = normals;
+    cl->base = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&cl->base, sizeof(float) * cl->stride * (normals ? 6 : 3), c->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        delete cl;
+        return fail(c, PCR_ERR_OOM, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    *out = cl;
+    return PCR_OK;
+}
+
+__global__ void fill_value_kernel(float *__restrict__ p, size_t n, float v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void mask_to_u32_kernel(const uint8_t *__restrict__ keep, size_t n, uint32_t *__restrict__ flag) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) flag[i] = (i < n && keep[i]) ? 1u : 0u;
+}
+
+// cloud.rs:103-140 as a stream compaction: kept points keep their order, normals travel along
+__global__ void compact_kernel(const float *__restrict__ src, size_t src_stride, int n_arrays, size_t n,
+                               const uint32_t *__restrict__ pos /* exclusive scan of the flags, n + 1 */, float *__restrict__ dst,
+                               size_t dst_stride) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t p = pos[i];
+    if (pos[i + 1] == p) return;
+    for (int a = 0; a < n_arrays; a++) dst[(size_t)a * dst_stride + p] = src[(size_t)a * src_stride + i];
+}
+
+__global__ void gather_kernel(const float *__restrict__ src, size_t src_stride, int n_arrays, const uint32_t *__restrict__ idx, size_t m,
+                              float *__restrict__ dst, size_t dst_stride) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    const uint32_t i = idx[t];
+    for (int a = 0; a < n_arrays; a++) dst[(size_t)a * dst_stride + t] = src[(size_t)a * src_stride + i];
+}
+
+// new cloud = the points of `in` with keep != 0
+int cloud_compact(const pcr_cloud *in, const uint8_t *d_keep, pcr_cloud **out) {
+    Ctx *c = &in->owner->c;
+    const size_t n = in->n;
+    PCR_TRY(ensure(c, c->b_list, sizeof(uint32_t) * (n + 1)));
+    uint32_t *pos = (uint32_t *)c->b_list.p;
+    mask_to_u32_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, c->stream>>>(d_keep, n, pos);
+    PCR_LAUNCH_CHECK(c);
+    PCR_TRY(exclusive_scan_u32_dev(c, pos, n + 1));
+    uint32_t *mail = (uint32_t *)c->pinned + 96;
+    PCR_CUDA(c, cudaMemcpyAsync(mail, pos + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t m = *mail;
+    PCR_TRY(cloud_alloc(in->owner, m, in->has_normals, out));
+    if (m) {
+        compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(in->base, in->stride, in->has_normals ? 6 : 3, n, pos,
+                                                                           (*out)->base, (*out)->stride);
+        PCR_LAUNCH_CHECK(c);
+    }
+    return PCR_OK;
+}
+
+}  // namespace
+}  // namespace pcr
+
+
+extern "C" {
+
+#define PCR_CLOUD_CHECK(cl)                                                             \
+    if (!(cl) || !(cl)->owner) return fail(nullptr, PCR_ERR_INVALID_ARG, "cloud is NULL"); \
+    Ctx *c = &(cl)->owner->c;
+
+int pcr_cloud_upload(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n, pcr_cloud **out) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (!out || (n && (!x || !y || !z))) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    pcr_cloud *cl = nullptr;
+    PCR_TRY(cloud_alloc(ctx, n, false, &cl));
+    if (n) {
+        cudaMemcpyAsync(cl->x(), x, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(cl->y(), y, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(cl->z(), z, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream);
+    }
+    cudaError_t e = cudaStreamSynchronize(c->stream);  // the caller's buffers are free again on return
+    if (e != cudaSuccess) {
+        pcr_cloud_free(cl);
+        return fail(c, PCR_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = cl;
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+void pcr_cloud_free(pcr_cloud *cloud) {
+    if (!cloud) return;
+    if (cloud->base && cloud->owner) {
+        DevSetter ds(&cloud->owner->c);
+        cudaFreeAsync(cloud->base, cloud->owner->c.stream);
+    }
+    delete cloud;
+}
+
+size_t pcr_cloud_len(const pcr_cloud *cloud) { return cloud ? cloud->n : 0; }
+int pcr_cloud_has_normals(const pcr_cloud *cloud) { return cloud && cloud->has_normals ? 1 : 0; }
+
+int pcr_cloud_device_pointers(const pcr_cloud *cloud, const float **d_x, const float **d_y, const float **d_z, const float **d_nx,
+                              const float **d_ny, const float **d_nz) {
+    PCR_CLOUD_CHECK(cloud)
+    (void)c;
+    if (d_x) *d_x = cloud->x();
+    if (d_y) *d_y = cloud->y();
+    if (d_z) *d_z = cloud->z();
+    if (d_nx) *d_nx = cloud->has_normals ? cloud->nx() : nullptr;
+    if (d_ny) *d_ny = cloud->has_normals ? cloud->ny() : nullptr;
+    if (d_nz) *d_nz = cloud->has_normals ? cloud->nz() : nullptr;
+    return PCR_OK;
+}
+
+int pcr_cloud_download(const pcr_cloud *cloud, float *x, float *y, float *z) {
+    PCR_CLOUD_CHECK(cloud)
+    if (cloud->n && (!x || !y || !z)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (!cloud->n) return PCR_OK;
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    PCR_CUDA(c, cudaMemcpyAsync(x, cloud->x(), sizeof(float) * cloud->n, cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaMemcpyAsync(y, cloud->y(), sizeof(float) * cloud->n, cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaMemcpyAsync(z, cloud->z(), sizeof(float) * cloud->n, cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+int pcr_cloud_download_normals(const pcr_cloud *cloud, float *nx, float *ny, float *nz) {
+    PCR_CLOUD_CHECK(cloud)
+    if (!cloud->has_normals) return fail(c, PCR_ERR_INVALID_ARG, "the cloud has no normals");
+    if (cloud->n && (!nx || !ny || !nz)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (!cloud->n) return PCR_OK;
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    PCR_CUDA(c, cudaMemcpyAsync(nx, cloud->nx(), sizeof(float) * cloud->n, cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaMemcpyAsync(ny, cloud->ny(), sizeof(float) * cloud->n, cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaMemcpyAsync(nz, cloud->nz(), sizeof(float) * cloud->n, cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+int pcr_cloud_select(const pcr_cloud *cloud, const uint32_t *indices, size_t m, pcr_cloud **out) {
+    PCR_CLOUD_CHECK(cloud)
+    if (!out || (m && !indices)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    for (size_t t = 0; t < m; t++)  // cloud.rs:109: select panics on an out-of-bounds index
+        if (indices[t] >= cloud->n) return fail(c, PCR_ERR_INVALID_ARG, "index %u out of bounds for cloud with %zu points", indices[t], cloud->n);
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    PCR_TRY(cloud_alloc(cloud->owner, m, cloud->has_normals, out));
+    if (m) {
+        PCR_TRY(ensure(c, c->b_list, sizeof(uint32_t) * m));
+        PCR_CUDA(c, cudaMemcpyAsync(c->b_list.p, indices, sizeof(uint32_t) * m, cudaMemcpyHostToDevice, c->stream));
+        gather_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(cloud->base, cloud->stride, cloud->has_normals ? 6 : 3,
+                                                                          (const uint32_t *)c->b_list.p, m, (*out)->base, (*out)->stride);
+        PCR_LAUNCH_CHECK(c);
+        PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+int pcr_cloud_voxel_downsample(const pcr_cloud *cloud, float voxel_size, pcr_cloud **out) {
+    PCR_CLOUD_CHECK(cloud)
+    if (!out) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    if (!std::isfinite(voxel_size) || !(voxel_size > 0.f)) return fail(c, PCR_ERR_INVALID_ARG, "voxel_size must be > 0 and finite");
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    pcr_cloud *tmp = nullptr;
+    PCR_TRY(cloud_alloc(cloud->owner, cloud->n, false, &tmp));  // voxel_downsample.rs:64: xyz only
+    size_t m = 0;
+    int s = voxel_downsample_dev(c, cloud->x(), cloud->y(), cloud->z(), cloud->n, voxel_size, tmp->x(), tmp->y(), tmp->z(), &m);
+    if (s != PCR_OK) {
+        pcr_cloud_free(tmp);
+        return s;
+    }
+    tmp->n = m;  // (the allocation keeps its original stride)
+    *out = tmp;
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+int pcr_cloud_statistical_outlier_removal(const pcr_cloud *cloud, size_t k, float std_mul, pcr_cloud **out) {
+    PCR_CLOUD_CHECK(cloud)
+    if (!out) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    const size_t n = cloud->n;
+    if (n == 0 || k == 0) return cloud_alloc(cloud->owner, 0, false, out);  // statistical_outlier.rs:5-7: PointCloud::new()
+    PCR_TRY(ensure(c, c->b_in2, n + 256));
+    uint8_t *d_keep = (uint8_t *)c->b_in2.p;
+    PCR_TRY(pcr_sor_dev(cloud->owner, cloud->x(), cloud->y(), cloud->z(), n, k, std_mul, d_keep, nullptr));
+    return cloud_compact(cloud, d_keep, out);  // :68 select
+    PCR_API_END(c)
+}
+
+int pcr_cloud_radius_outlier_removal(const pcr_cloud *cloud, float radius, size_t min_neighbors, pcr_cloud **out) {
+    PCR_CLOUD_CHECK(cloud)
+    if (!out) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    const size_t n = cloud->n;
+    if (n == 0) return cloud_alloc(cloud->owner, 0, cloud->has_normals, out);
+    PCR_TRY(ensure(c, c->b_in2, n + 256));
+    uint8_t *d_keep = (uint8_t *)c->b_in2.p;
+    PCR_TRY(pcr_radius_outlier_dev(cloud->owner, cloud->x(), cloud->y(), cloud->z(), n, radius, min_neighbors, d_keep));
+    return cloud_compact(cloud, d_keep, out);
+    PCR_API_END(c)
+}
+
+int pcr_cloud_estimate_normals(const pcr_cloud *cloud, size_t k, const float viewpoint[3], pcr_cloud **out) {
+    PCR_CLOUD_CHECK(cloud)
+    if (!out) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    // estimate.rs:25-31 returns EMPTY normals for k == 0, which no consumer accepts (icp_plane.rs:27-32): reported here
+    if (k == 0) return fail(c, PCR_ERR_INVALID_ARG, "k must be > 0");
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    const size_t n = cloud->n;
+    pcr_cloud *res = nullptr;
+    PCR_TRY(cloud_alloc(cloud->owner, n, true, &res));
+    if (n) {
+        cudaMemcpyAsync(res->x(), cloud->x(), sizeof(float) * n, cudaMemcpyDeviceToDevice, c->stream);
+        cudaMemcpyAsync(res->y(), cloud->y(), sizeof(float) * n, cudaMemcpyDeviceToDevice, c->stream);
+        cudaMemcpyAsync(res->z(), cloud->z(), sizeof(float) * n, cudaMemcpyDeviceToDevice, c->stream);
+        const float vp0[3] = {0.f, 0.f, 0.f};  // estimate.rs:13-15
+        int s = pcr_estimate_normals_dev(cloud->owner, cloud->x(), cloud->y(), cloud->z(), n, k, viewpoint ? viewpoint : vp0, res->nx(),
+                                     res->ny(), res->nz());
+        if (s != PCR_OK) {
+            pcr_cloud_free(res);
+            return s;
+        }
+    }
+    *out = res;
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+int pcr_cloud_euclidean_cluster(const pcr_cloud *cloud, float distance_threshold, size_t min_size, size_t max_size, uint32_t *offsets,
+                                uint32_t *indices, size_t *n_clusters) {
+    PCR_CLOUD_CHECK(cloud)
+    if (n_clusters) *n_clusters = 0;
+    if (!offsets || !n_clusters) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    offsets[0] = 0;
+    const size_t n = cloud->n;
+    if (n && !indices) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (n == 0 || distance_threshold <= 0.0f || min_size == 0) return PCR_OK;
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    PCR_TRY(ensure(c, c->b_out, n * sizeof(uint32_t)));
+    uint32_t *d_labels = (uint32_t *)c->b_out.p;
+    PCR_TRY(cluster_labels_dev(c, cloud->x(), cloud->y(), cloud->z(), n, distance_threshold, d_labels));
+    std::vector<uint32_t> labels(n), scratch;
+    PCR_CUDA(c, cudaMemcpyAsync(labels.data(), d_labels, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    *n_clusters = clusters_from_labels(labels.data(), n, min_size, max_size, offsets, indices, scratch);
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+int pcr_cloud_apply_transform(const pcr_cloud *cloud, const float rotation[9], const float translation[3], pcr_cloud **out) {
+    PCR_CLOUD_CHECK(cloud)
+    if (!out || !rotation || !translation) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    pcr_cloud *res = nullptr;
+    PCR_TRY(cloud_alloc(cloud->owner, cloud->n, false, &res));  // icp.rs:91: xyz only
+    if (cloud->n) {
+        int s = apply_transform_dev(c, cloud->x(), cloud->y(), cloud->z(), cloud->n, rotation, translation, res->x(), res->y(), res->z());
+        if (s != PCR_OK) {
+            pcr_cloud_free(res);
+            return s;
+        }
+    }
+    *out = res;
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+int pcr_cloud_icp_point_to_point(const pcr_cloud *source, const pcr_cloud *target, const pcr_icp_params *params, pcr_icp_result *result) {
+    PCR_CLOUD_CHECK(source)
+    if (!target || target->owner != source->owner) return fail(c, PCR_ERR_INVALID_ARG, "source and target must live on the same context");
+    return pcr_icp_point_to_point_dev(source->owner, source->x(), source->y(), source->z(), source->n, target->x(), target->y(), target->z(),
+                                      target->n, params, result);
+}
+
+int pcr_cloud_icp_point_to_plane(const pcr_cloud *source, const pcr_cloud *target, const pcr_icp_params *params, pcr_icp_result *result) {
+    PCR_CLOUD_CHECK(source)
+    if (!target || target->owner != source->owner) return fail(c, PCR_ERR_INVALID_ARG, "source and target must live on the same context");
+    if (!target->has_normals)  // crates/python/src/registration.rs:80-86
+        return fail(c, PCR_ERR_INVALID_ARG, "target cloud must have normals (call estimate_normals first)");
+    return pcr_icp_point_to_plane_dev(source->owner, source->x(), source->y(), source->z(), source->n, target->x(), target->y(), target->z(),
+                                      target->n, target->nx(), target->ny(), target->nz(), target->n, params, result);
 }
 
 }  // extern "C"

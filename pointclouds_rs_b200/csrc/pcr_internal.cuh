@@ -215,6 +215,19 @@ int comm_allreduce_f64(Ctx *ctx, double *d_buf, size_t count);
 // ------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------
+}  // namespace pcr
+
+// the opaque handles of the C ABI
+struct pcr_ctx {
+    pcr::Ctx c;
+};
+struct pcr_index {
+    pcr::Index *ix;
+    pcr_ctx *owner;
+};
+
+namespace pcr {
+
 #ifdef __CUDACC__
 
 #define PCR_FULL 0xffffffffu

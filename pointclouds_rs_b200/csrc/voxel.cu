@@ -10,7 +10,7 @@
 //   vox_range_kernel   key range of the finite points (warp redux + atomics)             12 B/pt
 //   vox_pack_kernel    packed u64 key per point (non-finite points sort last)            12 + 12 B/pt
 //   radix passes       8 bits per pass over the significant bits only (KITTI frame at 5 cm: 29 bits,
-//                      4 passes); one WARP owns a tile of 1024 consecutive pairs and walks it in order,
+//                      4 passes); one WARP owns a tile of 256 consecutive pairs and walks it in order,
 //                      __match_any_sync ranks equal digits inside a round of 32, running per-digit
 //                      offsets in shared memory carry the order across rounds: stable by construction
 //   vox_heads_kernel   run heads -> voxel ids (exclusive scan) -> run starts
@@ -25,8 +25,8 @@ namespace pcr {
 
 namespace {
 
-constexpr int kSortRounds = 32;                  // rounds of 32 pairs per warp tile
-constexpr int kSortTile = 32 * kSortRounds;      // 1024 pairs
+constexpr int kSortRounds = 8;                   // rounds of 32 pairs per warp tile (more tiles = more warps in flight)
+constexpr int kSortTile = 32 * kSortRounds;      // 256 pairs
 constexpr int kSortWarps = 4;                    // warps (tiles) per block
 
 struct VoxRange {

@@ -1,0 +1,90 @@
+"""Device-resident clouds: every step must give exactly what the host-pointer call gives (and hence what
+the oracle gives), `select` must keep order and carry normals (crates/core/src/cloud.rs:103-140)."""
+import numpy as np
+import pytest
+
+from pointclouds_rs_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def test_upload_download_select(pcr):
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-5, 5, (5000, 3)).astype(np.float32)
+    d = pcr.DeviceCloud.from_numpy(pts)
+    assert len(d) == 5000 and not d.has_normals() and not d.is_empty()
+    assert np.array_equal(d.to_numpy(), pts)
+    idx = rng.integers(0, 5000, 777)
+    assert np.array_equal(d.select(idx).to_numpy(), pts[idx])          # arbitrary order and repeats, like the reference
+    assert len(d.select([])) == 0
+    with pytest.raises(IndexError):                                    # crates/python/src/cloud.rs:56-61
+        d.select([5000])
+    dn = d.estimate_normals(10)
+    sel = dn.select(idx)
+    assert sel.has_normals() and np.array_equal(sel.normals_to_numpy(), dn.normals_to_numpy()[idx])
+    empty = pcr.DeviceCloud.from_numpy(np.zeros((0, 3), np.float32))
+    assert len(empty) == 0 and empty.to_numpy().shape == (0, 3)
+
+
+def test_pipeline_matches_host_api_and_oracle(pcr, oracle):
+    """BASELINE configs[1] end to end on the device: voxel 0.05 -> SOR k=10 -> normals k=20, then clustering."""
+    pts = scenes.kitti_scene(5, (30_000, 1500, 250, 650))
+    d = pcr.DeviceCloud.from_numpy(pts)
+    v = d.voxel_downsample(0.05)
+    o_v = oracle.voxel_downsample(pts, 0.05)
+    assert np.array_equal(v.to_numpy(), o_v)
+    s = v.statistical_outlier_removal(10, 1.0)
+    o_keep, _, _ = oracle.sor(o_v, 10, 1.0, threads=8)
+    o_s = o_v[o_keep.astype(bool)]
+    assert np.array_equal(s.to_numpy(), o_s)
+    nrm = s.estimate_normals(20)
+    assert np.array_equal(nrm.to_numpy(), o_s)
+    host_n = pcr.normals_array(pcr.PointCloud.from_numpy(o_s), 20)
+    assert np.array_equal(nrm.normals_to_numpy(), host_n)                # same kernels, same bits
+    o_n = oracle.normals(o_s, 20, threads=8)
+    a, b = nrm.normals_to_numpy().astype(np.float64), o_n.astype(np.float64)
+    ang = np.arctan2(np.linalg.norm(np.cross(a, b), axis=1), np.abs(np.sum(a * b, axis=1)))
+    assert ang.max() < 1e-4
+    got = s.euclidean_cluster(0.5, 30, 25000)
+    want = [list(map(int, c)) for c in oracle.euclidean_cluster(o_s, 0.5, 30, 25000)]
+    assert got == want
+    r = s.radius_outlier_removal(0.5, 5)
+    keep, _ = pcr.ror_mask(pcr.PointCloud.from_numpy(o_s), 0.5, 5)
+    assert np.array_equal(r.to_numpy(), o_s[keep.astype(bool)])
+
+
+def test_filters_carry_normals_and_edge_cases(pcr):
+    pts = scenes.uniform_cube(3000, 2, 0, 5)
+    d = pcr.DeviceCloud.from_numpy(pts).estimate_normals(8)
+    s = d.statistical_outlier_removal(6, 0.5)                            # select keeps the normals (cloud.rs:117-128)
+    keep, _, _, _ = pcr.sor_mask(pcr.PointCloud.from_numpy(pts), 6, 0.5)
+    assert s.has_normals() and np.array_equal(s.normals_to_numpy(), d.normals_to_numpy()[keep.astype(bool)])
+    assert len(d.statistical_outlier_removal(0, 1.0)) == 0               # statistical_outlier.rs:5-7
+    one = pcr.DeviceCloud.from_numpy(np.array([[1, 2, 3]], np.float32))
+    assert np.array_equal(one.statistical_outlier_removal(5, 1.0).to_numpy(), [[1, 2, 3]])   # :10-12
+    # one point: zero covariance -> (0,0,1) (estimate.rs:174-177), flipped towards the origin (:99-107)
+    assert np.array_equal(one.estimate_normals(5).normals_to_numpy(), pcr.normals_array(pcr.PointCloud.from_numpy(np.array([[1, 2, 3]], np.float32)), 5))
+    assert one.estimate_normals(5).normals_to_numpy().tolist() == [[-0.0, -0.0, -1.0]]
+    with pytest.raises(ValueError):                                       # k == 0: reported (the reference attaches empty normals)
+        one.estimate_normals(0)
+    with pytest.raises(ValueError):
+        d.voxel_downsample(0.0)
+
+
+def test_device_icp_matches_host_api(pcr, oracle):
+    tgt = scenes.hemisphere(6000, seed=3, radius=5.0)
+    src = oracle.apply_transform(tgt, scenes.rot_z(0.04), [0.2, -0.1, 0.05])
+    d_t = pcr.DeviceCloud.from_numpy(tgt).estimate_normals(15)
+    d_s = pcr.DeviceCloud.from_numpy(src)
+    h_t = pcr.estimate_normals(pcr.PointCloud.from_numpy(tgt), 15)
+    h_s = pcr.PointCloud.from_numpy(src)
+    for dev, host in ((d_s.icp_point_to_plane(d_t, 15, 0.0), pcr.icp_point_to_plane(h_s, h_t, 15, 0.0)),
+                      (d_s.icp_point_to_point(d_t, 15, 0.0), pcr.icp_point_to_point(h_s, h_t, 15, 0.0))):
+        assert dev.num_iterations == host.num_iterations == 15
+        assert np.array_equal(np.array(dev.rotation), np.array(host.rotation))
+        assert np.array_equal(np.array(dev.translation), np.array(host.translation))
+    with pytest.raises(ValueError):                                      # registration.rs:80-86
+        d_s.icp_point_to_plane(pcr.DeviceCloud.from_numpy(tgt))
+    R, t = scenes.rot_z(0.3), [1.0, 2.0, 3.0]
+    moved = d_s.apply_transform(R, t)
+    assert np.array_equal(moved.to_numpy(), oracle.apply_transform(src, R, t))
