@@ -6,16 +6,18 @@
 
 Metric (BASELINE.json): SOR + normals points/sec, k = 10 / 20.
 Workload at every N (weak scaling, one process per GPU, no data-path collective): BASELINE
-configs[1] -- a KITTI-shaped synthetic frame of 122 000 points (numpy PCG64, seed 42 + rank),
-voxel_downsample(0.05) as untimed input preparation, then per step
+configs[1] -- a KITTI-shaped synthetic frame of 122 000 points (numpy PCG64, seed 42 + rank); per step
 
-    statistical_outlier_removal(k = 10, std_mul = 1.0)  ->  estimate_normals(k = 20) on the kept points
+    voxel_downsample(0.05) -> statistical_outlier_removal(k = 10, std_mul = 1.0) -> estimate_normals(k = 20)
+    on the kept points
 
-A step is one pass of that hot path over one frame.
-  value : points/s, inputs resident in HBM (pcr_sor_normals_batch_dev), CUDA events on the stream
-          the kernels run on, max over ranks, L2 flushed between steps.
-  e2e   : the same through the host-pointer C-ABI call (pcr_sor_normals_batch) from PINNED host
-          buffers: H2D of x/y/z and D2H of mask + normals inside the timed region (wall clock).
+A step is one pass of that pipeline over one frame; points/s counts the RAW input points.
+  value : points/s, the raw frame resident in HBM (pcr_cloud_voxel_downsample + pcr_cloud_sor_normals on
+          a device-resident pcr_cloud), CUDA events on the stream the kernels run on, max over ranks,
+          L2 flushed between steps.
+  e2e   : the same through the C ABI from PINNED host buffers: pcr_cloud_upload of x/y/z, the two
+          calls, pcr_cloud_download of the kept points and their normals, all inside the timed region
+          (wall clock).
   roofline     : the dominant kernel (KNN + fused normals, grid level 0), algorithmic bytes / its
                  device time measured live with cudaEvents inside the library (pcr_ctx_get_timing).
   cpu_baseline : the CPU oracle (C port of the reference path) timed on this box's host cores on a
@@ -57,16 +59,16 @@ def load_peaks():
 def make_frame(rank: int):
     from pointclouds_rs_b200 import scenes
 
-    raw = scenes.kitti_scene(seed=42 + rank)
-    pts = scenes.voxel_downsample_np(raw, VOXEL)  # untimed input preparation (not on the KNN path)
+    raw = np.ascontiguousarray(scenes.kitti_scene(seed=42 + rank), np.float32)
+    pts = scenes.voxel_downsample_np(raw, VOXEL)  # what the voxel step hands to SOR (used for sizes and the roofline only)
     return raw, np.ascontiguousarray(pts, np.float32)
 
 
 def workload_config(n_raw: int, n_in: int, world: int):
     return {
         "workload": "BASELINE configs[1]: KITTI-shaped synthetic frame 122K pts: voxel 0.05 -> SOR k=10 -> normals",
-        "points_raw_per_frame": n_raw,
-        "points_per_step_per_gpu": n_in,
+        "points_per_step_per_gpu": n_raw,
+        "points_after_voxel": n_in,
         "k_sor": K_SOR,
         "std_mul": STD_MUL,
         "k_normals": K_NORMALS,
@@ -133,15 +135,17 @@ class ClockSampler(threading.Thread):
         }
 
 
-def cpu_reference_run(pts: np.ndarray, reps: int, threads_normals: int):
-    """The CPU port of the reference path, threaded the way the reference is: SOR is a serial loop
-    (statistical_outlier.rs:19), normals run on all cores (rayon par_iter, estimate.rs:42-44)."""
+def cpu_reference_run(raw: np.ndarray, reps: int, threads_normals: int):
+    """The CPU port of the reference path, threaded the way the reference is: voxel_downsample and SOR
+    are serial loops (voxel_downsample.rs:24, statistical_outlier.rs:19), normals run on all cores
+    (rayon par_iter, estimate.rs:42-44)."""
     from oracle import oracle as O  # the checker, used here only as the timed CPU baseline
 
     O.lib()
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
+        pts = O.voxel_downsample(raw, VOXEL)
         keep, _, _ = O.sor(pts, K_SOR, STD_MUL, threads=1)
         kept = pts[keep.astype(bool)]
         O.normals(kept, K_NORMALS, threads=threads_normals)
@@ -149,10 +153,11 @@ def cpu_reference_run(pts: np.ndarray, reps: int, threads_normals: int):
     return times
 
 
-def cpu_reference_all_threads(pts: np.ndarray, threads: int):
+def cpu_reference_all_threads(raw: np.ndarray, threads: int):
     from oracle import oracle as O
 
     t0 = time.perf_counter()
+    pts = O.voxel_downsample(raw, VOXEL)
     keep, _, _ = O.sor(pts, K_SOR, STD_MUL, threads=threads)
     O.normals(pts[keep.astype(bool)], K_NORMALS, threads=threads)
     return time.perf_counter() - t0
@@ -165,14 +170,14 @@ def run_reference_arm(args):
     raw, pts = make_frame(0)
     cores = os.cpu_count() or 1
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_run(pts, 1, cores)
-    steps = max(1, min(args.steps, 8))  # bounded: each step is ~0.5 s of CPU work
-    times = cpu_reference_run(pts, steps, cores)
+        cpu_reference_run(raw, 1, cores)
+    steps = max(1, min(args.steps, 8))  # bounded: each step is ~0.3 s of CPU work
+    times = cpu_reference_run(raw, steps, cores)
     t = float(np.mean(times))
-    value = len(pts) / t
-    t_all = cpu_reference_all_threads(pts, cores)
-    sample = (f"{steps} step(s) of the full workload (one {len(pts)}-point frame per step); SOR on 1 thread (the reference's "
-              f"loop is serial), normals on {cores} threads (reference: rayon); C port of the reference path (oracle/)")
+    value = len(raw) / t
+    t_all = cpu_reference_all_threads(raw, cores)
+    sample = (f"{steps} step(s) of the full workload (one {len(raw)}-point frame per step); voxel and SOR on 1 thread (the "
+              f"reference's loops are serial), normals on {cores} threads (reference: rayon); C port of the reference path (oracle/)")
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
@@ -180,7 +185,7 @@ def run_reference_arm(args):
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(len(raw), len(pts), 1),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "all_threads_value": len(pts) / t_all},
+                         "all_threads_value": len(raw) / t_all},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -222,30 +227,34 @@ def main():
     ctx = pcr.Context(device=local_rank, stream=stream.cuda_stream)
 
     raw, pts = make_frame(rank)
-    n = len(pts)
-    offsets = np.array([0, n], np.uint64)
-    vp = np.zeros(3, np.float32)
+    n_raw, n = len(raw), len(pts)
 
-    # device-resident inputs / outputs (torch only provides the memory and the stream)
-    d_xyz = torch.from_numpy(np.ascontiguousarray(pts.T)).cuda()  # (3, n): x | y | z
-    d_keep = torch.empty(n, dtype=torch.uint8, device="cuda")
-    d_nrm = torch.empty((3, n), dtype=torch.float32, device="cuda")
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
-    # pinned host buffers for the end-to-end arm
-    h_xyz = torch.from_numpy(np.ascontiguousarray(pts.T)).pin_memory()
-    h_keep = torch.empty(n, dtype=torch.uint8).pin_memory()
-    h_nrm = torch.empty((3, n), dtype=torch.float32).pin_memory()
-    h_kept = np.zeros(1, np.uint64)
+    # the raw frame resident in HBM (device arm) and in pinned host memory (end-to-end arm)
+    h_raw = torch.from_numpy(np.ascontiguousarray(raw.T)).pin_memory()  # (3, n_raw): x | y | z
+    h_out = torch.empty((6, n_raw), dtype=torch.float32).pin_memory()   # kept x, y, z, nx, ny, nz
+    d_raw = pcr.DeviceCloud.upload_raw(ctx, h_raw[0].data_ptr(), h_raw[1].data_ptr(), h_raw[2].data_ptr(), n_raw)
+    last = {}
+
+    def pipeline(cloud):
+        v = cloud.voxel_downsample(VOXEL)
+        o = v.sor_normals(K_SOR, STD_MUL, K_NORMALS)
+        v.free()
+        return o
 
     def step_device():
-        pcr.sor_normals_batch_raw(ctx, d_xyz[0].data_ptr(), d_xyz[1].data_ptr(), d_xyz[2].data_ptr(), n, offsets, K_SOR, STD_MUL,
-                                  K_NORMALS, vp, d_keep.data_ptr(), d_nrm[0].data_ptr(), d_nrm[1].data_ptr(), d_nrm[2].data_ptr(),
-                                  device=True)
+        o = pipeline(d_raw)
+        if "dev" in last:
+            last["dev"].free()
+        last["dev"] = o
 
     def step_e2e():
-        pcr.sor_normals_batch_raw(ctx, h_xyz[0].data_ptr(), h_xyz[1].data_ptr(), h_xyz[2].data_ptr(), n, offsets, K_SOR, STD_MUL,
-                                  K_NORMALS, vp, h_keep.data_ptr(), h_nrm[0].data_ptr(), h_nrm[1].data_ptr(), h_nrm[2].data_ptr(),
-                                  kept=h_kept, device=False)
+        d = pcr.DeviceCloud.upload_raw(ctx, h_raw[0].data_ptr(), h_raw[1].data_ptr(), h_raw[2].data_ptr(), n_raw)
+        o = pipeline(d)
+        d.free()
+        o.download_raw(*[h_out[j].data_ptr() for j in range(6)])
+        last["e2e_len"] = len(o)
+        o.free()
 
     def barrier():
         torch.cuda.synchronize()
@@ -258,7 +267,7 @@ def main():
         step_device()
         step_e2e()
     torch.cuda.synchronize()
-    n_kept = int(d_keep.sum().item())
+    n_kept = len(last["dev"])
 
     # ---- timed region 1: device-resident ------------------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -292,10 +301,12 @@ def main():
 
     dev_ms_max = pdist.max_over_ranks(dist if distributed else None, dev_ms, "cuda")
     e2e_s_max = pdist.max_over_ranks(dist if distributed else None, e2e_s, "cuda")
-    n_total = pdist.sum_over_ranks(dist if distributed else None, float(n), "cuda")
+    n_total = pdist.sum_over_ranks(dist if distributed else None, float(n_raw), "cuda")
 
     # parity spot check of the timed configuration against the e2e arm (same inputs, same results)
-    same = bool(torch.equal(d_keep.cpu(), h_keep)) and bool(torch.equal(d_nrm.cpu(), h_nrm))
+    dev_pts, dev_nrm = last["dev"].to_numpy(), last["dev"].normals_to_numpy()
+    m = last["e2e_len"]
+    same = (m == len(dev_pts) and np.array_equal(dev_pts.T, h_out[0:3, :m].numpy()) and np.array_equal(dev_nrm.T, h_out[3:6, :m].numpy()))
 
     value = n_total * args.steps / (dev_ms_max * 1e-3)
     e2e_value = n_total * args.steps / e2e_s_max
@@ -309,13 +320,15 @@ def main():
     dur_normals = knn_n_ms / max(knn_n_cnt, 1) * 1e-3
     achieved = bytes_normals / dur_normals / 1e9 if dur_normals > 0 else 0.0
     roofline = {
-        "bound": "hbm", "kernel": "normals_kernel<false,32> (grid KNN k=20 + covariance + Cardano, level 0)",
+        "bound": "hbm", "kernel": "knn_thread_kernel<20,2> (grid KNN k=20 + covariance + Cardano eigensolve, level 0, thread per query)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
         "traffic": None,
         "algorithmic_bytes_per_launch": bytes_normals, "avg_launch_ms": dur_normals * 1e3,
         "note": "a 119 K-point frame is L2-resident: the kernel is bound by FP32/integer issue, not by HBM (DESIGN.md)",
         "stage_ms_per_step": {k: v[0] / args.steps for k, v in stage.items() if v[1]},
         "sor_knn_kernel": {"avg_launch_ms": knn_s_ms / max(knn_s_cnt, 1), "algorithmic_bytes_per_launch": n * (16 + 4)},
+        "device": {"name": torch.cuda.get_device_name(local_rank), "sm_count": torch.cuda.get_device_properties(local_rank).multi_processor_count,
+                   "l2_bytes": torch.cuda.get_device_properties(local_rank).L2_cache_size},
     }
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(prof):
@@ -335,13 +348,13 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        times = cpu_reference_run(pts, 3, cores)
-        t_all = cpu_reference_all_threads(pts, cores)
+        times = cpu_reference_run(raw, 3, cores)
+        t_all = cpu_reference_all_threads(raw, cores)
         cpu_baseline = {
-            "value": n / float(np.mean(times)), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": (f"3 steps of the same frame ({n} points): SOR on 1 thread (reference loop is serial), normals on {cores} "
-                       "threads (reference: rayon); C port of the reference (oracle/), not the Rust build"),
-            "all_threads_value": n / t_all,
+            "value": n_raw / float(np.mean(times)), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": (f"3 steps of the same frame ({n_raw} points): voxel and SOR on 1 thread (the reference's loops are serial), "
+                       f"normals on {cores} threads (reference: rayon); C port of the reference (oracle/), not the Rust build"),
+            "all_threads_value": n_raw / t_all,
         }
 
     if rank == 0:
@@ -350,8 +363,9 @@ def main():
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(len(raw), n, world),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * 4 * n, "d2h_bytes_per_step": n + 3 * 4 * n + 8,
-                    "ms_per_step": e2e_s_max / args.steps * 1e3, "timer": "wall clock around the synchronous C-ABI call, pinned host buffers"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * 4 * n_raw, "d2h_bytes_per_step": 6 * 4 * n_kept,
+                    "ms_per_step": e2e_s_max / args.steps * 1e3,
+                    "timer": "wall clock around pcr_cloud_upload -> voxel -> sor_normals -> pcr_cloud_download, pinned host buffers"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

@@ -262,6 +262,10 @@ int pcr_cloud_radius_outlier_removal(const pcr_cloud *cloud, float radius, size_
                                      pcr_cloud **out);                                                /* radius_outlier.rs:4 */
 /* estimate.rs:19: a copy of the cloud with normals attached (viewpoint NULL = origin, :13-15) */
 int pcr_cloud_estimate_normals(const pcr_cloud *cloud, size_t k, const float viewpoint[3], pcr_cloud **out);
+/* statistical_outlier_removal then estimate_normals on the kept points, one index for both (the
+ * single-frame form of pcr_sor_normals_batch): the kept points with their normals */
+int pcr_cloud_sor_normals(const pcr_cloud *cloud, size_t k_sor, float std_mul, size_t k_normals,
+                          const float viewpoint[3], pcr_cloud **out);
 int pcr_cloud_euclidean_cluster(const pcr_cloud *cloud, float distance_threshold, size_t min_size,
                                 size_t max_size, uint32_t *offsets, uint32_t *indices,
                                 size_t *n_clusters);                                                  /* euclidean_cluster.rs:96 */

@@ -511,10 +511,27 @@ class DeviceCloud:
     def from_cloud(cloud: PointCloud, ctx: Optional[Context] = None) -> "DeviceCloud":
         ctx = ctx or default_context()
         h = C.c_void_p()
-        st = _ffi.load().pcr_cloud_upload(ctx._h, _p(cloud.x, _ffi.f32p), _p(cloud.y, _ffi.f32p), _p(cloud.z, _ffi.f32p), len(cloud),
-                                          C.byref(h))
+        st = _ffi.load().pcr_cloud_upload(ctx._h, cloud.x.ctypes.data, cloud.y.ctypes.data, cloud.z.ctypes.data, len(cloud), C.byref(h))
         _ffi.check(st, ctx._h)
         return DeviceCloud(h, ctx)
+
+    @staticmethod
+    def upload_raw(ctx: Context, x_ptr: int, y_ptr: int, z_ptr: int, n: int) -> "DeviceCloud":
+        """Upload from raw host addresses (e.g. pinned buffers)."""
+        h = C.c_void_p()
+        _ffi.check(_ffi.load().pcr_cloud_upload(ctx._h, x_ptr, y_ptr, z_ptr, n, C.byref(h)), ctx._h)
+        return DeviceCloud(h, ctx)
+
+    def download_raw(self, x_ptr: int, y_ptr: int, z_ptr: int, nx_ptr: int = 0, ny_ptr: int = 0, nz_ptr: int = 0):
+        """Download into raw host addresses (arrays of len()); normals too if the three pointers are given."""
+        _ffi.check(_ffi.load().pcr_cloud_download(self._h, x_ptr, y_ptr, z_ptr), self._ctx._h)
+        if nx_ptr:
+            _ffi.check(_ffi.load().pcr_cloud_download_normals(self._h, nx_ptr, ny_ptr, nz_ptr), self._ctx._h)
+
+    def free(self):
+        if self._h:
+            _ffi.load().pcr_cloud_free(self._h)
+            self._h = None
 
     def _new(self, fn, *args) -> "DeviceCloud":
         h = C.c_void_p()
@@ -538,7 +555,7 @@ class DeviceCloud:
     def to_numpy(self) -> np.ndarray:
         n = self.len()
         x, y, z = (np.zeros(max(n, 1), np.float32) for _ in range(3))
-        _ffi.check(_ffi.load().pcr_cloud_download(self._h, _p(x, _ffi.f32p), _p(y, _ffi.f32p), _p(z, _ffi.f32p)), self._ctx._h)
+        _ffi.check(_ffi.load().pcr_cloud_download(self._h, x.ctypes.data, y.ctypes.data, z.ctypes.data), self._ctx._h)
         return np.stack([x[:n], y[:n], z[:n]], axis=1)
 
     def normals_to_numpy(self) -> Optional[np.ndarray]:
@@ -546,7 +563,7 @@ class DeviceCloud:
             return None
         n = self.len()
         x, y, z = (np.zeros(max(n, 1), np.float32) for _ in range(3))
-        _ffi.check(_ffi.load().pcr_cloud_download_normals(self._h, _p(x, _ffi.f32p), _p(y, _ffi.f32p), _p(z, _ffi.f32p)), self._ctx._h)
+        _ffi.check(_ffi.load().pcr_cloud_download_normals(self._h, x.ctypes.data, y.ctypes.data, z.ctypes.data), self._ctx._h)
         return np.stack([x[:n], y[:n], z[:n]], axis=1)
 
     def to_cloud(self) -> PointCloud:
@@ -580,6 +597,11 @@ class DeviceCloud:
     def estimate_normals(self, k: int, viewpoint=(0.0, 0.0, 0.0)) -> "DeviceCloud":
         vp = np.asarray(viewpoint, np.float32)
         return self._new(_ffi.load().pcr_cloud_estimate_normals, int(k), _p(vp, _ffi.f32p))
+
+    def sor_normals(self, k_sor: int, std_mul: float, k_normals: int, viewpoint=(0.0, 0.0, 0.0)) -> "DeviceCloud":
+        """statistical_outlier_removal(k_sor, std_mul) then estimate_normals(k_normals) on the kept points, one index."""
+        vp = np.asarray(viewpoint, np.float32)
+        return self._new(_ffi.load().pcr_cloud_sor_normals, int(k_sor), float(std_mul), int(k_normals), _p(vp, _ffi.f32p))
 
     def euclidean_cluster(self, distance_threshold: float, min_size: int, max_size: int) -> List[List[int]]:
         n = self.len()

@@ -98,18 +98,19 @@ SIGNATURES = {
     "pcr_euclidean_cluster": (C.c_int, [vp, f32p, f32p, f32p, C.c_size_t, C.c_float, C.c_size_t, C.c_size_t, u32p, u32p, szp]),
     "pcr_cluster_labels_dev": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_float, vp]),
     "pcr_radius_outlier_dev": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_float, C.c_size_t, vp]),
-    "pcr_cloud_upload": (C.c_int, [vp, f32p, f32p, f32p, C.c_size_t, C.POINTER(vp)]),
+    "pcr_cloud_upload": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.POINTER(vp)]),
     "pcr_cloud_free": (None, [vp]),
     "pcr_cloud_len": (C.c_size_t, [vp]),
     "pcr_cloud_has_normals": (C.c_int, [vp]),
-    "pcr_cloud_download": (C.c_int, [vp, f32p, f32p, f32p]),
-    "pcr_cloud_download_normals": (C.c_int, [vp, f32p, f32p, f32p]),
+    "pcr_cloud_download": (C.c_int, [vp, vp, vp, vp]),
+    "pcr_cloud_download_normals": (C.c_int, [vp, vp, vp, vp]),
     "pcr_cloud_device_pointers": (C.c_int, [vp] + [C.POINTER(vp)] * 6),
     "pcr_cloud_select": (C.c_int, [vp, u32p, C.c_size_t, C.POINTER(vp)]),
     "pcr_cloud_voxel_downsample": (C.c_int, [vp, C.c_float, C.POINTER(vp)]),
     "pcr_cloud_statistical_outlier_removal": (C.c_int, [vp, C.c_size_t, C.c_float, C.POINTER(vp)]),
     "pcr_cloud_radius_outlier_removal": (C.c_int, [vp, C.c_float, C.c_size_t, C.POINTER(vp)]),
     "pcr_cloud_estimate_normals": (C.c_int, [vp, C.c_size_t, f32p, C.POINTER(vp)]),
+    "pcr_cloud_sor_normals": (C.c_int, [vp, C.c_size_t, C.c_float, C.c_size_t, f32p, C.POINTER(vp)]),
     "pcr_cloud_euclidean_cluster": (C.c_int, [vp, C.c_float, C.c_size_t, C.c_size_t, u32p, u32p, szp]),
     "pcr_cloud_apply_transform": (C.c_int, [vp, f32p, f32p, C.POINTER(vp)]),
     "pcr_cloud_icp_point_to_point": (C.c_int, [vp, vp, C.POINTER(IcpParams), C.POINTER(IcpResultC)]),

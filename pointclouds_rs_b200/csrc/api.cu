@@ -1296,6 +1296,40 @@ int pcr_cloud_estimate_normals(const pcr_cloud *cloud, size_t k, const float vie
     PCR_API_END(c)
 }
 
+// statistical_outlier_removal followed by estimate_normals on the kept points with ONE index (the points
+// SOR removes are tombstoned in place, see batch_core): the fused form of the two calls above
+int pcr_cloud_sor_normals(const pcr_cloud *cloud, size_t k_sor, float std_mul, size_t k_normals, const float viewpoint[3],
+                          pcr_cloud **out) {
+    PCR_CLOUD_CHECK(cloud)
+    if (!out) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    if (k_normals == 0) return fail(c, PCR_ERR_INVALID_ARG, "k_normals must be > 0");
+    if (!std::isfinite(std_mul) || std_mul < 0.f) return fail(c, PCR_ERR_INVALID_ARG, "std_mul must be >= 0 and finite");
+    if (k_sor + 1 > PCR_MAX_K || k_normals > PCR_MAX_K) return fail(c, PCR_ERR_UNSUPPORTED, "k exceeds PCR_MAX_K");
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    const size_t n = cloud->n;
+    if (n == 0 || k_sor == 0) return cloud_alloc(cloud->owner, 0, true, out);  // statistical_outlier.rs:5-7
+    pcr_cloud *full = nullptr;
+    PCR_TRY(cloud_alloc(cloud->owner, n, true, &full));
+    struct G {
+        pcr_cloud *p;
+        ~G() { pcr_cloud_free(p); }
+    } g{full};
+    cudaMemcpyAsync(full->x(), cloud->x(), sizeof(float) * n, cudaMemcpyDeviceToDevice, c->stream);
+    cudaMemcpyAsync(full->y(), cloud->y(), sizeof(float) * n, cudaMemcpyDeviceToDevice, c->stream);
+    cudaMemcpyAsync(full->z(), cloud->z(), sizeof(float) * n, cudaMemcpyDeviceToDevice, c->stream);
+    PCR_TRY(ensure(c, c->b_in2, n + 512));
+    uint8_t *d_keep = (uint8_t *)c->b_in2.p;
+    unsigned long long *d_kept = (unsigned long long *)((char *)c->b_in2.p + ((n + 255) & ~(size_t)255));
+    const uint64_t offs[2] = {0, n};
+    const float vp0[3] = {0.f, 0.f, 0.f};
+    PCR_TRY(batch_core(c, cloud->x(), cloud->y(), cloud->z(), offs, 1, n, k_sor, std_mul, k_normals, viewpoint ? viewpoint : vp0, d_keep,
+                       full->nx(), full->ny(), full->nz(), d_kept));
+    return cloud_compact(full, d_keep, out);
+    PCR_API_END(c)
+}
+
 int pcr_cloud_euclidean_cluster(const pcr_cloud *cloud, float distance_threshold, size_t min_size, size_t max_size, uint32_t *offsets,
                                 uint32_t *indices, size_t *n_clusters) {
     PCR_CLOUD_CHECK(cloud)

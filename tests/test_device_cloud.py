@@ -45,6 +45,8 @@ def test_pipeline_matches_host_api_and_oracle(pcr, oracle):
     a, b = nrm.normals_to_numpy().astype(np.float64), o_n.astype(np.float64)
     ang = np.arctan2(np.linalg.norm(np.cross(a, b), axis=1), np.abs(np.sum(a * b, axis=1)))
     assert ang.max() < 1e-4
+    fused = v.sor_normals(10, 1.0, 20)                                   # one index for both steps: same bits
+    assert np.array_equal(fused.to_numpy(), o_s) and np.array_equal(fused.normals_to_numpy(), host_n)
     got = s.euclidean_cluster(0.5, 30, 25000)
     want = [list(map(int, c)) for c in oracle.euclidean_cluster(o_s, 0.5, 30, 25000)]
     assert got == want
