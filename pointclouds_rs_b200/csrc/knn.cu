@@ -475,7 +475,13 @@ __global__ void __launch_bounds__(kTQThreads) knn_thread_kernel(LevelArgs a, Thr
         acc.reset();
         if (searchable) {
             const GridDesc g = a.grids[f];
-            resolved = thread_grid_search(acc, g, a.cell_start, a.pts, px, py, pz, t.kk, a.max_rings, a.last_level != 0);
+            // short lists tighten quickly, so skipping the rows / cells beyond the current k-th best pays
+            // (SOR k = 10 on the 122 K frame: 153 -> 112 us); for k = 20 the extra per-row arithmetic and the
+            // more ragged trip counts cost more than the skipped candidates save (212 -> 225 us, measured)
+            if constexpr (KC <= 12)
+                resolved = thread_grid_search_pruned(acc, g, a.cell_start, a.pts, px, py, pz, t.kk, a.max_rings, a.last_level != 0);
+            else
+                resolved = thread_grid_search(acc, g, a.cell_start, a.pts, px, py, pz, t.kk, a.max_rings, a.last_level != 0);
             cnt = acc.count();
         }
     }

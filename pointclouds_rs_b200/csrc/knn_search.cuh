@@ -182,8 +182,9 @@ __device__ __forceinline__ void scan_runs(TopK &tk, const float4 *__restrict__ p
 template <class TopK>
 __device__ __forceinline__ bool warp_knn_search(TopK &tk, const GridDesc &g, const uint32_t *__restrict__ cell_start,
                                                 const float4 *__restrict__ pts, float qx, float qy, float qz,
-                                                int max_rings, bool last_level) {
+                                                int max_rings, bool last_level, unsigned long long seed = PCR_EMPTY_KEY) {
     tk.reset(PCR_EMPTY_KEY);
+    if (seed != PCR_EMPTY_KEY) tk.insert(seed);  // a known candidate (ICP: last iteration's neighbour) bounds the search from the start
     const uint32_t m = g.pt_end - g.pt_begin;
     if (m == 0) return true;
     if (m <= kBruteFrame || m <= (uint32_t)tk.kk) {
@@ -404,6 +405,119 @@ __device__ __forceinline__ bool thread_grid_search(Acc &acc, const GridDesc &g, 
         } else if (R >= max_rings) {
             acc.reset();  // restart with a whole-frame pass (re-offering a listed key would duplicate it)
             whole = true;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same search with PRUNED rows.  ncu on the ICP 1-NN kernel (1 M queries, 2 points per cell)
+// showed half of its 185 warp instructions per query in the enumeration of cell rows and most of the
+// rest in candidates that could not win: once the query's own row has been scanned the best d^2 is
+// usually far below the cell size.  Here every row of a shell is first tested against the current
+// k-th best tau: with gp = squared in-plane gap (in cells) between the query and the row, the row is
+// skipped if gp > tau, and otherwise only the cells within sqrt(tau - gp) of the query along the fast
+// axis are read.
+// Exactness: the trim keeps every point whose TRUE squared distance is <= tau * (1 + 1e-5) (+ an
+// absolute 1e-8 cell^2 for the f32 copies of the fractions), which covers the <= 3 ulp rounding of the
+// f32 d^2 the lists are built from; a point outside it can neither enter the list nor tie with its
+// last entry.  While the list is not full tau is +inf and nothing is trimmed.  The ring rule and the
+// deferral rule are those of thread_grid_search, so both functions return the same lists.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float axis_gap(int e, float f) {  // distance, in cells, to the cells `e` columns away
+    const float d = e > 0 ? (float)e - f : (e < 0 ? f - (float)e - 1.0f : 0.0f);
+    return fmaxf(d, 0.0f);
+}
+
+template <class Acc>
+__device__ __forceinline__ float acc_tau(const Acc &acc) {  // k-th best d^2 so far, +inf while the list is short
+    const unsigned long long k = acc.kth();
+    return k == PCR_EMPTY_KEY ? INFINITY : key_d2(k);
+}
+
+template <class Acc>
+__device__ __forceinline__ void scan_row_pruned(Acc &acc, const GridDesc &g, const uint32_t *__restrict__ cell_start,
+                                                const float4 *__restrict__ pts, int a0, int a1, int zl, int zh, float gp, int c2,
+                                                float f2, float inv_h2, float qx, float qy, float qz) {
+    if (zl > zh) return;
+    const float tau_c = acc_tau(acc) * inv_h2 * (1.0f + 1e-5f) + 1e-8f;  // cell units^2 (+inf: no pruning)
+    if (gp > tau_c) return;
+    if (tau_c < 1e12f && fabsf(f2) < 1e4f) {
+        const float w = sqrtf(tau_c - gp) * (1.0f + 1e-5f) + 1e-5f;
+        zl = max(zl, c2 + (int)floorf(f2 - w));
+        zh = min(zh, c2 + (int)floorf(f2 + w));
+        if (zl > zh) return;
+    }
+    const uint32_t lin = cell_linear(g, a0, a1, zl);
+    thread_scan_run(acc, pts, __ldg(&cell_start[lin]), __ldg(&cell_start[lin + (uint32_t)(zh - zl) + 1u]), qx, qy, qz);
+}
+
+template <class Acc>
+__device__ __forceinline__ bool thread_grid_search_pruned(Acc &acc, const GridDesc &g, const uint32_t *__restrict__ cell_start,
+                                                          const float4 *__restrict__ pts, float qx, float qy, float qz, int kk,
+                                                          int max_rings, bool last_level, bool seeded = false) {
+    // seeded: `acc` already holds real candidates of this index (k = 1 only: ICP's neighbour of the
+    // previous iteration) -- they bound the search from the first row on and cannot change its result
+    if (!seeded) acc.reset();
+    const uint32_t m = g.pt_end - g.pt_begin;
+    if (m == 0) return true;
+    if (m <= kBruteFrame || m <= (uint32_t)kk) {  // tiny frame: one run = everything
+        thread_scan_run(acc, pts, g.pt_begin, g.pt_end, qx, qy, qz);
+        return true;
+    }
+    double f0, f1, f2;
+    const int c0 = cell_coord(g, 0, pick_axis(g.ax[0], qx, qy, qz), &f0);
+    const int c1 = cell_coord(g, 1, pick_axis(g.ax[1], qx, qy, qz), &f1);
+    const int c2 = cell_coord(g, 2, pick_axis(g.ax[2], qx, qy, qz), &f2);
+    const float ff0 = (float)f0, ff1 = (float)f1, ff2 = (float)f2;
+    const int d0n = g.dims[0], d1n = g.dims[1], d2n = g.dims[2];
+    const float inv_h2 = (float)(g.inv_h * g.inv_h);
+    for (int S = 1;; S++) {
+        // shell S (S == 1 also takes the centre, the query's own row first): border rows are full runs,
+        // interior rows contribute their two end cells
+        const int side = 2 * S + 1, T = side * side;
+        const int zlo = max(c2 - S, 0), zhi = min(c2 + S, d2n - 1);
+#pragma unroll 1
+        for (int r = 0; r < T; r++) {
+            int e0 = r / side, e1 = r - e0 * side;
+            if (S == 1) {
+                e0 = e0 == 0 ? 0 : (e0 == 1 ? -1 : 1);
+                e1 = e1 == 0 ? 0 : (e1 == 1 ? -1 : 1);
+            } else {
+                e0 -= S;
+                e1 -= S;
+            }
+            const int a0 = c0 + e0, a1 = c1 + e1;
+            if (a0 < 0 || a0 >= d0n || a1 < 0 || a1 >= d1n) continue;
+            const float g0 = axis_gap(e0, ff0), g1 = axis_gap(e1, ff1);
+            const float gp = g0 * g0 + g1 * g1;
+            if (S == 1 || e0 == S || e0 == -S || e1 == S || e1 == -S) {
+                scan_row_pruned(acc, g, cell_start, pts, a0, a1, zlo, zhi, gp, c2, ff2, inv_h2, qx, qy, qz);
+            } else {
+                if (c2 - S >= 0) scan_row_pruned(acc, g, cell_start, pts, a0, a1, c2 - S, c2 - S, gp, c2, ff2, inv_h2, qx, qy, qz);
+                if (c2 + S < d2n) scan_row_pruned(acc, g, cell_start, pts, a0, a1, c2 + S, c2 + S, gp, c2, ff2, inv_h2, qx, qy, qz);
+            }
+        }
+        double bound2;
+        if (!ring_bound2(g, c0, c1, c2, f0, f1, f2, S, bound2)) return true;
+        const unsigned long long kth = acc.kth();
+        if (kth != PCR_EMPTY_KEY && (double)key_d2(kth) < bound2 * (1.0 - 1e-6)) return true;
+        if (!last_level) {
+            if (S >= max_rings) return false;
+            // a seeded query knows how far it has to look: walk one more shell only if that shell settles
+            // it ((S + 1) cells >= its current best distance); otherwise the next level is the cheaper
+            // place to look (the seed goes along)
+            if (seeded && kth != PCR_EMPTY_KEY) {
+                const double reach = (double)(S + 1) * g.h;
+                if ((double)key_d2(kth) > reach * reach) return false;
+            }
+            // (the count below can be smaller than in thread_grid_search once rows are trimmed, but
+            // rows are only trimmed when the list is already full, i.e. cnt == kk)
+            const int cnt = acc.count();
+            if ((S == 1 && cnt * 4 < kk) || (S >= 2 && cnt < kk)) return false;
+        } else if (S >= max_rings) {
+            if (!seeded) acc.reset();  // coarsest level: scan the whole frame instead (min over everything: a kept seed is harmless for k = 1)
+            thread_scan_run(acc, pts, g.pt_begin, g.pt_end, qx, qy, qz);
+            return true;
         }
     }
 }
