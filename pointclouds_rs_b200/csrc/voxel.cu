@@ -65,12 +65,32 @@ __global__ void __launch_bounds__(256) vox_range_kernel(const float *__restrict_
         mx[a] = __reduce_max_sync(PCR_FULL, mx[a]);
     }
     cnt = __reduce_add_sync(PCR_FULL, cnt);
-    if ((threadIdx.x & 31) == 0 && cnt) {
+    // block-level combine first: seven same-address atomics per WARP cost 20 us on the 122 K frame
+    __shared__ int smn[3][8], smx[3][8];
+    __shared__ unsigned scnt[8];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
         for (int a = 0; a < 3; a++) {
-            atomicMin(&r->mn[a], mn[a]);
-            atomicMax(&r->mx[a], mx[a]);
+            smn[a][w] = mn[a];
+            smx[a][w] = mx[a];
         }
-        atomicAdd(&r->finite, cnt);
+        scnt[w] = cnt;
+    }
+    __syncthreads();
+    if (w == 0) {
+        const bool in = lane < (int)(blockDim.x >> 5);
+        for (int a = 0; a < 3; a++) {
+            mn[a] = __reduce_min_sync(PCR_FULL, in ? smn[a][lane] : 2147483647);
+            mx[a] = __reduce_max_sync(PCR_FULL, in ? smx[a][lane] : -2147483647 - 1);
+        }
+        cnt = __reduce_add_sync(PCR_FULL, in ? scnt[lane] : 0u);
+        if (lane == 0 && cnt) {
+            for (int a = 0; a < 3; a++) {
+                atomicMin(&r->mn[a], mn[a]);
+                atomicMax(&r->mx[a], mx[a]);
+            }
+            atomicAdd(&r->finite, cnt);
+        }
     }
 }
 
@@ -262,7 +282,7 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
     VoxRange *h_range = (VoxRange *)ctx->pinned;
     vox_init_kernel<<<1, 1, 0, st>>>(d_range);
     PCR_LAUNCH_CHECK(ctx);
-    const unsigned bx = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
+    const unsigned bx = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 2);
     vox_range_kernel<<<bx, 256, 0, st>>>(dx, dy, dz, n, voxel, d_range);
     PCR_LAUNCH_CHECK(ctx);
     PCR_CUDA(ctx, cudaMemcpyAsync(h_range, d_range, sizeof(VoxRange), cudaMemcpyDeviceToHost, st));
