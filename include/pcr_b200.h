@@ -223,6 +223,20 @@ int pcr_euclidean_cluster(pcr_ctx *ctx, const float *x, const float *y, const fl
 int pcr_cluster_labels_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z,
                            size_t n, float distance_threshold, uint32_t *d_labels);
 
+typedef struct pcr_cloud pcr_cloud; /* device-resident cloud, see the end of this header */
+
+/* ---- plane segmentation -------------------------------------------------------------
+ * ransac_plane_seeded (crates/segmentation/src/ransac_plane.rs:56-129) AFTER its sampling step: `samples`
+ * holds the m index triples exactly as the reference's sample_three_distinct produced them (StdRng stays on
+ * the Rust side).  Fits, inlier counts (m x n distances), the reference's choice rule (sequential with the
+ * adaptive early exit, or first-maximum when n >= 10000 and m >= 16) and the inlier list run here.
+ * model = {nx, ny, nz, d} (default (0,0,1,0) if n < 3 or no sample is valid); inliers sized n, ascending. */
+int pcr_ransac_plane_samples(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n,
+                             float distance_threshold, const uint32_t *samples, size_t m, float model[4],
+                             uint32_t *inliers, size_t *n_inliers);
+int pcr_cloud_ransac_plane_samples(const pcr_cloud *cloud, float distance_threshold, const uint32_t *samples,
+                                   size_t m, float model[4], uint32_t *inliers, size_t *n_inliers);
+
 /* ---- multi-frame batch (BASELINE config 5) ------------------------------------------------------
  * Frames are independent clouds stored back to back: frame f = points [frame_offsets[f],
  * frame_offsets[f+1]).  Per frame: SOR(k_sor, std_mul) then normals(k_normals, viewpoint) on the
@@ -243,7 +257,6 @@ int pcr_sor_normals_batch_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, 
  * one download, `select` (cloud.rs:103-140) as a device compaction that carries the normals along.
  * Every function that returns a cloud allocates a new handle (free it with pcr_cloud_free); inputs
  * are never modified.  Edge cases follow the reference functions named on each line. */
-typedef struct pcr_cloud pcr_cloud;
 int pcr_cloud_upload(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n, pcr_cloud **out);
 void pcr_cloud_free(pcr_cloud *cloud);
 size_t pcr_cloud_len(const pcr_cloud *cloud);

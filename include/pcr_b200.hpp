@@ -13,6 +13,7 @@
 //   pcr::icp_point_to_point / _plane     crates/registration/src/icp.rs:125, icp_plane.rs:20
 //   pcr::voxel_downsample                crates/filters/src/voxel_downsample.rs:12
 //   pcr::euclidean_cluster               crates/segmentation/src/euclidean_cluster.rs:96
+//   pcr::ransac_plane_samples            crates/segmentation/src/ransac_plane.rs:56 (after its sampling step)
 //   pcr::DeviceCloud                     the same calls on a cloud that stays in HBM between steps
 #pragma once
 
@@ -22,6 +23,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "pcr_b200.h"
@@ -294,6 +296,31 @@ inline std::vector<std::vector<size_t>> euclidean_cluster(const PointCloud &clou
     std::vector<std::vector<size_t>> out(nc);
     for (size_t c = 0; c < nc; c++) out[c].assign(idx.begin() + off[c], idx.begin() + off[c + 1]);
     return out;
+}
+
+// crates/segmentation/src/ransac_plane.rs:7-31
+struct PlaneModel {
+    float normal[3] = {0.f, 0.f, 1.f};
+    float d = 0.f;
+};
+
+// ransac_plane_seeded (ransac_plane.rs:56-129) for index triples drawn by the caller (the reference draws them
+// from StdRng, :75-78; a Rust host keeps doing that and passes them on)
+inline std::pair<PlaneModel, std::vector<size_t>> ransac_plane_samples(const PointCloud &cloud, float distance_threshold,
+                                                                       const std::vector<uint32_t> &samples /* 3 per hypothesis */,
+                                                                       Context &ctx = default_context()) {
+    const size_t n = cloud.len();
+    float model[4];
+    std::vector<uint32_t> inl(n ? n : 1);
+    size_t k = 0;
+    ctx.check(pcr_ransac_plane_samples(ctx.get(), cloud.x.data(), cloud.y.data(), cloud.z.data(), n, distance_threshold, samples.data(),
+                                       samples.size() / 3, model, inl.data(), &k));
+    PlaneModel m;
+    m.normal[0] = model[0];
+    m.normal[1] = model[1];
+    m.normal[2] = model[2];
+    m.d = model[3];
+    return {m, std::vector<size_t>(inl.begin(), inl.begin() + k)};
 }
 
 // A PointCloud that stays in HBM between the steps of a pipeline (one upload, one download).

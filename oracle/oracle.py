@@ -94,6 +94,8 @@ def lib():
         for fn in (L.orc_euclidean_cluster, L.orc_euclidean_cluster_brute):
             fn.restype = C.c_size_t
             fn.argtypes = [_f32p, _f32p, _f32p, C.c_size_t, C.c_float, C.c_size_t, C.c_size_t, _u32p, _u32p]
+        L.orc_ransac_plane_samples.restype = C.c_size_t
+        L.orc_ransac_plane_samples.argtypes = [_f32p, _f32p, _f32p, C.c_size_t, C.c_float, _u32p, C.c_size_t, _f32p, _u32p]
         L.orc_voxel_downsample.restype = C.c_size_t
         L.orc_voxel_downsample.argtypes = [_f32p, _f32p, _f32p, C.c_size_t, C.c_float, _f32p, _f32p, _f32p]
         L.orc_read_pcd_ascii.restype = C.c_long
@@ -322,6 +324,17 @@ def euclidean_cluster(pts, distance_threshold, min_size, max_size, brute=False):
     fn = lib().orc_euclidean_cluster_brute if brute else lib().orc_euclidean_cluster
     nc = fn(_p(x, _f32p), _p(y, _f32p), _p(z, _f32p), n, float(distance_threshold), int(min_size), int(max_size), _p(off, _u32p), _p(idx, _u32p))
     return [idx[off[c]:off[c + 1]].copy() for c in range(nc)]
+
+
+def ransac_plane_samples(pts, threshold, samples):
+    """ransac_plane.rs:56-129 for given (m,3) sample triples -> (model [nx,ny,nz,d] f32, inlier indices u32)."""
+    x, y, z = _xyz(pts)
+    n = len(x)
+    smp = np.ascontiguousarray(np.asarray(samples, np.uint32).reshape(-1, 3))
+    model = np.zeros(4, np.float32)
+    inl = np.zeros(max(n, 1), np.uint32)
+    k = lib().orc_ransac_plane_samples(_p(x, _f32p), _p(y, _f32p), _p(z, _f32p), n, float(threshold), _p(smp, _u32p), len(smp), _p(model, _f32p), _p(inl, _u32p))
+    return model, inl[:k].copy()
 
 
 def voxel_downsample(pts, voxel_size):

@@ -1336,6 +1336,72 @@ size_t orc_euclidean_cluster_brute(const float *x, const float *y, const float *
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* ransac_plane_seeded  (crates/segmentation/src/ransac_plane.rs:56-129) for GIVEN samples     */
+/* ------------------------------------------------------------------------------------------ */
+
+/* :166-190; returns 0 if the three points are collinear */
+static int fit_plane3(const float p0[3], const float p1[3], const float p2[3], float model[4]) {
+    const float v1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+    const float v2[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+    const float nx = v1[1] * v2[2] - v1[2] * v2[1];
+    const float ny = v1[2] * v2[0] - v1[0] * v2[2];
+    const float nz = v1[0] * v2[1] - v1[1] * v2[0];
+    const float len = sqrtf(nx * nx + ny * ny + nz * nz);
+    if (len < 1e-10f) return 0;
+    model[0] = nx / len;
+    model[1] = ny / len;
+    model[2] = nz / len;
+    model[3] = -(model[0] * p0[0] + model[1] * p0[1] + model[2] * p0[2]);
+    return 1;
+}
+
+static inline float plane_dist(const float m[4], float x, float y, float z) { /* :17-20 */
+    return fabsf(m[0] * x + m[1] * y + m[2] * z + m[3]);
+}
+
+/* The sampling (StdRng = ChaCha12, :75-78, :140-163) stays with the caller: `samples` holds m index
+ * triples exactly as sample_three_distinct produced them.  model = {nx, ny, nz, d}; inliers sized n. */
+size_t orc_ransac_plane_samples(const float *x, const float *y, const float *z, size_t n, float threshold,
+                                const uint32_t *samples, size_t m, float model[4], uint32_t *inliers) {
+    float best[4] = {0.f, 0.f, 1.f, 0.f}; /* PlaneModel::default(), :23-30 */
+    memcpy(model, best, sizeof(best));
+    if (n < 3) return 0; /* :64-66 */
+    size_t best_count = 0;
+    int have = 0;
+    const int parallel = n >= 10000 && m >= 16; /* :80 */
+    for (size_t it = 0; it < m; it++) {
+        const uint32_t i0 = samples[3 * it], i1 = samples[3 * it + 1], i2 = samples[3 * it + 2];
+        const float p0[3] = {x[i0], y[i0], z[i0]}, p1[3] = {x[i1], y[i1], z[i1]}, p2[3] = {x[i2], y[i2], z[i2]};
+        float cand[4];
+        if (!fit_plane3(p0, p1, p2, cand)) continue; /* :86 / :98-101 */
+        size_t cnt = 0;
+        for (size_t j = 0; j < n; j++) cnt += plane_dist(cand, x[j], y[j], z[j]) <= threshold ? 1 : 0; /* :132-137 */
+        if (parallel) {
+            /* :84-93: reduce_with(|a, b| if a.1 >= b.1 { a } else { b }) over an ordered iterator keeps the FIRST
+             * hypothesis with the largest count; the default model is used only if no hypothesis is valid */
+            if (!have || cnt > best_count) {
+                have = 1;
+                best_count = cnt;
+                memcpy(best, cand, sizeof(best));
+            }
+        } else if (cnt > best_count) { /* :106 */
+            best_count = cnt;
+            memcpy(best, cand, sizeof(best));
+            const double w = (double)best_count / (double)n; /* :110-117 adaptive early termination */
+            if (w > 0.5) {
+                const double needed = log(1.0 - 0.999) / log(1.0 - w * w * w);
+                if ((double)it > needed) break;
+            }
+        }
+    }
+    memcpy(model, best, sizeof(best));
+    size_t k = 0; /* :123-126 */
+    for (size_t j = 0; j < n; j++)
+        if (plane_dist(best, x[j], y[j], z[j]) <= threshold) inliers[k++] = (uint32_t)j;
+    return k;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* ASCII PCD body reader (crates/io/src/pcd.rs:202-234)                                       */
 /* ------------------------------------------------------------------------------------------ */
 

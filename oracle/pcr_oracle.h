@@ -127,6 +127,14 @@ size_t orc_euclidean_cluster(const float *x, const float *y, const float *z, siz
 size_t orc_euclidean_cluster_brute(const float *x, const float *y, const float *z, size_t n, float distance_threshold,
                                    size_t min_size, size_t max_size, uint32_t *offsets, uint32_t *indices);
 
+/* crates/segmentation/src/ransac_plane.rs:56-129 for GIVEN samples: the sampling (:75-78, :140-163) uses
+ * StdRng = ChaCha12, whose stream cannot be reproduced here, so `samples` holds the m index triples exactly as
+ * sample_three_distinct would hand them over.  Both execution paths are followed: sequential with the adaptive
+ * early exit (:95-121) and, for n >= 10000 and >= 16 samples, the order-preserving parallel reduction (:82-93).
+ * model = {nx, ny, nz, d}; inliers sized n; returns the inlier count. */
+size_t orc_ransac_plane_samples(const float *x, const float *y, const float *z, size_t n, float threshold,
+                                const uint32_t *samples, size_t m, float model[4], uint32_t *inliers);
+
 /* crates/filters/src/voxel_downsample.rs:12-65.  Outputs sized n; returns voxel count,
  * or (size_t)-1 if voxel_size is not finite / <= 0 (the reference panics, :13-16). */
 size_t orc_voxel_downsample(const float *x, const float *y, const float *z, size_t n,

@@ -31,7 +31,7 @@ __all__ = [
     "PointCloud", "KdTree", "IcpResult", "Context",
     "statistical_outlier_removal", "radius_outlier_removal", "estimate_normals",
     "icp_point_to_point", "icp_point_to_plane", "apply_transform", "find_correspondences",
-    "sor_normals_batch", "default_context", "PcrError", "euclidean_cluster", "voxel_downsample", "DeviceCloud",
+    "sor_normals_batch", "default_context", "PcrError", "euclidean_cluster", "voxel_downsample", "DeviceCloud", "ransac_plane", "PlaneResult",
 ]
 
 
@@ -369,6 +369,63 @@ def euclidean_cluster(cloud: PointCloud, distance_threshold: float, min_size: in
     return [idx[off[c]:off[c + 1]].tolist() for c in range(int(nc.value))]
 
 
+class PlaneResult:
+    """crates/python/src/segmentation.rs:19-36."""
+
+    def __init__(self, normal, d, inliers):
+        self.normal = [float(v) for v in normal]
+        self.d = float(d)
+        self.inliers = inliers
+
+    def __repr__(self) -> str:
+        return f"PlaneResult(normal={self.normal}, d={self.d:.4f}, inliers={len(self.inliers)})"
+
+
+def draw_plane_samples(n: int, iterations: int, seed=None) -> np.ndarray:
+    """The reference's sample_three_distinct (ransac_plane.rs:140-163) with numpy's generator: same procedure,
+    NOT the same stream as Rust's StdRng (ChaCha12).  A Rust host passes its own triples to the C ABI."""
+    rng = np.random.default_rng(seed)
+    out = []
+    if n < 3:
+        return np.zeros((0, 3), np.uint32)
+    for _ in range(int(iterations)):
+        i0 = int(rng.integers(n))
+        i1, tries = int(rng.integers(n)), 0
+        while i1 == i0 and tries <= 100:
+            i1, tries = int(rng.integers(n)), tries + 1
+        if i1 == i0:
+            continue
+        i2, tries = int(rng.integers(n)), 0
+        while i2 in (i0, i1) and tries <= 100:
+            i2, tries = int(rng.integers(n)), tries + 1
+        if i2 in (i0, i1):
+            continue
+        out.append((i0, i1, i2))
+    return np.asarray(out, np.uint32).reshape(-1, 3)
+
+
+def ransac_plane_samples(cloud: PointCloud, distance_threshold: float, samples, ctx: Optional[Context] = None) -> PlaneResult:
+    """ransac_plane_seeded (ransac_plane.rs:56-129) for given index triples."""
+    ctx = ctx or default_context()
+    n = len(cloud)
+    smp = np.ascontiguousarray(np.asarray(samples, np.uint32).reshape(-1, 3))
+    if len(smp) and int(smp.max()) >= n:
+        raise IndexError(f"sample index {int(smp.max())} out of bounds for cloud with {n} points")
+    model = np.zeros(4, np.float32)
+    inl = np.zeros(max(n, 1), np.uint32)
+    k = C.c_size_t()
+    st = _ffi.load().pcr_ransac_plane_samples(ctx._h, _p(cloud.x, _ffi.f32p), _p(cloud.y, _ffi.f32p), _p(cloud.z, _ffi.f32p), n,
+                                              float(distance_threshold), _p(smp, _ffi.u32p), len(smp), _p(model, _ffi.f32p),
+                                              _p(inl, _ffi.u32p), C.byref(k))
+    _ffi.check(st, ctx._h)
+    return PlaneResult(model[:3], model[3], inl[:int(k.value)].tolist())
+
+
+def ransac_plane(cloud: PointCloud, distance_threshold: float, iterations: int, ctx: Optional[Context] = None) -> PlaneResult:
+    """crates/python/src/segmentation.rs:42-55: a random seed per call, like the reference's ransac_plane (:36-43)."""
+    return ransac_plane_samples(cloud, distance_threshold, draw_plane_samples(len(cloud), iterations), ctx)
+
+
 def cluster_arrays(cloud: PointCloud, distance_threshold: float, min_size: int, max_size: int, ctx: Optional[Context] = None):
     """Same call, CSR form (offsets, indices) without building Python lists."""
     ctx = ctx or default_context()
@@ -612,6 +669,22 @@ class DeviceCloud:
                                                      _p(idx, _ffi.u32p), C.byref(nc))
         _ffi.check(st, self._ctx._h)
         return [idx[off[c]:off[c + 1]].tolist() for c in range(int(nc.value))]
+
+    def ransac_plane_samples(self, distance_threshold: float, samples) -> "PlaneResult":
+        n = self.len()
+        smp = np.ascontiguousarray(np.asarray(samples, np.uint32).reshape(-1, 3))
+        if len(smp) and int(smp.max()) >= n:
+            raise IndexError(f"sample index {int(smp.max())} out of bounds for cloud with {n} points")
+        model = np.zeros(4, np.float32)
+        inl = np.zeros(max(n, 1), np.uint32)
+        k = C.c_size_t()
+        st = _ffi.load().pcr_cloud_ransac_plane_samples(self._h, float(distance_threshold), _p(smp, _ffi.u32p), len(smp),
+                                                        _p(model, _ffi.f32p), _p(inl, _ffi.u32p), C.byref(k))
+        _ffi.check(st, self._ctx._h)
+        return PlaneResult(model[:3], model[3], inl[:int(k.value)].tolist())
+
+    def ransac_plane(self, distance_threshold: float, iterations: int) -> "PlaneResult":
+        return self.ransac_plane_samples(distance_threshold, draw_plane_samples(self.len(), iterations))
 
     def apply_transform(self, rotation, translation) -> "DeviceCloud":
         r = np.ascontiguousarray(np.asarray(rotation, np.float32).reshape(9))

@@ -1352,6 +1352,43 @@ int pcr_cloud_euclidean_cluster(const pcr_cloud *cloud, float distance_threshold
     PCR_API_END(c)
 }
 
+static int ransac_common(Ctx *c, const float *dx, const float *dy, const float *dz, size_t n, float thr, const uint32_t *samples, size_t m,
+                         float model[4], uint32_t *inliers, size_t *n_inliers) {
+    PCR_TRY(ensure(c, c->b_out, sizeof(uint32_t) * std::max<size_t>(n, 1)));
+    uint32_t *d_inl = (uint32_t *)c->b_out.p;
+    size_t k = 0;
+    PCR_TRY(ransac_plane_samples_dev(c, dx, dy, dz, n, thr, samples, m, model, d_inl, &k));
+    if (k) {
+        PCR_CUDA(c, cudaMemcpyAsync(inliers, d_inl, sizeof(uint32_t) * k, cudaMemcpyDeviceToHost, c->stream));
+        PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    *n_inliers = k;
+    return PCR_OK;
+}
+
+int pcr_ransac_plane_samples(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n, float distance_threshold,
+                             const uint32_t *samples, size_t m, float model[4], uint32_t *inliers, size_t *n_inliers) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (!model || !n_inliers || (m && !samples) || (n && (!x || !y || !z || !inliers))) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    float *dx = nullptr, *dy = nullptr, *dz = nullptr;
+    if (n >= 3) PCR_TRY(stage_xyz(c, c->b_in, x, y, z, n, &dx, &dy, &dz));
+    return ransac_common(c, dx, dy, dz, n, distance_threshold, samples, m, model, inliers, n_inliers);
+    PCR_API_END(c)
+}
+
+int pcr_cloud_ransac_plane_samples(const pcr_cloud *cloud, float distance_threshold, const uint32_t *samples, size_t m, float model[4],
+                                   uint32_t *inliers, size_t *n_inliers) {
+    PCR_CLOUD_CHECK(cloud)
+    if (!model || !n_inliers || (m && !samples) || (cloud->n && !inliers)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    return ransac_common(c, cloud->x(), cloud->y(), cloud->z(), cloud->n, distance_threshold, samples, m, model, inliers, n_inliers);
+    PCR_API_END(c)
+}
+
 int pcr_cloud_apply_transform(const pcr_cloud *cloud, const float rotation[9], const float translation[3], pcr_cloud **out) {
     PCR_CLOUD_CHECK(cloud)
     if (!out || !rotation || !translation) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");

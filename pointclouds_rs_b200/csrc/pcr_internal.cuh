@@ -206,6 +206,10 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
 int radix_sort_pairs_dev(Ctx *ctx, unsigned long long **keys, uint32_t **vals, unsigned long long **keys_alt, uint32_t **vals_alt,
                          size_t n, int bits, uint32_t *d_hist);
 
+// ransac_plane_seeded for given samples (ransac.cu); h_samples: HOST array of m index triples
+int ransac_plane_samples_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz, size_t n, float threshold,
+                             const uint32_t *h_samples, size_t m, float model_out[4], uint32_t *d_inliers, size_t *n_inliers);
+
 // NCCL plumbing (comm.cu)
 int comm_unique_id(void *out);
 int comm_init(Ctx *ctx, const void *id, int rank, int world);
