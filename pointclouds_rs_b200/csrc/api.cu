@@ -220,6 +220,8 @@ void pcr_ctx_destroy(pcr_ctx *ctx) {
     free_buf(c, c->b_misc2);
     free_buf(c, c->b_small);
     free_buf(c, c->b_table);
+    free_buf(c, c->b_list);
+    for (auto &b : c->b_cells) free_buf(c, b);
     cudaStreamSynchronize(c->stream);
     for (auto &sp : c->spans) {
         cudaEventDestroy(sp.a);
@@ -461,6 +463,7 @@ static int sor_core(Ctx *c, const float *dx, const float *dy, const float *dz, s
                     float *d_mean, float *d_stats, unsigned long long *d_kept) {
     BuildOpts bo;
     bo.k_hint = k + 1;
+    bo.transient = true;
     Index *ix = nullptr;
     PCR_TRY(index_build_dev(c, dx, dy, dz, n, bo, &ix));
     int s = sor_mean_dist_dev(ix, k, d_mean);
@@ -570,6 +573,7 @@ static int ror_core(Ctx *c, const float *dx, const float *dy, const float *dz, s
     const float saved = c->forced_cell;
     if (saved == 0.f && radius > 0.f && std::isfinite(radius)) c->forced_cell = radius;
     BuildOpts bo;
+    bo.transient = true;
     Index *ix = nullptr;
     int s = index_build_dev(c, dx, dy, dz, n, bo, &ix);
     c->forced_cell = saved;
@@ -719,6 +723,7 @@ int pcr_estimate_normals_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, c
     DevSetter ds(c);
     BuildOpts bo;
     bo.k_hint = k;
+    bo.transient = true;
     Index *ix = nullptr;
     PCR_TRY(index_build_dev(c, d_x, d_y, d_z, n, bo, &ix));
     int s = normals_dev(ix, k, viewpoint, d_nx, d_ny, d_nz, nullptr);
@@ -743,6 +748,7 @@ int pcr_estimate_normals(pcr_ctx *ctx, const float *x, const float *y, const flo
     float *dnx = (float *)c->b_out.p, *dny = dnx + stride, *dnz = dny + stride;
     BuildOpts bo;
     bo.k_hint = k;
+    bo.transient = true;
     Index *ix = nullptr;
     PCR_TRY(index_build_dev(c, dx, dy, dz, n, bo, &ix));
     int s = normals_dev(ix, k, viewpoint, dnx, dny, dnz, nullptr);
@@ -925,6 +931,7 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
     bo.k_hint = std::max(k_sor + 1, k_normals);
     if (const char *e = getenv("PCR_BATCH_KHINT")) bo.k_hint = (size_t)atoi(e);
     bo.n_frames = F;
+    bo.transient = true;
     bo.frame_offsets = frame_offsets;
     Index *ix = nullptr;
     PCR_TRY(index_build_dev(c, dx, dy, dz, n, bo, &ix));

@@ -15,6 +15,7 @@
 #include "pcr_internal.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 
 namespace pcr {
@@ -520,7 +521,7 @@ void index_free(Index *ix) {
         cudaStream_t s = ix->ctx->stream;
         if (ix->grids) cudaFreeAsync(ix->grids, s);
         if (ix->sorted) cudaFreeAsync(ix->sorted, s);
-        if (ix->cell_start) cudaFreeAsync(ix->cell_start, s);
+        if (ix->cell_start && ix->cell_slot < 0) cudaFreeAsync(ix->cell_start, s);
         if (!ix->shares_orig4) {
             if (ix->frame_in_off) cudaFreeAsync(ix->frame_in_off, s);
             if (ix->orig4) cudaFreeAsync(ix->orig4, s);
@@ -597,7 +598,13 @@ int index_coarser_level(Index *ix, Index **out) {
     }
     c->total_cells = (uint32_t)base;
     PCR_CUDA(ctx, cudaMemcpyAsync(c->grids, c->grids_h.data(), sizeof(GridDesc) * F, cudaMemcpyHostToDevice, st));
-    PCR_CUDA(ctx, cudaMallocAsync((void **)&c->cell_start, sizeof(uint32_t) * ((size_t)base + 1), st));
+    if (ix->cell_slot >= 0 && ix->cell_slot + 1 < (int)(sizeof(ctx->b_cells) / sizeof(ctx->b_cells[0]))) {
+        c->cell_slot = ix->cell_slot + 1;
+        PCR_TRY(ensure(ctx, ctx->b_cells[c->cell_slot], sizeof(uint32_t) * ((size_t)base + 1)));
+        c->cell_start = (uint32_t *)ctx->b_cells[c->cell_slot].p;
+    } else {
+        PCR_CUDA(ctx, cudaMallocAsync((void **)&c->cell_start, sizeof(uint32_t) * ((size_t)base + 1), st));
+    }
     PCR_CUDA(ctx, cudaMemsetAsync(c->cell_start, 0, sizeof(uint32_t) * ((size_t)base + 1), st));
     PCR_CUDA(ctx, cudaMallocAsync((void **)&c->sorted, sizeof(float4) * std::max<size_t>(n, 1), st));
     PCR_TRY(ensure(ctx, ctx->b_misc, sizeof(uint32_t) * 2 * std::max<size_t>(n, 1)));
@@ -666,6 +673,9 @@ int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz,
         PCR_CUDA(ctx, cudaMallocAsync((void **)&ix->sorted, sizeof(float4) * n, st));
     }
 
+    const bool dbg_t = getenv("PCR_DEBUG_BUILD") != nullptr;
+    auto now_us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now_us();
     // ---- K0: bounding boxes -------------------------------------------------------------------
     PCR_TRY(ensure(ctx, ctx->b_small, sizeof(FrameStats) * F + sizeof(ProbeStats) * F + 256));
     PCR_TRY(ensure_pinned(ctx, sizeof(FrameStats) * F + sizeof(ProbeStats) * F + 256));
@@ -746,6 +756,7 @@ int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz,
     };
     const unsigned count_bx = std::max(1u, (max_frame + kBuildThreads * kItems - 1) / (kBuildThreads * kItems));
 
+    if (dbg_t) { cudaStreamSynchronize(st); fprintf(stderr, "[build] bbox done +%.0f us\n", now_us() - t_begin); }
     // ---- probe rounds: measure occupancy, solve for the cell size ------------------------------
     if (!forced && n_indexed > 0) {
         for (int round = 0; round < 2; round++) {
@@ -781,23 +792,35 @@ int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz,
         }
     }
 
+    if (dbg_t) { cudaStreamSynchronize(st); fprintf(stderr, "[build] probe done +%.0f us\n", now_us() - t_begin); }
     // ---- final grid: count, scan, scatter ------------------------------------------------------
     uint32_t total = 0;
     PCR_TRY(layout(&total));
     ix->total_cells = total;
-    PCR_CUDA(ctx, cudaMallocAsync((void **)&ix->cell_start, sizeof(uint32_t) * ((size_t)total + 1), st));
+    if (opts.transient) {
+        ix->cell_slot = 0;
+        PCR_TRY(ensure(ctx, ctx->b_cells[0], sizeof(uint32_t) * ((size_t)total + 1)));
+        ix->cell_start = (uint32_t *)ctx->b_cells[0].p;
+    } else {
+        PCR_CUDA(ctx, cudaMallocAsync((void **)&ix->cell_start, sizeof(uint32_t) * ((size_t)total + 1), st));
+    }
+    if (dbg_t) { fprintf(stderr, "[build] malloc issued +%.0f us\n", now_us() - t_begin); }
     PCR_CUDA(ctx, cudaMemsetAsync(ix->cell_start, 0, sizeof(uint32_t) * ((size_t)total + 1), st));
+    if (dbg_t) { cudaStreamSynchronize(st); fprintf(stderr, "[build] memset done +%.0f us\n", now_us() - t_begin); }
     if (n > 0) {
         count_kernel<<<dim3(count_bx, F), kBuildThreads, 0, st>>>(dx, dy, dz, ix->frame_in_off, n, opts.d_mask, ix->grids,
                                                                   ix->cell_start, d_cell_id, d_rank, ix->orig4);
         PCR_LAUNCH_CHECK(ctx);
     }
+    if (dbg_t) { cudaStreamSynchronize(st); fprintf(stderr, "[build] count done +%.0f us\n", now_us() - t_begin); }
     PCR_TRY(exclusive_scan_u32_dev(ctx, ix->cell_start, (size_t)total + 1));
+    if (dbg_t) { cudaStreamSynchronize(st); fprintf(stderr, "[build] scan done +%.0f us\n", now_us() - t_begin); }
     if (n > 0) {
         scatter_kernel<<<(unsigned)((n + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0, st>>>(
             ix->orig4, n, ix->cell_start, d_cell_id, d_rank, ix->sorted);
         PCR_LAUNCH_CHECK(ctx);
     }
+    if (dbg_t) { cudaStreamSynchronize(st); fprintf(stderr, "[build] final done +%.0f us (total cells %u)\n", now_us() - t_begin, total); }
     guard.ix = nullptr;
     *out = ix;
     return PCR_OK;

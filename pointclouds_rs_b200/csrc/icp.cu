@@ -657,6 +657,7 @@ int icp_dev(Ctx *ctx, const IcpArgs &a, pcr_icp_result *result) {
     Index *tgt = nullptr;
     BuildOpts bo;
     bo.k_hint = 1;
+    bo.transient = true;
     PCR_TRY(index_build_dev(ctx, a.d_tx, a.d_ty, a.d_tz, a.nt, bo, &tgt));
     struct Guard {
         Index *ix;

@@ -61,6 +61,7 @@ struct Index {
     const uint8_t *d_mask = nullptr;  // keep-mask the index was built with (caller memory)
     Index *coarser = nullptr;         // next grid level (8x the cell size), built on demand
     bool shares_orig4 = false;        // coarser levels borrow orig4 / grids layout from level 0
+    int cell_slot = -1;               // >= 0: cell_start lives in ctx->b_cells[cell_slot] (transient index), not owned
 };
 
 struct Ctx {
@@ -80,6 +81,10 @@ struct Ctx {
     DevBuf b_small;    // reductions, statistics, ICP state
     DevBuf b_table;    // probe cell table
     DevBuf b_list;     // deferred-query lists of the level loop
+    // cell tables of TRANSIENT indices (the ones an entry point builds and frees itself), one per grid
+    // level.  A 100-frame batch needs a 280 MB table: taking it from the stream-ordered pool on every
+    // call cost 4-16 ms (the pool had just carved the freed block up for the smaller arrays).
+    DevBuf b_cells[6];
     void *pinned = nullptr;  // small pinned host mailbox
     size_t pinned_cap = 0;
     // optional per-stage device timing (cudaEvents on the context's stream; bench.py's roofline)
@@ -148,6 +153,7 @@ struct BuildOpts {
     int n_frames = 1;
     const uint64_t *frame_offsets = nullptr;  // host, n_frames + 1 (nullptr if n_frames == 1)
     const uint8_t *d_mask = nullptr;          // optional device keep-mask: index only points with mask != 0
+    bool transient = false;                   // the caller frees the index before it returns: use the context's cached cell tables
 };
 int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz, size_t n,
                     const BuildOpts &opts, Index **out);
