@@ -939,11 +939,31 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
         Index *ix;
         ~IxGuard() { index_free(ix); }
     } g{ix};
+    // Fused form: the SOR pass searches K = max(k_sor, k_normals) + 1 neighbours once and keeps the lists;
+    // the normals of the kept points are computed from them (a kept point's nearest kept neighbours are
+    // its nearest neighbours minus the removed ones), and only the queries that lose more neighbours
+    // than the margin allows are searched again.  One KNN pass instead of two.
+    const size_t K = std::max(k_sor, k_normals) + 1;
+    static const bool no_fuse = getenv("PCR_NO_LIST_REUSE") != nullptr;  // A/B hook
+    const bool fused = !no_fuse && k_sor > 0 && k_normals > 0 && K <= 32 && n > 1 && ix->n_indexed > 0;
+    SorLists sl;
+    void *list_mem = nullptr;
+    FreeLater f3{nullptr, c->stream};
+    if (fused) {
+        sl.K = K;
+        sl.stride = (ix->n_indexed + 63) & ~(size_t)63;
+        const size_t bytes = sizeof(uint32_t) * (K * sl.stride + sl.stride + 64) + sl.stride;
+        PCR_CUDA(c, cudaMallocAsync(&list_mem, bytes, c->stream));
+        f3.p = list_mem;
+        sl.lists = (uint32_t *)list_mem;
+        sl.fallback = sl.lists + K * sl.stride;
+        sl.cnt = (uint8_t *)(sl.fallback + sl.stride + 64);
+    }
     if (k_sor == 0) {  // statistical_outlier.rs:5-7: empty result
         PCR_CUDA(c, cudaMemsetAsync(d_keep, 0, n, c->stream));
         PCR_CUDA(c, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long) * F, c->stream));
     } else {
-        PCR_TRY(sor_mean_dist_dev(ix, k_sor, d_mean));
+        PCR_TRY(sor_mean_dist_dev(ix, k_sor, d_mean, fused ? &sl : nullptr));
         PCR_TRY(sor_threshold_mask_dev(c, d_mean, ix->frame_in_off, F, n, std_mul, d_keep, d_stats, d_kept));
         if (F > 1 || n == 1) {  // a one-point frame is returned as is, even if the point is not finite
             single_point_frames_kernel<<<(F + 127) / 128, 128, 0, c->stream>>>(ix->frame_in_off, F, n, d_keep, d_kept);
@@ -952,7 +972,8 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
     }
     if (k_normals == 0) return PCR_OK;
     PCR_TRY(index_apply_mask_dev(ix, d_keep));
-    // removed points get 0 and kept non-finite points (0,0,1) inside normals_dev
+    // removed points get 0 and kept non-finite points (0,0,1) inside normals_dev / normals_from_lists_dev
+    if (fused) return normals_from_lists_dev(ix, k_normals, vp, sl, d_keep, d_nx, d_ny, d_nz);
     return normals_dev(ix, k_normals, vp, d_nx, d_ny, d_nz, d_keep);
 }
 

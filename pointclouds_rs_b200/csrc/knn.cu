@@ -390,6 +390,11 @@ struct ThreadArgs {
     float vx, vy, vz;
     float *nx, *ny, *nz;
     int kk;
+    // MODE 3: SOR whose neighbour lists are kept for the normals of the same pipeline
+    uint32_t *lists;     // [kk][list_stride]: entry j of the query at cell-sorted position q at lists[j * list_stride + q]
+    uint8_t *list_cnt;   // [list_stride]: valid entries (0xff = no list: the query was deferred)
+    size_t list_stride;
+    int kk_sor;          // k_sor + 1 <= kk: the SOR statistic uses the first kk_sor entries
 };
 
 constexpr int kTQThreads = 128;
@@ -505,6 +510,21 @@ __global__ void __launch_bounds__(kTQThreads) knn_thread_kernel(LevelArgs a, Thr
                 if (rd) rd[j] = v ? __fsqrt_rn(key_d2(acc.K[j])) : INFINITY;  // kdtree.rs:76
             }
         if (t.counts) t.counts[q] = (uint32_t)cnt;
+    } else if (MODE == 3) {
+        // SOR on the first kk_sor entries of the list (the top-kk list starts with the top-kk_sor list), and
+        // the whole list kept for normals_from_lists_kernel
+        const int cs = cnt < t.kk_sor ? cnt : t.kk_sor;
+        const int first = cs > 1 ? 1 : 0;
+        float sum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < KC; j++)
+            if (j >= first && j < cs) sum = __fadd_rn(sum, __fsqrt_rn(key_d2(acc.K[j])));
+        const int m = cs - first;
+        t.mean_d[out] = m > 0 ? __fdiv_rn(sum, (float)m) : INFINITY;
+#pragma unroll
+        for (int j = 0; j < KC; j++)
+            if (j < t.kk) t.lists[(size_t)j * t.list_stride + q] = j < cnt ? key_idx(acc.K[j]) : 0xffffffffu;
+        t.list_cnt[q] = (uint8_t)cnt;
     } else if (MODE == 1) {
         // statistical_outlier.rs:28-37: drop the first (self) if there is more than one result,
         // sequential f32 sum in ascending-distance order, divide by the count
@@ -648,14 +668,15 @@ int set_smem(Ctx *ctx, Kern kern, size_t bytes) {
 // count costs one small D2H + sync per level that is actually needed (clouds without far outliers
 // finish on level 0 and pay exactly one).
 template <class Launch>
-int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch) {
+int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *init_list = nullptr) {
+    // init_list: level 0 runs over these nq query ids only (warp kernels) instead of over all queries
     Ctx *ctx = ix->ctx;
     if (nq == 0) return PCR_OK;
     PCR_TRY(ensure(ctx, ctx->b_list, (size_t)nq * 2 * sizeof(uint32_t) + 256));
     uint32_t *counters = (uint32_t *)ctx->b_list.p;  // [2]
     uint32_t *lists[2] = {counters + 64, counters + 64 + nq};
     Index *cur = ix;
-    const uint32_t *qlist = nullptr;
+    const uint32_t *qlist = init_list;
     uint32_t n_cur = nq;
     for (int level = 0;; level++) {
         const bool last = level == kMaxLevels - 1;
@@ -675,7 +696,7 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch) {
         a.last_level = last ? 1 : 0;
         {
             TimeScope ts(ctx, level == 0 ? tag0 : kTagKnnDeferred);
-            PCR_TRY(launch(a, level == 0 ? kQPW0 : kQPWL));
+            PCR_TRY(launch(a, level == 0 && !init_list ? kQPW0 : kQPWL));
         }
         if (last) break;
         uint32_t *mail = (uint32_t *)ctx->pinned + 32;
@@ -729,7 +750,7 @@ int knn_queries_dev(Index *ix, const float *dqx, const float *dqy, const float *
     });
 }
 
-int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d) {
+int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep_lists) {
     Ctx *ctx = ix->ctx;
     if (ix->n == 0) return PCR_OK;
     const size_t kk = k + 1;  // statistical_outlier.rs:25
@@ -747,7 +768,16 @@ int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d) {
     ThreadArgs ta = {};
     ta.mean_d = d_mean_d;
     ta.kk = (int)kk;
+    if (keep_lists) {  // search K >= kk neighbours on level 0 and keep the lists (deferred queries get none)
+        ta.kk = (int)keep_lists->K;
+        ta.kk_sor = (int)kk;
+        ta.lists = keep_lists->lists;
+        ta.list_cnt = keep_lists->cnt;
+        ta.list_stride = keep_lists->stride;
+        PCR_CUDA(ctx, cudaMemsetAsync(keep_lists->cnt, 0xff, keep_lists->stride, ctx->stream));
+    }
     return run_levels(ix, (uint32_t)ix->n_indexed, kTagKnn, [&](const LevelArgs &a, int qpw) -> int {
+        if (qpw == kQPW0 && keep_lists) return launch_thread_kernel<3>(ctx, a, ta);
         if (qpw == kQPW0 && kk <= 32) return launch_thread_kernel<1>(ctx, a, ta);
         unsigned blocks = blocks_for(a.nq, qpw);
         if (kk <= 32) {
@@ -799,6 +829,125 @@ int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny
         PCR_LAUNCH_CHECK(ctx);
         return PCR_OK;
     });
+}
+
+// ---- normals of the kept points from the SOR pass's neighbour lists -------------------------------
+// The K nearest of a point among ALL points, filtered by the keep mask, are its nearest among the KEPT
+// points, in the same (d^2, index) order -- as long as k of them survive (or the list is complete).
+// Queries without a usable list go to `fallback` and are searched again on the tombstoned index.
+namespace {
+__global__ void __launch_bounds__(128) normals_from_lists_kernel(const float4 *__restrict__ qpts, uint32_t nq,
+                                                                 const uint32_t *__restrict__ lists, const uint8_t *__restrict__ list_cnt,
+                                                                 size_t stride, int K, int k, const uint8_t *__restrict__ keep,
+                                                                 const float4 *__restrict__ orig4, float vx_, float vy_, float vz_,
+                                                                 float *__restrict__ nx, float *__restrict__ ny, float *__restrict__ nz,
+                                                                 uint32_t *__restrict__ fallback, uint32_t *__restrict__ fallback_count) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float4 p = __ldg(&qpts[q]);
+    if (p.x != p.x) return;  // removed by SOR (tombstoned): not a point of the kept cloud
+    const int c = list_cnt[q];
+    bool ok = c != 0xff;
+    int taken = 0;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (ok) {
+        for (int j = 0; j < c && taken < k; j++) {  // estimate.rs:54-65, neighbour order
+            const uint32_t i = __ldg(&lists[(size_t)j * stride + q]);
+            if (!keep[i]) continue;
+            const float4 t = __ldg(&orig4[i]);
+            cx = __fadd_rn(cx, t.x);
+            cy = __fadd_rn(cy, t.y);
+            cz = __fadd_rn(cz, t.z);
+            taken++;
+        }
+        ok = taken == k || c < K;  // a truncated list with fewer than k survivors cannot be trusted
+    }
+    if (!ok) {
+        fallback[atomicAdd(fallback_count, 1u)] = q;
+        return;
+    }
+    float ox = 0.f, oy = 0.f, oz = 1.f;
+    if (taken >= 1) {
+        const float count = (float)taken;
+        cx = __fdiv_rn(cx, count);
+        cy = __fdiv_rn(cy, count);
+        cz = __fdiv_rn(cz, count);
+        float c00 = 0.f, c01 = 0.f, c02 = 0.f, c11 = 0.f, c12 = 0.f, c22 = 0.f;
+        int seen = 0;
+        for (int j = 0; j < c && seen < k; j++) {  // estimate.rs:68-84
+            const uint32_t i = __ldg(&lists[(size_t)j * stride + q]);
+            if (!keep[i]) continue;
+            const float4 t = __ldg(&orig4[i]);
+            const float dx = __fsub_rn(t.x, cx), dy = __fsub_rn(t.y, cy), dz = __fsub_rn(t.z, cz);
+            c00 = __fadd_rn(c00, __fmul_rn(dx, dx));
+            c01 = __fadd_rn(c01, __fmul_rn(dx, dy));
+            c02 = __fadd_rn(c02, __fmul_rn(dx, dz));
+            c11 = __fadd_rn(c11, __fmul_rn(dy, dy));
+            c12 = __fadd_rn(c12, __fmul_rn(dy, dz));
+            c22 = __fadd_rn(c22, __fmul_rn(dz, dz));
+            seen++;
+        }
+        float ex, ey, ez;
+        smallest_eigenvector_3x3(c00, c01, c02, c11, c12, c22, ex, ey, ez);
+        const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
+        if (len > 1e-10f) {
+            ex = __fdiv_rn(ex, len);
+            ey = __fdiv_rn(ey, len);
+            ez = __fdiv_rn(ez, len);
+        }
+        const float vx = __fsub_rn(vx_, p.x), vy = __fsub_rn(vy_, p.y), vz = __fsub_rn(vz_, p.z);
+        const float dot = __fadd_rn(__fadd_rn(__fmul_rn(ex, vx), __fmul_rn(ey, vy)), __fmul_rn(ez, vz));
+        if (dot < 0.0f) {
+            ex = -ex; ey = -ey; ez = -ez;
+        }
+        ox = ex; oy = ey; oz = ez;
+    }
+    const uint32_t oi = __float_as_uint(p.w);
+    nx[oi] = ox;
+    ny[oi] = oy;
+    nz[oi] = oz;
+}
+}  // namespace
+
+// normals of the kept points of `ix` (already tombstoned with d_keep) from the lists of the SOR pass;
+// the few queries without a usable list are searched again (warp kernels on the tombstoned levels)
+int normals_from_lists_dev(Index *ix, size_t k, const float vp[3], const SorLists &sl, const uint8_t *d_keep, float *d_nx, float *d_ny,
+                           float *d_nz) {
+    Ctx *ctx = ix->ctx;
+    if (ix->n == 0 || k == 0) return PCR_OK;
+    fill_unindexed_normals_kernel<<<(unsigned)((ix->n + 255) / 256), 256, 0, ctx->stream>>>(ix->orig4, d_keep, ix->n, d_nx, d_ny, d_nz);
+    PCR_LAUNCH_CHECK(ctx);
+    const uint32_t nq = (uint32_t)ix->n_indexed;
+    if (nq == 0) return PCR_OK;
+    uint32_t *d_fb_count = sl.fallback + sl.stride;  // one counter behind the list
+    PCR_CUDA(ctx, cudaMemsetAsync(d_fb_count, 0, sizeof(uint32_t), ctx->stream));
+    {
+        TimeScope ts(ctx, kTagKnnNormals);
+        normals_from_lists_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(ix->sorted, nq, sl.lists, sl.cnt, sl.stride, (int)sl.K, (int)k,
+                                                                            d_keep, ix->orig4, vp[0], vp[1], vp[2], d_nx, d_ny, d_nz,
+                                                                            sl.fallback, d_fb_count);
+        PCR_LAUNCH_CHECK(ctx);
+    }
+    uint32_t *mail = (uint32_t *)ctx->pinned + 40;
+    PCR_CUDA(ctx, cudaMemcpyAsync(mail, d_fb_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint32_t n_fb = *mail;
+    if (getenv("PCR_DEBUG")) fprintf(stderr, "[pcr] normals from SOR lists: %u of %u queries fall back to a search\n", n_fb, nq);
+    if (n_fb == 0) return PCR_OK;
+    const size_t smem = k <= 32 ? (k * 3 * 33 + 64) * sizeof(float) * kWarps : sizeof(unsigned long long) * k * kWarps;
+    if (k <= 32) PCR_TRY(set_smem(ctx, normals_kernel<false, kQPWL>, smem));
+    else PCR_TRY(set_smem(ctx, normals_kernel<true, kQPWL>, smem));
+    const float v0 = vp[0], v1 = vp[1], v2 = vp[2];
+    return run_levels(
+        ix, n_fb, kTagKnnDeferred,
+        [&](const LevelArgs &a, int qpw) -> int {
+            const unsigned blocks = blocks_for(a.nq, qpw);
+            if (k <= 32) normals_kernel<false, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);
+            else normals_kernel<true, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);
+            PCR_LAUNCH_CHECK(ctx);
+            return PCR_OK;
+        },
+        sl.fallback);
 }
 
 int radius_count_dev(Index *ix, const float *dqx, const float *dqy, const float *dqz, size_t nq, float radius,

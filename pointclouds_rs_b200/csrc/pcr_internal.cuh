@@ -165,7 +165,18 @@ int index_coarser_level(Index *ix, Index **out);
 int knn_queries_dev(Index *ix, const float *dqx, const float *dqy, const float *dqz, size_t nq,
                     size_t k, uint32_t *d_idx, float *d_dist, uint32_t *d_counts);
 // mean neighbour distance of every point of the indexed cloud(s) (SOR, k+1 neighbours, drop self)
-int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d);
+// Neighbour lists a fused SOR -> normals pipeline keeps from its SOR pass (knn.cu): entry j of the query at
+// cell-sorted position q is lists[j * stride + q]; cnt[q] = valid entries, 0xff = no list.
+struct SorLists {
+    size_t K = 0;         // neighbours searched per query (>= k_sor + 1 and >= k_normals + 1, <= 32)
+    size_t stride = 0;    // >= n_indexed
+    uint32_t *lists = nullptr;
+    uint8_t *cnt = nullptr;
+    uint32_t *fallback = nullptr;  // stride + 1 entries: query ids without a usable list, then their count
+};
+int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep_lists = nullptr);
+int normals_from_lists_dev(Index *ix, size_t k, const float vp[3], const SorLists &sl, const uint8_t *d_keep, float *d_nx, float *d_ny,
+                           float *d_nz);
 // normals of every point of the indexed cloud(s); points not indexed get (0,0,1) (no neighbours)
 int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny, float *d_nz,
                 const uint8_t *d_mask);

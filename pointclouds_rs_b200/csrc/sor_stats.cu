@@ -81,19 +81,36 @@ int sor_threshold_mask_dev(Ctx *ctx, const float *d_mean_d, const uint32_t *d_fr
     TimeScope ts(ctx, kTagSorStats);
     {
         // a cluster of 8 CTAs per frame (one CTA for small frames: fewer cluster barriers)
-        const unsigned cs = n / (size_t)n_frames > 4 * (size_t)kFoldTile ? 8u : 1u;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)n_frames * cs);
-        cfg.blockDim = dim3(kFoldThreads);
-        cfg.stream = ctx->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = cs;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        PCR_CUDA(ctx, cudaLaunchKernelEx(&cfg, sor_stats_kernel, d_mean_d, d_frame_off, n, std_mul, (SorFrameStats *)d_stats));
+        // 16 CTAs per frame for long frames (non-portable cluster size: fewer cluster-wide passes per fold)
+        static const unsigned big = getenv("PCR_FOLD_CLUSTER") ? (unsigned)atoi(getenv("PCR_FOLD_CLUSTER")) : 16u;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(sor_stats_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            cudaGetLastError();
+            attr_set = true;
+        }
+        const size_t per_frame = n / (size_t)n_frames;
+        // (many frames already fill the GPU: 16-CTA clusters then only cost scheduling freedom -- 0.84 -> 1.67 ms on 100 frames)
+        const unsigned cs = (per_frame > 12 * (size_t)kFoldTile && n_frames <= 4) ? big : (per_frame > 4 * (size_t)kFoldTile ? 8u : 1u);
+        unsigned use = cs;
+        for (;;) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)n_frames * use);
+            cfg.blockDim = dim3(kFoldThreads);
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = use;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, sor_stats_kernel, d_mean_d, d_frame_off, n, std_mul, (SorFrameStats *)d_stats);
+            if (e == cudaSuccess) break;
+            cudaGetLastError();
+            if (use <= 8) return fail(ctx, PCR_ERR_CUDA, "sor_stats_kernel launch failed: %s", cudaGetErrorString(e));
+            use = 8;  // the non-portable 16-CTA cluster could not be scheduled: the portable size always can
+        }
         ctx->launches++;
     }
     PCR_CUDA(ctx, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long) * n_frames, ctx->stream));
