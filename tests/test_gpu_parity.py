@@ -397,3 +397,41 @@ def test_batch_large_k_generic_path(pcr, oracle):
         assert np.array_equal(keep[sl], o_keep)
         sel = np.nonzero(o_keep)[0]
         assert np.nanmax(_angles(nrm[sl][sel], oracle.normals(fr[sel], 40, threads=T))) < 1e-4
+
+
+# ---- fused SOR -> normals: one search, the normals from the SOR pass's neighbour lists ----------------
+@pytest.mark.parametrize("k_sor,std,k_nrm", [(10, 1.0, 20), (20, 2.0, 15), (5, 0.0, 8), (31, 1.0, 10), (10, 0.3, 31), (3, 1.0, 1)])
+def test_fused_lists_equal_the_two_step_path(pcr, oracle, k_sor, std, k_nrm):
+    """K = max(k_sor, k_nrm) + 1 <= 32 takes the fused path.  std = 0 / 0.3 remove a third to a half of the points, so
+    most lists lose more neighbours than their margin and the fallback search carries the result; the normals must be
+    BIT-identical to estimate_normals on the filtered cloud (same kernels' arithmetic, same neighbour order)."""
+    pts = np.vstack([scenes.kitti_scene(31, (6_000, 300, 60, 140)), [[np.nan, 0, 0], [1, np.inf, 2]]]).astype(np.float32)
+    off = np.array([0, len(pts)], np.uint64)
+    keep, nrm, kept = pcr.sor_normals_batch(pts, off, k_sor, std, k_nrm)
+    o_keep, _, _ = oracle.sor(pts, k_sor, std, threads=T)
+    assert np.array_equal(keep, o_keep) and kept[0] == o_keep.sum()
+    sel = np.nonzero(o_keep)[0]
+    two_step = pcr.normals_array(_cloud(pcr, pts[sel]), k_nrm)      # a fresh search on the filtered cloud
+    assert np.array_equal(nrm[sel].view(np.uint32), two_step.view(np.uint32))
+    assert np.nanmax(_angles(nrm[sel], oracle.normals(pts[sel], k_nrm, threads=T))) < 1e-4
+    assert (nrm[o_keep == 0] == 0).all()
+    dev = pcr.DeviceCloud.from_numpy(pts).sor_normals(k_sor, std, k_nrm)
+    assert np.array_equal(dev.to_numpy(), pts[sel], equal_nan=True) and np.array_equal(dev.normals_to_numpy().view(np.uint32), two_step.view(np.uint32))
+
+
+def test_fused_lists_multi_frame_edge_cases(pcr, oracle):
+    frames = [scenes.kitti_scene(40, (3_000, 150, 30, 70)), np.zeros((0, 3), np.float32), np.array([[1, 2, 3]], np.float32),
+              scenes.uniform_cube(15, 4, 0, 1), np.repeat(scenes.uniform_cube(200, 5, 0, 3), 4, axis=0),
+              scenes.kitti_scene(41, (2_000, 100, 20, 400))]
+    off = np.concatenate([[0], np.cumsum([len(f) for f in frames])])
+    keep, nrm, kept = pcr.sor_normals_batch(np.vstack(frames), off, 10, 1.0, 20)
+    for f, fr in enumerate(frames):
+        sl = slice(off[f], off[f + 1])
+        if len(fr) == 0:
+            continue
+        o_keep, _, _ = oracle.sor(fr, 10, 1.0, threads=T)
+        assert np.array_equal(keep[sl], o_keep), f"frame {f}"
+        sel = np.nonzero(o_keep)[0]
+        if len(sel):
+            two_step = pcr.normals_array(_cloud(pcr, fr[sel]), 20)
+            assert np.array_equal(nrm[sl][sel].view(np.uint32), two_step.view(np.uint32)), f"frame {f}"
