@@ -454,9 +454,12 @@ __device__ __forceinline__ void scan_row_pruned(Acc &acc, const GridDesc &g, con
 template <class Acc>
 __device__ __forceinline__ bool thread_grid_search_pruned(Acc &acc, const GridDesc &g, const uint32_t *__restrict__ cell_start,
                                                           const float4 *__restrict__ pts, float qx, float qy, float qz, int kk,
-                                                          int max_rings, bool last_level, bool seeded = false) {
-    // seeded: `acc` already holds real candidates of this index (k = 1 only: ICP's neighbour of the
-    // previous iteration) -- they bound the search from the first row on and cannot change its result
+                                                          int max_rings, bool last_level, int seed_mode = 0) {
+    // seed_mode != 0: `acc` already holds a real candidate of this index (k = 1 only: ICP's neighbour of
+    // the previous iteration) -- it bounds the search from the first row on and cannot change its result.
+    //   1: walk a further shell only if that shell is guaranteed to settle the query, else defer
+    //   2: walk up to max_rings shells (the deferred pass on the fine grid: the seed keeps the shells cheap)
+    const bool seeded = seed_mode != 0;
     if (!seeded) acc.reset();
     const uint32_t m = g.pt_end - g.pt_begin;
     if (m == 0) return true;
@@ -506,7 +509,7 @@ __device__ __forceinline__ bool thread_grid_search_pruned(Acc &acc, const GridDe
             // a seeded query knows how far it has to look: walk one more shell only if that shell settles
             // it ((S + 1) cells >= its current best distance); otherwise the next level is the cheaper
             // place to look (the seed goes along)
-            if (seeded && kth != PCR_EMPTY_KEY) {
+            if (seed_mode == 1 && kth != PCR_EMPTY_KEY) {
                 const double reach = (double)(S + 1) * g.h;
                 if ((double)key_d2(kth) > reach * reach) return false;
             }
@@ -520,6 +523,62 @@ __device__ __forceinline__ bool thread_grid_search_pruned(Acc &acc, const GridDe
             return true;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ball scan for a SEEDED 1-NN query (ICP: the neighbour of the previous iteration, r0 away).  The answer
+// lies inside the ball of radius r0 around the query, so instead of walking shells and proving a ring bound
+// the thread visits the rows (e0, e1) of the square |e| <= ceil(r0 / h) centre-out, skips every row whose
+// in-plane gap exceeds the current best and reads only the cells within sqrt(tau - gap^2) along the fast
+// axis: O(R^2) row tests instead of the O(R^3) cell visits of a shell walk, and tau shrinks as it goes.
+// Returns false (nothing scanned) if the ball spans more than max_cells cells: the caller defers the query.
+// Exactness: scan_row_pruned keeps every point with d^2 <= tau (1 + 1e-5); rows and cells outside that bound
+// hold nothing that could beat or tie the current best, and every row inside it is visited.
+// ------------------------------------------------------------------------------------------------
+template <class Acc>
+__device__ __forceinline__ bool thread_ball_search(Acc &acc, const GridDesc &g, const uint32_t *__restrict__ cell_start,
+                                                   const float4 *__restrict__ pts, float qx, float qy, float qz, int max_cells) {
+    const float tau0 = acc_tau(acc);
+    const float r_cells = sqrtf(tau0) * (float)g.inv_h * (1.0f + 1e-5f) + 1e-3f;
+    if (!(r_cells < (float)max_cells)) return false;  // also catches an empty list (tau = +inf)
+    const int R0 = (int)ceilf(r_cells);
+    double f0, f1, f2;
+    const int c0 = cell_coord(g, 0, pick_axis(g.ax[0], qx, qy, qz), &f0);
+    const int c1 = cell_coord(g, 1, pick_axis(g.ax[1], qx, qy, qz), &f1);
+    const int c2 = cell_coord(g, 2, pick_axis(g.ax[2], qx, qy, qz), &f2);
+    const float ff0 = (float)f0, ff1 = (float)f1, ff2 = (float)f2;
+    if (fabsf(ff0) > 1e4f || fabsf(ff1) > 1e4f || fabsf(ff2) > 1e4f) return false;  // far outside the grid: not a ball-scan case
+    const int d0n = g.dims[0], d1n = g.dims[1], d2n = g.dims[2];
+    const float inv_h2 = (float)(g.inv_h * g.inv_h);
+    for (int r = 0; r <= R0; r++) {
+        // every row of square ring r is at least (r - 1) cells away in the plane: stop once that exceeds the best
+        if (r >= 2) {
+            const float lo = (float)(r - 1);
+            if (lo * lo > acc_tau(acc) * inv_h2 * (1.0f + 1e-5f) + 1e-8f) break;
+        }
+        const int side = 2 * r + 1;
+        const int T = r == 0 ? 1 : 8 * r;  // cells on the perimeter of the (2r+1)^2 square
+#pragma unroll 1
+        for (int t = 0; t < T; t++) {
+            int e0, e1;
+            if (r == 0) {
+                e0 = 0; e1 = 0;
+            } else if (t < side) {  // top edge
+                e0 = -r; e1 = t - r;
+            } else if (t < 2 * side) {  // bottom edge
+                e0 = r; e1 = t - side - r;
+            } else {  // left / right edges without the corners
+                const int u = t - 2 * side;
+                e0 = (u >> 1) - r + 1;
+                e1 = (u & 1) ? r : -r;
+            }
+            const int a0 = c0 + e0, a1 = c1 + e1;
+            if (a0 < 0 || a0 >= d0n || a1 < 0 || a1 >= d1n) continue;
+            const float g0 = axis_gap(e0, ff0), g1 = axis_gap(e1, ff1);
+            scan_row_pruned(acc, g, cell_start, pts, a0, a1, 0, d2n - 1, g0 * g0 + g1 * g1, c2, ff2, inv_h2, qx, qy, qz);
+        }
+    }
+    return true;
 }
 
 }  // namespace pcr
