@@ -758,7 +758,17 @@ int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz,
 
     if (dbg_t) { cudaStreamSynchronize(st); fprintf(stderr, "[build] bbox done +%.0f us\n", now_us() - t_begin); }
     // ---- probe rounds: measure occupancy, solve for the cell size ------------------------------
-    if (!forced && n_indexed > 0) {
+    bool cached = false;
+    if (!forced && F == 1 && n_indexed > 0 && ctx->cell_cache.valid && ctx->cell_cache.k_hint == opts.k_hint && !getenv("PCR_NO_CELL_CACHE")) {
+        const auto &cc = ctx->cell_cache;
+        auto close = [](double a, double b) { return a <= b * 1.125 + 1e-9 && b <= a * 1.125 + 1e-9; };
+        if (close((double)box[0].count, (double)cc.count) && close(box[0].ext[0], cc.ext[0]) && close(box[0].ext[1], cc.ext[1]) &&
+            close(box[0].ext[2], cc.ext[2])) {
+            hsel[0] = cc.h;
+            cached = true;
+        }
+    }
+    if (!forced && !cached && n_indexed > 0) {
         for (int round = 0; round < 2; round++) {
             uint32_t total = 0;
             PCR_TRY(layout(&total));
@@ -793,6 +803,13 @@ int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz,
     }
 
     if (dbg_t) { cudaStreamSynchronize(st); fprintf(stderr, "[build] probe done +%.0f us\n", now_us() - t_begin); }
+    if (!forced && !cached && F == 1 && n_indexed > 0) {
+        ctx->cell_cache.valid = true;
+        ctx->cell_cache.k_hint = opts.k_hint;
+        ctx->cell_cache.count = box[0].count;
+        for (int a = 0; a < 3; a++) ctx->cell_cache.ext[a] = box[0].ext[a];
+        ctx->cell_cache.h = hsel[0];
+    }
     // ---- final grid: count, scan, scatter ------------------------------------------------------
     uint32_t total = 0;
     PCR_TRY(layout(&total));

@@ -72,6 +72,15 @@ struct Ctx {
     std::string err;
     uint64_t launches = 0;
     float forced_cell = 0.f;
+    // cell size chosen by the last single-frame probe, reused for the next cloud of the same shape (a stream of
+    // LiDAR frames): skips the probe grid and its host round trip.  Only speed depends on the cell size.
+    struct {
+        bool valid = false;
+        size_t k_hint = 0;
+        uint32_t count = 0;
+        double ext[3] = {0, 0, 0};
+        double h = 0;
+    } cell_cache;
     // scratch
     DevBuf b_in;       // staged input x|y|z
     DevBuf b_in2;      // second cloud (ICP source)
