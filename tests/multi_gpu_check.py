@@ -54,8 +54,9 @@ def main():
                 print(f"{name} iters={iters} tol={tol}: sharded {r_sh} vs single {r_one}: identical on all ranks={same_everywhere} close={close}", flush=True)
             ok = ok and same_everywhere and close
 
-    # frame sharding: 6 frames dealt round-robin == the single-process batch
-    frames = [scenes.kitti_scene(s, (4000, 200, 40, 80)) for s in range(6)]
+    # frame sharding: frames dealt round-robin == the single-process batch (at least one frame per rank:
+    # with 6 frames on 8 ranks two ranks had nothing to stack and the others waited for them in the all-reduce)
+    frames = [scenes.kitti_scene(s, (4000, 200, 40, 80)) for s in range(max(6, 2 * world))]
     off = np.concatenate([[0], np.cumsum([len(f) for f in frames])])
     keep_all, nrm_all, kept_all = pcr.sor_normals_batch(np.vstack(frames), off, 10, 1.0, 20, ctx=solo)
     mine = pdist.deal_frames(len(frames), rank, world)
