@@ -17,6 +17,13 @@ int main() {
         pcr::PointCloud clean = pcr::statistical_outlier_removal(cloud, 10, 1.0f);
         pcr::Normals n = pcr::estimate_normals(clean, 20);
         std::printf("kept %zu of %zu, first normal (%g, %g, %g)\n", clean.len(), cloud.len(), n.nx[0], n.ny[0], n.nz[0]);
+        // the same pipeline without leaving the device: one upload, one download
+        pcr::DeviceCloud dev = pcr::DeviceCloud::upload(cloud);
+        pcr::DeviceCloud out = dev.voxel_downsample(0.05f).statistical_outlier_removal(10, 1.0f).estimate_normals(20);
+        auto clusters = out.euclidean_cluster(0.5f, 10, 100000);
+        pcr::PointCloud host = out.download();
+        std::printf("device pipeline: %zu points with normals, %zu clusters (largest %zu)\n", host.len(), clusters.size(),
+                    clusters.empty() ? 0 : clusters[0].size());
     } catch (const pcr::Error &e) {
         std::printf("pcr error %d: %s\n", e.code, e.what());  // e.g. 6 = no CUDA device (there is no CPU fallback)
         return e.code == PCR_ERR_NO_DEVICE ? 0 : 1;
