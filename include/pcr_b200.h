@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define PCR_B200_VERSION 110 /* 0.1.0 */
+#define PCR_B200_VERSION 110 /* 0.1.1: + voxel, cluster, RANSAC, device-resident clouds */
 
 typedef enum pcr_status {
     PCR_OK = 0,
