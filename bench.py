@@ -76,6 +76,7 @@ def workload_config(n_raw: int, n_in: int, world: int):
         "sharding": f"frames: one independent frame per GPU per step x {world} GPU(s), no data-path collective",
         "l2": "256 MiB buffer overwritten between timed steps (outside the events); the frame itself is L2-sized",
         "seed": "numpy PCG64, 42 + rank",
+        "frame_stream": "pcr_ctx_set_frame_stream(1): the cell size probed on the first frame is reused for the following frames",
     }
 
 
@@ -225,6 +226,7 @@ def main():
 
     stream = torch.cuda.current_stream()
     ctx = pcr.Context(device=local_rank, stream=stream.cuda_stream)
+    ctx.set_frame_stream(True)  # the steps are consecutive frames of one sensor: the probed cell size is reused (config.frame_stream)
 
     raw, pts = make_frame(rank)
     n_raw, n = len(raw), len(pts)

@@ -95,6 +95,11 @@ int pcr_ctx_get_timing(pcr_ctx *ctx, double *ms_per_tag /* [PCR_NUM_TIMING_TAGS]
                        uint64_t *spans_per_tag /* [PCR_NUM_TIMING_TAGS] or NULL */);
 /* Tuning: force the grid cell size (metres) for subsequent index builds; 0 = automatic. */
 int pcr_ctx_set_cell_size(pcr_ctx *ctx, float cell_size);
+/* Hint: the clouds this context sees come from one sensor stream (consecutive frames of similar size, extent and
+ * density).  The cell size found by one call's occupancy probe is then reused by the next call whose point count
+ * and bounding box are within 12.5 % of it, which skips the probe grid and its host round trip.  Results never
+ * depend on the cell size; an unrepresentative reuse only costs speed.  Off by default. */
+int pcr_ctx_set_frame_stream(pcr_ctx *ctx, int enable);
 
 /* ---- multi-GPU (one process per GPU; the host exchanges the id, e.g. torch.distributed) ------ */
 #define PCR_UNIQUE_ID_BYTES 128

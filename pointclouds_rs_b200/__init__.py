@@ -85,6 +85,10 @@ class Context:
         _ffi.check(_ffi.load().pcr_ctx_get_timing(self._h, ms, cnt), self._h)
         return {_ffi.TIMING_TAGS[i]: (ms[i], int(cnt[i])) for i in range(_ffi.PCR_NUM_TIMING_TAGS)}
 
+    def set_frame_stream(self, enable: bool = True):
+        """Consecutive clouds are frames of one sensor stream: reuse the probed cell size between similar frames."""
+        _ffi.check(_ffi.load().pcr_ctx_set_frame_stream(self._h, 1 if enable else 0), self._h)
+
     def set_cell_size(self, cell: float):
         _ffi.check(_ffi.load().pcr_ctx_set_cell_size(self._h, float(cell)), self._h)
 

@@ -67,6 +67,7 @@ SIGNATURES = {
     "pcr_last_error": (C.c_char_p, [vp]),
     "pcr_ctx_launch_count": (C.c_uint64, [vp]),
     "pcr_ctx_set_cell_size": (C.c_int, [vp, C.c_float]),
+    "pcr_ctx_set_frame_stream": (C.c_int, [vp, C.c_int]),
     "pcr_ctx_set_timing": (C.c_int, [vp, C.c_int]),
     "pcr_ctx_get_timing": (C.c_int, [vp, C.POINTER(C.c_double), u64p]),
     "pcr_comm_unique_id": (C.c_int, [vp]),

@@ -272,6 +272,13 @@ int pcr_ctx_get_timing(pcr_ctx *ctx, double *ms_per_tag, uint64_t *spans_per_tag
     return PCR_OK;
 }
 
+int pcr_ctx_set_frame_stream(pcr_ctx *ctx, int enable) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    ctx->c.frame_stream = enable != 0;
+    ctx->c.cell_cache.valid = false;
+    return PCR_OK;
+}
+
 int pcr_ctx_set_cell_size(pcr_ctx *ctx, float cell_size) {
     if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
     if (!(cell_size >= 0.f) || !std::isfinite(cell_size)) return fail(&ctx->c, PCR_ERR_INVALID_ARG, "cell_size must be >= 0 and finite");

@@ -759,7 +759,8 @@ int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz,
     if (dbg_t) { cudaStreamSynchronize(st); fprintf(stderr, "[build] bbox done +%.0f us\n", now_us() - t_begin); }
     // ---- probe rounds: measure occupancy, solve for the cell size ------------------------------
     bool cached = false;
-    if (!forced && F == 1 && n_indexed > 0 && ctx->cell_cache.valid && ctx->cell_cache.k_hint == opts.k_hint && !getenv("PCR_NO_CELL_CACHE")) {
+    if (!forced && F == 1 && n_indexed > 0 && ctx->frame_stream && ctx->cell_cache.valid && ctx->cell_cache.k_hint == opts.k_hint &&
+        !getenv("PCR_NO_CELL_CACHE")) {
         const auto &cc = ctx->cell_cache;
         auto close = [](double a, double b) { return a <= b * 1.125 + 1e-9 && b <= a * 1.125 + 1e-9; };
         if (close((double)box[0].count, (double)cc.count) && close(box[0].ext[0], cc.ext[0]) && close(box[0].ext[1], cc.ext[1]) &&

@@ -74,6 +74,7 @@ struct Ctx {
     float forced_cell = 0.f;
     // cell size chosen by the last single-frame probe, reused for the next cloud of the same shape (a stream of
     // LiDAR frames): skips the probe grid and its host round trip.  Only speed depends on the cell size.
+    bool frame_stream = false;  // pcr_ctx_set_frame_stream: enables the reuse below
     struct {
         bool valid = false;
         size_t k_hint = 0;

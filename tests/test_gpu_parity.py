@@ -435,3 +435,23 @@ def test_fused_lists_multi_frame_edge_cases(pcr, oracle):
         if len(sel):
             two_step = pcr.normals_array(_cloud(pcr, fr[sel]), 20)
             assert np.array_equal(nrm[sl][sel].view(np.uint32), two_step.view(np.uint32)), f"frame {f}"
+
+
+def test_cell_size_cache_never_changes_results(pcr, oracle):
+    """With pcr_ctx_set_frame_stream the context reuses the cell size of the previous probe for a cloud of the same size and extent.  Only speed may
+    depend on it: a cloud with a very different density profile inside the same box must give the same bits."""
+    rng = np.random.default_rng(3)
+    n = 20_000
+    flat = np.concatenate([rng.uniform(0, 40, (n, 2)), rng.normal(0, 0.02, (n, 1))], 1).astype(np.float32)
+    blob = np.concatenate([rng.normal(20, 0.5, (n, 2)), rng.normal(0, 0.02, (n, 1))], 1).astype(np.float32)
+    for arr in (flat, blob):  # same bounding box for both: the corners pin it
+        arr[:4] = [[0, 0, -0.1], [40, 40, 0.1], [0, 40, 0], [40, 0, 0]]
+    ctx = pcr.Context()
+    ctx.set_frame_stream(True)
+    first = pcr.sor_mask(_cloud(pcr, flat), 10, 1.0, ctx=ctx, want_mean=True)          # probes, fills the cache
+    second = pcr.sor_mask(_cloud(pcr, blob), 10, 1.0, ctx=ctx, want_mean=True)         # same n and box: cached cell size
+    fresh = pcr.sor_mask(_cloud(pcr, blob), 10, 1.0, ctx=pcr.Context(), want_mean=True)
+    assert np.array_equal(second[0], fresh[0]) and np.array_equal(second[2].view(np.uint32), fresh[2].view(np.uint32))
+    o_keep, o_mean, _ = oracle.sor(blob, 10, 1.0, threads=T)
+    assert np.array_equal(second[0], o_keep) and np.array_equal(second[2].view(np.uint32), o_mean.view(np.uint32))
+    assert np.array_equal(first[0], oracle.sor(flat, 10, 1.0, threads=T)[0])
