@@ -62,7 +62,8 @@ def main():
     mine = pdist.deal_frames(len(frames), rank, world)
     loc = [frames[f] for f in mine]
     loff = np.concatenate([[0], np.cumsum([len(f) for f in loc])])
-    keep, nrm, kept = pcr.sor_normals_batch(np.vstack(loc), loff, 10, 1.0, 20, ctx=ctx)
+    local_pts = np.vstack(loc) if loc else np.zeros((0, 3), np.float32)  # a rank may hold no frame
+    keep, nrm, kept = pcr.sor_normals_batch(local_pts, loff, 10, 1.0, 20, ctx=ctx)
     for j, f in enumerate(mine):
         a = slice(loff[j], loff[j + 1])
         g = slice(off[f], off[f + 1])
