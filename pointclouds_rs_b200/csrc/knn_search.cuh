@@ -53,6 +53,12 @@ __device__ __forceinline__ bool ring_bound2(const GridDesc &g, int c0, int c1, i
     return open;
 }
 
+// distance, in cells, from a query at fraction f of its cell to the cells `e` columns away along one axis
+__device__ __forceinline__ float axis_gap(int e, float f) {
+    const float d = e > 0 ? (float)e - f : (e < 0 ? f - (float)e - 1.0f : 0.0f);
+    return fmaxf(d, 0.0f);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Top-k containers.  Both keep the k best keys in ascending order.
 // ------------------------------------------------------------------------------------------------
@@ -159,9 +165,18 @@ __device__ __forceinline__ void scan_run(TopK &tk, const float4 *__restrict__ pt
 }
 
 // lane-parallel lookup of up to 32 runs, then the warp streams the non-empty ones
+// k-th best so far in cell units^2 with the pruning slack of scan_row_pruned (+inf while the list is short)
+template <class TopK>
+__device__ __forceinline__ float warp_tau_cells(const TopK &tk, float inv_h2) {
+    const unsigned long long kth = tk.kth();
+    return kth == PCR_EMPTY_KEY ? INFINITY : key_d2(kth) * inv_h2 * (1.0f + 1e-5f) + 1e-8f;
+}
+
+// gp = squared gap (cell units) between the query and this lane's run: a run further away than the current
+// k-th best is skipped when its turn comes (the list has usually tightened since the run was looked up)
 template <class TopK>
 __device__ __forceinline__ void scan_runs(TopK &tk, const float4 *__restrict__ pts, uint32_t b, uint32_t e,
-                                          unsigned first_mask, float qx, float qy, float qz) {
+                                          unsigned first_mask, float qx, float qy, float qz, float gp, float inv_h2) {
     unsigned ne = __ballot_sync(PCR_FULL, e > b);
     unsigned pri = ne & first_mask;  // runs to take first (the query's own row: tightens thr early)
     ne &= ~first_mask;
@@ -173,8 +188,21 @@ __device__ __forceinline__ void scan_runs(TopK &tk, const float4 *__restrict__ p
     while (ne) {
         int s = __ffs(ne) - 1;
         ne &= ne - 1;
+        if (__shfl_sync(PCR_FULL, gp, s) > warp_tau_cells(tk, inv_h2)) continue;
         scan_run(tk, pts, __shfl_sync(PCR_FULL, b, s), __shfl_sync(PCR_FULL, e, s), qx, qy, qz);
     }
+}
+
+// Trims a row's fast-axis cell range [z0, z1] to the cells that can hold a candidate within the current k-th
+// best (same bound and slack as scan_row_pruned); returns false if nothing is left.
+__device__ __forceinline__ bool trim_row(float tau_c, float gp, int c2, float f2, int &z0, int &z1) {
+    if (gp > tau_c) return false;
+    if (tau_c < 1e12f && fabsf(f2) < 1e4f) {
+        const float w = sqrtf(tau_c - gp) * (1.0f + 1e-5f) + 1e-5f;
+        z0 = max(z0, c2 + (int)floorf(f2 - w));
+        z1 = min(z1, c2 + (int)floorf(f2 + w));
+    }
+    return z0 <= z1;
 }
 
 // Warp-cooperative exact k-NN of (qx,qy,qz) in frame g.  All arguments are warp-uniform.
@@ -197,19 +225,30 @@ __device__ __forceinline__ bool warp_knn_search(TopK &tk, const GridDesc &g, con
     const int c1 = cell_coord(g, 1, pick_axis(g.ax[1], qx, qy, qz), &f1);
     const int c2 = cell_coord(g, 2, pick_axis(g.ax[2], qx, qy, qz), &f2);
     const int d0n = g.dims[0], d1n = g.dims[1], d2n = g.dims[2];
+    // rows and cells beyond the current k-th best are skipped (exactness: see scan_row_pruned); an isolated
+    // outlier a few metres above a dense surface otherwise streams the whole footprint of every shell
+    const float ff0 = (float)f0, ff1 = (float)f1, ff2 = (float)f2;
+    const float inv_h2 = (float)(g.inv_h * g.inv_h);
 
     {  // the 3x3x3 cube: 9 rows, one lane each
         uint32_t b = 0, e = 0;
+        float gp = 0.f;
+        const float tau_c = warp_tau_cells(tk, inv_h2);  // finite only for a seeded search
         if (lane < 9) {
-            int a0 = c0 + lane / 3 - 1, a1 = c1 + lane % 3 - 1;
+            const int e0 = lane / 3 - 1, e1 = lane % 3 - 1;
+            int a0 = c0 + e0, a1 = c1 + e1;
             if (a0 >= 0 && a0 < d0n && a1 >= 0 && a1 < d1n) {
                 int z0 = max(c2 - 1, 0), z1 = min(c2 + 1, d2n - 1);
-                uint32_t lin = cell_linear(g, a0, a1, z0);
-                b = __ldg(&cell_start[lin]);
-                e = __ldg(&cell_start[lin + (uint32_t)(z1 - z0) + 1u]);
+                const float g0 = axis_gap(e0, ff0), g1 = axis_gap(e1, ff1);
+                gp = g0 * g0 + g1 * g1;
+                if (trim_row(tau_c, gp, c2, ff2, z0, z1)) {
+                    uint32_t lin = cell_linear(g, a0, a1, z0);
+                    b = __ldg(&cell_start[lin]);
+                    e = __ldg(&cell_start[lin + (uint32_t)(z1 - z0) + 1u]);
+                }
             }
         }
-        scan_runs(tk, pts, b, e, 1u << 4, qx, qy, qz);
+        scan_runs(tk, pts, b, e, 1u << 4, qx, qy, qz, gp, inv_h2);
     }
     for (int R = 1;; R++) {
         // nearest face of the scanned cube that still has cells behind it
@@ -230,6 +269,8 @@ __device__ __forceinline__ bool warp_knn_search(TopK &tk, const GridDesc &g, con
         for (int t0 = 0; t0 < T; t0 += 32) {
             int t = t0 + lane;
             uint32_t b = 0, e = 0;
+            float gp = 0.f;
+            const float tau_c = warp_tau_cells(tk, inv_h2);
             if (t < T) {
                 int slot = t & 1, r = t >> 1;
                 int i0 = r / side, i1 = r - i0 * side;
@@ -249,13 +290,17 @@ __device__ __forceinline__ bool warp_knn_search(TopK &tk, const GridDesc &g, con
                         z0 = z1 = z;
                     }
                     if (ok) {
-                        uint32_t lin = cell_linear(g, a0, a1, z0);
-                        b = __ldg(&cell_start[lin]);
-                        e = __ldg(&cell_start[lin + (uint32_t)(z1 - z0) + 1u]);
+                        const float g0 = axis_gap(e0, ff0), g1 = axis_gap(e1, ff1);
+                        gp = g0 * g0 + g1 * g1;
+                        if (trim_row(tau_c, gp, c2, ff2, z0, z1)) {
+                            uint32_t lin = cell_linear(g, a0, a1, z0);
+                            b = __ldg(&cell_start[lin]);
+                            e = __ldg(&cell_start[lin + (uint32_t)(z1 - z0) + 1u]);
+                        }
                     }
                 }
             }
-            scan_runs(tk, pts, b, e, 0u, qx, qy, qz);
+            scan_runs(tk, pts, b, e, 0u, qx, qy, qz, gp, inv_h2);
         }
     }
 }
@@ -434,11 +479,6 @@ __device__ __forceinline__ bool thread_grid_search(Acc &acc, const GridDesc &g, 
 // last entry.  While the list is not full tau is +inf and nothing is trimmed.  The ring rule and the
 // deferral rule are those of thread_grid_search, so both functions return the same lists.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float axis_gap(int e, float f) {  // distance, in cells, to the cells `e` columns away
-    const float d = e > 0 ? (float)e - f : (e < 0 ? f - (float)e - 1.0f : 0.0f);
-    return fmaxf(d, 0.0f);
-}
-
 template <class Acc>
 __device__ __forceinline__ float acc_tau(const Acc &acc) {  // k-th best d^2 so far, +inf while the list is short
     const unsigned long long k = acc.kth();
