@@ -160,60 +160,32 @@ __global__ void __launch_bounds__(kIcpThreads) icp_search_kernel(const GridDesc 
     nn[i] = best;
 }
 
-// (A') deferred source points on a coarser level, persistent over the device-side list: one warp
-//      per point (measured faster than thread-per-point here: a coarse cell holds ~70 points, so the
-//      lanes are busy; kThreadPerPoint is kept for experiments).
-template <bool kThreadPerPoint>
-__global__ void __launch_bounds__(128) icp_deferred_kernel(const GridDesc *__restrict__ grids,
-                                                           const uint32_t *__restrict__ cell_start,
+// (A') deferred source points on a coarser level, persistent over the device-side list: one warp per point
+//      (a coarse cell holds ~70 points, so the lanes are busy).  nn[i] carries the warm-start candidate the
+//      search kernel left there (or EMPTY); the warp search inserts it first and prunes with it.
+__global__ void __launch_bounds__(128) icp_deferred_kernel(const GridDesc *__restrict__ grids, const uint32_t *__restrict__ cell_start,
                                                            const float4 *__restrict__ pts, const float4 *__restrict__ cur,
-                                                           const IcpState *__restrict__ state,
-                                                           const uint32_t *__restrict__ in_list,
-                                                           const uint32_t *__restrict__ in_count,
-                                                           unsigned long long *__restrict__ nn, uint32_t *__restrict__ out_list,
-                                                           uint32_t *__restrict__ out_count, int last_level, int fine_rings) {
+                                                           const IcpState *__restrict__ state, const uint32_t *__restrict__ in_list,
+                                                           const uint32_t *__restrict__ in_count, unsigned long long *__restrict__ nn,
+                                                           uint32_t *__restrict__ out_list, uint32_t *__restrict__ out_count,
+                                                           int last_level) {
     if (state->done) return;
     const uint32_t n = *in_count;
     const GridDesc g = grids[0];
-    if (kThreadPerPoint) {
-        // Seeded points on the FINE grid, one thread each: the neighbour of the previous iteration is r0 away,
-        // so only the cells inside that ball are read (thread_ball_search) -- for a point a few metres from the
-        // target that is a few dozen candidates, where the coarse-level warp kernel below streams ~2000.  The list
-        // is compact, so every lane of a warp has this kind of work.  Points without a seed (first iteration) or
-        // whose ball spans more than fine_rings cells go on to the coarse levels.
-        const uint32_t threads = gridDim.x * blockDim.x;
-        for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += threads) {
-            const uint32_t i = in_list[j];
-            const unsigned long long seed = nn[i];
-            bool done = false;
-            if (seed != PCR_EMPTY_KEY) {
-                const float4 p = cur[i];
-                ThreadBest1 acc;
-                acc.reset();
-                acc.offer(seed);
-                if (thread_ball_search(acc, g, cell_start, pts, p.x, p.y, p.z, fine_rings)) {
-                    nn[i] = acc.best;
-                    done = true;
-                }
-            }
-            if (!done) out_list[atomicAdd(out_count, 1u)] = i;
-        }
-    } else {
-        const int lane = threadIdx.x & 31;
-        const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-        RegTopK tk;
-        tk.kk = 1;
-        tk.lane = lane;
-        for (uint32_t j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += warps) {
-            const uint32_t i = in_list[j];
-            const float4 p = cur[i];
-            const unsigned long long seed = nn[i];  // the search kernel left the warm-start candidate here (or EMPTY)
-            if (warp_knn_search(tk, g, cell_start, pts, p.x, p.y, p.z, last_level ? kMaxRings : kLevelRings, last_level != 0, seed)) {
-                unsigned long long best = __shfl_sync(PCR_FULL, tk.K, 0);
-                if (lane == 0) nn[i] = best;
-            } else if (lane == 0) {
-                out_list[atomicAdd(out_count, 1u)] = i;
-            }
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    RegTopK tk;
+    tk.kk = 1;
+    tk.lane = lane;
+    for (uint32_t j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += warps) {
+        const uint32_t i = in_list[j];
+        const float4 p = cur[i];
+        const unsigned long long seed = nn[i];
+        if (warp_knn_search(tk, g, cell_start, pts, p.x, p.y, p.z, last_level ? kMaxRings : kLevelRings, last_level != 0, seed)) {
+            unsigned long long best = __shfl_sync(PCR_FULL, tk.K, 0);
+            if (lane == 0) nn[i] = best;
+        } else if (lane == 0) {
+            out_list[atomicAdd(out_count, 1u)] = i;
         }
     }
 }
@@ -720,7 +692,7 @@ int icp_dev(Ctx *ctx, const IcpArgs &a, pcr_icp_result *result) {
     FreeLater f3{nn, st};
     PCR_CUDA(ctx, cudaMallocAsync((void **)&dlist, sizeof(uint32_t) * (2 * std::max<size_t>(ns, 1) + 64), st));
     FreeLater f4{dlist, st};
-    uint32_t *dcount = dlist;  // [kMaxLevels + 1]: search kernel, fine-grid pass, coarse levels 1..
+    uint32_t *dcount = dlist;  // [kMaxLevels]
     uint32_t *dl[2] = {dlist + 64, dlist + 64 + std::max<size_t>(ns, 1)};
 
     const int n_blocks = (int)std::max<size_t>(1, std::min<size_t>((ns + kIcpThreads - 1) / kIcpThreads, (size_t)ctx->sm_count * 4));
@@ -738,25 +710,21 @@ int icp_dev(Ctx *ctx, const IcpArgs &a, pcr_icp_result *result) {
     auto one_pass = [&](int metrics_only) -> int {
         {
             TimeScope ts(ctx, kTagIcpStep);
-            PCR_CUDA(ctx, cudaMemsetAsync(dcount, 0, sizeof(uint32_t) * (kMaxLevels + 1), st));
+            PCR_CUDA(ctx, cudaMemsetAsync(dcount, 0, sizeof(uint32_t) * kMaxLevels, st));
             if (ns > 0) {
                 icp_search_kernel<<<(unsigned)((ns + kIcpThreads - 1) / kIcpThreads), kIcpThreads, 0, st>>>(
                     tgt->grids, tgt->cell_start, tgt->sorted, tgt->orig4, cur, ns, d_state, nn, dl[0], dcount + 0, 0);
                 PCR_LAUNCH_CHECK(ctx);
-                // deferred points (no host round trip: the list lengths stay on the device): first the seeded ones
-                // on the fine grid, thread per point ...
-                static const int fine_rings = getenv("PCR_ICP_FINE_RINGS") ? atoi(getenv("PCR_ICP_FINE_RINGS")) : 8;
-                icp_deferred_kernel<true><<<ctx->sm_count * 8, 128, 0, st>>>(tgt->grids, tgt->cell_start, tgt->sorted, cur, d_state, dl[0],
-                                                                             dcount + 0, nn, dl[1], dcount + 1, 0, fine_rings);
-                PCR_LAUNCH_CHECK(ctx);
-                // ... then whatever is left on the coarser levels, warp per point
+                // deferred points on the coarser levels, warp per point (no host round trip: the list lengths stay on
+                // the device).  The warp search is seeded with nn[i] and skips rows / cells beyond the current best.
+                // (Measured and dropped: thread-per-point on the coarse levels, 1.8x slower; a seeded thread-per-point
+                // ball scan on the fine grid before the coarse levels, 0.43 -> 0.47-0.52 ms per iteration.)
                 for (int l = 1; l < kMaxLevels; l++) {
                     const bool last = l == kMaxLevels - 1;
                     // level 1 may hold 10-20 % of a badly aligned source: give it more resident warps
-                    // (thread-per-point on the COARSE levels measured 1.8x slower, with and without the warm start)
-                    icp_deferred_kernel<false><<<ctx->sm_count * (l == 1 ? 8 : 2), 128, 0, st>>>(
-                        levels[l]->grids, levels[l]->cell_start, levels[l]->sorted, cur, d_state, dl[l & 1], dcount + l, nn,
-                        dl[(l + 1) & 1], dcount + (l + 1), last ? 1 : 0, 0);
+                    icp_deferred_kernel<<<ctx->sm_count * (l == 1 ? 8 : 2), 128, 0, st>>>(
+                        levels[l]->grids, levels[l]->cell_start, levels[l]->sorted, cur, d_state, dl[(l - 1) & 1], dcount + (l - 1), nn,
+                        dl[l & 1], dcount + l, last ? 1 : 0);
                     PCR_LAUNCH_CHECK(ctx);
                 }
             }
@@ -769,10 +737,10 @@ int icp_dev(Ctx *ctx, const IcpArgs &a, pcr_icp_result *result) {
             PCR_LAUNCH_CHECK(ctx);
         }
         if (getenv("PCR_DEBUG")) {
-            uint32_t hc[kMaxLevels + 1];
+            uint32_t hc[kMaxLevels];
             cudaMemcpyAsync(hc, dcount, sizeof(hc), cudaMemcpyDeviceToHost, st);
             cudaStreamSynchronize(st);
-            fprintf(stderr, "[pcr] icp pass: deferred after search %u, after the fine pass %u, per coarse level %u %u %u of %zu (cells %.3g / %.3g)\n", hc[0], hc[1], hc[2], hc[3], hc[4], ns,
+            fprintf(stderr, "[pcr] icp pass: deferred per level %u %u %u %u of %zu (cells %.3g / %.3g)\n", hc[0], hc[1], hc[2], hc[3], ns,
                     levels[0]->grids_h[0].h, levels[1]->grids_h[0].h);
         }
         TimeScope ts2(ctx, kTagIcpSolve);
