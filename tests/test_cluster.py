@@ -157,3 +157,33 @@ def test_gpu_determinism(pcr):  # cluster_differential.rs:330-360
     for _ in range(10):
         again = pcr.cluster_arrays(c, 0.8, 1, len(pts))
         assert np.array_equal(first[0], again[0]) and np.array_equal(first[1], again[1])
+
+
+def test_oracle_against_scipy_components(oracle):
+    """Independent pin: connected components of the r-ball graph from scipy (f64 distances).  Clouds are drawn so that no
+    pair sits within 1e-4 of the threshold, where f32 and f64 could disagree."""
+    scipy_spatial = pytest.importorskip("scipy.spatial")
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+
+    rng = np.random.default_rng(12)
+    checked = 0
+    for _ in range(40):
+        n = int(rng.integers(50, 1500))
+        thr = float(rng.uniform(0.5, 4.0))
+        pts = rng.uniform(-25, 25, (n, 3)).astype(np.float32)
+        tree = scipy_spatial.cKDTree(pts.astype(np.float64))
+        near = tree.query_pairs(thr * (1 + 1e-4), output_type="ndarray")
+        sure = tree.query_pairs(thr * (1 - 1e-4), output_type="ndarray")
+        if len(near) != len(sure):
+            continue  # a pair too close to the threshold: skip this draw
+        checked += 1
+        g = coo_matrix((np.ones(len(sure)), (sure[:, 0], sure[:, 1])), shape=(n, n))
+        _, lab = connected_components(g, directed=False)
+        comps = {}
+        for i, l in enumerate(lab):
+            comps.setdefault(l, []).append(i)
+        want = sorted(comps.values(), key=lambda c: (-len(c), c[0]))
+        got = as_lists(oracle.euclidean_cluster(pts, thr, 1, n))
+        assert got == want
+    assert checked >= 20
