@@ -423,6 +423,8 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
         int ys = 0;
         static const int ys_max = getenv("PCR_VOXEL_YS") ? atoi(getenv("PCR_VOXEL_YS")) : 0;  // tuning hook
         while (ys < ys_max && nz < (1ull << (32 - (ys + 1))) && nx * ((ny + (2ull << ys) - 1) >> (ys + 1)) >= (uint64_t)m) ys++;
+        // ... and widened automatically when a one-voxel-wide table would not fit
+        while (ys < 4 && nz < (1ull << (32 - (ys + 1))) && nx * ((ny + (1ull << ys) - 1) >> ys) > (1ull << 24)) ys++;
         const uint64_t nyc64 = (ny + (1ull << ys) - 1) >> ys;
         const uint64_t n_cols64 = nx * nyc64;  // (both < 2^32: no overflow)
         static const bool no_cols = getenv("PCR_VOXEL_RADIX") != nullptr;  // A/B hook: force the radix path
