@@ -73,11 +73,21 @@ def test_product_does_not_import_the_oracle():
                 assert "pcr_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
 
 
+def test_tools_do_not_import_the_oracle():
+    """tools/ holds profiling helpers for the product path; anything that checks against the oracle lives in tests/."""
+    tdir = os.path.join(ROOT, "tools")
+    for f in os.listdir(tdir):
+        if f.endswith(".py"):
+            text = open(os.path.join(tdir, f), errors="ignore").read()
+            assert "from oracle" not in text and "import oracle" not in text, f
+
+
 def test_python_surface_mirrors_reference_names():
     import pointclouds_rs_b200 as pcr
 
     for name in ("PointCloud", "statistical_outlier_removal", "radius_outlier_removal", "estimate_normals", "IcpResult",
-                 "icp_point_to_point", "icp_point_to_plane", "apply_transform"):
+                 "icp_point_to_point", "icp_point_to_plane", "apply_transform", "voxel_downsample", "euclidean_cluster", "ransac_plane",
+                 "PlaneResult"):
         assert hasattr(pcr, name)
     pc = pcr.PointCloud.from_numpy(__import__("numpy").arange(12, dtype="float64").reshape(4, 3))
     assert pc.len() == 4 and len(pc) == 4 and not pc.is_empty() and repr(pc) == "PointCloud(n=4)"

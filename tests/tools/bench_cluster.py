@@ -1,6 +1,6 @@
 """Developer timing: euclidean_cluster on the KITTI-shaped frame (host API wall time + device stages)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import pointclouds_rs_b200 as pcr
 from pointclouds_rs_b200 import scenes

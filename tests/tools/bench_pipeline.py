@@ -1,7 +1,7 @@
 """Developer timing: the KITTI pipeline of configs[1] three ways -- host-pointer calls (one PCIe round trip per step),
 device-resident DeviceCloud, and the CPU oracle -- plus voxel / cluster alone."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import pointclouds_rs_b200 as pcr
 from pointclouds_rs_b200 import scenes
