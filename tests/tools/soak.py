@@ -1,5 +1,5 @@
 """Randomised soak of the newer paths against the oracle (cluster, voxel, RANSAC, fused SOR->normals, KNN k<=12 pruned
-walk, warp-pruned deferred levels).  usage: python tools/soak.py [seconds] [seed]"""
+walk, warp-pruned deferred levels).  usage: python tests/tools/soak.py [seconds] [seed]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
