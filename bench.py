@@ -251,10 +251,10 @@ def main():
         last["dev"] = o
 
     def step_e2e():
-        d = pcr.DeviceCloud.upload_raw(ctx, h_raw[0].data_ptr(), h_raw[1].data_ptr(), h_raw[2].data_ptr(), n_raw)
+        d = pcr.DeviceCloud.upload_block(ctx, h_raw.data_ptr(), n_raw, n_raw)  # x | y | z rows of one pinned block
         o = pipeline(d)
         d.free()
-        o.download_raw(*[h_out[j].data_ptr() for j in range(6)])
+        o.download_block(h_out.data_ptr(), n_raw, with_normals=True)           # x | y | z | nx | ny | nz rows
         last["e2e_len"] = len(o)
         o.free()
 
@@ -372,7 +372,7 @@ def main():
             "config": workload_config(len(raw), n, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * 4 * n_raw, "d2h_bytes_per_step": 6 * 4 * n_kept,
                     "ms_per_step": e2e_s_max / args.steps * 1e3,
-                    "timer": "wall clock around pcr_cloud_upload -> voxel -> sor_normals -> pcr_cloud_download, pinned host buffers"},
+                    "timer": "wall clock around pcr_cloud_upload_block -> voxel -> sor_normals -> pcr_cloud_download_block, pinned host buffers"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

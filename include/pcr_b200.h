@@ -268,6 +268,10 @@ size_t pcr_cloud_len(const pcr_cloud *cloud);
 int pcr_cloud_has_normals(const pcr_cloud *cloud);
 int pcr_cloud_download(const pcr_cloud *cloud, float *x, float *y, float *z);            /* arrays of pcr_cloud_len */
 int pcr_cloud_download_normals(const pcr_cloud *cloud, float *nx, float *ny, float *nz);
+/* The same for callers that keep their SoA arrays in ONE block, `stride` floats apart (x | y | z [| nx | ny | nz]):
+ * a single strided transfer each way instead of three or six. */
+int pcr_cloud_upload_block(pcr_ctx *ctx, const float *xyz, size_t stride, size_t n, pcr_cloud **out);
+int pcr_cloud_download_block(const pcr_cloud *cloud, float *dst, size_t stride, int with_normals);
 /* device pointers of the SoA arrays (valid until the cloud is freed; normals NULL if absent) */
 int pcr_cloud_device_pointers(const pcr_cloud *cloud, const float **d_x, const float **d_y, const float **d_z,
                               const float **d_nx, const float **d_ny, const float **d_nz);

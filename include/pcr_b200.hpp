@@ -331,6 +331,16 @@ class DeviceCloud {
         ctx.check(pcr_cloud_upload(ctx.get(), cloud.x.data(), cloud.y.data(), cloud.z.data(), cloud.len(), &h));
         return DeviceCloud(h, &ctx);
     }
+    // x | y | z rows of one host block, `stride` floats apart: one strided transfer
+    static DeviceCloud upload_block(const float *xyz, size_t stride, size_t n, Context &ctx = default_context()) {
+        pcr_cloud *h = nullptr;
+        ctx.check(pcr_cloud_upload_block(ctx.get(), xyz, stride, n, &h));
+        return DeviceCloud(h, &ctx);
+    }
+    // x | y | z [| nx | ny | nz] rows into one host block
+    void download_block(float *dst, size_t stride, bool with_normals) const {
+        ctx_->check(pcr_cloud_download_block(h_, dst, stride, with_normals ? 1 : 0));
+    }
     ~DeviceCloud() { pcr_cloud_free(h_); }
     DeviceCloud(DeviceCloud &&o) noexcept : h_(o.h_), ctx_(o.ctx_) { o.h_ = nullptr; }
     DeviceCloud &operator=(DeviceCloud &&o) noexcept {

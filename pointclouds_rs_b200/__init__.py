@@ -583,6 +583,17 @@ class DeviceCloud:
         _ffi.check(_ffi.load().pcr_cloud_upload(ctx._h, x_ptr, y_ptr, z_ptr, n, C.byref(h)), ctx._h)
         return DeviceCloud(h, ctx)
 
+    @staticmethod
+    def upload_block(ctx: Context, ptr: int, stride: int, n: int) -> "DeviceCloud":
+        """Upload x | y | z from ONE host block (rows `stride` floats apart): a single strided transfer."""
+        h = C.c_void_p()
+        _ffi.check(_ffi.load().pcr_cloud_upload_block(ctx._h, ptr, stride, n, C.byref(h)), ctx._h)
+        return DeviceCloud(h, ctx)
+
+    def download_block(self, ptr: int, stride: int, with_normals: bool = False):
+        """Download x | y | z [| nx | ny | nz] into ONE host block (rows `stride` floats apart)."""
+        _ffi.check(_ffi.load().pcr_cloud_download_block(self._h, ptr, stride, 1 if with_normals else 0), self._ctx._h)
+
     def download_raw(self, x_ptr: int, y_ptr: int, z_ptr: int, nx_ptr: int = 0, ny_ptr: int = 0, nz_ptr: int = 0):
         """Download into raw host addresses (arrays of len()); normals too if the three pointers are given."""
         _ffi.check(_ffi.load().pcr_cloud_download(self._h, x_ptr, y_ptr, z_ptr), self._ctx._h)

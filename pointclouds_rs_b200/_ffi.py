@@ -100,6 +100,8 @@ SIGNATURES = {
     "pcr_cluster_labels_dev": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_float, vp]),
     "pcr_radius_outlier_dev": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_float, C.c_size_t, vp]),
     "pcr_cloud_upload": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.POINTER(vp)]),
+    "pcr_cloud_upload_block": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, C.POINTER(vp)]),
+    "pcr_cloud_download_block": (C.c_int, [vp, vp, C.c_size_t, C.c_int]),
     "pcr_cloud_free": (None, [vp]),
     "pcr_cloud_len": (C.c_size_t, [vp]),
     "pcr_cloud_has_normals": (C.c_int, [vp]),

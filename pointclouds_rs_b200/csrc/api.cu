@@ -1231,6 +1231,44 @@ int pcr_cloud_download_normals(const pcr_cloud *cloud, float *nx, float *ny, flo
     PCR_API_END(c)
 }
 
+// One strided copy each way for callers that keep their SoA arrays in one block (x | y | z [| nx | ny | nz], `stride`
+// floats apart): a single cudaMemcpy2DAsync instead of three or six separate transfers.
+int pcr_cloud_upload_block(pcr_ctx *ctx, const float *xyz, size_t stride, size_t n, pcr_cloud **out) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (!out || (n && !xyz) || stride < n) return fail(c, PCR_ERR_INVALID_ARG, "null pointer or stride < n");
+    *out = nullptr;
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    pcr_cloud *cl = nullptr;
+    PCR_TRY(cloud_alloc(ctx, n, false, &cl));
+    cudaError_t e = cudaSuccess;
+    if (n) e = cudaMemcpy2DAsync(cl->base, cl->stride * sizeof(float), xyz, stride * sizeof(float), n * sizeof(float), 3, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // the caller's buffer is free again on return
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        pcr_cloud_free(cl);
+        return fail(c, PCR_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = cl;
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+int pcr_cloud_download_block(const pcr_cloud *cloud, float *dst, size_t stride, int with_normals) {
+    PCR_CLOUD_CHECK(cloud)
+    if (with_normals && !cloud->has_normals) return fail(c, PCR_ERR_INVALID_ARG, "the cloud has no normals");
+    if ((cloud->n && !dst) || stride < cloud->n) return fail(c, PCR_ERR_INVALID_ARG, "null pointer or stride < len");
+    if (!cloud->n) return PCR_OK;
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    PCR_CUDA(c, cudaMemcpy2DAsync(dst, stride * sizeof(float), cloud->base, cloud->stride * sizeof(float), cloud->n * sizeof(float),
+                                  with_normals ? 6 : 3, cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
 int pcr_cloud_select(const pcr_cloud *cloud, const uint32_t *indices, size_t m, pcr_cloud **out) {
     PCR_CLOUD_CHECK(cloud)
     if (!out || (m && !indices)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");

@@ -22,6 +22,14 @@ def test_upload_download_select(pcr):
     dn = d.estimate_normals(10)
     sel = dn.select(idx)
     assert sel.has_normals() and np.array_equal(sel.normals_to_numpy(), dn.normals_to_numpy()[idx])
+    block = np.ascontiguousarray(pts.T)                                 # x | y | z rows of one block: one strided transfer each way
+    b = pcr.DeviceCloud.upload_block(pcr.default_context(), block.ctypes.data, block.shape[1], block.shape[1])
+    assert np.array_equal(b.to_numpy(), pts)
+    outb = np.zeros((6, 5000 + 24), np.float32)                          # a stride larger than the cloud
+    dn.download_block(outb.ctypes.data, outb.shape[1], with_normals=True)
+    assert np.array_equal(outb[:3, :5000].T, pts) and np.array_equal(outb[3:, :5000].T, dn.normals_to_numpy())
+    with pytest.raises(ValueError):
+        d.download_block(outb.ctypes.data, outb.shape[1], with_normals=True)   # no normals on this cloud
     empty = pcr.DeviceCloud.from_numpy(np.zeros((0, 3), np.float32))
     assert len(empty) == 0 and empty.to_numpy().shape == (0, 3)
 
