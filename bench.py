@@ -351,6 +351,10 @@ def main():
             extra["icp"] = icp_measurement(pcr, ctx)
         except Exception as ex:  # the headline must not die on the secondary measurement
             extra["icp"] = {"error": str(ex)}
+        try:
+            extra["frames_in_flight"] = frames_in_flight_measurement(pcr, local_rank, h_raw, n_raw, h_out, last["e2e_len"])
+        except Exception as ex:
+            extra["frames_in_flight"] = {"error": str(ex)}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -386,6 +390,52 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def frames_in_flight_measurement(pcr, device, h_raw, n_raw, h_ref, m_ref, flights=(2, 4), steps=60):
+    """Secondary figure (NOT the headline): the same end-to-end step with several frames in flight.  One frame is
+    latency-bound (short kernels, host round trips for counts), and contexts are independent, so T host threads --
+    each with its own context, stream and pinned output block -- overlap their frames on the one GPU."""
+    import threading
+
+    import torch
+
+    def worker(ctx, out, n_steps, go, lens):
+        go.wait()
+        for _ in range(n_steps):
+            d = pcr.DeviceCloud.upload_block(ctx, h_raw.data_ptr(), n_raw, n_raw)
+            v = d.voxel_downsample(VOXEL)
+            o = v.sor_normals(K_SOR, STD_MUL, K_NORMALS)
+            d.free()
+            v.free()
+            o.download_block(out.data_ptr(), n_raw, with_normals=True)
+            lens.append(len(o))
+            o.free()
+
+    res = {"note": "T host threads x (context, stream), same frame and calls as e2e; wall clock; results compared with the e2e arm"}
+    for T in flights:
+        ctxs = [pcr.Context(device=device) for _ in range(T)]
+        outs = [torch.empty((6, n_raw), dtype=torch.float32).pin_memory() for _ in range(T)]
+        for c in ctxs:
+            c.set_frame_stream(True)
+        dt, lens = 0.0, []
+        for n_steps in (5, steps):  # warm-up, then timed
+            go, lens = threading.Event(), []
+            th = [threading.Thread(target=worker, args=(ctxs[t], outs[t], n_steps, go, lens)) for t in range(T)]
+            for t in th:
+                t.start()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            go.set()
+            for t in th:
+                t.join()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        same = all(m == m_ref for m in lens) and all(np.array_equal(o[:, :m_ref].numpy(), h_ref[:, :m_ref].numpy()) for o in outs)
+        res[str(T)] = {"value": n_raw * steps * T / dt, "unit": UNIT, "ms_per_frame": dt / (steps * T) * 1e3, "identical_to_e2e": bool(same)}
+        for c in ctxs:
+            c.close()
+    return res
 
 
 def icp_measurement(pcr, ctx):

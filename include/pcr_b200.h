@@ -261,7 +261,10 @@ int pcr_sor_normals_batch_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, 
  * PointCloud (crates/core/src/cloud.rs:4-18) kept in HBM between the steps of a pipeline: one upload,
  * one download, `select` (cloud.rs:103-140) as a device compaction that carries the normals along.
  * Every function that returns a cloud allocates a new handle (free it with pcr_cloud_free); inputs
- * are never modified.  Edge cases follow the reference functions named on each line. */
+ * are never modified.  Edge cases follow the reference functions named on each line.
+ * A cloud belongs to the context that made it: free it before pcr_ctx_destroy, and use it only from
+ * the thread that drives that context.  Contexts are independent of one another, so several host
+ * threads, each with its own context, can keep several frames in flight on one GPU. */
 int pcr_cloud_upload(pcr_ctx *ctx, const float *x, const float *y, const float *z, size_t n, pcr_cloud **out);
 void pcr_cloud_free(pcr_cloud *cloud);
 size_t pcr_cloud_len(const pcr_cloud *cloud);

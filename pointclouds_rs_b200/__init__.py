@@ -20,6 +20,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import weakref
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -56,9 +57,12 @@ class Context:
         _ffi.check(st)
         self._h = h
         self.device = device
+        self._clouds = weakref.WeakSet()  # live DeviceClouds: they must be freed before the context is destroyed
 
     def close(self):
         if getattr(self, "_h", None):
+            for cl in list(getattr(self, "_clouds", ())):
+                cl.free()
             _ffi.load().pcr_ctx_destroy(self._h)
             self._h = None
 
@@ -555,12 +559,11 @@ class DeviceCloud:
     def __init__(self, handle, ctx: Context):
         self._h = handle
         self._ctx = ctx
+        ctx._clouds.add(self)
 
     def __del__(self):
         try:
-            if getattr(self, "_h", None):
-                _ffi.load().pcr_cloud_free(self._h)
-                self._h = None
+            self.free()
         except Exception:
             pass
 
@@ -601,9 +604,9 @@ class DeviceCloud:
             _ffi.check(_ffi.load().pcr_cloud_download_normals(self._h, nx_ptr, ny_ptr, nz_ptr), self._ctx._h)
 
     def free(self):
-        if self._h:
-            _ffi.load().pcr_cloud_free(self._h)
-            self._h = None
+        h, self._h = getattr(self, "_h", None), None
+        if h and self._ctx._h:  # a closed context has already freed its clouds
+            _ffi.load().pcr_cloud_free(h)
 
     def _new(self, fn, *args) -> "DeviceCloud":
         h = C.c_void_p()

@@ -98,3 +98,36 @@ def test_device_icp_matches_host_api(pcr, oracle):
     R, t = scenes.rot_z(0.3), [1.0, 2.0, 3.0]
     moved = d_s.apply_transform(R, t)
     assert np.array_equal(moved.to_numpy(), oracle.apply_transform(src, R, t))
+
+
+def test_frames_in_flight_on_independent_contexts(pcr):
+    """Contexts share nothing but the device: host threads, each with its own context and stream, run whole
+    pipelines concurrently and every one gets the bits the single-threaded run gets."""
+    import threading
+
+    frames = [scenes.kitti_scene(20 + i, (12_000, 600, 100, 260)) for i in range(3)]
+    want = []
+    for f in frames:
+        o = pcr.DeviceCloud.from_numpy(f).voxel_downsample(0.05).sor_normals(10, 1.0, 20)
+        want.append((o.to_numpy(), o.normals_to_numpy(), o.euclidean_cluster(0.5, 30, 25000)))
+    errors = []
+
+    def worker(t):
+        try:
+            ctx = pcr.Context(device=0)
+            ctx.set_frame_stream(t % 2 == 0)
+            for rep in range(6):
+                i = (t + rep) % len(frames)
+                o = pcr.DeviceCloud.from_numpy(frames[i], ctx).voxel_downsample(0.05).sor_normals(10, 1.0, 20)
+                assert np.array_equal(o.to_numpy(), want[i][0]) and np.array_equal(o.normals_to_numpy(), want[i][1])
+                assert o.euclidean_cluster(0.5, 30, 25000) == want[i][2]
+            ctx.close()
+        except Exception as ex:  # surfaced in the main thread
+            errors.append(repr(ex))
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
