@@ -320,58 +320,120 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = s;
 }
 
-// data[i] <- sum of data[0..i) ; each block first folds the sums of the tiles before it
-__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint32_t *__restrict__ data, size_t n,
-                                                                  const uint32_t *__restrict__ tile_sums) {
-    __shared__ uint32_t sh[kScanThreads / 32];
-    __shared__ uint32_t warp_off[kScanThreads / 32];
-    uint32_t pre = 0;
-    for (uint32_t t = threadIdx.x; t < blockIdx.x; t += kScanThreads) pre += tile_sums[t];
-    pre = block_sum_u32(pre, sh);
-    // thread-contiguous items: thread t owns [t*16, t*16+16) of the tile
-    size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
-    uint32_t v[kScanItems];
-    uint32_t tsum = 0;
-#pragma unroll
-    for (int it = 0; it < kScanItems; it++) {
-        size_t i = base + it;
-        v[it] = i < n ? data[i] : 0u;
-        tsum += v[it];
+// ---- single-pass exclusive scan (decoupled look-back) ---------------------------------------------
+// One launch instead of two, the data read once.  Tiles take a ticket (so a tile only ever waits for tiles that
+// are already running), publish their aggregate, then warp 0 walks back over the published words of the tiles
+// before it, 32 at a time, until it meets one that already holds an inclusive prefix.
+// State word: [63:34] epoch | [33:32] status (1 = tile aggregate, 2 = inclusive prefix) | [31:0] value.  The
+// epoch changes with every scan of the context, so the words are never cleared between scans.
+constexpr unsigned long long kScanAgg = 1ull << 32, kScanPre = 2ull << 32;
+
+__device__ __forceinline__ uint4 scan_load4(const uint32_t *data, size_t i, size_t n, bool vec) {
+    if (vec && i + 3 < n) return *reinterpret_cast<const uint4 *>(data + i);
+    uint4 v;
+    v.x = i < n ? data[i] : 0u;
+    v.y = i + 1 < n ? data[i + 1] : 0u;
+    v.z = i + 2 < n ? data[i + 2] : 0u;
+    v.w = i + 3 < n ? data[i + 3] : 0u;
+    return v;
+}
+
+__device__ __forceinline__ void scan_store4(uint32_t *data, size_t i, size_t n, bool vec, uint4 v) {
+    if (vec && i + 3 < n) {
+        *reinterpret_cast<uint4 *>(data + i) = v;
+        return;
     }
-    // exclusive scan of the per-thread sums across the block
-    uint32_t incl = tsum;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t u = __shfl_up_sync(PCR_FULL, incl, o);
-        if (lane >= o) incl += u;
-    }
-    if (lane == 31) warp_off[w] = incl;
+    if (i < n) data[i] = v.x;
+    if (i + 1 < n) data[i + 1] = v.y;
+    if (i + 2 < n) data[i + 2] = v.z;
+    if (i + 3 < n) data[i + 3] = v.w;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(uint32_t *__restrict__ data, size_t n,
+                                                                     unsigned long long *state, uint32_t *ticket,
+                                                                     uint32_t epoch, uint32_t tiles, int vec) {
+    constexpr int kWarps = kScanThreads / 32, kRows = kScanItems / 4;
+    __shared__ uint32_t s_tile, s_pre;
+    __shared__ uint32_t warp_tot[kWarps];
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
-    if (threadIdx.x < 32) {
-        uint32_t ws = threadIdx.x < kScanThreads / 32 ? warp_off[threadIdx.x] : 0u;
-        uint32_t wi = ws;
+    const uint32_t tile = s_tile;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // a warp owns 32 * kScanItems consecutive elements, read as kRows coalesced rows of uint4
+    const size_t wbase = (size_t)tile * kScanTile + (size_t)w * (kScanItems * 32);
+    uint4 v[kRows];
+    uint32_t ex[kRows];
+    uint32_t carry = 0;
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+        v[r] = scan_load4(data, wbase + (size_t)r * 128 + lane * 4, n, vec != 0);
+        const uint32_t s = v[r].x + v[r].y + v[r].z + v[r].w;
+        uint32_t incl = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t u = __shfl_up_sync(PCR_FULL, wi, o);
-            if (lane >= o) wi += u;
+            uint32_t u = __shfl_up_sync(PCR_FULL, incl, o);
+            if (lane >= o) incl += u;
         }
-        if (threadIdx.x < kScanThreads / 32) warp_off[threadIdx.x] = wi - ws;
+        ex[r] = carry + incl - s;
+        carry += __shfl_sync(PCR_FULL, incl, 31);
+    }
+    if (lane == 0) warp_tot[w] = carry;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int j = 0; j < kWarps; j++) {
+        const uint32_t t = warp_tot[j];
+        if (j < w) woff += t;
+        total += t;
+    }
+    if (w == 0) {
+        const unsigned long long tag = (unsigned long long)epoch << 34;
+        volatile unsigned long long *vs = state;
+        uint32_t pre = 0;
+        if (tile > 0) {
+            if (lane == 0) vs[tile] = tag | kScanAgg | total;
+            long long look = (long long)tile - 1;
+            for (;;) {
+                const long long t = look - lane;
+                const bool need = t >= 0;
+                unsigned long long sv = 0;
+                uint32_t polls = 0;
+                bool ready;
+                do {
+                    if (need) sv = vs[t];
+                    ready = !need || ((sv >> 34) == epoch && ((sv >> 32) & 3ull) != 0);
+                    if (++polls > (1u << 26)) __trap();  // a predecessor never published: fail loudly, do not hang
+                } while (!__all_sync(PCR_FULL, ready));
+                const unsigned pm = __ballot_sync(PCR_FULL, need && ((sv >> 32) & 3ull) == 2ull);
+                const int stop = pm ? __ffs(pm) - 1 : 32;
+                pre += __reduce_add_sync(PCR_FULL, (need && lane <= stop) ? (uint32_t)sv : 0u);
+                if (pm || look < 32) break;
+                look -= 32;
+            }
+        }
+        if (lane == 0) {
+            vs[tile] = tag | kScanPre | (uint32_t)(pre + total);
+            s_pre = pre;
+        }
     }
     __syncthreads();
-    uint32_t run = pre + warp_off[w] + (incl - tsum);
+    const uint32_t base = s_pre + woff;
 #pragma unroll
-    for (int it = 0; it < kScanItems; it++) {
-        size_t i = base + it;
-        if (i < n) data[i] = run;
-        run += v[it];
+    for (int r = 0; r < kRows; r++) {
+        uint4 o;
+        o.x = base + ex[r];
+        o.y = o.x + v[r].x;
+        o.z = o.y + v[r].y;
+        o.w = o.z + v[r].z;
+        scan_store4(data, wbase + (size_t)r * 128 + lane * 4, n, vec != 0, o);
     }
+    if (tile == tiles - 1 && threadIdx.x == 0) *ticket = 0;  // every ticket has been handed out by now
 }
 
 __global__ void __launch_bounds__(kScanThreads) scan_apply_u64_kernel(const uint32_t *__restrict__ in,
                                                                       uint64_t *__restrict__ out, size_t n,
                                                                       const uint32_t *__restrict__ tile_sums) {
-    // same as scan_apply_kernel but widening to u64 and writing out[n] = total as well
+    // two-pass variant (tile sums, then apply) widening to u64 and writing out[n] = total as well
     __shared__ unsigned long long sh64[kScanThreads / 32];
     __shared__ unsigned long long warp_off[kScanThreads / 32];
     unsigned long long pre = 0;
@@ -423,12 +485,18 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_u64_kernel(const uint
 
 int exclusive_scan_u32_dev(Ctx *ctx, uint32_t *d_data, size_t n) {
     if (n == 0) return PCR_OK;
-    size_t tiles = (n + kScanTile - 1) / kScanTile;
-    PCR_TRY(ensure(ctx, ctx->b_misc2, tiles * sizeof(uint32_t)));
-    uint32_t *tile_sums = (uint32_t *)ctx->b_misc2.p;
-    scan_tile_sums_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(d_data, n, tile_sums);
-    PCR_LAUNCH_CHECK(ctx);
-    scan_apply_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(d_data, n, tile_sums);
+    const size_t tiles = (n + kScanTile - 1) / kScanTile;
+    const size_t cap_before = ctx->b_scan.cap;
+    PCR_TRY(ensure(ctx, ctx->b_scan, 16 + tiles * sizeof(unsigned long long)));
+    if (ctx->b_scan.cap != cap_before || ctx->scan_epoch >= (1u << 30) - 2) {  // fresh memory (or epoch wrap): no tag may match
+        PCR_CUDA(ctx, cudaMemsetAsync(ctx->b_scan.p, 0, ctx->b_scan.cap, ctx->stream));
+        ctx->scan_epoch = 0;
+    }
+    const uint32_t epoch = ++ctx->scan_epoch;
+    uint32_t *ticket = (uint32_t *)ctx->b_scan.p;
+    unsigned long long *state = (unsigned long long *)((char *)ctx->b_scan.p + 16);
+    const int vec = ((uintptr_t)d_data & 15) == 0;
+    scan_lookback_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(d_data, n, state, ticket, epoch, (uint32_t)tiles, vec);
     PCR_LAUNCH_CHECK(ctx);
     return PCR_OK;
 }

@@ -90,6 +90,8 @@ struct Ctx {
     DevBuf b_misc2;
     DevBuf b_small;    // reductions, statistics, ICP state
     DevBuf b_table;    // probe cell table
+    DevBuf b_scan;     // single-pass scan: ticket + one state word per tile (tagged with scan_epoch, never cleared between scans)
+    uint32_t scan_epoch = 0;
     DevBuf b_list;     // deferred-query lists of the level loop
     // cell tables of TRANSIENT indices (the ones an entry point builds and frees itself), one per grid
     // level.  A 100-frame batch needs a 280 MB table: taking it from the stream-ordered pool on every
