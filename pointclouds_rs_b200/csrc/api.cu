@@ -919,7 +919,8 @@ __global__ void single_point_frames_kernel(const uint32_t *__restrict__ frame_of
 // every kernel runs once for the whole batch (frames are an extra axis of the cell table).
 static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz, const uint64_t *frame_offsets, size_t n_frames,
                       size_t n, size_t k_sor, float std_mul, size_t k_normals, const float vp[3], uint8_t *d_keep, float *d_nx,
-                      float *d_ny, float *d_nz, unsigned long long *d_kept /* n_frames */) {
+                      float *d_ny, float *d_nz, unsigned long long *d_kept /* n_frames */,
+                      unsigned long long *h_kept0 = nullptr /* single frame: set if the count came back with another round trip */) {
     const int F = (int)n_frames;
     float *d_mean = nullptr, *d_stats = nullptr;
     PCR_CUDA(c, cudaMallocAsync((void **)&d_mean, sizeof(float) * std::max<size_t>(n, 1), c->stream));
@@ -981,7 +982,7 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
     if (k_normals == 0) return PCR_OK;
     PCR_TRY(index_apply_mask_dev(ix, d_keep));
     // removed points get 0 and kept non-finite points (0,0,1) inside normals_dev / normals_from_lists_dev
-    if (fused) return normals_from_lists_dev(ix, k_normals, vp, sl, d_keep, d_nx, d_ny, d_nz);
+    if (fused) return normals_from_lists_dev(ix, k_normals, vp, sl, d_keep, d_nx, d_ny, d_nz, F == 1 ? d_kept : nullptr, h_kept0);
     return normals_dev(ix, k_normals, vp, d_nx, d_ny, d_nz, d_keep);
 }
 
@@ -1103,15 +1104,17 @@ __global__ void mask_to_u32_kernel(const uint8_t *__restrict__ keep, size_t n, u
     if (i <= n) flag[i] = (i < n && keep[i]) ? 1u : 0u;
 }
 
-// cloud.rs:103-140 as a stream compaction: kept points keep their order, normals travel along
-__global__ void compact_kernel(const float *__restrict__ src, size_t src_stride, int n_arrays, size_t n,
-                               const uint32_t *__restrict__ pos /* exclusive scan of the flags, n + 1 */, float *__restrict__ dst,
-                               size_t dst_stride) {
+// cloud.rs:103-140 as a stream compaction: kept points keep their order, normals travel along.  Rows 0..n_a-1
+// come from `a`, rows n_a..n_a+n_b-1 from `b` (normals computed into a scratch block).
+__global__ void compact_kernel(const float *__restrict__ a, size_t a_stride, int n_a, const float *__restrict__ b, size_t b_stride, int n_b,
+                               size_t n, const uint32_t *__restrict__ pos /* exclusive scan of the flags, n + 1 */,
+                               float *__restrict__ dst, size_t dst_stride) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t p = pos[i];
     if (pos[i + 1] == p) return;
-    for (int a = 0; a < n_arrays; a++) dst[(size_t)a * dst_stride + p] = src[(size_t)a * src_stride + i];
+    for (int r = 0; r < n_a; r++) dst[(size_t)r * dst_stride + p] = a[(size_t)r * a_stride + i];
+    for (int r = 0; r < n_b; r++) dst[(size_t)(n_a + r) * dst_stride + p] = b[(size_t)r * b_stride + i];
 }
 
 __global__ void gather_kernel(const float *__restrict__ src, size_t src_stride, int n_arrays, const uint32_t *__restrict__ idx, size_t m,
@@ -1122,8 +1125,11 @@ __global__ void gather_kernel(const float *__restrict__ src, size_t src_stride, 
     for (int a = 0; a < n_arrays; a++) dst[(size_t)a * dst_stride + t] = src[(size_t)a * src_stride + i];
 }
 
-// new cloud = the points of `in` with keep != 0
-int cloud_compact(const pcr_cloud *in, const uint8_t *d_keep, pcr_cloud **out) {
+// new cloud = the points of `in` with keep != 0.  `nrm` (optional): normals of the points of `in`, three rows
+// `nrm_stride` apart, for an `in` that carries none.  `known_m`: the number of kept points if the caller
+// already has it on the host (saves the round trip), else SIZE_MAX.
+int cloud_compact(const pcr_cloud *in, const uint8_t *d_keep, pcr_cloud **out, const float *nrm = nullptr, size_t nrm_stride = 0,
+                  size_t known_m = SIZE_MAX) {
     Ctx *c = &in->owner->c;
     const size_t n = in->n;
     PCR_TRY(ensure(c, c->b_list, sizeof(uint32_t) * (n + 1)));
@@ -1131,14 +1137,19 @@ int cloud_compact(const pcr_cloud *in, const uint8_t *d_keep, pcr_cloud **out) {
     mask_to_u32_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, c->stream>>>(d_keep, n, pos);
     PCR_LAUNCH_CHECK(c);
     PCR_TRY(exclusive_scan_u32_dev(c, pos, n + 1));
-    uint32_t *mail = (uint32_t *)c->pinned + 96;
-    PCR_CUDA(c, cudaMemcpyAsync(mail, pos + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
-    const size_t m = *mail;
-    PCR_TRY(cloud_alloc(in->owner, m, in->has_normals, out));
+    size_t m = known_m;
+    if (m == SIZE_MAX) {
+        uint32_t *mail = (uint32_t *)c->pinned + 96;
+        PCR_CUDA(c, cudaMemcpyAsync(mail, pos + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+        m = *mail;
+    }
+    const bool with_normals = nrm || in->has_normals;
+    PCR_TRY(cloud_alloc(in->owner, m, with_normals, out));
     if (m) {
-        compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(in->base, in->stride, in->has_normals ? 6 : 3, n, pos,
-                                                                           (*out)->base, (*out)->stride);
+        const int n_a = nrm ? 3 : (in->has_normals ? 6 : 3), n_b = nrm ? 3 : 0;
+        compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(in->base, in->stride, n_a, nrm, nrm_stride, n_b, n, pos, (*out)->base,
+                                                                           (*out)->stride);
         PCR_LAUNCH_CHECK(c);
     }
     return PCR_OK;
@@ -1384,23 +1395,25 @@ int pcr_cloud_sor_normals(const pcr_cloud *cloud, size_t k_sor, float std_mul, s
     DevSetter ds(c);
     const size_t n = cloud->n;
     if (n == 0 || k_sor == 0) return cloud_alloc(cloud->owner, 0, true, out);  // statistical_outlier.rs:5-7
-    pcr_cloud *full = nullptr;
-    PCR_TRY(cloud_alloc(cloud->owner, n, true, &full));
+    // normals by original index go to a scratch block; the kept points and their normals are compacted from the
+    // input cloud and that block in one pass
+    const size_t stride = (n + 63) & ~(size_t)63;
+    float *d_nrm = nullptr;
+    PCR_CUDA(c, cudaMallocAsync((void **)&d_nrm, sizeof(float) * 3 * stride, c->stream));
     struct G {
-        pcr_cloud *p;
-        ~G() { pcr_cloud_free(p); }
-    } g{full};
-    cudaMemcpyAsync(full->x(), cloud->x(), sizeof(float) * n, cudaMemcpyDeviceToDevice, c->stream);
-    cudaMemcpyAsync(full->y(), cloud->y(), sizeof(float) * n, cudaMemcpyDeviceToDevice, c->stream);
-    cudaMemcpyAsync(full->z(), cloud->z(), sizeof(float) * n, cudaMemcpyDeviceToDevice, c->stream);
+        float *p;
+        cudaStream_t s;
+        ~G() { cudaFreeAsync(p, s); }
+    } g{d_nrm, c->stream};
     PCR_TRY(ensure(c, c->b_in2, n + 512));
     uint8_t *d_keep = (uint8_t *)c->b_in2.p;
     unsigned long long *d_kept = (unsigned long long *)((char *)c->b_in2.p + ((n + 255) & ~(size_t)255));
     const uint64_t offs[2] = {0, n};
     const float vp0[3] = {0.f, 0.f, 0.f};
+    unsigned long long h_kept = ~0ull;
     PCR_TRY(batch_core(c, cloud->x(), cloud->y(), cloud->z(), offs, 1, n, k_sor, std_mul, k_normals, viewpoint ? viewpoint : vp0, d_keep,
-                       full->nx(), full->ny(), full->nz(), d_kept));
-    return cloud_compact(full, d_keep, out);
+                       d_nrm, d_nrm + stride, d_nrm + 2 * stride, d_kept, &h_kept));
+    return cloud_compact(cloud, d_keep, out, d_nrm, stride, h_kept == ~0ull ? SIZE_MAX : (size_t)h_kept);
     PCR_API_END(c)
 }
 

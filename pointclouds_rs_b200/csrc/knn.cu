@@ -845,7 +845,13 @@ __global__ void __launch_bounds__(128) normals_from_lists_kernel(const float4 *_
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     const float4 p = __ldg(&qpts[q]);
-    if (p.x != p.x) return;  // removed by SOR (tombstoned): not a point of the kept cloud
+    if (p.x != p.x) {  // removed by SOR (tombstoned): not a point of the kept cloud -> 0 (like the unindexed fill)
+        const uint32_t oi = __float_as_uint(p.w);
+        nx[oi] = 0.f;
+        ny[oi] = 0.f;
+        nz[oi] = 0.f;
+        return;
+    }
     const int c = list_cnt[q];
     bool ok = c != 0xff;
     int taken = 0;
@@ -912,11 +918,13 @@ __global__ void __launch_bounds__(128) normals_from_lists_kernel(const float4 *_
 // normals of the kept points of `ix` (already tombstoned with d_keep) from the lists of the SOR pass;
 // the few queries without a usable list are searched again (warp kernels on the tombstoned levels)
 int normals_from_lists_dev(Index *ix, size_t k, const float vp[3], const SorLists &sl, const uint8_t *d_keep, float *d_nx, float *d_ny,
-                           float *d_nz) {
+                           float *d_nz, const unsigned long long *d_kept0, unsigned long long *h_kept0) {
     Ctx *ctx = ix->ctx;
     if (ix->n == 0 || k == 0) return PCR_OK;
-    fill_unindexed_normals_kernel<<<(unsigned)((ix->n + 255) / 256), 256, 0, ctx->stream>>>(ix->orig4, d_keep, ix->n, d_nx, d_ny, d_nz);
-    PCR_LAUNCH_CHECK(ctx);
+    if (ix->n_indexed < ix->n) {  // points outside the index (non-finite); the removed indexed ones are zeroed by the kernel below
+        fill_unindexed_normals_kernel<<<(unsigned)((ix->n + 255) / 256), 256, 0, ctx->stream>>>(ix->orig4, d_keep, ix->n, d_nx, d_ny, d_nz);
+        PCR_LAUNCH_CHECK(ctx);
+    }
     const uint32_t nq = (uint32_t)ix->n_indexed;
     if (nq == 0) return PCR_OK;
     uint32_t *d_fb_count = sl.fallback + sl.stride;  // one counter behind the list
@@ -930,8 +938,12 @@ int normals_from_lists_dev(Index *ix, size_t k, const float vp[3], const SorList
     }
     uint32_t *mail = (uint32_t *)ctx->pinned + 40;
     PCR_CUDA(ctx, cudaMemcpyAsync(mail, d_fb_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long *mail_kept = (unsigned long long *)((uint32_t *)ctx->pinned + 42);
+    if (d_kept0 && h_kept0)  // the caller's compaction needs the kept count: it rides along with this round trip
+        PCR_CUDA(ctx, cudaMemcpyAsync(mail_kept, d_kept0, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     PCR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const uint32_t n_fb = *mail;
+    if (d_kept0 && h_kept0) *h_kept0 = *mail_kept;
     if (getenv("PCR_DEBUG")) fprintf(stderr, "[pcr] normals from SOR lists: %u of %u queries fall back to a search\n", n_fb, nq);
     if (n_fb == 0) return PCR_OK;
     const size_t smem = k <= 32 ? (k * 3 * 33 + 64) * sizeof(float) * kWarps : sizeof(unsigned long long) * k * kWarps;
