@@ -920,7 +920,8 @@ __global__ void single_point_frames_kernel(const uint32_t *__restrict__ frame_of
 static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz, const uint64_t *frame_offsets, size_t n_frames,
                       size_t n, size_t k_sor, float std_mul, size_t k_normals, const float vp[3], uint8_t *d_keep, float *d_nx,
                       float *d_ny, float *d_nz, unsigned long long *d_kept /* n_frames */,
-                      unsigned long long *h_kept0 = nullptr /* single frame: set if the count came back with another round trip */) {
+                      unsigned long long *h_kept0 = nullptr /* single frame: set if the count came back with another round trip */,
+                      const CloudStats *known_stats = nullptr /* single frame: its box and finite count, if already measured */) {
     const int F = (int)n_frames;
     float *d_mean = nullptr, *d_stats = nullptr;
     PCR_CUDA(c, cudaMallocAsync((void **)&d_mean, sizeof(float) * std::max<size_t>(n, 1), c->stream));
@@ -941,6 +942,7 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
     if (const char *e = getenv("PCR_BATCH_KHINT")) bo.k_hint = (size_t)atoi(e);
     bo.n_frames = F;
     bo.transient = true;
+    bo.known_stats = known_stats;
     bo.frame_offsets = frame_offsets;
     Index *ix = nullptr;
     PCR_TRY(index_build_dev(c, dx, dy, dz, n, bo, &ix));
@@ -1064,6 +1066,7 @@ struct pcr_cloud {
     size_t n, stride;
     float *base;
     bool has_normals;
+    pcr::CloudStats stats;  // bounding box + finite count if the step that wrote the cloud measured them (stats.valid)
     float *x() const { return base; }
     float *y() const { return base + stride; }
     float *z() const { return base + 2 * stride; }
@@ -1312,7 +1315,7 @@ int pcr_cloud_voxel_downsample(const pcr_cloud *cloud, float voxel_size, pcr_clo
     pcr_cloud *tmp = nullptr;
     PCR_TRY(cloud_alloc(cloud->owner, cloud->n, false, &tmp));  // voxel_downsample.rs:64: xyz only
     size_t m = 0;
-    int s = voxel_downsample_dev(c, cloud->x(), cloud->y(), cloud->z(), cloud->n, voxel_size, tmp->x(), tmp->y(), tmp->z(), &m);
+    int s = voxel_downsample_dev(c, cloud->x(), cloud->y(), cloud->z(), cloud->n, voxel_size, tmp->x(), tmp->y(), tmp->z(), &m, &tmp->stats);
     if (s != PCR_OK) {
         pcr_cloud_free(tmp);
         return s;
@@ -1412,7 +1415,7 @@ int pcr_cloud_sor_normals(const pcr_cloud *cloud, size_t k_sor, float std_mul, s
     const float vp0[3] = {0.f, 0.f, 0.f};
     unsigned long long h_kept = ~0ull;
     PCR_TRY(batch_core(c, cloud->x(), cloud->y(), cloud->z(), offs, 1, n, k_sor, std_mul, k_normals, viewpoint ? viewpoint : vp0, d_keep,
-                       d_nrm, d_nrm + stride, d_nrm + 2 * stride, d_kept, &h_kept));
+                       d_nrm, d_nrm + stride, d_nrm + 2 * stride, d_kept, &h_kept, cloud->stats.valid ? &cloud->stats : nullptr));
     return cloud_compact(cloud, d_keep, out, d_nrm, stride, h_kept == ~0ull ? SIZE_MAX : (size_t)h_kept);
     PCR_API_END(c)
 }

@@ -25,20 +25,12 @@ namespace {
 constexpr int kBuildThreads = 256;
 constexpr int kItems = 4;  // points per thread in the streaming kernels
 
-struct FrameStats {
-    unsigned mn[3], mx[3];  // order-preserving uint encoding of f32
-    unsigned count;
-    unsigned pad;
-};
+using FrameStats = CloudStats;  // mn / mx: order-preserving uint encoding of f32
 
 struct ProbeStats {
     double sum_log_own, sum_log_super;
 };
 
-__device__ __forceinline__ unsigned f32_ordered(float f) {
-    unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
 static inline float ordered_f32(unsigned u) {
     unsigned b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
     float f;
@@ -104,7 +96,7 @@ __global__ void init_stats_kernel(FrameStats *stats, int n_frames) {
         stats[f].mn[0] = stats[f].mn[1] = stats[f].mn[2] = 0xffffffffu;
         stats[f].mx[0] = stats[f].mx[1] = stats[f].mx[2] = 0u;
         stats[f].count = 0;
-        stats[f].pad = 0;
+        stats[f].valid = 0;
     }
 }
 
@@ -751,6 +743,9 @@ int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz,
     ProbeStats *d_probe = (ProbeStats *)((char *)ctx->b_small.p + sizeof(FrameStats) * F);
     FrameStats *h_stats = (FrameStats *)ctx->pinned;
     ProbeStats *h_probe = (ProbeStats *)((char *)ctx->pinned + sizeof(FrameStats) * F);
+    if (opts.known_stats && opts.known_stats->valid && F == 1 && !opts.d_mask) {
+        h_stats[0] = *opts.known_stats;  // the step that wrote the cloud measured it: no kernel, no round trip
+    } else {
     init_stats_kernel<<<(F + 255) / 256, 256, 0, st>>>(d_stats, F);
     PCR_LAUNCH_CHECK(ctx);
     if (n > 0) {
@@ -762,6 +757,7 @@ int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz,
     }
     PCR_CUDA(ctx, cudaMemcpyAsync(h_stats, d_stats, sizeof(FrameStats) * F, cudaMemcpyDeviceToHost, st));
     PCR_CUDA(ctx, cudaStreamSynchronize(st));
+    }
 
     std::vector<FrameBox> box(F);
     size_t n_indexed = 0;

@@ -160,7 +160,16 @@ int ensure_pinned(Ctx *ctx, size_t bytes);
 // ------------------------------------------------------------------------------------------------
 // host entry points implemented across the .cu files (all asynchronous on ctx->stream)
 // ------------------------------------------------------------------------------------------------
+// Bounding box and finite-point count of one frame, as the index build measures them (order-preserving u32
+// encodings of f32).  A step that has just written a cloud can hand them on and save the build a round trip.
+struct CloudStats {
+    unsigned mn[3], mx[3];
+    unsigned count;
+    unsigned valid;  // host side: 1 once filled (always 0 on the device)
+};
+
 struct BuildOpts {
+    const CloudStats *known_stats = nullptr;  // host; single unmasked frame only
     size_t k_hint = 0;
     int n_frames = 1;
     const uint64_t *frame_offsets = nullptr;  // host, n_frames + 1 (nullptr if n_frames == 1)
@@ -232,7 +241,7 @@ size_t clusters_from_labels(const uint32_t *labels, size_t n, size_t min_size, s
 
 // voxel_downsample + the stable radix sort it uses (voxel.cu)
 int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz, size_t n, float voxel, float *d_ox, float *d_oy,
-                         float *d_oz, size_t *n_out);
+                         float *d_oz, size_t *n_out, CloudStats *stats_out = nullptr /* host; filled (valid = 1) when it comes for free */);
 int radix_sort_pairs_dev(Ctx *ctx, unsigned long long **keys, uint32_t **vals, unsigned long long **keys_alt, uint32_t **vals_alt,
                          size_t n, int bits, uint32_t *d_hist);
 
@@ -288,6 +297,11 @@ __device__ __forceinline__ float key_d2(unsigned long long k) { return __uint_as
 __device__ __forceinline__ uint32_t key_idx(unsigned long long k) { return (uint32_t)k; }
 
 __device__ __forceinline__ bool finite3(float a, float b, float c) { return isfinite(a) && isfinite(b) && isfinite(c); }
+// order-preserving map f32 -> u32 (so min / max of floats are integer atomics)
+__device__ __forceinline__ unsigned f32_ordered(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 
 __device__ __forceinline__ float pick_axis(int ax, float x, float y, float z) { return ax == 0 ? x : (ax == 1 ? y : z); }
 

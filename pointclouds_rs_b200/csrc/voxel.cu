@@ -40,12 +40,16 @@ struct VoxRange {
 // voxel_downsample.rs:32-36: (p / voxel).floor() as i32 -- IEEE division, round down, saturate, NaN -> 0
 __device__ __forceinline__ int vox_cell(float v, float voxel) { return __float2int_rd(__fdiv_rn(v, voxel)); }
 
-__global__ void vox_init_kernel(VoxRange *r) {
+__global__ void vox_init_kernel(VoxRange *r, CloudStats *out_stats) {
     for (int a = 0; a < 3; a++) {
         r->mn[a] = 2147483647;
         r->mx[a] = -2147483647 - 1;
+        out_stats->mn[a] = 0xffffffffu;
+        out_stats->mx[a] = 0u;
     }
     r->finite = 0;
+    out_stats->count = 0;
+    out_stats->valid = 0;
 }
 
 __global__ void __launch_bounds__(256) vox_range_kernel(const float *__restrict__ x, const float *__restrict__ y,
@@ -361,6 +365,52 @@ __global__ void __launch_bounds__(256) vox_col_emit_kernel(const float *__restri
     }
 }
 
+// Bounding box and finite count of the cloud just written, its length still on the device: what the index
+// build of the next step would otherwise measure with a kernel and a round trip of its own.
+__global__ void __launch_bounds__(256) vox_out_stats_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                                                            const float *__restrict__ z, const uint32_t *__restrict__ d_n,
+                                                            CloudStats *stats) {
+    const uint32_t n = *d_n;
+    unsigned mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u}, cnt = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float px = x[i], py = y[i], pz = z[i];
+        if (!finite3(px, py, pz)) continue;
+        const unsigned u[3] = {f32_ordered(px), f32_ordered(py), f32_ordered(pz)};
+        for (int a = 0; a < 3; a++) {
+            mn[a] = min(mn[a], u[a]);
+            mx[a] = max(mx[a], u[a]);
+        }
+        cnt++;
+    }
+    for (int a = 0; a < 3; a++) {
+        mn[a] = __reduce_min_sync(PCR_FULL, mn[a]);
+        mx[a] = __reduce_max_sync(PCR_FULL, mx[a]);
+    }
+    cnt = __reduce_add_sync(PCR_FULL, cnt);
+    __shared__ unsigned s_mn[3], s_mx[3], s_cnt;
+    if (threadIdx.x == 0) {
+        s_mn[0] = s_mn[1] = s_mn[2] = 0xffffffffu;
+        s_mx[0] = s_mx[1] = s_mx[2] = 0u;
+        s_cnt = 0;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        for (int a = 0; a < 3; a++) {
+            atomicMin(&s_mn[a], mn[a]);
+            atomicMax(&s_mx[a], mx[a]);
+        }
+        atomicAdd(&s_cnt, cnt);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) {
+        for (int a = 0; a < 3; a++) {
+            atomicMin(&stats->mn[a], s_mn[a]);
+            atomicMax(&stats->mx[a], s_mx[a]);
+        }
+        atomicAdd(&stats->count, s_cnt);
+    }
+}
+
 int bits_for(uint64_t range) {  // smallest b with 2^b >= range
     int b = 0;
     while (b < 64 && (1ull << b) < range) b++;
@@ -391,8 +441,9 @@ int radix_sort_pairs_dev(Ctx *ctx, unsigned long long **keys, uint32_t **vals, u
 // voxel_downsample on device arrays.  Outputs sized n; *n_out = number of voxels.  One host round trip
 // (key range), one more for the count.
 int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz, size_t n, float voxel, float *d_ox, float *d_oy,
-                         float *d_oz, size_t *n_out) {
+                         float *d_oz, size_t *n_out, CloudStats *stats_out) {
     *n_out = 0;
+    if (stats_out) stats_out->valid = 0;
     if (n == 0) return PCR_OK;  // :18-20
     if (n > 0x7fffffffull) return fail(ctx, PCR_ERR_UNSUPPORTED, "clouds above 2^31 points are not supported");
     cudaStream_t st = ctx->stream;
@@ -402,7 +453,8 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
     VoxRange *d_range = (VoxRange *)ctx->b_small.p;
     uint32_t *d_nvox = (uint32_t *)((char *)ctx->b_small.p + 256);
     VoxRange *h_range = (VoxRange *)ctx->pinned;
-    vox_init_kernel<<<1, 1, 0, st>>>(d_range);
+    CloudStats *d_ostats = (CloudStats *)((char *)ctx->b_small.p + 512);
+    vox_init_kernel<<<1, 1, 0, st>>>(d_range, d_ostats);
     PCR_LAUNCH_CHECK(ctx);
     const unsigned bx = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 2);
     vox_range_kernel<<<bx, 256, 0, st>>>(dx, dy, dz, n, voxel, d_range);
@@ -455,9 +507,19 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
             vox_col_emit_kernel<<<nbc, 256, 0, st>>>(dx, dy, dz, count, nvox, n_cols, members, d_ox, d_oy, d_oz);
             PCR_LAUNCH_CHECK(ctx);
             uint32_t *mail = (uint32_t *)ctx->pinned + 64;
+            CloudStats *mail_stats = (CloudStats *)((uint32_t *)ctx->pinned + 72);
+            if (stats_out) {  // the next step's index build wants the box of what was just written: one round trip for both
+                vox_out_stats_kernel<<<(unsigned)ctx->sm_count, 256, 0, st>>>(d_ox, d_oy, d_oz, nvox + n_cols, d_ostats);
+                PCR_LAUNCH_CHECK(ctx);
+                PCR_CUDA(ctx, cudaMemcpyAsync(mail_stats, d_ostats, sizeof(CloudStats), cudaMemcpyDeviceToHost, st));
+            }
             PCR_CUDA(ctx, cudaMemcpyAsync(mail, nvox + n_cols, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             PCR_CUDA(ctx, cudaStreamSynchronize(st));
             *n_out = *mail;
+            if (stats_out) {
+                *stats_out = *mail_stats;
+                stats_out->valid = 1;
+            }
             return PCR_OK;
         }
     }
