@@ -5,6 +5,9 @@
 
 #include <stdarg.h>
 
+#include <chrono>
+#include <utility>
+#include <vector>
 #include <algorithm>
 #include <new>
 
@@ -44,6 +47,22 @@ TimeScope::TimeScope(Ctx *ctx, int tag) : c(ctx) {
 }
 TimeScope::~TimeScope() {
     if (idx >= 0) cudaEventRecord(c->spans[idx].b, c->stream);
+}
+
+bool g_trace_on = getenv("PCR_TRACE") != nullptr;
+namespace {
+thread_local std::vector<std::pair<const char *, double>> t_trace;
+}
+void trace_mark(const char *label) {
+    t_trace.emplace_back(label, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count());
+}
+static void trace_dump() {
+    if (!g_trace_on || t_trace.empty()) return;
+    const size_t n = t_trace.size(), b = n > 160 ? n - 160 : 0;
+    for (size_t i = b; i < n; i++)
+        fprintf(stderr, "[trace] %9.1f us  +%6.1f  %s\n", t_trace[i].second - t_trace[b].second, i > b ? t_trace[i].second - t_trace[i - 1].second : 0.0,
+                t_trace[i].first);
+    t_trace.clear();
 }
 
 int ensure(Ctx *ctx, DevBuf &b, size_t bytes) {
@@ -209,6 +228,7 @@ int pcr_ctx_create_on_stream(int device, void *cuda_stream, pcr_ctx **out) { ret
 
 void pcr_ctx_destroy(pcr_ctx *ctx) {
     if (!ctx) return;
+    trace_dump();
     Ctx *c = &ctx->c;
     DevSetter ds(c);
     cudaStreamSynchronize(c->stream);
@@ -229,6 +249,7 @@ void pcr_ctx_destroy(pcr_ctx *ctx) {
         cudaEventDestroy(sp.b);
     }
     for (auto e : c->event_pool) cudaEventDestroy(e);
+    if (c->ev_count) cudaEventDestroy(c->ev_count);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->owns_stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
@@ -945,7 +966,9 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
     bo.known_stats = known_stats;
     bo.frame_offsets = frame_offsets;
     Index *ix = nullptr;
+    PCR_MARK("core: build begin");
     PCR_TRY(index_build_dev(c, dx, dy, dz, n, bo, &ix));
+    PCR_MARK("core: build queued");
     struct IxGuard {
         Index *ix;
         ~IxGuard() { index_free(ix); }
@@ -975,7 +998,9 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
         PCR_CUDA(c, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long) * F, c->stream));
     } else {
         PCR_TRY(sor_mean_dist_dev(ix, k_sor, d_mean, fused ? &sl : nullptr));
+        PCR_MARK("core: sor search done");
         PCR_TRY(sor_threshold_mask_dev(c, d_mean, ix->frame_in_off, F, n, std_mul, d_keep, d_stats, d_kept));
+        PCR_MARK("core: stats queued");
         if (F > 1 || n == 1) {  // a one-point frame is returned as is, even if the point is not finite
             single_point_frames_kernel<<<(F + 127) / 128, 128, 0, c->stream>>>(ix->frame_in_off, F, n, d_keep, d_kept);
             PCR_LAUNCH_CHECK(c);
@@ -1312,6 +1337,7 @@ int pcr_cloud_voxel_downsample(const pcr_cloud *cloud, float voxel_size, pcr_clo
     if (!std::isfinite(voxel_size) || !(voxel_size > 0.f)) return fail(c, PCR_ERR_INVALID_ARG, "voxel_size must be > 0 and finite");
     PCR_API_BEGIN
     DevSetter ds(c);
+    PCR_MARK("voxel: enter");
     pcr_cloud *tmp = nullptr;
     PCR_TRY(cloud_alloc(cloud->owner, cloud->n, false, &tmp));  // voxel_downsample.rs:64: xyz only
     size_t m = 0;
@@ -1322,6 +1348,7 @@ int pcr_cloud_voxel_downsample(const pcr_cloud *cloud, float voxel_size, pcr_clo
     }
     tmp->n = m;  // (the allocation keeps its original stride)
     *out = tmp;
+    PCR_MARK("voxel: exit");
     return PCR_OK;
     PCR_API_END(c)
 }
@@ -1398,6 +1425,7 @@ int pcr_cloud_sor_normals(const pcr_cloud *cloud, size_t k_sor, float std_mul, s
     DevSetter ds(c);
     const size_t n = cloud->n;
     if (n == 0 || k_sor == 0) return cloud_alloc(cloud->owner, 0, true, out);  // statistical_outlier.rs:5-7
+    PCR_MARK("sor_normals: enter");
     // normals by original index go to a scratch block; the kept points and their normals are compacted from the
     // input cloud and that block in one pass
     const size_t stride = (n + 63) & ~(size_t)63;
@@ -1416,7 +1444,10 @@ int pcr_cloud_sor_normals(const pcr_cloud *cloud, size_t k_sor, float std_mul, s
     unsigned long long h_kept = ~0ull;
     PCR_TRY(batch_core(c, cloud->x(), cloud->y(), cloud->z(), offs, 1, n, k_sor, std_mul, k_normals, viewpoint ? viewpoint : vp0, d_keep,
                        d_nrm, d_nrm + stride, d_nrm + 2 * stride, d_kept, &h_kept, cloud->stats.valid ? &cloud->stats : nullptr));
-    return cloud_compact(cloud, d_keep, out, d_nrm, stride, h_kept == ~0ull ? SIZE_MAX : (size_t)h_kept);
+    PCR_MARK("sor_normals: core done");
+    const int rc = cloud_compact(cloud, d_keep, out, d_nrm, stride, h_kept == ~0ull ? SIZE_MAX : (size_t)h_kept);
+    PCR_MARK("sor_normals: exit");
+    return rc;
     PCR_API_END(c)
 }
 

@@ -35,6 +35,7 @@ struct LevelArgs {
     const float4 *qpts;        // level-0 sorted points: where self-queries are read from
     const uint32_t *qlist;     // nullptr on level 0 (query id == position)
     uint32_t nq;
+    const uint32_t *nq_dev;    // optional: the real count, still on the device (nq is then the launch capacity)
     uint32_t *defer_list;      // queries this pass could not finish within max_rings shells
     uint32_t *defer_count;
     int max_rings;
@@ -293,7 +294,8 @@ __global__ void __launch_bounds__(kThreads) normals_kernel(LevelArgs a, const fl
     extern __shared__ unsigned long long smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t q0 = (blockIdx.x * kWarps + w) * QPW;
-    if (q0 >= a.nq) return;
+    const uint32_t nq = a.nq_dev ? min(a.nq, *a.nq_dev) : a.nq;
+    if (q0 >= nq) return;
     if constexpr (!kSmem) {
         float *sc = reinterpret_cast<float *>(smem_raw) + (size_t)w * (kk * 3 * 33 + 64);
         int *scnt = reinterpret_cast<int *>(sc + kk * 3 * 33);
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(kThreads) normals_kernel(LevelArgs a, const fl
         int f = -1;
         GridDesc g;
         for (int t = 0; t < QPW; t++) {
-            if (q0 + t >= a.nq) break;
+            if (q0 + t >= nq) break;
             const uint32_t pos = a.qlist ? a.qlist[q0 + t] : q0 + t;
             if (f < 0 || pos >= g.pt_end || pos < g.pt_begin) {
                 f = frame_of_sorted(a.grids, a.n_frames, pos);
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(kThreads) normals_kernel(LevelArgs a, const fl
             }
         }
         __syncwarp();
-        if (lane < QPW && q0 + lane < a.nq && scnt[lane] >= 0) {
+        if (lane < QPW && q0 + lane < nq && scnt[lane] >= 0) {
             float4 q = __ldg(&a.qpts[spos[lane]]);
             float ox, oy, oz;
             normal_from_neighbours(scnt[lane], [&](int j, int c) { return sc[(j * 3 + c) * 33 + lane]; }, q.x, q.y, q.z, vx, vy,
@@ -348,7 +350,7 @@ __global__ void __launch_bounds__(kThreads) normals_kernel(LevelArgs a, const fl
         tk.lane = lane;
         tk.s = smem_raw + (size_t)w * kk;
         for (int t = 0; t < QPW; t++) {
-            if (q0 + t >= a.nq) break;
+            if (q0 + t >= nq) break;
             const uint32_t pos = a.qlist ? a.qlist[q0 + t] : q0 + t;
             const GridDesc g = a.grids[frame_of_sorted(a.grids, a.n_frames, pos)];
             float4 q = __ldg(&a.qpts[pos]);
@@ -668,8 +670,9 @@ int set_smem(Ctx *ctx, Kern kern, size_t bytes) {
 // count costs one small D2H + sync per level that is actually needed (clouds without far outliers
 // finish on level 0 and pay exactly one).
 template <class Launch>
-int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *init_list = nullptr) {
+int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *init_list = nullptr, const uint32_t *nq_dev = nullptr) {
     // init_list: level 0 runs over these nq query ids only (warp kernels) instead of over all queries
+    // nq_dev:    the length of init_list is still on the device; nq is the capacity level 0 is launched for
     Ctx *ctx = ix->ctx;
     if (nq == 0) return PCR_OK;
     PCR_TRY(ensure(ctx, ctx->b_list, (size_t)nq * 2 * sizeof(uint32_t) + 256));
@@ -690,6 +693,7 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
         a.qpts = ix->sorted;
         a.qlist = qlist;
         a.nq = n_cur;
+        a.nq_dev = level == 0 ? nq_dev : nullptr;
         a.defer_list = lists[level & 1];
         a.defer_count = cnt;
         a.max_rings = last ? kMaxRings : kLevelRings;
@@ -701,8 +705,28 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
         if (last) break;
         uint32_t *mail = (uint32_t *)ctx->pinned + 32;
         PCR_CUDA(ctx, cudaMemcpyAsync(mail, cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        PCR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (const auto &pg : ctx->piggy)  // small results other steps want from the same round trip
+            PCR_CUDA(ctx, cudaMemcpyAsync(pg.dst, pg.src, pg.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->piggy.clear();
+        // A frame stream whose previous frame needed the next level will need it again: queue its build behind the
+        // count's copy and wait on an event, so the GPU builds while the host wakes up and reads the count.
+        const bool speculate = level == 0 && !init_list && ctx->frame_stream && ctx->spec_coarser && !cur->coarser;
+        PCR_MARK("levels: wait for deferred count");
+        if (speculate) {
+            if (!ctx->ev_count) PCR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_count, cudaEventDisableTiming));
+            PCR_CUDA(ctx, cudaEventRecord(ctx->ev_count, ctx->stream));
+            Index *pre = nullptr;
+            {
+                TimeScope ts(ctx, kTagKnnDeferred);
+                PCR_TRY(index_coarser_level(cur, &pre));
+            }
+            PCR_CUDA(ctx, cudaEventSynchronize(ctx->ev_count));
+        } else {
+            PCR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        PCR_MARK("levels: got deferred count");
         n_cur = *mail;
+        if (level == 0 && !init_list) ctx->spec_coarser = n_cur > 0;
         if (getenv("PCR_DEBUG")) fprintf(stderr, "[pcr] level %d: %u of %u queries deferred (cell %.4g)\n", level, n_cur, a.nq, cur->grids_h[0].h);
         if (n_cur == 0) break;
         Index *next = nullptr;
@@ -936,30 +960,37 @@ int normals_from_lists_dev(Index *ix, size_t k, const float vp[3], const SorList
                                                                             sl.fallback, d_fb_count);
         PCR_LAUNCH_CHECK(ctx);
     }
+    // The queries that fall back are few, and their count is still on the device: launch their level-0 pass now for a
+    // fixed capacity (the kernel reads the count itself) and let the count, the kept count the caller's compaction
+    // wants and the pass's own deferred count come back in ONE round trip.
     uint32_t *mail = (uint32_t *)ctx->pinned + 40;
-    PCR_CUDA(ctx, cudaMemcpyAsync(mail, d_fb_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     unsigned long long *mail_kept = (unsigned long long *)((uint32_t *)ctx->pinned + 42);
-    if (d_kept0 && h_kept0)  // the caller's compaction needs the kept count: it rides along with this round trip
-        PCR_CUDA(ctx, cudaMemcpyAsync(mail_kept, d_kept0, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    PCR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const uint32_t n_fb = *mail;
-    if (d_kept0 && h_kept0) *h_kept0 = *mail_kept;
-    if (getenv("PCR_DEBUG")) fprintf(stderr, "[pcr] normals from SOR lists: %u of %u queries fall back to a search\n", n_fb, nq);
-    if (n_fb == 0) return PCR_OK;
+    ctx->piggy.clear();
+    ctx->piggy.push_back({mail, d_fb_count, sizeof(uint32_t)});
+    if (d_kept0 && h_kept0) ctx->piggy.push_back({mail_kept, d_kept0, sizeof(unsigned long long)});
     const size_t smem = k <= 32 ? (k * 3 * 33 + 64) * sizeof(float) * kWarps : sizeof(unsigned long long) * k * kWarps;
     if (k <= 32) PCR_TRY(set_smem(ctx, normals_kernel<false, kQPWL>, smem));
     else PCR_TRY(set_smem(ctx, normals_kernel<true, kQPWL>, smem));
     const float v0 = vp[0], v1 = vp[1], v2 = vp[2];
-    return run_levels(
-        ix, n_fb, kTagKnnDeferred,
-        [&](const LevelArgs &a, int qpw) -> int {
-            const unsigned blocks = blocks_for(a.nq, qpw);
-            if (k <= 32) normals_kernel<false, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);
-            else normals_kernel<true, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);
-            PCR_LAUNCH_CHECK(ctx);
-            return PCR_OK;
-        },
-        sl.fallback);
+    auto launch = [&](const LevelArgs &a, int qpw) -> int {
+        const unsigned blocks = blocks_for(a.nq, qpw);
+        if (k <= 32) normals_kernel<false, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);
+        else normals_kernel<true, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);
+        PCR_LAUNCH_CHECK(ctx);
+        return PCR_OK;
+    };
+    uint32_t cap = std::min<uint32_t>(nq, 2048u);
+    if (const char *e = getenv("PCR_FALLBACK_CAP")) cap = std::max(1u, std::min<uint32_t>(nq, (uint32_t)atoi(e)));  // test hook
+    PCR_MARK("normals: fallback pass queued blind");
+    const int rc = run_levels(ix, cap, kTagKnnDeferred, launch, sl.fallback, d_fb_count);
+    ctx->piggy.clear();
+    PCR_TRY(rc);
+    PCR_MARK("normals: fallback pass done");
+    const uint32_t n_fb = *mail;
+    if (d_kept0 && h_kept0) *h_kept0 = *mail_kept;
+    if (getenv("PCR_DEBUG")) fprintf(stderr, "[pcr] normals from SOR lists: %u of %u queries fall back to a search\n", n_fb, nq);
+    if (n_fb <= cap) return PCR_OK;
+    return run_levels(ix, n_fb - cap, kTagKnnDeferred, launch, sl.fallback + cap);  // more than the blind pass covered
 }
 
 int radius_count_dev(Index *ix, const float *dqx, const float *dqy, const float *dqz, size_t nq, float radius,

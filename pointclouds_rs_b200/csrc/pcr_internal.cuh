@@ -90,6 +90,14 @@ struct Ctx {
     DevBuf b_misc2;
     DevBuf b_small;    // reductions, statistics, ICP state
     DevBuf b_table;    // probe cell table
+    struct Piggy {     // a small device->host copy that rides along with the next round trip of run_levels
+        void *dst;
+        const void *src;
+        size_t bytes;
+    };
+    std::vector<Piggy> piggy;
+    bool spec_coarser = false;         // frame stream: the previous frame's level-0 pass deferred queries
+    cudaEvent_t ev_count = nullptr;    // marks the deferred count's copy when work is queued behind it
     DevBuf b_scan;     // single-pass scan: ticket + one state word per tile (tagged with scan_epoch, never cleared between scans)
     uint32_t scan_epoch = 0;
     DevBuf b_list;     // deferred-query lists of the level loop
@@ -146,6 +154,15 @@ void set_thread_error(const char *msg);
 
 // stage tags of the timing spans (pcr_ctx_get_timing)
 enum TimeTag { kTagBuild = 0, kTagKnn = 1, kTagKnnDeferred = 2, kTagSorStats = 3, kTagIcpStep = 4, kTagIcpSolve = 5, kTagKnnNormals = 6, kTagOther = 7, kNumTags = 8 };
+
+// Host-side trace for latency work (PCR_TRACE=1): time stamps at the marks, the last ones printed when the context
+// is destroyed.  Off by default; a mark is then one predictable branch.
+extern bool g_trace_on;
+void trace_mark(const char *label);
+#define PCR_MARK(label)                            \
+    do {                                           \
+        if (pcr::g_trace_on) pcr::trace_mark(label); \
+    } while (0)
 
 struct TimeScope {  // records an event pair around a stage when timing is enabled
     Ctx *c;

@@ -460,7 +460,9 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
     vox_range_kernel<<<bx, 256, 0, st>>>(dx, dy, dz, n, voxel, d_range);
     PCR_LAUNCH_CHECK(ctx);
     PCR_CUDA(ctx, cudaMemcpyAsync(h_range, d_range, sizeof(VoxRange), cudaMemcpyDeviceToHost, st));
+    PCR_MARK("voxel: wait for range");
     PCR_CUDA(ctx, cudaStreamSynchronize(st));
+    PCR_MARK("voxel: got range");
     const uint32_t m = h_range->finite;
     if (m == 0) return PCR_OK;  // :45-47
     // ---- column path ------------------------------------------------------------------------------------
@@ -514,7 +516,9 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
                 PCR_CUDA(ctx, cudaMemcpyAsync(mail_stats, d_ostats, sizeof(CloudStats), cudaMemcpyDeviceToHost, st));
             }
             PCR_CUDA(ctx, cudaMemcpyAsync(mail, nvox + n_cols, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            PCR_MARK("voxel: wait for count");
             PCR_CUDA(ctx, cudaStreamSynchronize(st));
+            PCR_MARK("voxel: got count");
             *n_out = *mail;
             if (stats_out) {
                 *stats_out = *mail_stats;

@@ -419,6 +419,17 @@ def test_fused_lists_equal_the_two_step_path(pcr, oracle, k_sor, std, k_nrm):
     assert np.array_equal(dev.to_numpy(), pts[sel], equal_nan=True) and np.array_equal(dev.normals_to_numpy().view(np.uint32), two_step.view(np.uint32))
 
 
+def test_fused_fallback_beyond_the_blind_pass(pcr, monkeypatch):
+    """The fallback pass is launched before its length is known, for a fixed capacity; what exceeds it runs afterwards.
+    A capacity of 5 forces that second pass: the result must not change by a bit."""
+    pts = scenes.kitti_scene(32, (6_000, 300, 60, 140))
+    want = pcr.DeviceCloud.from_numpy(pts).sor_normals(10, 0.3, 20)
+    monkeypatch.setenv("PCR_FALLBACK_CAP", "5")
+    got = pcr.DeviceCloud.from_numpy(pts).sor_normals(10, 0.3, 20)
+    assert np.array_equal(got.to_numpy(), want.to_numpy())
+    assert np.array_equal(got.normals_to_numpy().view(np.uint32), want.normals_to_numpy().view(np.uint32))
+
+
 def test_fused_lists_multi_frame_edge_cases(pcr, oracle):
     frames = [scenes.kitti_scene(40, (3_000, 150, 30, 70)), np.zeros((0, 3), np.float32), np.array([[1, 2, 3]], np.float32),
               scenes.uniform_cube(15, 4, 0, 1), np.repeat(scenes.uniform_cube(200, 5, 0, 3), 4, axis=0),
