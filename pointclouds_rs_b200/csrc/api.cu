@@ -298,6 +298,7 @@ int pcr_ctx_set_frame_stream(pcr_ctx *ctx, int enable) {
     if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
     ctx->c.frame_stream = enable != 0;
     ctx->c.cell_cache.valid = false;
+    ctx->c.vox_cache.valid = false;
     return PCR_OK;
 }
 

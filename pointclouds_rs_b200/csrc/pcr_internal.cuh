@@ -82,6 +82,15 @@ struct Ctx {
         double ext[3] = {0, 0, 0};
         double h = 0;
     } cell_cache;
+    // voxel key box of the last frame, padded: a frame stream sizes its column table from it without measuring the
+    // new frame first (a point outside it raises a flag and the frame is redone the exact way).
+    struct {
+        bool valid = false;
+        float voxel = 0.f;
+        int mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+        int uses = 0;       // frames since the box was last measured
+        int pad_shift = 6;  // pad = extent >> pad_shift on each side; widened after a miss
+    } vox_cache;
     // scratch
     DevBuf b_in;       // staged input x|y|z
     DevBuf b_in2;      // second cloud (ICP source)
@@ -258,7 +267,8 @@ size_t clusters_from_labels(const uint32_t *labels, size_t n, size_t min_size, s
 
 // voxel_downsample + the stable radix sort it uses (voxel.cu)
 int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz, size_t n, float voxel, float *d_ox, float *d_oy,
-                         float *d_oz, size_t *n_out, CloudStats *stats_out = nullptr /* host; filled (valid = 1) when it comes for free */);
+                         float *d_oz, size_t *n_out, CloudStats *stats_out = nullptr /* host; filled (valid = 1) when it comes for free */,
+                         bool allow_guess = true /* frame streams: size the table from the previous frame's key box */);
 int radix_sort_pairs_dev(Ctx *ctx, unsigned long long **keys, uint32_t **vals, unsigned long long **keys_alt, uint32_t **vals_alt,
                          size_t n, int bits, uint32_t *d_hist);
 

@@ -40,7 +40,7 @@ struct VoxRange {
 // voxel_downsample.rs:32-36: (p / voxel).floor() as i32 -- IEEE division, round down, saturate, NaN -> 0
 __device__ __forceinline__ int vox_cell(float v, float voxel) { return __float2int_rd(__fdiv_rn(v, voxel)); }
 
-__global__ void vox_init_kernel(VoxRange *r, CloudStats *out_stats) {
+__global__ void vox_init_kernel(VoxRange *r, CloudStats *out_stats, uint32_t *outside) {
     for (int a = 0; a < 3; a++) {
         r->mn[a] = 2147483647;
         r->mx[a] = -2147483647 - 1;
@@ -50,6 +50,7 @@ __global__ void vox_init_kernel(VoxRange *r, CloudStats *out_stats) {
     r->finite = 0;
     out_stats->count = 0;
     out_stats->valid = 0;
+    *outside = 0;
 }
 
 __global__ void __launch_bounds__(256) vox_range_kernel(const float *__restrict__ x, const float *__restrict__ y,
@@ -253,8 +254,10 @@ __global__ void __launch_bounds__(128) vox_mean_kernel(const float *__restrict__
 // index order inside a voxel gives its summation order (:38-42).
 __global__ void __launch_bounds__(256) vox_col_count_kernel(const float *__restrict__ x, const float *__restrict__ y,
                                                             const float *__restrict__ z, size_t n, float voxel, int mn0, int mn1,
-                                                            uint32_t nyc, int ys, uint32_t *__restrict__ count,
-                                                            uint32_t *__restrict__ col_of, uint32_t *__restrict__ rank_of) {
+                                                            int mn2, unsigned long long nx, unsigned long long ny,
+                                                            unsigned long long nz, uint32_t nyc, int ys, uint32_t *__restrict__ count,
+                                                            uint32_t *__restrict__ col_of, uint32_t *__restrict__ rank_of,
+                                                            uint32_t *__restrict__ outside) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float px = x[i], py = y[i], pz = z[i];
@@ -262,7 +265,15 @@ __global__ void __launch_bounds__(256) vox_col_count_kernel(const float *__restr
         col_of[i] = 0xffffffffu;
         return;
     }
-    const uint32_t col = (uint32_t)(vox_cell(px, voxel) - mn0) * nyc + ((uint32_t)(vox_cell(py, voxel) - mn1) >> ys);
+    const int kx = vox_cell(px, voxel), ky = vox_cell(py, voxel), kz = vox_cell(pz, voxel);
+    // the key box may be a guess (the previous frame's, padded): a point outside it voids the pass
+    if ((unsigned long long)((long long)kx - mn0) >= nx || (unsigned long long)((long long)ky - mn1) >= ny ||
+        (unsigned long long)((long long)kz - mn2) >= nz) {
+        col_of[i] = 0xffffffffu;
+        *outside = 1u;
+        return;
+    }
+    const uint32_t col = (uint32_t)(kx - mn0) * nyc + ((uint32_t)(ky - mn1) >> ys);
     col_of[i] = col;
     rank_of[i] = atomicAdd(&count[col], 1u);
 }
@@ -441,7 +452,7 @@ int radix_sort_pairs_dev(Ctx *ctx, unsigned long long **keys, uint32_t **vals, u
 // voxel_downsample on device arrays.  Outputs sized n; *n_out = number of voxels.  One host round trip
 // (key range), one more for the count.
 int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz, size_t n, float voxel, float *d_ox, float *d_oy,
-                         float *d_oz, size_t *n_out, CloudStats *stats_out) {
+                         float *d_oz, size_t *n_out, CloudStats *stats_out, bool allow_guess) {
     *n_out = 0;
     if (stats_out) stats_out->valid = 0;
     if (n == 0) return PCR_OK;  // :18-20
@@ -454,17 +465,48 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
     uint32_t *d_nvox = (uint32_t *)((char *)ctx->b_small.p + 256);
     VoxRange *h_range = (VoxRange *)ctx->pinned;
     CloudStats *d_ostats = (CloudStats *)((char *)ctx->b_small.p + 512);
-    vox_init_kernel<<<1, 1, 0, st>>>(d_range, d_ostats);
+    uint32_t *d_outside = (uint32_t *)((char *)ctx->b_small.p + 768);
+    vox_init_kernel<<<1, 1, 0, st>>>(d_range, d_ostats, d_outside);
     PCR_LAUNCH_CHECK(ctx);
-    const unsigned bx = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 2);
-    vox_range_kernel<<<bx, 256, 0, st>>>(dx, dy, dz, n, voxel, d_range);
-    PCR_LAUNCH_CHECK(ctx);
-    PCR_CUDA(ctx, cudaMemcpyAsync(h_range, d_range, sizeof(VoxRange), cudaMemcpyDeviceToHost, st));
-    PCR_MARK("voxel: wait for range");
-    PCR_CUDA(ctx, cudaStreamSynchronize(st));
-    PCR_MARK("voxel: got range");
-    const uint32_t m = h_range->finite;
-    if (m == 0) return PCR_OK;  // :45-47
+    // A frame stream sizes the table from the previous frame's key box (padded) and skips the measuring pass and its
+    // round trip; every 32nd frame is measured again so that the box follows the scene.
+    auto &vc = ctx->vox_cache;
+    static const bool no_guess = getenv("PCR_NO_VOXEL_GUESS") != nullptr;  // A/B hook
+    const bool guessed = allow_guess && !no_guess && ctx->frame_stream && vc.valid && vc.voxel == voxel && vc.uses < 32;
+    uint32_t m;
+    if (guessed) {
+        vc.uses++;
+        for (int a = 0; a < 3; a++) {
+            h_range->mn[a] = vc.mn[a];
+            h_range->mx[a] = vc.mx[a];
+        }
+        m = (uint32_t)n;  // (an upper bound is all the sizing below needs)
+    } else {
+        const unsigned bx = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 2);
+        vox_range_kernel<<<bx, 256, 0, st>>>(dx, dy, dz, n, voxel, d_range);
+        PCR_LAUNCH_CHECK(ctx);
+        PCR_CUDA(ctx, cudaMemcpyAsync(h_range, d_range, sizeof(VoxRange), cudaMemcpyDeviceToHost, st));
+        PCR_MARK("voxel: wait for range");
+        PCR_CUDA(ctx, cudaStreamSynchronize(st));
+        PCR_MARK("voxel: got range");
+        m = h_range->finite;
+        if (m == 0) return PCR_OK;  // :45-47
+        vc.valid = false;
+        if (ctx->frame_stream) {  // remember the box, padded, for the next frames
+            bool ok = true;
+            for (int a = 0; a < 3; a++) {
+                const long long ext = (long long)h_range->mx[a] - (long long)h_range->mn[a] + 1;
+                const long long pad = std::max<long long>(2, ext >> vc.pad_shift);
+                const long long lo = (long long)h_range->mn[a] - pad, hi = (long long)h_range->mx[a] + pad;
+                if (lo < -2147483647ll || hi > 2147483646ll) ok = false;
+                vc.mn[a] = (int)lo;
+                vc.mx[a] = (int)hi;
+            }
+            vc.valid = ok;
+            vc.voxel = voxel;
+            vc.uses = 0;
+        }
+    }
     // ---- column path ------------------------------------------------------------------------------------
     {
         const uint64_t nx = (uint64_t)((int64_t)h_range->mx[0] - (int64_t)h_range->mn[0]) + 1;
@@ -497,8 +539,8 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
             unsigned long long *members = (unsigned long long *)(base + o_mem);
             PCR_CUDA(ctx, cudaMemsetAsync(count, 0, o_nvox, st));
             const unsigned nbp = (unsigned)((n + 255) / 256), nbc = (n_cols + 1 + 255) / 256;
-            vox_col_count_kernel<<<nbp, 256, 0, st>>>(dx, dy, dz, n, voxel, h_range->mn[0], h_range->mn[1], (uint32_t)nyc64, ys, count, col_of,
-                                                      rank_of);
+            vox_col_count_kernel<<<nbp, 256, 0, st>>>(dx, dy, dz, n, voxel, h_range->mn[0], h_range->mn[1], h_range->mn[2], nx, ny, nz,
+                                                      (uint32_t)nyc64, ys, count, col_of, rank_of, d_outside);
             PCR_LAUNCH_CHECK(ctx);
             PCR_TRY(exclusive_scan_u32_dev(ctx, count, (size_t)n_cols + 1));
             vox_col_scatter_kernel<<<nbp, 256, 0, st>>>(dy, dz, n, voxel, h_range->mn[1], h_range->mn[2], ys, count, col_of, rank_of, members);
@@ -516,9 +558,15 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
                 PCR_CUDA(ctx, cudaMemcpyAsync(mail_stats, d_ostats, sizeof(CloudStats), cudaMemcpyDeviceToHost, st));
             }
             PCR_CUDA(ctx, cudaMemcpyAsync(mail, nvox + n_cols, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            if (guessed) PCR_CUDA(ctx, cudaMemcpyAsync(mail + 1, d_outside, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             PCR_MARK("voxel: wait for count");
             PCR_CUDA(ctx, cudaStreamSynchronize(st));
             PCR_MARK("voxel: got count");
+            if (guessed && mail[1]) {  // a point fell outside the guessed box: measure, with a wider pad from now on
+                vc.valid = false;
+                vc.pad_shift = std::max(2, vc.pad_shift - 1);
+                return voxel_downsample_dev(ctx, dx, dy, dz, n, voxel, d_ox, d_oy, d_oz, n_out, stats_out, false);
+            }
             *n_out = *mail;
             if (stats_out) {
                 *stats_out = *mail_stats;
@@ -526,6 +574,10 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
             }
             return PCR_OK;
         }
+    }
+    if (guessed) {  // the padded box does not suit the column path: measure
+        vc.valid = false;
+        return voxel_downsample_dev(ctx, dx, dy, dz, n, voxel, d_ox, d_oy, d_oz, n_out, stats_out, false);
     }
     // ---- radix path -------------------------------------------------------------------------------------
     int bits[3];

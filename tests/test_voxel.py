@@ -94,3 +94,41 @@ def test_gpu_config2_input_full_size(pcr, oracle):
     _gpu_equal(pcr, oracle, pts, 0.05)
     _gpu_equal(pcr, oracle, pts, 0.5)
     _gpu_equal(pcr, oracle, scenes.aerial_scene(), 0.5)
+
+
+@pytest.mark.gpu
+def test_gpu_frame_stream_guessed_key_box(pcr, oracle):
+    """A frame stream sizes the column table from the previous frame's key box (padded) without measuring the new frame;
+    a point outside the box must be noticed and the frame redone the exact way.  Every frame bit-exact, hit or miss."""
+    ctx = pcr.Context(device=0)
+    ctx.set_frame_stream(True)
+    rng = np.random.default_rng(12)
+    a = scenes.kitti_scene(41, (9_000, 400, 80, 200))
+    inside = a[rng.integers(0, len(a), 500)] + rng.uniform(-0.01, 0.01, (500, 3)).astype(np.float32)
+    bad = a.copy()
+    bad[::53, 1] = np.nan
+    frames = [
+        a,                                                               # measured (first frame)
+        a[::-1].copy(),                                                  # hit
+        np.vstack([a, [[500.0, -3.0, 1.0]]]).astype(np.float32),         # miss in x
+        a,                                                               # measured again after the miss ... then hits
+        np.vstack([a, [[0.0, 0.0, -90.0]]]).astype(np.float32),          # miss in z
+        inside.astype(np.float32),                                       # hit, table mostly empty
+        bad,                                                             # hit with non-finite points
+        (a + np.float32(300.0)).astype(np.float32),                      # miss: everything outside
+        np.full((5, 3), np.nan, np.float32),                             # nothing finite
+        a,
+    ] + [a] * 34                                                         # long enough to pass the periodic re-measure
+    for i, f in enumerate(frames):
+        want = oracle.voxel_downsample(f, 0.05)
+        got = pcr.voxel_downsample(pcr.PointCloud.from_numpy(f), 0.05, ctx).to_numpy()
+        assert np.array_equal(got, want), f"frame {i}"
+        dev = pcr.DeviceCloud.from_numpy(f, ctx).voxel_downsample(0.05)
+        assert np.array_equal(dev.to_numpy(), want), f"frame {i} (device cloud)"
+        if len(want) > 50:                                               # the box handed to the index build must be right too
+            s = dev.sor_normals(10, 1.0, 20)
+            s2 = pcr.DeviceCloud.from_numpy(want).sor_normals(10, 1.0, 20)
+            assert np.array_equal(s.to_numpy(), s2.to_numpy()) and np.array_equal(s.normals_to_numpy(), s2.normals_to_numpy())
+    got = pcr.voxel_downsample(pcr.PointCloud.from_numpy(a), 0.2, ctx).to_numpy()   # another voxel size: the box is not reused
+    assert np.array_equal(got, oracle.voxel_downsample(a, 0.2))
+    ctx.close()
