@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define PCR_B200_VERSION 110 /* 0.1.1: + voxel, cluster, RANSAC, device-resident clouds */
+#define PCR_B200_VERSION 111 /* 0.1.1: + voxel, cluster, RANSAC, device-resident clouds; 111: + block upload / download */
 
 typedef enum pcr_status {
     PCR_OK = 0,
