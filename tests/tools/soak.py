@@ -12,6 +12,8 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 T = min(16, os.cpu_count() or 1)
 t0 = time.time()
 n_cases = 0
+fs = pcr.Context()          # a second context marked as a frame stream: guessed voxel key boxes (hits and misses on
+fs.set_frame_stream(True)   # these unrelated clouds), reused cell sizes, the coarser level queued ahead of its count
 while time.time() - t0 < budget:
     kind = rng.integers(0, 4)
     n = int(rng.integers(50, 6000))
@@ -37,6 +39,8 @@ while time.time() - t0 < budget:
     # voxel
     v = float(rng.uniform(0.02, 3.0))
     assert np.array_equal(pcr.voxel_downsample(cloud, v).to_numpy().view(np.uint32), O.voxel_downsample(pts, v).view(np.uint32)), ("voxel", kind, n, v)
+    dv = pcr.DeviceCloud.from_numpy(pts, fs).voxel_downsample(v)
+    assert np.array_equal(dv.to_numpy().view(np.uint32), O.voxel_downsample(pts, v).view(np.uint32)), ("voxel, frame stream", kind, n, v)
     # ransac
     smp = pcr.draw_plane_samples(len(pts), int(rng.integers(1, 80)), int(rng.integers(1 << 30)))
     r = pcr.ransac_plane_samples(cloud, float(rng.uniform(0.01, 0.5)) if False else 0.1, smp)
@@ -51,6 +55,15 @@ while time.time() - t0 < budget:
     if len(sel):
         two = pcr.normals_array(pcr.PointCloud.from_numpy(np.ascontiguousarray(pts[sel])), kn)
         assert np.array_equal(nrm[sel].view(np.uint32), two.view(np.uint32)), ("fused normals", kind, n, ks, kn, std)
+    ds = pcr.DeviceCloud.from_numpy(pts, fs).sor_normals(ks, std, kn)
+    assert np.array_equal(ds.to_numpy().view(np.uint32), pts[sel].view(np.uint32)), ("device sor_normals points", kind, n, ks, kn, std)
+    if len(sel):
+        assert np.array_equal(ds.normals_to_numpy().view(np.uint32), nrm[sel].view(np.uint32)), ("device sor_normals normals", kind, n, ks, kn, std)
+    if len(dv) > 1:  # the box the voxel step hands to the index build
+        a = dv.sor_normals(ks, std, kn)
+        b = pcr.DeviceCloud.from_numpy(dv.to_numpy()).sor_normals(ks, std, kn)
+        assert np.array_equal(a.to_numpy().view(np.uint32), b.to_numpy().view(np.uint32)) and \
+            np.array_equal(a.normals_to_numpy().view(np.uint32), b.normals_to_numpy().view(np.uint32)), ("voxel -> sor_normals", kind, n, v, ks, kn)
     # KNN lists (k <= 12 uses the pruned walk; far queries exercise the deferred, warp-pruned levels)
     k = int(rng.integers(1, 13))
     q = np.vstack([pts[rng.integers(0, len(pts), 200)], rng.uniform(-60, 60, (50, 3))]).astype(np.float32)
