@@ -98,7 +98,10 @@ int pcr_ctx_set_cell_size(pcr_ctx *ctx, float cell_size);
 /* Hint: the clouds this context sees come from one sensor stream (consecutive frames of similar size, extent and
  * density).  The cell size found by one call's occupancy probe is then reused by the next call whose point count
  * and bounding box are within 12.5 % of it, which skips the probe grid and its host round trip.  Results never
- * depend on the cell size; an unrepresentative reuse only costs speed.  Off by default. */
+ * depend on the cell size; an unrepresentative reuse only costs speed.  The same hint lets voxel_downsample size
+ * its table from the previous frame's key box (padded) without measuring the new frame first -- a point outside the
+ * box is detected and the frame redone the exact way -- and lets the KNN levels queue the next-coarser grid before
+ * the count that decides whether it is needed has come back.  Off by default. */
 int pcr_ctx_set_frame_stream(pcr_ctx *ctx, int enable);
 
 /* ---- multi-GPU (one process per GPU; the host exchanges the id, e.g. torch.distributed) ------ */
