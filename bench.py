@@ -333,7 +333,8 @@ def main():
         "traffic": None,
         "algorithmic_bytes_per_launch": bytes_knn, "avg_launch_ms": dur_knn * 1e3,
         "note": "a 119 K-point frame is L2-resident: the kernel is bound by instruction issue and per-warp latency, not by HBM (DESIGN.md)",
-        "stage_ms_per_step": {k: v[0] / args.steps for k, v in stage.items() if v[1]},
+        # (the library's catch-all tag "other" holds only the voxel step in this pipeline)
+        "stage_ms_per_step": {("voxel" if k == "other" else k): v[0] / args.steps for k, v in stage.items() if v[1]},
         "normals_from_lists_kernel": {"avg_launch_ms": knn_n_ms / max(knn_n_cnt, 1), "algorithmic_bytes_per_launch": n_kept * (16 + 4 * K_LIST + 1 + 12)},
         "device": {"name": torch.cuda.get_device_name(local_rank), "sm_count": props.multi_processor_count, "l2_bytes": props.L2_cache_size},
     }
