@@ -267,15 +267,21 @@ __global__ void __launch_bounds__(kBuildThreads) scatter_kernel(const float4 *__
 }
 
 // ---- tombstones: drop masked-out points from a built level without rebuilding it ------------------
-__global__ void __launch_bounds__(256) tombstone_kernel(float4 *__restrict__ sorted, uint32_t n_sorted,
-                                                        const uint8_t *__restrict__ keep) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_sorted) return;
-    float4 p = sorted[i];
-    if (!keep[__float_as_uint(p.w)]) {
-        const float qnan = __int_as_float(0x7fc00000);
-        p.x = p.y = p.z = qnan;  // every distance to it is NaN: its key can never enter a top-k
-        sorted[i] = p;
+struct TombLevels {
+    float4 *sorted[4];
+    uint32_t n[4];
+    int levels;
+};
+__global__ void __launch_bounds__(256) tombstone_kernel(TombLevels t, const uint8_t *__restrict__ keep) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int l = 0; l < t.levels; l++) {
+        if (i >= t.n[l]) continue;
+        float4 p = t.sorted[l][i];
+        if (!keep[__float_as_uint(p.w)]) {
+            const float qnan = __int_as_float(0x7fc00000);
+            p.x = p.y = p.z = qnan;  // every distance to it is NaN: its key can never enter a top-k
+            t.sorted[l][i] = p;
+        }
     }
 }
 
@@ -592,14 +598,26 @@ void index_free(Index *ix) {
 
 int index_apply_mask_dev(Index *ix, const uint8_t *d_keep) {
     Ctx *ctx = ix->ctx;
-    for (Index *l = ix; l; l = l->coarser) {
-        l->d_mask = d_keep;  // levels built from now on leave the removed points out
-        if (l->n_indexed) {
-            tombstone_kernel<<<(unsigned)((l->n_indexed + 255) / 256), 256, 0, ctx->stream>>>(l->sorted, (uint32_t)l->n_indexed, d_keep);
+    TombLevels t = {};
+    uint32_t n_max = 0;
+    auto flush = [&]() -> int {  // (all levels of an index fit one launch; the loop is for generality)
+        if (t.levels && n_max) {
+            tombstone_kernel<<<(n_max + 255) / 256, 256, 0, ctx->stream>>>(t, d_keep);
             PCR_LAUNCH_CHECK(ctx);
         }
+        t = {};
+        n_max = 0;
+        return PCR_OK;
+    };
+    for (Index *l = ix; l; l = l->coarser) {
+        l->d_mask = d_keep;  // levels built from now on leave the removed points out
+        if (!l->n_indexed) continue;
+        t.sorted[t.levels] = l->sorted;
+        t.n[t.levels] = (uint32_t)l->n_indexed;
+        n_max = std::max(n_max, t.n[t.levels]);
+        if (++t.levels == 4) PCR_TRY(flush());
     }
-    return PCR_OK;
+    return flush();
 }
 
 // Next-coarser level: same points, same frames, cell size x kLevelFactor.  Reuses the bounding

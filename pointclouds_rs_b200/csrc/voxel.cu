@@ -31,6 +31,17 @@ constexpr int kSortRounds = 8;                   // rounds of 32 pairs per warp 
 constexpr int kSortTile = 32 * kSortRounds;      // 256 pairs
 constexpr int kSortWarps = 4;                    // warps (tiles) per block
 
+// Head of the column path's scratch block: zeroed together with the column counters by ONE memset, read back by ONE
+// copy.  The box is kept as maxima only (mn_c = complement of the ordered encoding), so that zero is its identity.
+struct VoxHeader {
+    unsigned mn_c[3], mx[3];  // bounding box of the cloud written (f32_ordered encodings)
+    unsigned count;           // finite points written
+    unsigned outside;         // a point fell outside a guessed key box
+    unsigned total;           // voxels written
+    unsigned pad[7];
+};
+static_assert(sizeof(VoxHeader) == 64, "header layout");
+
 struct VoxRange {
     int mn[3];
     int mx[3];
@@ -40,17 +51,12 @@ struct VoxRange {
 // voxel_downsample.rs:32-36: (p / voxel).floor() as i32 -- IEEE division, round down, saturate, NaN -> 0
 __device__ __forceinline__ int vox_cell(float v, float voxel) { return __float2int_rd(__fdiv_rn(v, voxel)); }
 
-__global__ void vox_init_kernel(VoxRange *r, CloudStats *out_stats, uint32_t *outside) {
+__global__ void vox_init_kernel(VoxRange *r) {
     for (int a = 0; a < 3; a++) {
         r->mn[a] = 2147483647;
         r->mx[a] = -2147483647 - 1;
-        out_stats->mn[a] = 0xffffffffu;
-        out_stats->mx[a] = 0u;
     }
     r->finite = 0;
-    out_stats->count = 0;
-    out_stats->valid = 0;
-    *outside = 0;
 }
 
 __global__ void __launch_bounds__(256) vox_range_kernel(const float *__restrict__ x, const float *__restrict__ y,
@@ -380,34 +386,35 @@ __global__ void __launch_bounds__(256) vox_col_emit_kernel(const float *__restri
 // build of the next step would otherwise measure with a kernel and a round trip of its own.
 __global__ void __launch_bounds__(256) vox_out_stats_kernel(const float *__restrict__ x, const float *__restrict__ y,
                                                             const float *__restrict__ z, const uint32_t *__restrict__ d_n,
-                                                            CloudStats *stats) {
+                                                            VoxHeader *hdr) {
     const uint32_t n = *d_n;
-    unsigned mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u}, cnt = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) hdr->total = n;
+    unsigned mn_c[3] = {0u, 0u, 0u}, mx[3] = {0u, 0u, 0u}, cnt = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float px = x[i], py = y[i], pz = z[i];
         if (!finite3(px, py, pz)) continue;
         const unsigned u[3] = {f32_ordered(px), f32_ordered(py), f32_ordered(pz)};
         for (int a = 0; a < 3; a++) {
-            mn[a] = min(mn[a], u[a]);
+            mn_c[a] = max(mn_c[a], ~u[a]);
             mx[a] = max(mx[a], u[a]);
         }
         cnt++;
     }
     for (int a = 0; a < 3; a++) {
-        mn[a] = __reduce_min_sync(PCR_FULL, mn[a]);
+        mn_c[a] = __reduce_max_sync(PCR_FULL, mn_c[a]);
         mx[a] = __reduce_max_sync(PCR_FULL, mx[a]);
     }
     cnt = __reduce_add_sync(PCR_FULL, cnt);
     __shared__ unsigned s_mn[3], s_mx[3], s_cnt;
     if (threadIdx.x == 0) {
-        s_mn[0] = s_mn[1] = s_mn[2] = 0xffffffffu;
+        s_mn[0] = s_mn[1] = s_mn[2] = 0u;
         s_mx[0] = s_mx[1] = s_mx[2] = 0u;
         s_cnt = 0;
     }
     __syncthreads();
     if ((threadIdx.x & 31) == 0 && cnt) {
         for (int a = 0; a < 3; a++) {
-            atomicMin(&s_mn[a], mn[a]);
+            atomicMax(&s_mn[a], mn_c[a]);
             atomicMax(&s_mx[a], mx[a]);
         }
         atomicAdd(&s_cnt, cnt);
@@ -415,10 +422,10 @@ __global__ void __launch_bounds__(256) vox_out_stats_kernel(const float *__restr
     __syncthreads();
     if (threadIdx.x == 0 && s_cnt) {
         for (int a = 0; a < 3; a++) {
-            atomicMin(&stats->mn[a], s_mn[a]);
-            atomicMax(&stats->mx[a], s_mx[a]);
+            atomicMax(&hdr->mn_c[a], s_mn[a]);
+            atomicMax(&hdr->mx[a], s_mx[a]);
         }
-        atomicAdd(&stats->count, s_cnt);
+        atomicAdd(&hdr->count, s_cnt);
     }
 }
 
@@ -464,10 +471,6 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
     VoxRange *d_range = (VoxRange *)ctx->b_small.p;
     uint32_t *d_nvox = (uint32_t *)((char *)ctx->b_small.p + 256);
     VoxRange *h_range = (VoxRange *)ctx->pinned;
-    CloudStats *d_ostats = (CloudStats *)((char *)ctx->b_small.p + 512);
-    uint32_t *d_outside = (uint32_t *)((char *)ctx->b_small.p + 768);
-    vox_init_kernel<<<1, 1, 0, st>>>(d_range, d_ostats, d_outside);
-    PCR_LAUNCH_CHECK(ctx);
     // A frame stream sizes the table from the previous frame's key box (padded) and skips the measuring pass and its
     // round trip; every 32nd frame is measured again so that the box follows the scene.
     auto &vc = ctx->vox_cache;
@@ -482,6 +485,8 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
         }
         m = (uint32_t)n;  // (an upper bound is all the sizing below needs)
     } else {
+        vox_init_kernel<<<1, 1, 0, st>>>(d_range);
+        PCR_LAUNCH_CHECK(ctx);
         const unsigned bx = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 2);
         vox_range_kernel<<<bx, 256, 0, st>>>(dx, dy, dz, n, voxel, d_range);
         PCR_LAUNCH_CHECK(ctx);
@@ -527,20 +532,22 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
         if (!no_cols && nx < (1ull << 31) && ny < (1ull << 31) && nz < (1ull << (32 - ys)) && n_cols64 <= (1ull << 24) &&
             n_cols64 <= 64ull * m + 65536ull) {
             const uint32_t n_cols = (uint32_t)n_cols64;
-            // scratch (b_table): count u32[n_cols + 1] | nvox u32[n_cols + 1] | col_of u32[n] | rank_of u32[n] | members u64[n]
-            const size_t o_nvox = sizeof(uint32_t) * ((size_t)n_cols + 1);
-            const size_t o_col = 2 * o_nvox;
+            // scratch (b_table): header 64 B | count u32[n_cols + 1] | nvox u32[n_cols + 1] | col_of u32[n] | rank_of u32[n] | members u64[n]
+            const size_t tab = (sizeof(uint32_t) * ((size_t)n_cols + 1) + 15) & ~(size_t)15;  // (16 B-aligned tables: the scan's vector path)
+            const size_t o_count = sizeof(VoxHeader), o_nvox = o_count + tab;
+            const size_t o_col = (o_nvox + tab + 15) & ~(size_t)15;
             const size_t o_rank = o_col + sizeof(uint32_t) * n;
             const size_t o_mem = (o_rank + sizeof(uint32_t) * n + 15) & ~(size_t)15;
             PCR_TRY(ensure(ctx, ctx->b_table, o_mem + sizeof(unsigned long long) * n));
             char *base = (char *)ctx->b_table.p;
-            uint32_t *count = (uint32_t *)base, *nvox = (uint32_t *)(base + o_nvox);
+            VoxHeader *d_hdr = (VoxHeader *)base;
+            uint32_t *count = (uint32_t *)(base + o_count), *nvox = (uint32_t *)(base + o_nvox);
             uint32_t *col_of = (uint32_t *)(base + o_col), *rank_of = (uint32_t *)(base + o_rank);
             unsigned long long *members = (unsigned long long *)(base + o_mem);
-            PCR_CUDA(ctx, cudaMemsetAsync(count, 0, 2 * o_nvox, st));  // counters and nvox (contiguous)
+            PCR_CUDA(ctx, cudaMemsetAsync(base, 0, o_nvox + tab, st));  // header, counters and nvox in one go
             const unsigned nbp = (unsigned)((n + 255) / 256);
             vox_col_count_kernel<<<nbp, 256, 0, st>>>(dx, dy, dz, n, voxel, h_range->mn[0], h_range->mn[1], h_range->mn[2], nx, ny, nz,
-                                                      (uint32_t)nyc64, ys, count, col_of, rank_of, d_outside);
+                                                      (uint32_t)nyc64, ys, count, col_of, rank_of, &d_hdr->outside);
             PCR_LAUNCH_CHECK(ctx);
             PCR_TRY(exclusive_scan_u32_dev(ctx, count, (size_t)n_cols + 1));
             vox_col_scatter_kernel<<<nbp, 256, 0, st>>>(dy, dz, n, voxel, h_range->mn[1], h_range->mn[2], ys, count, col_of, rank_of, members);
@@ -550,26 +557,27 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
             PCR_TRY(exclusive_scan_u32_dev(ctx, nvox, (size_t)n_cols + 1));
             vox_col_emit_kernel<<<nbp, 256, 0, st>>>(dx, dy, dz, col_of, rank_of, n, count, nvox, members, d_ox, d_oy, d_oz);
             PCR_LAUNCH_CHECK(ctx);
-            uint32_t *mail = (uint32_t *)ctx->pinned + 64;
-            CloudStats *mail_stats = (CloudStats *)((uint32_t *)ctx->pinned + 72);
-            if (stats_out) {  // the next step's index build wants the box of what was just written: one round trip for both
-                vox_out_stats_kernel<<<(unsigned)ctx->sm_count, 256, 0, st>>>(d_ox, d_oy, d_oz, nvox + n_cols, d_ostats);
-                PCR_LAUNCH_CHECK(ctx);
-                PCR_CUDA(ctx, cudaMemcpyAsync(mail_stats, d_ostats, sizeof(CloudStats), cudaMemcpyDeviceToHost, st));
-            }
-            PCR_CUDA(ctx, cudaMemcpyAsync(mail, nvox + n_cols, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            if (guessed) PCR_CUDA(ctx, cudaMemcpyAsync(mail + 1, d_outside, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            // the box and count of what was written (the next step's index build wants them), the voxel count and the
+            // outside flag come back together
+            vox_out_stats_kernel<<<(unsigned)ctx->sm_count, 256, 0, st>>>(d_ox, d_oy, d_oz, nvox + n_cols, d_hdr);
+            PCR_LAUNCH_CHECK(ctx);
+            VoxHeader *mail = (VoxHeader *)((uint32_t *)ctx->pinned + 64);
+            PCR_CUDA(ctx, cudaMemcpyAsync(mail, d_hdr, sizeof(VoxHeader), cudaMemcpyDeviceToHost, st));
             PCR_MARK("voxel: wait for count");
             PCR_CUDA(ctx, cudaStreamSynchronize(st));
             PCR_MARK("voxel: got count");
-            if (guessed && mail[1]) {  // a point fell outside the guessed box: measure, with a wider pad from now on
+            if (guessed && mail->outside) {  // a point fell outside the guessed box: measure, with a wider pad from now on
                 vc.valid = false;
                 vc.pad_shift = std::max(2, vc.pad_shift - 1);
                 return voxel_downsample_dev(ctx, dx, dy, dz, n, voxel, d_ox, d_oy, d_oz, n_out, stats_out, false);
             }
-            *n_out = *mail;
+            *n_out = mail->total;
             if (stats_out) {
-                *stats_out = *mail_stats;
+                for (int a = 0; a < 3; a++) {
+                    stats_out->mn[a] = ~mail->mn_c[a];
+                    stats_out->mx[a] = mail->mx[a];
+                }
+                stats_out->count = mail->count;
                 stats_out->valid = 1;
             }
             return PCR_OK;
