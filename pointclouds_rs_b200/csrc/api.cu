@@ -1123,11 +1123,6 @@ int cloud_alloc(pcr_ctx *ctx, size_t n, bool normals, pcr_cloud **out) {
     return PCR_OK;
 }
 
-__global__ void fill_value_kernel(float *__restrict__ p, size_t n, float v) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-
 __global__ void mask_to_u32_kernel(const uint8_t *__restrict__ keep, size_t n, uint32_t *__restrict__ flag) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= n) flag[i] = (i < n && keep[i]) ? 1u : 0u;
