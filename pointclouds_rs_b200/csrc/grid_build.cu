@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(uint32_t *_
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
+    if (tile >= tiles) return;  // (a ticket left over from an aborted scan: never write out of bounds)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     // a warp owns 32 * kScanItems consecutive elements, read as kRows coalesced rows of uint4
     const size_t wbase = (size_t)tile * kScanTile + (size_t)w * (kScanItems * 32);
