@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define PCR_B200_VERSION 111 /* 0.1.1: + voxel, cluster, RANSAC, device-resident clouds; 111: + block upload / download */
+#define PCR_B200_VERSION 112 /* 0.1.1: + voxel, cluster, RANSAC, device-resident clouds; 111/112: + block upload / download, nowait */
 
 typedef enum pcr_status {
     PCR_OK = 0,
@@ -277,6 +277,10 @@ int pcr_cloud_download_normals(const pcr_cloud *cloud, float *nx, float *ny, flo
 /* The same for callers that keep their SoA arrays in ONE block, `stride` floats apart (x | y | z [| nx | ny | nz]):
  * a single strided transfer each way instead of three or six. */
 int pcr_cloud_upload_block(pcr_ctx *ctx, const float *xyz, size_t stride, size_t n, pcr_cloud **out);
+/* The same without waiting for the copy: the steps queued next run right behind it.  `xyz` (pinned memory, or the
+ * copy is staged and waits anyway) must stay unchanged until a later call on this context has returned data that
+ * depends on the cloud (any filter's result, a download) or pcr_ctx_synchronize has returned. */
+int pcr_cloud_upload_block_nowait(pcr_ctx *ctx, const float *xyz, size_t stride, size_t n, pcr_cloud **out);
 int pcr_cloud_download_block(const pcr_cloud *cloud, float *dst, size_t stride, int with_normals);
 /* device pointers of the SoA arrays (valid until the cloud is freed; normals NULL if absent) */
 int pcr_cloud_device_pointers(const pcr_cloud *cloud, const float **d_x, const float **d_y, const float **d_z,

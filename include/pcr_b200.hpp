@@ -332,9 +332,9 @@ class DeviceCloud {
         return DeviceCloud(h, &ctx);
     }
     // x | y | z rows of one host block, `stride` floats apart: one strided transfer
-    static DeviceCloud upload_block(const float *xyz, size_t stride, size_t n, Context &ctx = default_context()) {
+    static DeviceCloud upload_block(const float *xyz, size_t stride, size_t n, Context &ctx = default_context(), bool wait = true) {
         pcr_cloud *h = nullptr;
-        ctx.check(pcr_cloud_upload_block(ctx.get(), xyz, stride, n, &h));
+        ctx.check(wait ? pcr_cloud_upload_block(ctx.get(), xyz, stride, n, &h) : pcr_cloud_upload_block_nowait(ctx.get(), xyz, stride, n, &h));
         return DeviceCloud(h, &ctx);
     }
     // x | y | z [| nx | ny | nz] rows into one host block

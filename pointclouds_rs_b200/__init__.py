@@ -587,10 +587,14 @@ class DeviceCloud:
         return DeviceCloud(h, ctx)
 
     @staticmethod
-    def upload_block(ctx: Context, ptr: int, stride: int, n: int) -> "DeviceCloud":
-        """Upload x | y | z from ONE host block (rows `stride` floats apart): a single strided transfer."""
+    def upload_block(ctx: Context, ptr: int, stride: int, n: int, wait: bool = True) -> "DeviceCloud":
+        """Upload x | y | z from ONE host block (rows `stride` floats apart): a single strided transfer.
+        wait=False does not wait for the copy (pinned block, left unchanged until a result that depends on the
+        cloud has come back): the next steps queue right behind it."""
         h = C.c_void_p()
-        _ffi.check(_ffi.load().pcr_cloud_upload_block(ctx._h, ptr, stride, n, C.byref(h)), ctx._h)
+        lib = _ffi.load()
+        fn = lib.pcr_cloud_upload_block if wait else lib.pcr_cloud_upload_block_nowait
+        _ffi.check(fn(ctx._h, ptr, stride, n, C.byref(h)), ctx._h)
         return DeviceCloud(h, ctx)
 
     def download_block(self, ptr: int, stride: int, with_normals: bool = False):

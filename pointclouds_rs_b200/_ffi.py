@@ -101,6 +101,7 @@ SIGNATURES = {
     "pcr_radius_outlier_dev": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_float, C.c_size_t, vp]),
     "pcr_cloud_upload": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.POINTER(vp)]),
     "pcr_cloud_upload_block": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, C.POINTER(vp)]),
+    "pcr_cloud_upload_block_nowait": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, C.POINTER(vp)]),
     "pcr_cloud_download_block": (C.c_int, [vp, vp, C.c_size_t, C.c_int]),
     "pcr_cloud_free": (None, [vp]),
     "pcr_cloud_len": (C.c_size_t, [vp]),

@@ -1269,7 +1269,14 @@ int pcr_cloud_download_normals(const pcr_cloud *cloud, float *nx, float *ny, flo
 
 // One strided copy each way for callers that keep their SoA arrays in one block (x | y | z [| nx | ny | nz], `stride`
 // floats apart): a single cudaMemcpy2DAsync instead of three or six separate transfers.
+static int upload_block(pcr_ctx *ctx, const float *xyz, size_t stride, size_t n, pcr_cloud **out, bool wait);
 int pcr_cloud_upload_block(pcr_ctx *ctx, const float *xyz, size_t stride, size_t n, pcr_cloud **out) {
+    return upload_block(ctx, xyz, stride, n, out, true);
+}
+int pcr_cloud_upload_block_nowait(pcr_ctx *ctx, const float *xyz, size_t stride, size_t n, pcr_cloud **out) {
+    return upload_block(ctx, xyz, stride, n, out, false);
+}
+static int upload_block(pcr_ctx *ctx, const float *xyz, size_t stride, size_t n, pcr_cloud **out, bool wait) {
     if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
     Ctx *c = &ctx->c;
     if (!out || (n && !xyz) || stride < n) return fail(c, PCR_ERR_INVALID_ARG, "null pointer or stride < n");
@@ -1280,7 +1287,7 @@ int pcr_cloud_upload_block(pcr_ctx *ctx, const float *xyz, size_t stride, size_t
     PCR_TRY(cloud_alloc(ctx, n, false, &cl));
     cudaError_t e = cudaSuccess;
     if (n) e = cudaMemcpy2DAsync(cl->base, cl->stride * sizeof(float), xyz, stride * sizeof(float), n * sizeof(float), 3, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // the caller's buffer is free again on return
+    if (e == cudaSuccess && wait) e = cudaStreamSynchronize(c->stream);  // the caller's buffer is free again on return
     if (e != cudaSuccess) {
         cudaGetLastError();
         pcr_cloud_free(cl);

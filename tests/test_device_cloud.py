@@ -25,6 +25,8 @@ def test_upload_download_select(pcr):
     block = np.ascontiguousarray(pts.T)                                 # x | y | z rows of one block: one strided transfer each way
     b = pcr.DeviceCloud.upload_block(pcr.default_context(), block.ctypes.data, block.shape[1], block.shape[1])
     assert np.array_equal(b.to_numpy(), pts)
+    b2 = pcr.DeviceCloud.upload_block(pcr.default_context(), block.ctypes.data, block.shape[1], block.shape[1], wait=False)
+    assert np.array_equal(b2.to_numpy(), pts)                            # (the download waits for the queued copy)
     outb = np.zeros((6, 5000 + 24), np.float32)                          # a stride larger than the cloud
     dn.download_block(outb.ctypes.data, outb.shape[1], with_normals=True)
     assert np.array_equal(outb[:3, :5000].T, pts) and np.array_equal(outb[3:, :5000].T, dn.normals_to_numpy())
