@@ -101,3 +101,21 @@ def test_python_surface_mirrors_reference_names():
         pcr.PointCloud.from_numpy(__import__("numpy").zeros((3, 4), "float32"))
     with pytest.raises(ValueError):
         pcr.PointCloud.from_numpy(__import__("numpy").asfortranarray(__import__("numpy").zeros((3, 3), "float32")))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` needs no GPU: one bounded step of the CPU port, one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "sor_normals_points_per_sec" and line["unit"] == "points/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert "workload" in line["config"]
