@@ -11,9 +11,15 @@ The module mirrors the names and argument meaning of the reference's PyO3 module
                                                         crates/python/src/registration.rs:4-109
     KdTree (batched)                                    crates/spatial/src/kdtree.rs:14-164
 
+and for the steps either side of it:
+
+    voxel_downsample(cloud, voxel_size)                 crates/python/src/filters.rs (voxel_downsample.rs:12-65)
+    euclidean_cluster(cloud, threshold, min, max)       crates/segmentation/src/euclidean_cluster.rs:96-187
+    ransac_plane(cloud, threshold, iterations)          crates/segmentation/src/ransac_plane.rs:56-129 (after the sampling step)
+    DeviceCloud                                         a PointCloud that stays in HBM between the steps of a pipeline
+
 Everything runs through the C ABI (include/pcr_b200.h) of lib/libpcr_b200.so: hand-written sm_100a
-CUDA, no PyTorch on the path, no CPU fallback.  Functions outside the KNN path (voxel_downsample,
-passthrough_filter, ransac_plane, euclidean_cluster, file IO) are out of scope here.
+CUDA, no PyTorch on the path, no CPU fallback.  Out of scope: passthrough_filter and file IO.
 """
 from __future__ import annotations
 

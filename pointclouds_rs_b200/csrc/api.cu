@@ -5,6 +5,7 @@
 
 #include <stdarg.h>
 
+#include <atomic>
 #include <chrono>
 #include <utility>
 #include <vector>
@@ -14,8 +15,13 @@
 namespace pcr {
 
 static thread_local std::string g_thread_error = "no error";
+static thread_local uint64_t g_thread_err_seq = 0;
+static std::atomic<uint64_t> g_err_seq{0};
 
-void set_thread_error(const char *msg) { g_thread_error = msg ? msg : "unknown error"; }
+void set_thread_error(const char *msg) {
+    g_thread_error = msg ? msg : "unknown error";
+    g_thread_err_seq = ++g_err_seq;
+}
 
 int fail(Ctx *ctx, int code, const char *fmt, ...) {
     char buf[512];
@@ -23,8 +29,12 @@ int fail(Ctx *ctx, int code, const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
-    if (ctx) ctx->err = buf;
     g_thread_error = buf;
+    g_thread_err_seq = ++g_err_seq;
+    if (ctx) {
+        ctx->err = buf;
+        ctx->err_seq = g_thread_err_seq;
+    }
     return code;
 }
 
@@ -115,9 +125,14 @@ int ctx_create(int device, void *stream, bool have_stream, Ctx **out) {
     Ctx *ctx = new (std::nothrow) Ctx();
     if (!ctx) return fail(nullptr, PCR_ERR_OOM, "host allocation failed");
     ctx->device = device;
-    struct Guard {
+    struct Guard {  // a half-made context: give back what it already owns
         Ctx *c;
-        ~Guard() { delete c; }
+        ~Guard() {
+            if (!c) return;
+            if (c->pinned) cudaFreeHost(c->pinned);
+            if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
+            delete c;
+        }
     } g{ctx};
     PCR_CUDA(ctx, cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -201,7 +216,9 @@ int pcr_device_count(void) {
 }
 
 const char *pcr_last_error(const pcr_ctx *ctx) {
-    if (ctx && !ctx->c.err.empty()) return ctx->c.err.c_str();
+    // the context's message only if it is newer than this thread's last failure (which may have been reported
+    // without a context: NULL-argument checks, cloud-handle checks, the NCCL id)
+    if (ctx && !ctx->c.err.empty() && ctx->c.err_seq >= g_thread_err_seq) return ctx->c.err.c_str();
     return g_thread_error.c_str();
 }
 
@@ -1169,13 +1186,20 @@ int cloud_compact(const pcr_cloud *in, const uint8_t *d_keep, pcr_cloud **out, c
         m = *mail;
     }
     const bool with_normals = nrm || in->has_normals;
-    PCR_TRY(cloud_alloc(in->owner, m, with_normals, out));
+    pcr_cloud *tmp = nullptr;  // *out is set on success only: a failed call hands the caller no live handle
+    PCR_TRY(cloud_alloc(in->owner, m, with_normals, &tmp));
     if (m) {
         const int n_a = nrm ? 3 : (in->has_normals ? 6 : 3), n_b = nrm ? 3 : 0;
-        compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(in->base, in->stride, n_a, nrm, nrm_stride, n_b, n, pos, (*out)->base,
-                                                                           (*out)->stride);
-        PCR_LAUNCH_CHECK(c);
+        compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(in->base, in->stride, n_a, nrm, nrm_stride, n_b, n, pos, tmp->base,
+                                                                           tmp->stride);
+        c->launches++;
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            pcr_cloud_free(tmp);
+            return fail(c, PCR_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e), __FILE__, __LINE__);
+        }
     }
+    *out = tmp;
     return PCR_OK;
 }
 
@@ -1198,12 +1222,14 @@ int pcr_cloud_upload(pcr_ctx *ctx, const float *x, const float *y, const float *
     DevSetter ds(c);
     pcr_cloud *cl = nullptr;
     PCR_TRY(cloud_alloc(ctx, n, false, &cl));
+    cudaError_t e = cudaSuccess;
     if (n) {
-        cudaMemcpyAsync(cl->x(), x, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream);
-        cudaMemcpyAsync(cl->y(), y, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream);
-        cudaMemcpyAsync(cl->z(), z, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream);
+        e = cudaMemcpyAsync(cl->x(), x, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(cl->y(), y, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(cl->z(), z, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream);
     }
-    cudaError_t e = cudaStreamSynchronize(c->stream);  // the caller's buffers are free again on return
+    const cudaError_t es = cudaStreamSynchronize(c->stream);  // the caller's buffers are free again on return
+    if (e == cudaSuccess) e = es;
     if (e != cudaSuccess) {
         pcr_cloud_free(cl);
         return fail(c, PCR_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
@@ -1320,15 +1346,23 @@ int pcr_cloud_select(const pcr_cloud *cloud, const uint32_t *indices, size_t m, 
         if (indices[t] >= cloud->n) return fail(c, PCR_ERR_INVALID_ARG, "index %u out of bounds for cloud with %zu points", indices[t], cloud->n);
     PCR_API_BEGIN
     DevSetter ds(c);
-    PCR_TRY(cloud_alloc(cloud->owner, m, cloud->has_normals, out));
-    if (m) {
+    pcr_cloud *tmp = nullptr;  // *out is set on success only
+    PCR_TRY(cloud_alloc(cloud->owner, m, cloud->has_normals, &tmp));
+    const int rc = [&]() -> int {
+        if (!m) return PCR_OK;
         PCR_TRY(ensure(c, c->b_list, sizeof(uint32_t) * m));
         PCR_CUDA(c, cudaMemcpyAsync(c->b_list.p, indices, sizeof(uint32_t) * m, cudaMemcpyHostToDevice, c->stream));
         gather_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(cloud->base, cloud->stride, cloud->has_normals ? 6 : 3,
-                                                                          (const uint32_t *)c->b_list.p, m, (*out)->base, (*out)->stride);
+                                                                          (const uint32_t *)c->b_list.p, m, tmp->base, tmp->stride);
         PCR_LAUNCH_CHECK(c);
         PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+        return PCR_OK;
+    }();
+    if (rc != PCR_OK) {
+        pcr_cloud_free(tmp);
+        return rc;
     }
+    *out = tmp;
     return PCR_OK;
     PCR_API_END(c)
 }

@@ -17,7 +17,7 @@ typedef struct {
 } ncclUniqueId_t;
 typedef void *ncclComm_t_;
 typedef int ncclResult_t_;
-enum { kNcclFloat64 = 8, kNcclSum = 0 };
+enum { kNcclUint8 = 1, kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0 };
 
 struct NcclApi {
     void *handle = nullptr;
@@ -25,15 +25,13 @@ struct NcclApi {
     ncclResult_t_ (*CommInitRank)(ncclComm_t_ *, int, ncclUniqueId_t, int) = nullptr;
     ncclResult_t_ (*CommDestroy)(ncclComm_t_) = nullptr;
     ncclResult_t_ (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t_, cudaStream_t) = nullptr;
+    ncclResult_t_ (*AllGather)(const void *, void *, size_t, int, ncclComm_t_, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t_) = nullptr;
     bool ok = false;
 };
 
-NcclApi &api() {
-    static NcclApi a;
-    static bool tried = false;
-    if (tried) return a;
-    tried = true;
+NcclApi load_nccl() {
+    NcclApi a;
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char *n : names) {  // a copy already mapped into the process wins
         a.handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
@@ -53,7 +51,14 @@ NcclApi &api() {
     a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.handle, "ncclCommDestroy");
     a.AllReduce = (decltype(a.AllReduce))dlsym(a.handle, "ncclAllReduce");
     a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.handle, "ncclGetErrorString");
-    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce;
+    a.AllGather = (decltype(a.AllGather))dlsym(a.handle, "ncclAllGather");
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.AllGather;
+    return a;
+}
+
+// resolved once, by whichever thread asks first (a C++11 magic static: concurrent callers wait for the loader)
+NcclApi &api() {
+    static NcclApi a = load_nccl();
     return a;
 }
 
@@ -114,6 +119,19 @@ int comm_allreduce_f64(Ctx *ctx, double *d_buf, size_t count) {
     if (!a.ok || !ctx->nccl_comm) return fail(ctx, PCR_ERR_NCCL, "communicator not initialised");
     int r = a.AllReduce(d_buf, d_buf, count, kNcclFloat64, kNcclSum, (ncclComm_t_)ctx->nccl_comm, ctx->stream);
     if (r != 0) return fail(ctx, PCR_ERR_NCCL, "ncclAllReduce: %s", a.GetErrorString ? a.GetErrorString(r) : "error");
+    return PCR_OK;
+}
+
+// every rank contributes `bytes` bytes at d_send; d_recv receives world * bytes, rank-major
+int comm_allgather_bytes(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes) {
+    if (ctx->world <= 1) {
+        if (d_send != d_recv && bytes) PCR_CUDA(ctx, cudaMemcpyAsync(d_recv, d_send, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        return PCR_OK;
+    }
+    NcclApi &a = api();
+    if (!a.ok || !ctx->nccl_comm) return fail(ctx, PCR_ERR_NCCL, "communicator not initialised");
+    int r = a.AllGather(d_send, d_recv, bytes, kNcclUint8, (ncclComm_t_)ctx->nccl_comm, ctx->stream);
+    if (r != 0) return fail(ctx, PCR_ERR_NCCL, "ncclAllGather: %s", a.GetErrorString ? a.GetErrorString(r) : "error");
     return PCR_OK;
 }
 

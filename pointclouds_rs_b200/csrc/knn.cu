@@ -40,6 +40,12 @@ struct LevelArgs {
     uint32_t *defer_count;
     int max_rings;
     int last_level;
+    // selection kernels (knn_sel_kernel): the first pass stops after the 27 cells and queues the queries the ring
+    // rule cannot confirm yet; a second launch of the same kernel takes them from cont_list through the shells
+    int first_only;  // shells the first pass walks (0: this is not a first pass)
+    uint32_t *cont_list;
+    uint32_t *cont_count;
+    int follow_up;  // this launch takes cont_list of the first pass (warp per query, same grid level)
 };
 
 __device__ __forceinline__ void defer_query(const LevelArgs &a, uint32_t qid, int lane) {
@@ -96,9 +102,10 @@ __global__ void __launch_bounds__(kThreads) knn_queries_kernel(LevelArgs a, cons
     tk.kk = kk;
     tk.lane = lane;
     if constexpr (kSmem) tk.s = smem_keys + (size_t)w * kk;
-    const uint32_t q0 = (blockIdx.x * kWarps + w) * QPW;
+    const uint32_t nq = a.nq_dev ? min(a.nq, *a.nq_dev) : a.nq;  // (a launch for a capacity strides over the real count)
+    for (uint32_t q0 = (blockIdx.x * kWarps + w) * QPW; q0 < nq; q0 += gridDim.x * kWarps * QPW)
     for (int t = 0; t < QPW; t++) {
-        if (q0 + t >= a.nq) break;
+        if (q0 + t >= nq) break;
         const uint32_t qi = a.qlist ? a.qlist[q0 + t] : q0 + t;
         float x = __ldg(&qx[qi]), y = __ldg(&qy[qi]), z = __ldg(&qz[qi]);
         int cnt = 0;
@@ -118,12 +125,15 @@ __global__ void __launch_bounds__(kThreads) knn_queries_kernel(LevelArgs a, cons
 
 // ---- SOR: mean distance to the k nearest neighbours (k+1 searched, self dropped) ----------------
 // smem per warp: dist[(kk)][33] f32 (transposed: neighbour-major) + cnt[32]
+// `lists` (optional, register path only): the fused SOR -> normals pipeline keeps the kk >= kk_sor neighbours
+// of every query (SorLists layout); the statistic then uses the first kk_sor entries.
 template <bool kSmem, int QPW>
-__global__ void __launch_bounds__(kThreads) sor_mean_kernel(LevelArgs a, int kk, float *__restrict__ mean_d) {
+__global__ void __launch_bounds__(kThreads) sor_mean_kernel(LevelArgs a, int kk, float *__restrict__ mean_d, uint32_t *__restrict__ lists,
+                                                            uint8_t *__restrict__ list_cnt, size_t list_stride, int kk_sor) {
     extern __shared__ unsigned long long smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t q0 = (blockIdx.x * kWarps + w) * QPW;
-    if (q0 >= a.nq) return;
+    const uint32_t nq = a.nq_dev ? min(a.nq, *a.nq_dev) : a.nq;  // (a launch for a capacity strides over the real count)
+    for (uint32_t q0 = (blockIdx.x * kWarps + w) * QPW; q0 < nq; q0 += gridDim.x * kWarps * QPW) {
     if constexpr (!kSmem) {
         float *sd = reinterpret_cast<float *>(smem_raw) + (size_t)w * (kk * 33 + 64);
         int *scnt = reinterpret_cast<int *>(sd + kk * 33);
@@ -134,7 +144,7 @@ __global__ void __launch_bounds__(kThreads) sor_mean_kernel(LevelArgs a, int kk,
         int f = -1;
         GridDesc g;
         for (int t = 0; t < QPW; t++) {
-            if (q0 + t >= a.nq) break;
+            if (q0 + t >= nq) break;
             const uint32_t pos = a.qlist ? a.qlist[q0 + t] : q0 + t;
             if (f < 0 || pos >= g.pt_end || pos < g.pt_begin) {
                 f = frame_of_sorted(a.grids, a.n_frames, pos);
@@ -152,18 +162,21 @@ __global__ void __launch_bounds__(kThreads) sor_mean_kernel(LevelArgs a, int kk,
                 cnt = -1;
             } else if (lane < kk) {
                 sd[lane * 33 + t] = __fsqrt_rn(key_d2(tk.K));  // kdtree.rs:76
+                if (lists) lists[(size_t)lane * list_stride + pos] = lane < cnt ? key_idx(tk.K) : 0xffffffffu;
             }
             if (lane == 0) {
                 scnt[t] = cnt;
                 spos[t] = pos;
+                if (lists && done) list_cnt[pos] = (uint8_t)cnt;
             }
         }
         __syncwarp();
-        if (lane < QPW && q0 + lane < a.nq) {
+        if (lane < QPW && q0 + lane < nq) {
             int cnt = scnt[lane];
             if (cnt >= 0) {
                 // statistical_outlier.rs:28-37: drop the first (self) if there is more than one
                 // result, sequential f32 sum in ascending-distance order, divide by the count
+                if (cnt > kk_sor) cnt = kk_sor;  // (the top-kk list starts with the top-kk_sor list)
                 int first = cnt > 1 ? 1 : 0;
                 float sum = 0.0f;
                 for (int j = first; j < cnt; j++) sum = __fadd_rn(sum, sd[j * 33 + lane]);
@@ -172,13 +185,14 @@ __global__ void __launch_bounds__(kThreads) sor_mean_kernel(LevelArgs a, int kk,
                 mean_d[__float_as_uint(__ldg(&a.qpts[spos[lane]]).w)] = md;
             }
         }
+        __syncwarp();
     } else {
         SmemTopK tk;
         tk.kk = kk;
         tk.lane = lane;
         tk.s = smem_raw + (size_t)w * kk;
         for (int t = 0; t < QPW; t++) {
-            if (q0 + t >= a.nq) break;
+            if (q0 + t >= nq) break;
             const uint32_t pos = a.qlist ? a.qlist[q0 + t] : q0 + t;
             const GridDesc g = a.grids[frame_of_sorted(a.grids, a.n_frames, pos)];
             float4 q = __ldg(&a.qpts[pos]);
@@ -197,6 +211,7 @@ __global__ void __launch_bounds__(kThreads) sor_mean_kernel(LevelArgs a, int kk,
             }
             __syncwarp();
         }
+    }
     }
 }
 
@@ -293,9 +308,8 @@ __global__ void __launch_bounds__(kThreads) normals_kernel(LevelArgs a, const fl
                                                            float *__restrict__ nz) {
     extern __shared__ unsigned long long smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t q0 = (blockIdx.x * kWarps + w) * QPW;
-    const uint32_t nq = a.nq_dev ? min(a.nq, *a.nq_dev) : a.nq;
-    if (q0 >= nq) return;
+    const uint32_t nq = a.nq_dev ? min(a.nq, *a.nq_dev) : a.nq;  // (a launch for a capacity strides over the real count)
+    for (uint32_t q0 = (blockIdx.x * kWarps + w) * QPW; q0 < nq; q0 += gridDim.x * kWarps * QPW) {
     if constexpr (!kSmem) {
         float *sc = reinterpret_cast<float *>(smem_raw) + (size_t)w * (kk * 3 * 33 + 64);
         int *scnt = reinterpret_cast<int *>(sc + kk * 3 * 33);
@@ -344,6 +358,7 @@ __global__ void __launch_bounds__(kThreads) normals_kernel(LevelArgs a, const fl
             ny[oi] = oy;
             nz[oi] = oz;
         }
+        __syncwarp();
     } else {
         SmemTopK tk;
         tk.kk = kk;
@@ -375,6 +390,7 @@ __global__ void __launch_bounds__(kThreads) normals_kernel(LevelArgs a, const fl
             }
             __syncwarp();
         }
+    }
     }
 }
 
@@ -547,7 +563,12 @@ __global__ void __launch_bounds__(kTQThreads) knn_thread_kernel(LevelArgs a, Thr
 }
 
 template <int MODE>
+int launch_sel_kernel(Ctx *ctx, const LevelArgs &a, const ThreadArgs &t);
+inline bool use_select(int kk);
+
+template <int MODE>
 int launch_thread_kernel(Ctx *ctx, const LevelArgs &a, const ThreadArgs &t) {
+    if (use_select(t.kk)) return launch_sel_kernel<MODE>(ctx, a, t);
     const unsigned blocks = (a.nq + kTQThreads - 1) / kTQThreads;
     const int kk = t.kk;
 #define PCR_TQ(KC)                                                                          \
@@ -559,6 +580,162 @@ int launch_thread_kernel(Ctx *ctx, const LevelArgs &a, const ThreadArgs &t) {
     PCR_TQ(2) PCR_TQ(4) PCR_TQ(8) PCR_TQ(11) PCR_TQ(12) PCR_TQ(16) PCR_TQ(20) PCR_TQ(21) PCR_TQ(24) PCR_TQ(32)
 #undef PCR_TQ
     return fail(ctx, PCR_ERR_UNSUPPORTED, "thread kernel: k too large");
+}
+
+// ---- level 0, k <= kSelMaxK: one thread per query, selection instead of insertion (knn_search.cuh) ----
+// The k best keys of a thread end up sorted in its column of the block's shared buffer; the epilogues are
+// the ones of knn_thread_kernel, reading the list from there.
+__device__ __forceinline__ void push_list(bool mine, uint32_t *__restrict__ list, uint32_t *__restrict__ count, uint32_t q, int lane) {
+    const unsigned mask = __ballot_sync(PCR_FULL, mine);
+    if (!mask) return;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(mask));
+    base = __shfl_sync(PCR_FULL, base, leader);
+    if (mine) list[base + __popc(mask & ((1u << lane) - 1u))] = q;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTQThreads, 6) knn_sel_kernel(LevelArgs a, ThreadArgs t) {
+    static_assert(kTQThreads == kSelStride, "one buffer column per thread");
+    const uint32_t nq = a.nq_dev ? min(a.nq, *a.nq_dev) : a.nq;
+    if (blockIdx.x * kTQThreads >= nq) return;  // (block-uniform: the follow-up pass is launched for a capacity)
+    const uint32_t slot = blockIdx.x * kTQThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool active = slot < nq;
+    const uint32_t q = active ? (a.qlist ? a.qlist[slot] : slot) : 0u;
+    ThreadSel acc;
+    acc.kk = t.kk;
+    bool searchable = false, skip = false;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    uint32_t out = q;
+    int f = 0;
+    if (active) {
+        if (MODE == 0) {
+            px = __ldg(&t.qx[q]);
+            py = __ldg(&t.qy[q]);
+            pz = __ldg(&t.qz[q]);
+            searchable = finite3(px, py, pz);  // kdtree.rs:65
+        } else {
+            const float4 p = __ldg(&a.qpts[q]);
+            px = p.x; py = p.y; pz = p.z;
+            out = __float_as_uint(p.w);
+            f = frame_of_sorted(a.grids, a.n_frames, q);
+            searchable = px == px;  // a tombstoned point (index_apply_mask_dev) is not a query either
+            skip = !searchable;
+        }
+    }
+    const int outcome = ws_grid_search(acc, searchable, a.grids + f, a.cell_start, a.pts, px, py, pz, a.max_rings, a.last_level != 0, a.first_only);
+    push_list(outcome == kSelDefer, a.defer_list, a.defer_count, q, lane);
+    if (a.cont_list) push_list(outcome == kSelContinue, a.cont_list, a.cont_count, q, lane);
+    if (!active || outcome != kSelDone || skip) return;
+    const int cnt = acc.count();
+    // (the list is read through acc.ord[j], j a literal: the ranking stays in registers)
+    if (MODE == 0) {
+        uint32_t *ri = t.idx + (size_t)q * t.kk;
+        float *rd = t.dist ? t.dist + (size_t)q * t.kk : nullptr;
+#pragma unroll
+        for (int j = 0; j < kSelMaxK; j++)
+            if (j < t.kk) {
+                const bool v = j < cnt;
+                const unsigned long long key = v ? acc.key_at(acc.ord[j]) : 0ull;
+                ri[j] = v ? key_idx(key) : 0xffffffffu;
+                if (rd) rd[j] = v ? __fsqrt_rn(key_d2(key)) : INFINITY;  // kdtree.rs:76
+            }
+        if (t.counts) t.counts[q] = (uint32_t)cnt;
+    } else if (MODE == 1 || MODE == 3) {
+        // statistical_outlier.rs:28-37: drop the first (self) if there is more than one result, sequential f32 sum in
+        // ascending-distance order, divide by the count.  MODE 3 searched kk >= kk_sor neighbours (the top-kk list
+        // starts with the top-kk_sor list) and keeps the whole list for normals_from_lists_kernel.
+        const int cs = MODE == 3 ? (cnt < t.kk_sor ? cnt : t.kk_sor) : cnt;
+        const int first = cs > 1 ? 1 : 0;
+        float sum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kSelMaxK; j++) {
+            const bool v = j < cnt;
+            const unsigned long long key = v ? acc.key_at(acc.ord[j]) : 0ull;
+            if (j >= first && j < cs) sum = __fadd_rn(sum, __fsqrt_rn(key_d2(key)));
+            if (MODE == 3 && j < t.kk) t.lists[(size_t)j * t.list_stride + q] = v ? key_idx(key) : 0xffffffffu;
+        }
+        const int m = cs - first;
+        t.mean_d[out] = m > 0 ? __fdiv_rn(sum, (float)m) : INFINITY;
+        if (MODE == 3) t.list_cnt[q] = (uint8_t)cnt;
+    } else {
+        // estimate.rs:47-109 (normal_from_neighbours with the list read through the ranking)
+        float ox = 0.f, oy = 0.f, oz = 1.f;
+        if (cnt >= 1) {
+            const float count = (float)cnt;
+            float cx = 0.f, cy = 0.f, cz = 0.f;
+#pragma unroll
+            for (int j = 0; j < kSelMaxK; j++)
+                if (j < cnt) {
+                    const float4 p = __ldg(&t.orig4[key_idx(acc.key_at(acc.ord[j]))]);
+                    cx = __fadd_rn(cx, p.x);
+                    cy = __fadd_rn(cy, p.y);
+                    cz = __fadd_rn(cz, p.z);
+                }
+            cx = __fdiv_rn(cx, count);
+            cy = __fdiv_rn(cy, count);
+            cz = __fdiv_rn(cz, count);
+            float c00 = 0.f, c01 = 0.f, c02 = 0.f, c11 = 0.f, c12 = 0.f, c22 = 0.f;
+#pragma unroll
+            for (int j = 0; j < kSelMaxK; j++)
+                if (j < cnt) {
+                    const float4 p = __ldg(&t.orig4[key_idx(acc.key_at(acc.ord[j]))]);  // second pass: L1 hits
+                    const float dx = __fsub_rn(p.x, cx), dy = __fsub_rn(p.y, cy), dz = __fsub_rn(p.z, cz);
+                    c00 = __fadd_rn(c00, __fmul_rn(dx, dx));
+                    c01 = __fadd_rn(c01, __fmul_rn(dx, dy));
+                    c02 = __fadd_rn(c02, __fmul_rn(dx, dz));
+                    c11 = __fadd_rn(c11, __fmul_rn(dy, dy));
+                    c12 = __fadd_rn(c12, __fmul_rn(dy, dz));
+                    c22 = __fadd_rn(c22, __fmul_rn(dz, dz));
+                }
+            float ex, ey, ez;
+            smallest_eigenvector_3x3(c00, c01, c02, c11, c12, c22, ex, ey, ez);
+            const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
+            if (len > 1e-10f) {
+                ex = __fdiv_rn(ex, len);
+                ey = __fdiv_rn(ey, len);
+                ez = __fdiv_rn(ez, len);
+            }
+            const float vx = __fsub_rn(t.vx, px), vy = __fsub_rn(t.vy, py), vz = __fsub_rn(t.vz, pz);
+            const float dot = __fadd_rn(__fadd_rn(__fmul_rn(ex, vx), __fmul_rn(ey, vy)), __fmul_rn(ez, vz));
+            if (dot < 0.0f) {
+                ex = -ex; ey = -ey; ez = -ez;
+            }
+            ox = ex; oy = ey; oz = ez;
+        }
+        t.nx[out] = ox;
+        t.ny[out] = oy;
+        t.nz[out] = oz;
+    }
+}
+
+enum KnnImpl { kImplInsert = 0, kImplSelect = 1 };
+inline int knn_impl() {  // A/B hook: PCR_KNN_IMPL=insert restores the round-1 insertion kernels
+    static const int impl = [] {
+        const char *e = getenv("PCR_KNN_IMPL");
+        return e && !strcmp(e, "insert") ? kImplInsert : kImplSelect;
+    }();
+    return impl;
+}
+inline bool use_select(int kk) { return kk <= kSelMaxK && knn_impl() == kImplSelect; }
+// shells the thread-per-query pass walks before it hands a query to the follow-up pass (tuning hook PCR_FIRST_SHELLS)
+inline int first_shells() {
+    static const int n = [] {
+        const char *e = getenv("PCR_FIRST_SHELLS");
+        const int v = e ? atoi(e) : 2;
+        return v < 1 ? 1 : (v > kLevelRings ? kLevelRings : v);
+    }();
+    return n;
+}
+
+template <int MODE>
+int launch_sel_kernel(Ctx *ctx, const LevelArgs &a, const ThreadArgs &t) {
+    const unsigned blocks = (a.nq + kTQThreads - 1) / kTQThreads;
+    knn_sel_kernel<MODE><<<blocks, kTQThreads, 0, ctx->stream>>>(a, t);
+    PCR_LAUNCH_CHECK(ctx);
+    return PCR_OK;
 }
 
 // value for points that are not in the index: non-finite points have no neighbours -> (0,0,1)
@@ -670,21 +847,27 @@ int set_smem(Ctx *ctx, Kern kern, size_t bytes) {
 // count costs one small D2H + sync per level that is actually needed (clouds without far outliers
 // finish on level 0 and pay exactly one).
 template <class Launch>
-int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *init_list = nullptr, const uint32_t *nq_dev = nullptr) {
+int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *init_list = nullptr, const uint32_t *nq_dev = nullptr,
+               int sel_kk = 0 /* > 0: level 0 is a thread-per-query launch for this many neighbours */) {
     // init_list: level 0 runs over these nq query ids only (warp kernels) instead of over all queries
     // nq_dev:    the length of init_list is still on the device; nq is the capacity level 0 is launched for
     Ctx *ctx = ix->ctx;
     if (nq == 0) return PCR_OK;
-    PCR_TRY(ensure(ctx, ctx->b_list, (size_t)nq * 2 * sizeof(uint32_t) + 256));
-    uint32_t *counters = (uint32_t *)ctx->b_list.p;  // [2]
+    // the selection kernels walk only the 27 cells in their first pass and queue what needs more shells for a second
+    // launch over that list (counters[2], cont); the launch is sized for the worst case and reads the count itself
+    const bool two_pass = !init_list && sel_kk > 0 && use_select(sel_kk);
+    PCR_TRY(ensure(ctx, ctx->b_list, (size_t)nq * (two_pass ? 3 : 2) * sizeof(uint32_t) + 256));
+    uint32_t *counters = (uint32_t *)ctx->b_list.p;  // [0], [1]: deferred counts of even / odd levels, [2]: follow-up count
     uint32_t *lists[2] = {counters + 64, counters + 64 + nq};
+    uint32_t *cont = counters + 64 + 2 * (size_t)nq;
     Index *cur = ix;
     const uint32_t *qlist = init_list;
     uint32_t n_cur = nq;
     for (int level = 0;; level++) {
         const bool last = level == kMaxLevels - 1;
         uint32_t *cnt = counters + (level & 1);
-        PCR_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(uint32_t), ctx->stream));
+        if (level == 0) PCR_CUDA(ctx, cudaMemsetAsync(counters, 0, 3 * sizeof(uint32_t), ctx->stream));
+        else PCR_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(uint32_t), ctx->stream));
         LevelArgs a;
         a.grids = cur->grids;
         a.n_frames = cur->n_frames;
@@ -698,13 +881,33 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
         a.defer_count = cnt;
         a.max_rings = last ? kMaxRings : kLevelRings;
         a.last_level = last ? 1 : 0;
+        const bool first_of_two = two_pass && level == 0;
+        a.follow_up = 0;
+        a.first_only = first_of_two ? first_shells() : 0;
+        a.cont_list = first_of_two ? cont : nullptr;
+        a.cont_count = first_of_two ? counters + 2 : nullptr;
         {
             TimeScope ts(ctx, level == 0 ? tag0 : kTagKnnDeferred);
             PCR_TRY(launch(a, level == 0 && !init_list ? kQPW0 : kQPWL));
         }
+        if (first_of_two) {
+            // the queries that need more than their 27 cells: warp per query over the shells of the same level (they
+            // are few and far apart in the list: a thread-per-query launch would leave most of the GPU idle)
+            LevelArgs b = a;
+            b.first_only = 0;
+            b.cont_list = nullptr;
+            b.cont_count = nullptr;
+            b.qlist = cont;
+            b.nq_dev = counters + 2;
+            b.follow_up = 1;
+            TimeScope ts(ctx, kTagKnnDeferred);
+            PCR_TRY(launch(b, kQPWL));
+        }
         if (last) break;
         uint32_t *mail = (uint32_t *)ctx->pinned + 32;
         PCR_CUDA(ctx, cudaMemcpyAsync(mail, cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        static const bool dbg = getenv("PCR_DEBUG") != nullptr;
+        if (dbg && first_of_two) PCR_CUDA(ctx, cudaMemcpyAsync(mail + 1, counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         for (const auto &pg : ctx->piggy)  // small results other steps want from the same round trip
             PCR_CUDA(ctx, cudaMemcpyAsync(pg.dst, pg.src, pg.bytes, cudaMemcpyDeviceToHost, ctx->stream));
         ctx->piggy.clear();
@@ -727,7 +930,8 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
         PCR_MARK("levels: got deferred count");
         n_cur = *mail;
         if (level == 0 && !init_list) ctx->spec_coarser = n_cur > 0;
-        if (getenv("PCR_DEBUG")) fprintf(stderr, "[pcr] level %d: %u of %u queries deferred (cell %.4g)\n", level, n_cur, a.nq, cur->grids_h[0].h);
+        if (dbg) fprintf(stderr, "[pcr] level %d: %u of %u queries deferred (cell %.4g)\n", level, n_cur, a.nq, cur->grids_h[0].h);
+        if (dbg && first_of_two) fprintf(stderr, "[pcr] level 0: %u of %u queries needed more than their 27 cells\n", mail[1], a.nq);
         if (n_cur == 0) break;
         Index *next = nullptr;
         {
@@ -741,6 +945,11 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
 }
 
 inline unsigned blocks_for(uint32_t nq, int qpw) { return (nq + kWarps * qpw - 1) / (kWarps * qpw); }
+// a launch whose real length is still on the device (a.nq is its capacity) strides over the list with a bounded grid
+inline unsigned blocks_for(Ctx *ctx, const LevelArgs &a, int qpw) {
+    const unsigned b = blocks_for(a.nq, qpw);
+    return a.nq_dev ? std::min<unsigned>(b, (unsigned)ctx->sm_count * 16u) : b;
+}
 
 }  // namespace
 
@@ -760,7 +969,7 @@ int knn_queries_dev(Index *ix, const float *dqx, const float *dqy, const float *
     ta.kk = kk;
     return run_levels(ix, (uint32_t)nq, kTagKnn, [&](const LevelArgs &a, int qpw) -> int {
         if (qpw == kQPW0 && k <= 32) return launch_thread_kernel<0>(ctx, a, ta);
-        unsigned blocks = blocks_for(a.nq, qpw);
+        unsigned blocks = blocks_for(ctx, a, qpw);
         size_t smem = k <= 32 ? 0 : sizeof(unsigned long long) * k * kWarps;
         if (k <= 32) {
             if (qpw == kQPW0) knn_queries_kernel<false, kQPW0><<<blocks, kThreads, 0, ctx->stream>>>(a, dqx, dqy, dqz, kk, d_idx, d_dist, d_counts);
@@ -771,7 +980,7 @@ int knn_queries_dev(Index *ix, const float *dqx, const float *dqy, const float *
         }
         PCR_LAUNCH_CHECK(ctx);
         return PCR_OK;
-    });
+    }, nullptr, nullptr, k <= 32 ? kk : 0);
 }
 
 int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep_lists) {
@@ -803,17 +1012,20 @@ int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep
     return run_levels(ix, (uint32_t)ix->n_indexed, kTagKnn, [&](const LevelArgs &a, int qpw) -> int {
         if (qpw == kQPW0 && keep_lists) return launch_thread_kernel<3>(ctx, a, ta);
         if (qpw == kQPW0 && kk <= 32) return launch_thread_kernel<1>(ctx, a, ta);
-        unsigned blocks = blocks_for(a.nq, qpw);
-        if (kk <= 32) {
-            if (qpw == kQPW0) sor_mean_kernel<false, kQPW0><<<blocks, kThreads, smem, ctx->stream>>>(a, (int)kk, d_mean_d);
-            else sor_mean_kernel<false, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, (int)kk, d_mean_d);
+        unsigned blocks = blocks_for(ctx, a, qpw);
+        if (a.follow_up && keep_lists) {  // the first pass's leftovers on the same level: K neighbours, lists kept
+            const size_t smem_k = ((size_t)ta.kk * 33 + 64) * sizeof(float) * kWarps;
+            sor_mean_kernel<false, kQPWL><<<blocks, kThreads, smem_k, ctx->stream>>>(a, ta.kk, d_mean_d, ta.lists, ta.list_cnt, ta.list_stride, ta.kk_sor);
+        } else if (kk <= 32) {
+            if (qpw == kQPW0) sor_mean_kernel<false, kQPW0><<<blocks, kThreads, smem, ctx->stream>>>(a, (int)kk, d_mean_d, nullptr, nullptr, 0, (int)kk);
+            else sor_mean_kernel<false, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, (int)kk, d_mean_d, nullptr, nullptr, 0, (int)kk);
         } else {
-            if (qpw == kQPW0) sor_mean_kernel<true, kQPW0><<<blocks, kThreads, smem, ctx->stream>>>(a, (int)kk, d_mean_d);
-            else sor_mean_kernel<true, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, (int)kk, d_mean_d);
+            if (qpw == kQPW0) sor_mean_kernel<true, kQPW0><<<blocks, kThreads, smem, ctx->stream>>>(a, (int)kk, d_mean_d, nullptr, nullptr, 0, (int)kk);
+            else sor_mean_kernel<true, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, (int)kk, d_mean_d, nullptr, nullptr, 0, (int)kk);
         }
         PCR_LAUNCH_CHECK(ctx);
         return PCR_OK;
-    });
+    }, nullptr, nullptr, keep_lists ? ta.kk : (kk <= 32 ? (int)kk : 0));
 }
 
 int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny, float *d_nz, const uint8_t *d_mask) {
@@ -842,7 +1054,7 @@ int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny
     ta.kk = (int)k;
     return run_levels(ix, (uint32_t)ix->n_indexed, kTagKnnNormals, [&](const LevelArgs &a, int qpw) -> int {
         if (qpw == kQPW0 && k <= 32) return launch_thread_kernel<2>(ctx, a, ta);
-        unsigned blocks = blocks_for(a.nq, qpw);
+        unsigned blocks = blocks_for(ctx, a, qpw);
         if (k <= 32) {
             if (qpw == kQPW0) normals_kernel<false, kQPW0><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);
             else normals_kernel<false, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);
@@ -852,7 +1064,7 @@ int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny
         }
         PCR_LAUNCH_CHECK(ctx);
         return PCR_OK;
-    });
+    }, nullptr, nullptr, k <= 32 ? (int)k : 0);
 }
 
 // ---- normals of the kept points from the SOR pass's neighbour lists -------------------------------
@@ -973,7 +1185,7 @@ int normals_from_lists_dev(Index *ix, size_t k, const float vp[3], const SorList
     else PCR_TRY(set_smem(ctx, normals_kernel<true, kQPWL>, smem));
     const float v0 = vp[0], v1 = vp[1], v2 = vp[2];
     auto launch = [&](const LevelArgs &a, int qpw) -> int {
-        const unsigned blocks = blocks_for(a.nq, qpw);
+        const unsigned blocks = blocks_for(ctx, a, qpw);
         if (k <= 32) normals_kernel<false, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);
         else normals_kernel<true, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);
         PCR_LAUNCH_CHECK(ctx);

@@ -19,6 +19,7 @@
 // depend on the scan order.
 #pragma once
 #include "pcr_internal.cuh"
+#include "sortnet32.cuh"
 
 namespace pcr {
 
@@ -630,6 +631,394 @@ __device__ __forceinline__ bool thread_ball_search(Acc &acc, const GridDesc &g, 
         }
     }
     return true;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Selection instead of insertion (round 2).  ncu on the insertion kernels: half of all warp
+// instructions were ThreadTopK::offer's unrolled shift network, executed at 14 of 32 lanes -- whenever ONE
+// lane accepts a candidate the whole warp pays ~150 instructions, and with ~60 acceptances per query
+// spread over ~150 candidates that is almost every step.  Here a candidate that passes the threshold is
+// only WRITTEN into a free slot of the thread's column of a shared-memory buffer (32 slots, one STS.64), and
+// the warp tightens the threshold together when any of its lanes runs out of slots:
+//   sort      the 32 slots are ranked by a register sorting network (Batcher, 191 exchanges) over ONE u32 per
+//             slot: the upper 27 bits of the d^2 bit pattern with the slot number in the low 5 bits, so an
+//             exchange is a umin/umax pair and no key ever moves in shared memory;
+//   compact   the kk-th ranked slot gives the new threshold tau (rounded up to the end of its 27-bit bucket);
+//             slots ranked behind that bucket are marked free again;
+//   finalize  (end of a shell) the ranking is EXACT unless two neighbours among the first kk+1 ranks share a
+//             27-bit bucket (d^2 equal to 4e-6 relative: ties, lattices, duplicates); then the warp orders its
+//             buffers by the full (d^2, index) keys with a plain insertion sort in shared memory (rare, small code).
+// All of it runs with the 32 lanes in lock step (the walk is warp-synchronous: row loops run to the warp's
+// longest run, lanes without work are predicated off), so no lane idles while another sorts.
+// Acceptance is `d2 <= tau` (one FSETP; ties are kept) and, once an exact list is known, `key < tau_key`.  A
+// candidate that fails either can neither enter the final list nor tie with its last entry, so the result is
+// the list ThreadTopK builds.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelCap = 32;      // slots per thread (the sorting network's width)
+constexpr int kSelStride = 128;  // threads per block
+constexpr int kSelMaxK = 21;     // kk <= kSelCap - 11: at least two groups of candidates fit between compactions
+constexpr uint32_t kSelPad = 0xffffffe0u;  // rank key of an empty slot (| slot): behind every real d^2 (bits <= 0x7f800000)
+constexpr int kSelBins = 2 * kSelCap;      // the threshold histogram lives in the (still empty) slots: 64 u32 counters
+constexpr uint32_t kSelHistMaxN = 384;     // more candidates than this in the 27 cells: a dense object, see ws_grid_search
+
+// 32 u64 slots per thread, laid out [warp][slot][lane] (file scope: every access below is a plain LDS / STS): a warp's
+// slots are one contiguous 8 KB block that no other warp touches (the warps of a block are not in step with each
+// other), and slot j of a warp's 32 lanes is one conflict-free 256 B row.
+__shared__ unsigned long long g_sel_buf[kSelCap * kSelStride];
+
+__device__ __forceinline__ unsigned long long &sel_slot(int j) {
+    return g_sel_buf[(threadIdx.x & ~31u) * kSelCap + j * 32 + (threadIdx.x & 31u)];
+}
+__device__ __forceinline__ uint32_t sel_slot_hi(int j) {
+    return reinterpret_cast<const uint32_t *>(g_sel_buf)[((threadIdx.x & ~31u) * kSelCap + j * 32 + (threadIdx.x & 31u)) * 2 + 1];
+}
+// The same block as 64 u32 counters per lane (the threshold histogram), [counter][lane]: conflict-free, one IMAD per address.
+__device__ __forceinline__ uint32_t &sel_word(int w) {
+    return reinterpret_cast<uint32_t *>(g_sel_buf)[(threadIdx.x & ~31u) * kSelCap * 2 + w * 32 + (threadIdx.x & 31u)];
+}
+
+// Exact order for the rare warp whose ranking has a bucket collision: occupied slots are moved to the front and
+// insertion-sorted by the full key; the kk smallest stay.  Returns the new free mask (slots >= min(cnt, kk)).
+static __device__ __noinline__ uint32_t sel_exact_slow(uint32_t free_mask, int kk) {
+    int n = 0;
+    for (int j = 0; j < kSelCap; j++)
+        if (!((free_mask >> j) & 1u)) {
+            const unsigned long long v = sel_slot(j);
+            int i = n++;
+            for (; i > 0 && sel_slot(i - 1) > v; i--) sel_slot(i) = sel_slot(i - 1);  // (i - 1 < j: already moved)
+            sel_slot(i) = v;
+        }
+    const int m = n < kk ? n : kk;
+    return m >= 32 ? 0u : ~((1u << m) - 1u);
+}
+
+struct ThreadSel {
+    unsigned long long tau_key;  // exact kk-th best key once a finalize has seen kk entries, else EMPTY
+    float tau;                   // accept d2 <= tau
+    uint32_t free_mask;          // bit j set: slot j is empty
+    int kk;
+    int m;                       // entries of the final list (valid after finalize)
+    uint32_t ord[kSelCap];       // after finalize(): ord[j] & 31 = slot of the j-th best (static indexing only: registers)
+
+    __device__ __forceinline__ void reset() {
+        free_mask = 0xffffffffu;
+        tau = INFINITY;
+        tau_key = PCR_EMPTY_KEY;
+        m = 0;
+    }
+    __device__ __forceinline__ void offer(float d2, uint32_t idx) {
+        if (d2 <= tau) {  // false for NaN (tombstoned points)
+            const unsigned long long key = make_key(d2, idx);
+            if (key < tau_key) {
+                const int slot = __ffs(free_mask) - 1;
+                free_mask &= free_mask - 1u;
+                sel_slot(slot) = key;
+            }
+        }
+    }
+    // one rank key per slot, sorted
+    __device__ __forceinline__ void rank_slots(uint32_t (&k)[kSelCap]) const {
+#pragma unroll
+        for (int j = 0; j < kSelCap; j++) k[j] = ((free_mask >> j) & 1u) ? (kSelPad | j) : ((sel_slot_hi(j) & ~31u) | j);
+#define PCR_CE32(i, j)                     \
+    {                                      \
+        const uint32_t x = k[i], y = k[j]; \
+        k[i] = min(x, y);                  \
+        k[j] = max(x, y);                  \
+    }
+        PCR_SORTNET32(PCR_CE32)
+#undef PCR_CE32
+    }
+    // warp-synchronous: call with all 32 lanes, after at most 4 offers
+    __device__ __forceinline__ void make_room() {
+        if (!__any_sync(PCR_FULL, __popc(free_mask) < 4)) return;
+        uint32_t k[kSelCap];
+        rank_slots(k);
+        const int cnt = kSelCap - __popc(free_mask);
+        if (cnt >= kk) {  // fewer than kk: nothing can be dropped yet
+            uint32_t kb = k[0];
+#pragma unroll
+            for (int j = 1; j < kSelCap; j++) kb = (j == kk - 1) ? k[j] : kb;
+            const uint32_t tb = kb | 31u;  // end of the kk-th best's bucket: every slot ranked behind it is farther
+            tau = fminf(tau, __uint_as_float(min(tb, 0x7f800000u)));  // (the bucket of +inf ends in NaN patterns)
+#pragma unroll
+            for (int j = 1; j < kSelCap; j++)
+                if (j >= kk && k[j] > tb && k[j] < kSelPad) free_mask |= 1u << (k[j] & 31u);
+        }
+        // a bucket that holds more than 11 candidates (ties, duplicates) keeps a buffer full: the exact list has kk entries
+        if (__any_sync(PCR_FULL, __popc(free_mask) < 4)) {
+            free_mask = sel_exact_slow(free_mask, kk);
+            if (kSelCap - __popc(free_mask) == kk) {
+                tau_key = sel_slot(kk - 1);
+                tau = key_d2(tau_key);
+            }
+        }
+    }
+    // warp-synchronous: the exact list (end of a shell)
+    __device__ __forceinline__ void finalize() {
+        rank_slots(ord);
+        int cnt = kSelCap - __popc(free_mask);
+        m = cnt < kk ? cnt : kk;
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j + 1 < kSelCap; j++)
+            if (j < m && j + 1 < cnt && ((ord[j] ^ ord[j + 1]) < 32u)) bad = true;  // two neighbours of the ranking in one bucket
+        if (__any_sync(PCR_FULL, bad)) {
+            free_mask = sel_exact_slow(free_mask, kk);  // slots 0 .. m-1 now hold the list in order
+#pragma unroll
+            for (int j = 0; j < kSelCap; j++) ord[j] = j < m ? ((sel_slot_hi(j) & ~31u) | j) : (kSelPad | j);
+        } else {
+#pragma unroll
+            for (int j = 1; j < kSelCap; j++)
+                if (j >= m && ord[j] < kSelPad) free_mask |= 1u << (ord[j] & 31u);
+        }
+        if (m == kk) {
+            tau_key = kth();
+            tau = key_d2(tau_key);
+        }
+    }
+    // valid after finalize()
+    __device__ __forceinline__ int count() const { return m; }
+    __device__ __forceinline__ unsigned long long key_at(uint32_t o) const { return sel_slot((int)(o & 31u)); }
+    __device__ __forceinline__ unsigned long long kth() const {
+        if (m != kk) return PCR_EMPTY_KEY;
+        uint32_t o = ord[0];
+#pragma unroll
+        for (int j = 1; j < kSelCap; j++) o = (j == kk - 1) ? ord[j] : o;
+        return key_at(o);
+    }
+
+    // ---- threshold from a histogram (before anything is buffered: the slots serve as 64 counters) ----
+    __device__ __forceinline__ void hist_clear() {
+#pragma unroll
+        for (int w = 0; w < kSelBins; w++) sel_word(w) = 0u;
+    }
+    __device__ __forceinline__ void hist_add(float d2, float scale) {
+        // fminf returns its non-NaN operand: a tombstoned point (d2 = NaN) lands in the last bin, which never counts
+        const int bin = __float2int_rz(fminf(__fmul_rn(d2, scale), (float)(kSelBins - 1)));
+        atomicAdd(&sel_word(bin), 1u);  // this thread's own counter: the atomic only spares the read-modify-write chain
+    }
+    // smallest bin edge with at least kk candidates below it -> tau (+inf if the kk-th falls into the last, open bin)
+    __device__ __forceinline__ void hist_threshold(float bin_width) {
+        uint32_t cum = 0;
+        int bstar = kSelBins - 1;
+#pragma unroll
+        for (int w = 0; w < kSelBins - 1; w++) {
+            cum += sel_word(w);
+            bstar = min(bstar, cum >= (uint32_t)kk ? w : kSelBins - 1);
+        }
+        // bin(d2) <= bstar  =>  d2 * scale < bstar + 1 (rounded product)  =>  d2 < (bstar + 1) * width * (1 + 1e-5)
+        tau = bstar >= kSelBins - 1 ? INFINITY : (float)(bstar + 1) * bin_width * (1.0f + 1e-5f);
+    }
+};
+
+// One run per lane against that lane's query, all 32 lanes in lock step: the loop runs to the warp's longest
+// run, four candidates per step.  kHist: the candidates only feed the threshold histogram.
+template <bool kHist>
+__device__ __forceinline__ void ws_scan_run(ThreadSel &acc, const float4 *__restrict__ pts, uint32_t b, uint32_t e, float qx, float qy,
+                                            float qz, float scale) {
+    const uint32_t n = e - b;
+    const uint32_t nmax = __reduce_max_sync(PCR_FULL, n);
+    for (uint32_t i = 0; i < nmax; i += 4) {
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            p[u].x = __int_as_float(0x7fc00000);  // a lane past the end of its run sees a NaN point: it fails every test below
+            if (i + u < n) p[u] = __ldg(&pts[b + i + u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const float d2 = dist2_exact(qx, qy, qz, p[u].x, p[u].y, p[u].z);
+            if (kHist) acc.hist_add(d2, scale);
+            else acc.offer(d2, __float_as_uint(p[u].w));
+        }
+        if (!kHist) acc.make_room();
+    }
+}
+
+enum SelOutcome { kSelDone = 0, kSelDefer = 1, kSelContinue = 2 };
+
+// thread_grid_search / thread_grid_search_pruned as a warp-synchronous program (same rows, same ring rule, same
+// deferral rule, same pruning bound -- see the comments there).  Call with all 32 lanes of a warp; `live` = this
+// lane has a query.  first_shells > 0: stop after that many shells; a lane whose list the ring rule cannot confirm
+// by then returns kSelContinue and the caller queues it for the follow-up pass (few lanes need more, and a warp
+// that walks another shell for one of them idles the other 31).
+__device__ __forceinline__ int ws_grid_search(ThreadSel &acc, bool live, const GridDesc *__restrict__ gp, const uint32_t *__restrict__ cell_start,
+                                              const float4 *__restrict__ pts, float qx, float qy, float qz, int max_rings, bool last_level,
+                                              int first_shells) {
+    // (the descriptor stays in memory: the walk keeps only the cell coordinates, the f32 fractions and the table
+    // shape in registers, and the shell-end test reloads what it needs -- the sorting network wants the registers)
+    acc.reset();
+    const int kk = acc.kk;
+    const uint32_t pt_begin = gp->pt_begin, pt_end = gp->pt_end;
+    const uint32_t m = live ? pt_end - pt_begin : 0u;
+    bool done = m == 0;
+    int outcome = kSelDone;
+    bool whole = !done && (m <= kBruteFrame || m <= (uint32_t)kk);  // tiny frame: one run = everything
+    int c0 = 0, c1 = 0, c2 = 0;
+    float ff0 = 0.f, ff1 = 0.f, ff2 = 0.f;
+    if (!done && !whole) {
+        const GridDesc g = *gp;
+        double f0, f1, f2;
+        c0 = cell_coord(g, 0, pick_axis(g.ax[0], qx, qy, qz), &f0);
+        c1 = cell_coord(g, 1, pick_axis(g.ax[1], qx, qy, qz), &f1);
+        c2 = cell_coord(g, 2, pick_axis(g.ax[2], qx, qy, qz), &f2);
+        ff0 = (float)f0;
+        ff1 = (float)f1;
+        ff2 = (float)f2;
+    }
+    const int d0n = gp->dims[0], d1n = gp->dims[1], d2n = gp->dims[2];
+    const uint32_t cell_base = gp->cell_base;
+    const float inv_h2 = (float)(gp->inv_h * gp->inv_h);
+
+    // this lane's run of row (e0, e1) of shell S (slot: the two end cells of an interior row), trimmed to the cells
+    // within the current threshold (bound and slack of scan_row_pruned; tau = +inf trims nothing)
+    auto row_run = [&](int S, int e0, int e1, bool border, int slot, uint32_t &b, uint32_t &e) {
+        b = 0;
+        e = 0;
+        const int a0 = c0 + e0, a1 = c1 + e1;
+        if (a0 < 0 || a0 >= d0n || a1 < 0 || a1 >= d1n) return;
+        int z0, z1;
+        if (border) {
+            z0 = max(c2 - S, 0);
+            z1 = min(c2 + S, d2n - 1);
+        } else {
+            z0 = z1 = slot == 0 ? c2 - S : (slot == 1 ? c2 + S : c2);  // (slot 2: the row's middle cell)
+            if (z0 < 0 || z0 >= d2n) return;
+        }
+        const float g0 = axis_gap(e0, ff0), g1 = axis_gap(e1, ff1);
+        const float tau_c = acc.tau * inv_h2 * (1.0f + 1e-5f) + 1e-8f;
+        if (!trim_row(tau_c, g0 * g0 + g1 * g1, c2, ff2, z0, z1)) return;
+        const uint32_t lin = cell_base + ((uint32_t)a0 * (uint32_t)d1n + (uint32_t)a1) * (uint32_t)d2n + (uint32_t)z0;
+        b = __ldg(&cell_start[lin]);
+        e = __ldg(&cell_start[lin + (uint32_t)(z1 - z0) + 1u]);
+    };
+    // row order of the 3x3x3 cube: the query's own row first, then its four face neighbours
+    auto cube_row = [](int r, int &e0, int &e1) {
+        e0 = r / 3;
+        e1 = r - e0 * 3;
+        e0 = e0 == 0 ? 0 : (e0 == 1 ? -1 : 1);
+        e1 = e1 == 0 ? 0 : (e1 == 1 ? -1 : 1);
+    };
+
+    // ---- threshold for the 27 cells from a histogram of the d^2 ------------------------------------------------
+    // Without it the first 32 candidates all enter the buffer and the threshold only tightens compaction by
+    // compaction (ncu: 4-7 per warp, half of the kernel's instructions; 15 and more for a query inside a dense
+    // object, whose warp then runs five times longer than the others and IS the kernel's duration).  One extra pass
+    // that only counts candidates into 64 linear d^2 bins gives a threshold with kk (+ the rest of one bin)
+    // candidates below it, so the collecting pass buffers ~kk keys and rarely compacts.
+    //   * up to kSelHistMaxN candidates in the 27 cells (surfaces): all 9 rows are counted; the bins span four times
+    //     the kk-th d^2 of a uniform sheet with that many points on the 3 x 3 cells;
+    //   * more (a volume: the 27 cells hold 20 x the candidates the list needs): only the query's cell and its six
+    //     face neighbours are counted -- the kk-th best of those 7 cells bounds the kk-th best of all, and with it the
+    //     collecting pass trims the edge and corner cells it would otherwise read; the bins span three times the
+    //     kk-th d^2 of a uniform volume with that many points in 7 cells.
+    // A kk-th beyond the last bin leaves tau = +inf, more than 11 candidates in its bin just mean compactions as
+    // before: the histogram only speeds things up, the result does not depend on it.
+    {
+        uint32_t n27 = 0, n7 = 0;
+        const bool walk = !done && !whole;
+        for (int r = 0; r < 9; r++) {
+            int e0, e1;
+            cube_row(r, e0, e1);
+            uint32_t b = 0, e = 0;
+            if (walk) row_run(1, e0, e1, true, 0, b, e);
+            n27 += e - b;
+            if (e0 == 0 || e1 == 0) {  // own row: all three cells; a face row: its middle cell
+                if (e0 != 0 || e1 != 0) {
+                    b = e = 0;
+                    if (walk) row_run(1, e0, e1, false, 2, b, e);
+                }
+                n7 += e - b;
+            }
+        }
+        const bool volume = n27 > kSelHistMaxN;
+        const uint32_t nh = volume ? n7 : n27;
+        const bool hist = walk && nh > (uint32_t)kSelCap - 4u;
+        if (__any_sync(PCR_FULL, hist)) {
+            const float h2 = 1.0f / inv_h2;
+            // sheet: n points on 9 h^2 -> r^2 = 9 h^2 kk / (pi n);  volume: n points in 7 h^3 -> r^2 = h^2 (21 kk / (4 pi n))^(2/3)
+            const float q = (float)kk / (float)(nh ? nh : 1u);
+            const float r2 = volume ? h2 * cbrtf(1.6711f * q) * cbrtf(1.6711f * q) : 2.8648f * h2 * q;
+            const float width = hist ? (volume ? 3.0f : 4.0f) * r2 / (float)kSelBins : 1.0f;
+            const float scale = 1.0f / width;
+            acc.hist_clear();
+#pragma unroll 1
+            for (int r = 0; r < 9; r++) {
+                int e0, e1;
+                cube_row(r, e0, e1);
+                uint32_t b = 0, e = 0;
+                if (hist && !(volume && e0 != 0 && e1 != 0)) row_run(1, e0, e1, !(volume && (e0 != 0 || e1 != 0)), 2, b, e);
+                ws_scan_run<true>(acc, pts, b, e, qx, qy, qz, scale);
+            }
+            if (hist) acc.hist_threshold(width);
+        }
+    }
+
+    for (int S = 1;; S++) {
+        const int side = 2 * S + 1, T = side * side;
+#pragma unroll 1
+        for (int r = 0; r < T; r++) {
+            int e0, e1;
+            if (S == 1) {
+                cube_row(r, e0, e1);
+            } else {
+                e0 = r / side;
+                e1 = r - e0 * side - S;
+                e0 -= S;
+            }
+            const bool border = S == 1 || e0 == S || e0 == -S || e1 == S || e1 == -S;  // warp-uniform
+            // border rows are full runs; interior rows contribute their two end cells (slot 0 / 1)
+#pragma unroll 1
+            for (int slot = 0; slot < (border ? 1 : 2); slot++) {
+                uint32_t b = 0, e = 0;
+                if (!done) {
+                    if (whole) {
+                        if (r == 0 && slot == 0) {
+                            b = pt_begin;
+                            e = pt_end;
+                        }
+                    } else {
+                        row_run(S, e0, e1, border, slot, b, e);
+                    }
+                }
+                ws_scan_run<false>(acc, pts, b, e, qx, qy, qz, 0.f);
+            }
+        }
+        acc.finalize();
+        if (!done) {
+            if (whole) {
+                done = true;
+            } else {
+                const GridDesc g = *gp;
+                double f0, f1, f2, bound2;
+                cell_coord(g, 0, pick_axis(g.ax[0], qx, qy, qz), &f0);
+                cell_coord(g, 1, pick_axis(g.ax[1], qx, qy, qz), &f1);
+                cell_coord(g, 2, pick_axis(g.ax[2], qx, qy, qz), &f2);
+                const unsigned long long kth = acc.kth();
+                if (!ring_bound2(g, c0, c1, c2, f0, f1, f2, S, bound2)) {
+                    done = true;  // the whole grid has been scanned
+                } else if (kth != PCR_EMPTY_KEY && (double)key_d2(kth) < bound2 * (1.0 - 1e-6)) {
+                    done = true;
+                } else if (!last_level) {
+                    const int cnt = acc.count();
+                    if (S >= max_rings || (S == 1 && cnt * 4 < kk) || (S >= 2 && cnt < kk)) {
+                        done = true;
+                        outcome = kSelDefer;
+                    } else if (first_shells && S >= first_shells) {
+                        done = true;
+                        outcome = kSelContinue;
+                    }
+                } else if (S >= max_rings) {
+                    acc.reset();  // coarsest level: restart with a whole-frame pass
+                    whole = true;
+                }
+            }
+        }
+        if (__all_sync(PCR_FULL, done)) break;
+    }
+    return outcome;
 }
 
 }  // namespace pcr

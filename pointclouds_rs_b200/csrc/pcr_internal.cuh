@@ -70,6 +70,7 @@ struct Ctx {
     bool owns_stream = false;
     int sm_count = 148;
     std::string err;
+    uint64_t err_seq = 0;  // stamp of `err` (pcr_last_error reports the more recent of this and the calling thread's last failure)
     uint64_t launches = 0;
     float forced_cell = 0.f;
     // cell size chosen by the last single-frame probe, reused for the next cloud of the same shape (a stream of
@@ -281,6 +282,7 @@ int comm_unique_id(void *out);
 int comm_init(Ctx *ctx, const void *id, int rank, int world);
 void comm_destroy(Ctx *ctx);
 int comm_allreduce_f64(Ctx *ctx, double *d_buf, size_t count);
+int comm_allgather_bytes(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes);
 
 // ------------------------------------------------------------------------------------------------
 // device helpers

@@ -38,8 +38,12 @@ struct VoxHeader {
     unsigned count;           // finite points written
     unsigned outside;         // a point fell outside a guessed key box
     unsigned total;           // voxels written
-    unsigned pad[7];
+    unsigned tall;            // a column holds more members than one thread should sort: the caller takes the radix path
+    unsigned pad[6];
 };
+// Members one thread sorts in place.  A coarse voxel, a wall or a dense small-footprint cloud can put 10^5..10^7 points
+// into one column; a serial sort of that in global memory would take seconds, the radix path sorts it in 4 passes.
+constexpr uint32_t kTallColumn = 256;
 static_assert(sizeof(VoxHeader) == 64, "header layout");
 
 struct VoxRange {
@@ -304,12 +308,17 @@ __global__ void __launch_bounds__(256) vox_col_scatter_kernel(const float *__res
 // the empty columns (and the slot of the total) was zeroed with the counters.
 __global__ void __launch_bounds__(256) vox_col_sort_kernel(const uint32_t *__restrict__ col_of, const uint32_t *__restrict__ rank_of,
                                                            size_t n, const uint32_t *__restrict__ start,
-                                                           unsigned long long *__restrict__ members, uint32_t *__restrict__ nvox) {
+                                                           unsigned long long *__restrict__ members, uint32_t *__restrict__ nvox,
+                                                           unsigned *__restrict__ tall) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t c = col_of[i];
     if (c == 0xffffffffu || rank_of[i] != 0u) return;
     const uint32_t b = start[c], e = start[c + 1], m = e - b;
+    if (m > kTallColumn) {  // not a job for one thread: flag it, the host redoes the cloud on the radix path
+        *tall = 1u;
+        return;
+    }
     unsigned long long *a = members + b;
     if (m <= 24) {  // insertion sort
         for (uint32_t i = 1; i < m; i++) {
@@ -362,6 +371,7 @@ __global__ void __launch_bounds__(256) vox_col_emit_kernel(const float *__restri
     const uint32_t c = col_of[t];
     if (c == 0xffffffffu || rank_of[t] != 0u) return;
     const uint32_t b = start[c], e = start[c + 1];
+    if (e - b > kTallColumn) return;  // flagged by vox_col_sort_kernel: this pass is void
     uint32_t v = vstart[c];
     uint32_t i = b;
     while (i < e) {
@@ -552,7 +562,7 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
             PCR_TRY(exclusive_scan_u32_dev(ctx, count, (size_t)n_cols + 1));
             vox_col_scatter_kernel<<<nbp, 256, 0, st>>>(dy, dz, n, voxel, h_range->mn[1], h_range->mn[2], ys, count, col_of, rank_of, members);
             PCR_LAUNCH_CHECK(ctx);
-            vox_col_sort_kernel<<<nbp, 256, 0, st>>>(col_of, rank_of, n, count, members, nvox);
+            vox_col_sort_kernel<<<nbp, 256, 0, st>>>(col_of, rank_of, n, count, members, nvox, &d_hdr->tall);
             PCR_LAUNCH_CHECK(ctx);
             PCR_TRY(exclusive_scan_u32_dev(ctx, nvox, (size_t)n_cols + 1));
             vox_col_emit_kernel<<<nbp, 256, 0, st>>>(dx, dy, dz, col_of, rank_of, n, count, nvox, members, d_ox, d_oy, d_oz);
@@ -571,8 +581,13 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
                 vc.pad_shift = std::max(2, vc.pad_shift - 1);
                 return voxel_downsample_dev(ctx, dx, dy, dz, n, voxel, d_ox, d_oy, d_oz, n_out, stats_out, false);
             }
-            *n_out = mail->total;
-            if (stats_out) {
+            const bool tall = mail->tall != 0;
+            if (tall && guessed) {  // (the guessed box is not what the radix path below wants: measure first)
+                vc.valid = false;
+                return voxel_downsample_dev(ctx, dx, dy, dz, n, voxel, d_ox, d_oy, d_oz, n_out, stats_out, false);
+            }
+            if (!tall) *n_out = mail->total;
+            if (!tall && stats_out) {
                 for (int a = 0; a < 3; a++) {
                     stats_out->mn[a] = ~mail->mn_c[a];
                     stats_out->mx[a] = mail->mx[a];
@@ -580,7 +595,8 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
                 stats_out->count = mail->count;
                 stats_out->valid = 1;
             }
-            return PCR_OK;
+            if (!tall) return PCR_OK;
+            // a tall column: fall through to the radix path (h_range is measured here: `guessed` was handled above)
         }
     }
     if (guessed) {  // the padded box does not suit the column path: measure

@@ -1,10 +1,11 @@
 """Top source lines (warp instructions executed, stall samples, active lanes) of one kernel from an ncu report.
-usage: python tools/src_hot.py report.ncu-rep kernel-regex [N]"""
+usage: python tools/src_hot.py report.ncu-rep kernel-regex [N] [launch-skip]   (launch-skip: take ONE launch, the n-th of the report)"""
 import csv, subprocess, sys, collections
 rep, kre = sys.argv[1], sys.argv[2]
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 25
 import re
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+SKIP = ["--launch-skip", sys.argv[4], "--launch-count", "1"] if len(sys.argv) > 4 else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + SKIP,
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 cur_file = None; hdr = None; func = None; take = False
