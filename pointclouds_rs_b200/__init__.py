@@ -99,6 +99,29 @@ class Context:
         """Consecutive clouds are frames of one sensor stream: reuse the probed cell size between similar frames."""
         _ffi.check(_ffi.load().pcr_ctx_set_frame_stream(self._h, 1 if enable else 0), self._h)
 
+    def knn_counters(self) -> dict:
+        """{queries, candidates}: work of the level-0 KNN kernel since the previous call (counted while timing is on)."""
+        out = (C.c_uint64 * 2)()
+        _ffi.check(_ffi.load().pcr_ctx_get_knn_counters(self._h, out), self._h)
+        return {"queries": int(out[0]), "candidates": int(out[1])}
+
+    def hint_stats(self) -> dict:
+        """How often the frame-stream hints held (pcr_ctx_get_hint_stats)."""
+        out = (C.c_uint64 * 6)()
+        _ffi.check(_ffi.load().pcr_ctx_get_hint_stats(self._h, out), self._h)
+        names = ("cell_size_reused", "cell_size_probed", "voxel_box_guess_held", "voxel_box_guess_missed", "coarser_level_ahead_needed",
+                 "coarser_level_ahead_unneeded")
+        return {k: int(v) for k, v in zip(names, out)}
+
+    def set_query_sharding(self, enable: bool = True):
+        """With a communicator (comm_init): SOR / normals / radius outlier removal of ONE cloud, given in full on every rank,
+        search only this rank's share of the queries and merge the results over NCCL."""
+        _ffi.check(_ffi.load().pcr_ctx_set_query_sharding(self._h, 1 if enable else 0), self._h)
+
+    def debug_set_shard(self, rank: int, world_size: int):
+        """Test hook (pcr_ctx_debug_set_shard): play one rank of a query-sharded call without a communicator."""
+        _ffi.check(_ffi.load().pcr_ctx_debug_set_shard(self._h, int(rank), int(world_size)), self._h)
+
     def set_cell_size(self, cell: float):
         _ffi.check(_ffi.load().pcr_ctx_set_cell_size(self._h, float(cell)), self._h)
 

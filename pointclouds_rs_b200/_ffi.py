@@ -68,6 +68,10 @@ SIGNATURES = {
     "pcr_ctx_launch_count": (C.c_uint64, [vp]),
     "pcr_ctx_set_cell_size": (C.c_int, [vp, C.c_float]),
     "pcr_ctx_set_frame_stream": (C.c_int, [vp, C.c_int]),
+    "pcr_ctx_get_hint_stats": (C.c_int, [vp, u64p]),
+    "pcr_ctx_get_knn_counters": (C.c_int, [vp, u64p]),
+    "pcr_ctx_set_query_sharding": (C.c_int, [vp, C.c_int]),
+    "pcr_ctx_debug_set_shard": (C.c_int, [vp, C.c_int, C.c_int]),
     "pcr_ctx_set_timing": (C.c_int, [vp, C.c_int]),
     "pcr_ctx_get_timing": (C.c_int, [vp, C.POINTER(C.c_double), u64p]),
     "pcr_comm_unique_id": (C.c_int, [vp]),

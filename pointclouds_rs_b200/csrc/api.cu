@@ -266,6 +266,7 @@ void pcr_ctx_destroy(pcr_ctx *ctx) {
         cudaEventDestroy(sp.b);
     }
     for (auto e : c->event_pool) cudaEventDestroy(e);
+    if (c->d_knn_stats) cudaFree(c->d_knn_stats);
     if (c->ev_count) cudaEventDestroy(c->ev_count);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->owns_stream) cudaStreamDestroy(c->stream);
@@ -284,7 +285,13 @@ uint64_t pcr_ctx_launch_count(const pcr_ctx *ctx) { return ctx ? ctx->c.launches
 
 int pcr_ctx_set_timing(pcr_ctx *ctx, int enable) {
     if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
-    ctx->c.timing = enable != 0;
+    Ctx *c = &ctx->c;
+    c->timing = enable != 0;
+    if (c->timing && !c->d_knn_stats) {  // counters of the level-0 selection kernel (pcr_ctx_get_knn_counters)
+        DevSetter ds(c);
+        PCR_CUDA(c, cudaMalloc((void **)&c->d_knn_stats, 2 * sizeof(unsigned long long)));
+        PCR_CUDA(c, cudaMemsetAsync(c->d_knn_stats, 0, 2 * sizeof(unsigned long long), c->stream));
+    }
     return PCR_OK;
 }
 
@@ -311,11 +318,51 @@ int pcr_ctx_get_timing(pcr_ctx *ctx, double *ms_per_tag, uint64_t *spans_per_tag
     return PCR_OK;
 }
 
+int pcr_ctx_get_knn_counters(pcr_ctx *ctx, uint64_t out[2]) {
+    if (!ctx || !out) return fail(ctx ? &ctx->c : nullptr, PCR_ERR_INVALID_ARG, "null pointer");
+    Ctx *c = &ctx->c;
+    out[0] = out[1] = 0;
+    if (!c->d_knn_stats) return PCR_OK;
+    DevSetter ds(c);
+    unsigned long long h[2] = {0, 0};
+    PCR_CUDA(c, cudaMemcpyAsync(h, c->d_knn_stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaMemsetAsync(c->d_knn_stats, 0, sizeof(h), c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    out[0] = h[0];
+    out[1] = h[1];
+    return PCR_OK;
+}
+
 int pcr_ctx_set_frame_stream(pcr_ctx *ctx, int enable) {
     if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
     ctx->c.frame_stream = enable != 0;
     ctx->c.cell_cache.valid = false;
     ctx->c.vox_cache.valid = false;
+    return PCR_OK;
+}
+
+int pcr_ctx_set_query_sharding(pcr_ctx *ctx, int enable) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    ctx->c.shard_queries = enable != 0;
+    return PCR_OK;
+}
+
+int pcr_ctx_debug_set_shard(pcr_ctx *ctx, int rank, int world_size) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (world_size < 1 || rank < 0 || rank >= world_size) return fail(c, PCR_ERR_INVALID_ARG, "bad rank/world");
+    comm_destroy(c);
+    c->rank = rank;
+    c->world = world_size;
+    c->fake_comm = world_size > 1;
+    return PCR_OK;
+}
+
+int pcr_ctx_get_hint_stats(pcr_ctx *ctx, uint64_t out[PCR_NUM_HINT_STATS]) {
+    if (!ctx || !out) return fail(ctx ? &ctx->c : nullptr, PCR_ERR_INVALID_ARG, "null pointer");
+    const Ctx &c = ctx->c;
+    const uint64_t v[PCR_NUM_HINT_STATS] = {c.stat_cell_hits, c.stat_cell_misses, c.stat_vox_hits, c.stat_vox_misses, c.stat_spec_hits, c.stat_spec_misses};
+    for (int i = 0; i < PCR_NUM_HINT_STATS; i++) out[i] = v[i];
     return PCR_OK;
 }
 
@@ -513,7 +560,9 @@ static int sor_core(Ctx *c, const float *dx, const float *dy, const float *dz, s
     bo.transient = true;
     Index *ix = nullptr;
     PCR_TRY(index_build_dev(c, dx, dy, dz, n, bo, &ix));
-    int s = sor_mean_dist_dev(ix, k, d_mean);
+    // (a query-sharded context: every rank searches its share, the mean distances are merged, and every rank runs the
+    // same exact fold over all of them -- the statistics and the mask do not depend on the number of ranks)
+    int s = sor_mean_dist_dev(ix, k, d_mean, nullptr, c->shard_queries);
     if (s == PCR_OK) s = sor_threshold_mask_dev(c, d_mean, nullptr, 1, n, std_mul, d_keep, d_stats, d_kept);
     index_free(ix);
     return s;
@@ -631,7 +680,16 @@ static int ror_core(Ctx *c, const float *dx, const float *dy, const float *dz, s
     } g{ix};
     PCR_TRY(ensure(c, c->b_misc, n * sizeof(uint32_t)));
     uint32_t *d_cnt = (uint32_t *)c->b_misc.p;
-    PCR_TRY(radius_count_dev(ix, dx, dy, dz, n, radius, d_cnt));
+    if (query_sharding_active(c, ix)) {
+        // the count kernel takes its queries in input order: this rank counts for the input range [b, e), the counts are
+        // merged like every sharded result (zero elsewhere, integer sum over NCCL), the mask is computed by every rank
+        const size_t b = n * (size_t)c->rank / (size_t)c->world, e = n * (size_t)(c->rank + 1) / (size_t)c->world;
+        PCR_CUDA(c, cudaMemsetAsync(d_cnt, 0, n * sizeof(uint32_t), c->stream));
+        PCR_TRY(radius_count_dev(ix, dx + b, dy + b, dz + b, e - b, radius, d_cnt + b));
+        PCR_TRY(comm_allreduce_u32(c, d_cnt, n));
+    } else {
+        PCR_TRY(radius_count_dev(ix, dx, dy, dz, n, radius, d_cnt));
+    }
     PCR_CUDA(c, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long), c->stream));
     ror_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_cnt, n, (uint64_t)min_neighbors, d_keep, d_kept);
     PCR_LAUNCH_CHECK(c);
@@ -773,7 +831,7 @@ int pcr_estimate_normals_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, c
     bo.transient = true;
     Index *ix = nullptr;
     PCR_TRY(index_build_dev(c, d_x, d_y, d_z, n, bo, &ix));
-    int s = normals_dev(ix, k, viewpoint, d_nx, d_ny, d_nz, nullptr);
+    int s = normals_dev(ix, k, viewpoint, d_nx, d_ny, d_nz, nullptr, c->shard_queries);
     index_free(ix);
     return s;
     PCR_API_END(c)
@@ -798,7 +856,7 @@ int pcr_estimate_normals(pcr_ctx *ctx, const float *x, const float *y, const flo
     bo.transient = true;
     Index *ix = nullptr;
     PCR_TRY(index_build_dev(c, dx, dy, dz, n, bo, &ix));
-    int s = normals_dev(ix, k, viewpoint, dnx, dny, dnz, nullptr);
+    int s = normals_dev(ix, k, viewpoint, dnx, dny, dnz, nullptr, c->shard_queries);
     index_free(ix);
     PCR_TRY(s);
     PCR_CUDA(c, cudaMemcpyAsync(nx, dnx, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));

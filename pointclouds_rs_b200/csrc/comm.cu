@@ -17,7 +17,7 @@ typedef struct {
 } ncclUniqueId_t;
 typedef void *ncclComm_t_;
 typedef int ncclResult_t_;
-enum { kNcclUint8 = 1, kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0 };
+enum { kNcclUint8 = 1, kNcclUint32 = 3, kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0 };
 
 struct NcclApi {
     void *handle = nullptr;
@@ -104,6 +104,7 @@ int comm_init(Ctx *ctx, const void *id, int rank, int world) {
 }
 
 void comm_destroy(Ctx *ctx) {
+    ctx->fake_comm = false;
     if (ctx->nccl_comm) {
         NcclApi &a = api();
         if (a.ok) a.CommDestroy((ncclComm_t_)ctx->nccl_comm);
@@ -118,6 +119,15 @@ int comm_allreduce_f64(Ctx *ctx, double *d_buf, size_t count) {
     NcclApi &a = api();
     if (!a.ok || !ctx->nccl_comm) return fail(ctx, PCR_ERR_NCCL, "communicator not initialised");
     int r = a.AllReduce(d_buf, d_buf, count, kNcclFloat64, kNcclSum, (ncclComm_t_)ctx->nccl_comm, ctx->stream);
+    if (r != 0) return fail(ctx, PCR_ERR_NCCL, "ncclAllReduce: %s", a.GetErrorString ? a.GetErrorString(r) : "error");
+    return PCR_OK;
+}
+
+int comm_allreduce_u32(Ctx *ctx, uint32_t *d_buf, size_t count) {
+    if (ctx->world <= 1 || count == 0 || ctx->fake_comm) return PCR_OK;
+    NcclApi &a = api();
+    if (!a.ok || !ctx->nccl_comm) return fail(ctx, PCR_ERR_NCCL, "communicator not initialised");
+    int r = a.AllReduce(d_buf, d_buf, count, kNcclUint32, kNcclSum, (ncclComm_t_)ctx->nccl_comm, ctx->stream);
     if (r != 0) return fail(ctx, PCR_ERR_NCCL, "ncclAllReduce: %s", a.GetErrorString ? a.GetErrorString(r) : "error");
     return PCR_OK;
 }

@@ -851,6 +851,8 @@ int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz,
             hsel[0] = cc.h;
             cached = true;
         }
+        if (cached) ctx->stat_cell_hits++;
+        else ctx->stat_cell_misses++;
     }
     if (!forced && !cached && n_indexed > 0) {
         for (int round = 0; round < 2; round++) {

@@ -35,6 +35,7 @@ struct LevelArgs {
     const float4 *qpts;        // level-0 sorted points: where self-queries are read from
     const uint32_t *qlist;     // nullptr on level 0 (query id == position)
     uint32_t nq;
+    uint32_t q_offset;         // level 0 without a list: query id = q_offset + slot (this rank's query shard)
     const uint32_t *nq_dev;    // optional: the real count, still on the device (nq is then the launch capacity)
     uint32_t *defer_list;      // queries this pass could not finish within max_rings shells
     uint32_t *defer_count;
@@ -46,6 +47,7 @@ struct LevelArgs {
     uint32_t *cont_list;
     uint32_t *cont_count;
     int follow_up;  // this launch takes cont_list of the first pass (warp per query, same grid level)
+    unsigned long long *stats;  // optional {queries, distance evaluations} counters of the selection kernel (timing on)
 };
 
 __device__ __forceinline__ void defer_query(const LevelArgs &a, uint32_t qid, int lane) {
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(kThreads) knn_queries_kernel(LevelArgs a, cons
     for (uint32_t q0 = (blockIdx.x * kWarps + w) * QPW; q0 < nq; q0 += gridDim.x * kWarps * QPW)
     for (int t = 0; t < QPW; t++) {
         if (q0 + t >= nq) break;
-        const uint32_t qi = a.qlist ? a.qlist[q0 + t] : q0 + t;
+        const uint32_t qi = a.qlist ? a.qlist[q0 + t] : a.q_offset + q0 + t;
         float x = __ldg(&qx[qi]), y = __ldg(&qy[qi]), z = __ldg(&qz[qi]);
         int cnt = 0;
         tk.reset(PCR_EMPTY_KEY);
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(kThreads) sor_mean_kernel(LevelArgs a, int kk,
         GridDesc g;
         for (int t = 0; t < QPW; t++) {
             if (q0 + t >= nq) break;
-            const uint32_t pos = a.qlist ? a.qlist[q0 + t] : q0 + t;
+            const uint32_t pos = a.qlist ? a.qlist[q0 + t] : a.q_offset + q0 + t;
             if (f < 0 || pos >= g.pt_end || pos < g.pt_begin) {
                 f = frame_of_sorted(a.grids, a.n_frames, pos);
                 g = a.grids[f];
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(kThreads) sor_mean_kernel(LevelArgs a, int kk,
         tk.s = smem_raw + (size_t)w * kk;
         for (int t = 0; t < QPW; t++) {
             if (q0 + t >= nq) break;
-            const uint32_t pos = a.qlist ? a.qlist[q0 + t] : q0 + t;
+            const uint32_t pos = a.qlist ? a.qlist[q0 + t] : a.q_offset + q0 + t;
             const GridDesc g = a.grids[frame_of_sorted(a.grids, a.n_frames, pos)];
             float4 q = __ldg(&a.qpts[pos]);
             if (q.x != q.x) continue;  // tombstoned point: not a query
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(kThreads) normals_kernel(LevelArgs a, const fl
         GridDesc g;
         for (int t = 0; t < QPW; t++) {
             if (q0 + t >= nq) break;
-            const uint32_t pos = a.qlist ? a.qlist[q0 + t] : q0 + t;
+            const uint32_t pos = a.qlist ? a.qlist[q0 + t] : a.q_offset + q0 + t;
             if (f < 0 || pos >= g.pt_end || pos < g.pt_begin) {
                 f = frame_of_sorted(a.grids, a.n_frames, pos);
                 g = a.grids[f];
@@ -366,7 +368,7 @@ __global__ void __launch_bounds__(kThreads) normals_kernel(LevelArgs a, const fl
         tk.s = smem_raw + (size_t)w * kk;
         for (int t = 0; t < QPW; t++) {
             if (q0 + t >= nq) break;
-            const uint32_t pos = a.qlist ? a.qlist[q0 + t] : q0 + t;
+            const uint32_t pos = a.qlist ? a.qlist[q0 + t] : a.q_offset + q0 + t;
             const GridDesc g = a.grids[frame_of_sorted(a.grids, a.n_frames, pos)];
             float4 q = __ldg(&a.qpts[pos]);
             if (q.x != q.x) continue;  // tombstoned point: not a query
@@ -470,9 +472,9 @@ __device__ __forceinline__ void normal_from_topk(const ThreadTopK<KC> &acc, int 
 
 template <int KC, int MODE>
 __global__ void __launch_bounds__(kTQThreads) knn_thread_kernel(LevelArgs a, ThreadArgs t) {
-    const uint32_t q = blockIdx.x * kTQThreads + threadIdx.x;
+    const uint32_t q = a.q_offset + blockIdx.x * kTQThreads + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const bool active = q < a.nq;
+    const bool active = q - a.q_offset < a.nq;
     ThreadTopK<KC> acc;
     acc.kk = t.kk;
     bool resolved = true, skip = false;
@@ -603,7 +605,7 @@ __global__ void __launch_bounds__(kTQThreads, 6) knn_sel_kernel(LevelArgs a, Thr
     const uint32_t slot = blockIdx.x * kTQThreads + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool active = slot < nq;
-    const uint32_t q = active ? (a.qlist ? a.qlist[slot] : slot) : 0u;
+    const uint32_t q = active ? (a.qlist ? a.qlist[slot] : a.q_offset + slot) : 0u;
     ThreadSel acc;
     acc.kk = t.kk;
     bool searchable = false, skip = false;
@@ -628,6 +630,13 @@ __global__ void __launch_bounds__(kTQThreads, 6) knn_sel_kernel(LevelArgs a, Thr
     const int outcome = ws_grid_search(acc, searchable, a.grids + f, a.cell_start, a.pts, px, py, pz, a.max_rings, a.last_level != 0, a.first_only);
     push_list(outcome == kSelDefer, a.defer_list, a.defer_count, q, lane);
     if (a.cont_list) push_list(outcome == kSelContinue, a.cont_list, a.cont_count, q, lane);
+    if (a.stats) {  // (bench.py: candidates per query of the dominant kernel)
+        const unsigned evals = __reduce_add_sync(PCR_FULL, acc.n_eval), nqw = __popc(__ballot_sync(PCR_FULL, searchable));
+        if (lane == 0) {
+            atomicAdd(&a.stats[0], (unsigned long long)nqw);
+            atomicAdd(&a.stats[1], (unsigned long long)evals);
+        }
+    }
     if (!active || outcome != kSelDone || skip) return;
     const int cnt = acc.count();
     // (the list is read through acc.ord[j], j a literal: the ranking stays in registers)
@@ -848,7 +857,8 @@ int set_smem(Ctx *ctx, Kern kern, size_t bytes) {
 // finish on level 0 and pay exactly one).
 template <class Launch>
 int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *init_list = nullptr, const uint32_t *nq_dev = nullptr,
-               int sel_kk = 0 /* > 0: level 0 is a thread-per-query launch for this many neighbours */) {
+               int sel_kk = 0 /* > 0: level 0 is a thread-per-query launch for this many neighbours */,
+               uint32_t q_offset = 0 /* level 0 takes the queries q_offset .. q_offset + nq (a rank's shard) */) {
     // init_list: level 0 runs over these nq query ids only (warp kernels) instead of over all queries
     // nq_dev:    the length of init_list is still on the device; nq is the capacity level 0 is launched for
     Ctx *ctx = ix->ctx;
@@ -875,6 +885,7 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
         a.pts = cur->sorted;
         a.qpts = ix->sorted;
         a.qlist = qlist;
+        a.q_offset = (level == 0 && !init_list) ? q_offset : 0u;
         a.nq = n_cur;
         a.nq_dev = level == 0 ? nq_dev : nullptr;
         a.defer_list = lists[level & 1];
@@ -883,6 +894,7 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
         a.last_level = last ? 1 : 0;
         const bool first_of_two = two_pass && level == 0;
         a.follow_up = 0;
+        a.stats = (ctx->timing && first_of_two) ? ctx->d_knn_stats : nullptr;
         a.first_only = first_of_two ? first_shells() : 0;
         a.cont_list = first_of_two ? cont : nullptr;
         a.cont_count = first_of_two ? counters + 2 : nullptr;
@@ -929,6 +941,7 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
         }
         PCR_MARK("levels: got deferred count");
         n_cur = *mail;
+        if (speculate) (n_cur > 0 ? ctx->stat_spec_hits : ctx->stat_spec_misses)++;
         if (level == 0 && !init_list) ctx->spec_coarser = n_cur > 0;
         if (dbg) fprintf(stderr, "[pcr] level %d: %u of %u queries deferred (cell %.4g)\n", level, n_cur, a.nq, cur->grids_h[0].h);
         if (dbg && first_of_two) fprintf(stderr, "[pcr] level 0: %u of %u queries needed more than their 27 cells\n", mail[1], a.nq);
@@ -952,6 +965,57 @@ inline unsigned blocks_for(Ctx *ctx, const LevelArgs &a, int qpw) {
 }
 
 }  // namespace
+
+// ---- query sharding over the ranks of a communicator (KNN / normals / SOR of ONE cloud) -------------
+// Every rank holds the whole cloud and builds the same index (cell membership and the cell table are deterministic;
+// the order of the points INSIDE a cell is not: it comes from atomics).  The queries are therefore split at CELL
+// boundaries of the cell-sorted order -- rank r takes the cells whose first point lies in [r n / G, (r + 1) n / G) --
+// so every rank derives the same partition of the points from its own copy.  Results are written at original
+// indices into zero-initialised arrays and merged with an integer sum over NCCL: every element is written by
+// exactly one rank, so the sum reproduces its bits (including -0.0 and inf), and every rank ends up with the
+// full result.  Points outside the index (non-finite) belong to rank 0.
+namespace {
+__global__ void shard_bounds_kernel(const uint32_t *__restrict__ cell_start, uint32_t total_cells, uint32_t n_indexed, int rank, int world,
+                                    uint32_t *__restrict__ out) {
+    const int t = threadIdx.x;  // 0: begin of this rank, 1: begin of the next
+    if (t > 1) return;
+    const uint32_t target = (uint32_t)(((unsigned long long)n_indexed * (unsigned)(rank + t)) / (unsigned)world);
+    uint32_t lo = 0, hi = total_cells;  // smallest cell c with cell_start[c] >= target (cell_start[total_cells] = n_indexed)
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (cell_start[mid] >= target) hi = mid;
+        else lo = mid + 1;
+    }
+    out[t] = cell_start[lo];
+}
+
+// SOR: non-finite points have mean distance INF (statistical_outlier.rs:22-24); only they are written here
+__global__ void fill_nonfinite_f32_kernel(const float4 *__restrict__ orig4, size_t n, float *__restrict__ p, float v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 q = orig4[i];
+    if (!finite3(q.x, q.y, q.z)) p[i] = v;
+}
+}  // namespace
+
+bool query_sharding_active(const Ctx *ctx, const Index *ix) { return ctx->shard_queries && ctx->world > 1 && ix->n_frames == 1; }
+
+int index_shard_queries(Index *ix) {
+    Ctx *ctx = ix->ctx;
+    ix->q_begin = 0;
+    ix->q_count = (uint32_t)ix->n_indexed;
+    if (!query_sharding_active(ctx, ix) || ix->n_indexed == 0) return PCR_OK;
+    PCR_TRY(ensure(ctx, ctx->b_small, 4096));
+    uint32_t *d_out = (uint32_t *)((char *)ctx->b_small.p + 2048);
+    shard_bounds_kernel<<<1, 32, 0, ctx->stream>>>(ix->cell_start, ix->total_cells, (uint32_t)ix->n_indexed, ctx->rank, ctx->world, d_out);
+    PCR_LAUNCH_CHECK(ctx);
+    uint32_t *mail = (uint32_t *)ctx->pinned + 48;
+    PCR_CUDA(ctx, cudaMemcpyAsync(mail, d_out, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ix->q_begin = mail[0];
+    ix->q_count = mail[1] - mail[0];
+    return PCR_OK;
+}
 
 int knn_queries_dev(Index *ix, const float *dqx, const float *dqy, const float *dqz, size_t nq, size_t k, uint32_t *d_idx,
                     float *d_dist, uint32_t *d_counts) {
@@ -983,12 +1047,25 @@ int knn_queries_dev(Index *ix, const float *dqx, const float *dqy, const float *
     }, nullptr, nullptr, k <= 32 ? kk : 0);
 }
 
-int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep_lists) {
+int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep_lists, bool allow_shard) {
     Ctx *ctx = ix->ctx;
     if (ix->n == 0) return PCR_OK;
     const size_t kk = k + 1;  // statistical_outlier.rs:25
     if (kk > PCR_MAX_K) return fail(ctx, PCR_ERR_UNSUPPORTED, "k = %zu exceeds PCR_MAX_K - 1", k);
-    if (ix->n_indexed < ix->n) {  // statistical_outlier.rs:22-24: non-finite points -> INF
+    // a rank of a query-sharded call searches its share of the cloud; the mean distances are merged at the end, so
+    // that every rank folds the same N values in the same order and gets the same statistics and mask
+    const bool shard = allow_shard && !keep_lists && query_sharding_active(ctx, ix);
+    uint32_t q_begin = 0, q_count = (uint32_t)ix->n_indexed;
+    if (shard) {
+        PCR_TRY(index_shard_queries(ix));
+        q_begin = ix->q_begin;
+        q_count = ix->q_count;
+        PCR_CUDA(ctx, cudaMemsetAsync(d_mean_d, 0, sizeof(float) * ix->n, ctx->stream));
+        if (ix->n_indexed < ix->n && ctx->rank == 0) {
+            fill_nonfinite_f32_kernel<<<(unsigned)((ix->n + 255) / 256), 256, 0, ctx->stream>>>(ix->orig4, ix->n, d_mean_d, INFINITY);
+            PCR_LAUNCH_CHECK(ctx);
+        }
+    } else if (ix->n_indexed < ix->n) {  // statistical_outlier.rs:22-24: non-finite points -> INF
         fill_f32_kernel<<<(unsigned)((ix->n + 255) / 256), 256, 0, ctx->stream>>>(d_mean_d, ix->n, INFINITY);
         PCR_LAUNCH_CHECK(ctx);
     }
@@ -1009,7 +1086,7 @@ int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep
         ta.list_stride = keep_lists->stride;
         PCR_CUDA(ctx, cudaMemsetAsync(keep_lists->cnt, 0xff, keep_lists->stride, ctx->stream));
     }
-    return run_levels(ix, (uint32_t)ix->n_indexed, kTagKnn, [&](const LevelArgs &a, int qpw) -> int {
+    const int rc = run_levels(ix, q_count, kTagKnn, [&](const LevelArgs &a, int qpw) -> int {
         if (qpw == kQPW0 && keep_lists) return launch_thread_kernel<3>(ctx, a, ta);
         if (qpw == kQPW0 && kk <= 32) return launch_thread_kernel<1>(ctx, a, ta);
         unsigned blocks = blocks_for(ctx, a, qpw);
@@ -1025,14 +1102,25 @@ int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep
         }
         PCR_LAUNCH_CHECK(ctx);
         return PCR_OK;
-    }, nullptr, nullptr, keep_lists ? ta.kk : (kk <= 32 ? (int)kk : 0));
+    }, nullptr, nullptr, keep_lists ? ta.kk : (kk <= 32 ? (int)kk : 0), q_begin);
+    PCR_TRY(rc);
+    if (shard) PCR_TRY(comm_allreduce_u32(ctx, reinterpret_cast<uint32_t *>(d_mean_d), ix->n));
+    return PCR_OK;
 }
 
-int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny, float *d_nz, const uint8_t *d_mask) {
+int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny, float *d_nz, const uint8_t *d_mask, bool allow_shard) {
     Ctx *ctx = ix->ctx;
     if (ix->n == 0 || k == 0) return PCR_OK;
     if (k > PCR_MAX_K) return fail(ctx, PCR_ERR_UNSUPPORTED, "k = %zu exceeds PCR_MAX_K = %d", k, PCR_MAX_K);
-    if (d_mask || ix->n_indexed < ix->n) {
+    const bool shard = allow_shard && query_sharding_active(ctx, ix);  // (see index_shard_queries)
+    uint32_t q_begin = 0, q_count = (uint32_t)ix->n_indexed;
+    if (shard) {
+        PCR_TRY(index_shard_queries(ix));
+        q_begin = ix->q_begin;
+        q_count = ix->q_count;
+        for (float *p : {d_nx, d_ny, d_nz}) PCR_CUDA(ctx, cudaMemsetAsync(p, 0, sizeof(float) * ix->n, ctx->stream));
+    }
+    if ((d_mask || ix->n_indexed < ix->n) && (!shard || ctx->rank == 0)) {
         fill_unindexed_normals_kernel<<<(unsigned)((ix->n + 255) / 256), 256, 0, ctx->stream>>>(ix->orig4, d_mask, ix->n, d_nx,
                                                                                                 d_ny, d_nz);
         PCR_LAUNCH_CHECK(ctx);
@@ -1052,7 +1140,7 @@ int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny
     ta.vx = v0; ta.vy = v1; ta.vz = v2;
     ta.nx = d_nx; ta.ny = d_ny; ta.nz = d_nz;
     ta.kk = (int)k;
-    return run_levels(ix, (uint32_t)ix->n_indexed, kTagKnnNormals, [&](const LevelArgs &a, int qpw) -> int {
+    const int rc = run_levels(ix, q_count, kTagKnnNormals, [&](const LevelArgs &a, int qpw) -> int {
         if (qpw == kQPW0 && k <= 32) return launch_thread_kernel<2>(ctx, a, ta);
         unsigned blocks = blocks_for(ctx, a, qpw);
         if (k <= 32) {
@@ -1064,7 +1152,11 @@ int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny
         }
         PCR_LAUNCH_CHECK(ctx);
         return PCR_OK;
-    }, nullptr, nullptr, k <= 32 ? (int)k : 0);
+    }, nullptr, nullptr, k <= 32 ? (int)k : 0, q_begin);
+    PCR_TRY(rc);
+    if (shard)
+        for (float *p : {d_nx, d_ny, d_nz}) PCR_TRY(comm_allreduce_u32(ctx, reinterpret_cast<uint32_t *>(p), ix->n));
+    return PCR_OK;
 }
 
 // ---- normals of the kept points from the SOR pass's neighbour lists -------------------------------

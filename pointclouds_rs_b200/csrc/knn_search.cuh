@@ -699,6 +699,7 @@ struct ThreadSel {
     uint32_t free_mask;          // bit j set: slot j is empty
     int kk;
     int m;                       // entries of the final list (valid after finalize)
+    uint32_t n_eval;             // distance evaluations of this query (both passes), for the bench's FP32 roofline
     uint32_t ord[kSelCap];       // after finalize(): ord[j] & 31 = slot of the j-th best (static indexing only: registers)
 
     __device__ __forceinline__ void reset() {
@@ -819,6 +820,7 @@ template <bool kHist>
 __device__ __forceinline__ void ws_scan_run(ThreadSel &acc, const float4 *__restrict__ pts, uint32_t b, uint32_t e, float qx, float qy,
                                             float qz, float scale) {
     const uint32_t n = e - b;
+    acc.n_eval += n;
     const uint32_t nmax = __reduce_max_sync(PCR_FULL, n);
     for (uint32_t i = 0; i < nmax; i += 4) {
         float4 p[4];
@@ -850,6 +852,7 @@ __device__ __forceinline__ int ws_grid_search(ThreadSel &acc, bool live, const G
     // (the descriptor stays in memory: the walk keeps only the cell coordinates, the f32 fractions and the table
     // shape in registers, and the shell-end test reloads what it needs -- the sorting network wants the registers)
     acc.reset();
+    acc.n_eval = 0;
     const int kk = acc.kk;
     const uint32_t pt_begin = gp->pt_begin, pt_end = gp->pt_end;
     const uint32_t m = live ? pt_end - pt_begin : 0u;

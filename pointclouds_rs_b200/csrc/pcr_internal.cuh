@@ -62,6 +62,9 @@ struct Index {
     Index *coarser = nullptr;         // next grid level (8x the cell size), built on demand
     bool shares_orig4 = false;        // coarser levels borrow orig4 / grids layout from level 0
     int cell_slot = -1;               // >= 0: cell_start lives in ctx->b_cells[cell_slot] (transient index), not owned
+    // query shard of this rank (sorted positions): set by index_shard_queries, default = every indexed point
+    uint32_t q_begin = 0;
+    uint32_t q_count = 0xffffffffu;
 };
 
 struct Ctx {
@@ -124,10 +127,17 @@ struct Ctx {
         int tag;
     };
     std::vector<TimedSpan> spans;
+    unsigned long long *d_knn_stats = nullptr;  // {queries, distance evaluations} of the level-0 selection kernel while timing is on
     std::vector<cudaEvent_t> event_pool;
     // NCCL (loaded lazily with dlopen, see comm.cu)
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
+    // pcr_ctx_set_query_sharding: with a communicator, sor / estimate_normals / radius_outlier_removal of ONE cloud
+    // given in full on every rank search only this rank's share of the queries and merge the results over NCCL
+    bool shard_queries = false;
+    bool fake_comm = false;  // pcr_ctx_debug_set_shard: rank / world without a communicator, collectives are no-ops (partition tests on one GPU)
+    // frame-stream bookkeeping for the bench line (pcr_ctx_get_hint_stats)
+    uint64_t stat_cell_hits = 0, stat_cell_misses = 0, stat_vox_hits = 0, stat_vox_misses = 0, stat_spec_hits = 0, stat_spec_misses = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -222,13 +232,17 @@ struct SorLists {
     uint8_t *cnt = nullptr;
     uint32_t *fallback = nullptr;  // stride + 1 entries: query ids without a usable list, then their count
 };
-int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep_lists = nullptr);
+int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep_lists = nullptr, bool allow_shard = false);
 int normals_from_lists_dev(Index *ix, size_t k, const float vp[3], const SorLists &sl, const uint8_t *d_keep, float *d_nx, float *d_ny,
                            float *d_nz,
                            const unsigned long long *d_kept0 = nullptr, unsigned long long *h_kept0 = nullptr);
 // normals of every point of the indexed cloud(s); points not indexed get (0,0,1) (no neighbours)
 int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny, float *d_nz,
-                const uint8_t *d_mask);
+                const uint8_t *d_mask, bool allow_shard = false);
+// Query sharding (one cloud, index replicated on every rank of the context's communicator): this rank's share of the
+// cell-sorted order, cut at cell boundaries so that every rank derives the same partition from its own copy of the index.
+bool query_sharding_active(const Ctx *ctx, const Index *ix);
+int index_shard_queries(Index *ix);
 // Removes the points with keep[idx] == 0 from every built level of the index IN PLACE (their
 // coordinates become NaN) and makes later-built levels skip them: the index of the SOR pass is
 // reused for the normals of the kept points without a rebuild.
@@ -283,6 +297,8 @@ int comm_init(Ctx *ctx, const void *id, int rank, int world);
 void comm_destroy(Ctx *ctx);
 int comm_allreduce_f64(Ctx *ctx, double *d_buf, size_t count);
 int comm_allgather_bytes(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes);
+// in-place sum of u32 words: merges result arrays in which every element was written by exactly one rank (zero elsewhere), bit for bit
+int comm_allreduce_u32(Ctx *ctx, uint32_t *d_buf, size_t count);
 
 // ------------------------------------------------------------------------------------------------
 // device helpers

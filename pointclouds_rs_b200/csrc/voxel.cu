@@ -576,6 +576,7 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
             PCR_MARK("voxel: wait for count");
             PCR_CUDA(ctx, cudaStreamSynchronize(st));
             PCR_MARK("voxel: got count");
+            if (guessed) (mail->outside ? ctx->stat_vox_misses : ctx->stat_vox_hits)++;
             if (guessed && mail->outside) {  // a point fell outside the guessed box: measure, with a wider pad from now on
                 vc.valid = false;
                 vc.pad_shift = std::max(2, vc.pad_shift - 1);

@@ -4,7 +4,8 @@
 
 Sharded point-to-plane / point-to-point ICP (source split over ranks, NCCL all-reduce of the normal
 equations inside the library) must give the same result on every rank and agree with the unsharded
-run on one GPU; frame-sharded SOR + normals must equal the single-process batch.
+run on one GPU; query-sharded SOR / normals / radius outlier removal of one cloud must be bit-identical to the
+unsharded call; frame-sharded SOR + normals must equal the single-process batch.
 """
 import os
 import sys
@@ -53,6 +54,26 @@ def main():
             if rank == 0:
                 print(f"{name} iters={iters} tol={tol}: sharded {r_sh} vs single {r_one}: identical on all ranks={same_everywhere} close={close}", flush=True)
             ok = ok and same_everywhere and close
+
+    # query sharding of ONE cloud (BASELINE configs[2] shape): every rank gets the whole cloud, searches
+    # its share, the library merges over NCCL -> every rank holds the full result, bit-identical to the unsharded call
+    aer = scenes.aerial_scene(42, 0.03)
+    aer[5] = [np.nan, 0, 0]  # a non-finite point (owned by rank 0)
+    cloud = pcr.PointCloud.from_numpy(aer)
+    ctx.set_query_sharding(True)
+    keep_s, kept_s, mean_s, stats_s = pcr.sor_mask(cloud, 10, 1.0, ctx=ctx, want_mean=True)
+    nrm_s = pcr.normals_array(cloud, 20, ctx=ctx)
+    ror_s, _ = pcr.ror_mask(cloud, 2.0, 5, ctx=ctx)
+    ctx.set_query_sharding(False)
+    keep_1, kept_1, mean_1, stats_1 = pcr.sor_mask(cloud, 10, 1.0, ctx=solo, want_mean=True)
+    nrm_1 = pcr.normals_array(cloud, 20, ctx=solo)
+    ror_1, _ = pcr.ror_mask(cloud, 2.0, 5, ctx=solo)
+    shard_ok = (np.array_equal(mean_s.view(np.uint32), mean_1.view(np.uint32)) and np.array_equal(stats_s.view(np.uint32), stats_1.view(np.uint32))
+                and np.array_equal(keep_s, keep_1) and kept_s == kept_1 and np.array_equal(nrm_s.view(np.uint32), nrm_1.view(np.uint32))
+                and np.array_equal(ror_s, ror_1))
+    if rank == 0:
+        print(f"query-sharded SOR / normals / radius outlier removal of one {len(aer)}-point cloud: bit-identical to one GPU = {shard_ok}", flush=True)
+    ok = ok and shard_ok
 
     # frame sharding: frames dealt round-robin == the single-process batch (at least one frame per rank:
     # with 6 frames on 8 ranks two ranks had nothing to stack and the others waited for them in the all-reduce)

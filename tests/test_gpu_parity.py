@@ -466,3 +466,41 @@ def test_cell_size_cache_never_changes_results(pcr, oracle):
     o_keep, o_mean, _ = oracle.sor(blob, 10, 1.0, threads=T)
     assert np.array_equal(second[0], o_keep) and np.array_equal(second[2].view(np.uint32), o_mean.view(np.uint32))
     assert np.array_equal(first[0], oracle.sor(flat, 10, 1.0, threads=T)[0])
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_query_shards_partition_the_cloud(pcr, oracle, world):
+    """SURVEY 8e rows 1-2 on ONE GPU: with pcr_ctx_debug_set_shard a context plays one rank of a query-sharded call and
+    returns that rank's part (zero bits where another rank writes).  The parts must be disjoint and their integer sum --
+    what the NCCL merge computes -- must be the unsharded result bit for bit, for SOR mean distances, normals and the
+    radius-outlier mask, with non-finite points (owned by rank 0) in the cloud."""
+    pts = scenes.kitti_scene(11, (9_000, 450, 80, 170))
+    pts[17] = [np.nan, 1, 2]
+    pts[4000] = [3, -np.inf, 0]
+    cloud = _cloud(pcr, pts)
+    _, _, mean_full, _ = pcr.sor_mask(cloud, 10, 1.0, want_mean=True)
+    nrm_full = pcr.normals_array(cloud, 20)
+    ror_full, _ = pcr.ror_mask(cloud, 0.5, 5)
+    assert np.array_equal(mean_full.view(np.uint32), oracle.sor(pts, 10, 1.0, threads=T)[1].view(np.uint32))
+    mean_sum = np.zeros(len(pts), np.uint64)
+    nrm_sum = np.zeros((len(pts), 3), np.uint64)
+    mean_owners = np.zeros(len(pts), np.int32)
+    nrm_owners = np.zeros(len(pts), np.int32)
+    ror_or = np.zeros(len(pts), np.uint8)
+    for r in range(world):
+        ctx = pcr.Context()
+        ctx.debug_set_shard(r, world)
+        ctx.set_query_sharding(True)
+        _, _, mean_r, _ = pcr.sor_mask(cloud, 10, 1.0, ctx=ctx, want_mean=True)
+        nrm_r = pcr.normals_array(cloud, 20, ctx=ctx)
+        ror_r, _ = pcr.ror_mask(cloud, 0.5, 5, ctx=ctx)
+        ctx.close()
+        mean_sum += mean_r.view(np.uint32)
+        nrm_sum += nrm_r.view(np.uint32)
+        mean_owners += mean_r.view(np.uint32) != 0
+        nrm_owners += np.any(nrm_r.view(np.uint32) != 0, axis=1)
+        ror_or |= ror_r
+    assert mean_owners.max() <= 1 and nrm_owners.max() == 1 and nrm_owners.min() == 1  # (a unit normal is never all zero)
+    assert np.array_equal(mean_sum.astype(np.uint32), mean_full.view(np.uint32))
+    assert np.array_equal(nrm_sum.astype(np.uint32), nrm_full.view(np.uint32))
+    assert np.array_equal(ror_or, ror_full)
