@@ -267,6 +267,11 @@ void pcr_ctx_destroy(pcr_ctx *ctx) {
     }
     for (auto e : c->event_pool) cudaEventDestroy(e);
     if (c->d_knn_stats) cudaFree(c->d_knn_stats);
+    for (int i = 0; i < 2; i++) {
+        if (c->side[i]) cudaStreamDestroy(c->side[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_count) cudaEventDestroy(c->ev_count);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->owns_stream) cudaStreamDestroy(c->stream);

@@ -24,6 +24,7 @@ constexpr int kWarps = 4;              // warps per block
 constexpr int kThreads = kWarps * 32;
 constexpr int kQPW0 = 32;              // queries per warp on level 0 (consecutive in cell order)
 constexpr int kQPWL = 1;               // queries per warp on the deferred lists (few, long queries)
+constexpr int kQPWS = 4;               // queries per warp on level 0 when a warp takes one query at a time (warp_select_cube)
 
 // One pass over one level of the grid.  Level 0 takes every query; level l > 0 takes the queries
 // the previous level deferred (qlist) and searches the 8x coarser grid of that level.
@@ -93,11 +94,12 @@ __device__ __forceinline__ void emit_row<SmemTopK>(const SmemTopK &tk, int cnt, 
 }
 
 template <bool kSmem, int QPW>
-__global__ void __launch_bounds__(kThreads) knn_queries_kernel(LevelArgs a, const float *__restrict__ qx,
+__global__ void __launch_bounds__(kThreads, (!kSmem && QPW == kQPWS) ? 8 : 1) knn_queries_kernel(LevelArgs a, const float *__restrict__ qx,
                                                                const float *__restrict__ qy, const float *__restrict__ qz,
                                                                int kk, uint32_t *__restrict__ idx, float *__restrict__ dist,
                                                                uint32_t *__restrict__ counts) {
     extern __shared__ unsigned long long smem_keys[];
+    __shared__ WarpSelScratch s_sel[kWarps];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const GridDesc g = a.grids[0];
     typename std::conditional<kSmem, SmemTopK, RegTopK>::type tk;
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(kThreads) knn_queries_kernel(LevelArgs a, cons
         int cnt = 0;
         tk.reset(PCR_EMPTY_KEY);
         if (finite3(x, y, z)) {  // kdtree.rs:65
-            if (!warp_knn_search(tk, g, a.cell_start, a.pts, x, y, z, a.max_rings, a.last_level != 0)) {
+            if (!warp_knn_search(tk, g, a.cell_start, a.pts, x, y, z, a.max_rings, a.last_level != 0, PCR_EMPTY_KEY, QPW == kQPWS ? &s_sel[w] : nullptr)) {
                 defer_query(a, qi, lane);
                 continue;
             }
@@ -130,15 +132,17 @@ __global__ void __launch_bounds__(kThreads) knn_queries_kernel(LevelArgs a, cons
 // `lists` (optional, register path only): the fused SOR -> normals pipeline keeps the kk >= kk_sor neighbours
 // of every query (SorLists layout); the statistic then uses the first kk_sor entries.
 template <bool kSmem, int QPW>
-__global__ void __launch_bounds__(kThreads) sor_mean_kernel(LevelArgs a, int kk, float *__restrict__ mean_d, uint32_t *__restrict__ lists,
+__global__ void __launch_bounds__(kThreads, (!kSmem && QPW == kQPWS) ? 8 : 1) sor_mean_kernel(LevelArgs a, int kk, float *__restrict__ mean_d, uint32_t *__restrict__ lists,
                                                             uint8_t *__restrict__ list_cnt, size_t list_stride, int kk_sor) {
     extern __shared__ unsigned long long smem_raw[];
+    __shared__ WarpSelScratch s_sel[kWarps];
+    constexpr int kCol = QPW + 1;  // column stride of the parked results (conflict-free transposed reads)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t nq = a.nq_dev ? min(a.nq, *a.nq_dev) : a.nq;  // (a launch for a capacity strides over the real count)
     for (uint32_t q0 = (blockIdx.x * kWarps + w) * QPW; q0 < nq; q0 += gridDim.x * kWarps * QPW) {
     if constexpr (!kSmem) {
-        float *sd = reinterpret_cast<float *>(smem_raw) + (size_t)w * (kk * 33 + 64);
-        int *scnt = reinterpret_cast<int *>(sd + kk * 33);
+        float *sd = reinterpret_cast<float *>(smem_raw) + (size_t)w * (kk * kCol + 64);
+        int *scnt = reinterpret_cast<int *>(sd + kk * kCol);
         uint32_t *spos = reinterpret_cast<uint32_t *>(scnt + 32);
         RegTopK tk;
         tk.kk = kk;
@@ -157,13 +161,13 @@ __global__ void __launch_bounds__(kThreads) sor_mean_kernel(LevelArgs a, int kk,
                 if (lane == 0) scnt[t] = -1;
                 continue;
             }
-            bool done = warp_knn_search(tk, g, a.cell_start, a.pts, q.x, q.y, q.z, a.max_rings, a.last_level != 0);
+            bool done = warp_knn_search(tk, g, a.cell_start, a.pts, q.x, q.y, q.z, a.max_rings, a.last_level != 0, PCR_EMPTY_KEY, QPW == kQPWS ? &s_sel[w] : nullptr);
             int cnt = tk.count();
             if (!done) {
                 defer_query(a, pos, lane);
                 cnt = -1;
             } else if (lane < kk) {
-                sd[lane * 33 + t] = __fsqrt_rn(key_d2(tk.K));  // kdtree.rs:76
+                sd[lane * kCol + t] = __fsqrt_rn(key_d2(tk.K));  // kdtree.rs:76
                 if (lists) lists[(size_t)lane * list_stride + pos] = lane < cnt ? key_idx(tk.K) : 0xffffffffu;
             }
             if (lane == 0) {
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(kThreads) sor_mean_kernel(LevelArgs a, int kk,
                 if (cnt > kk_sor) cnt = kk_sor;  // (the top-kk list starts with the top-kk_sor list)
                 int first = cnt > 1 ? 1 : 0;
                 float sum = 0.0f;
-                for (int j = first; j < cnt; j++) sum = __fadd_rn(sum, sd[j * 33 + lane]);
+                for (int j = first; j < cnt; j++) sum = __fadd_rn(sum, sd[j * kCol + lane]);
                 int m = cnt - first;
                 float md = m > 0 ? __fdiv_rn(sum, (float)m) : INFINITY;
                 mean_d[__float_as_uint(__ldg(&a.qpts[spos[lane]]).w)] = md;
@@ -305,16 +309,18 @@ __device__ __forceinline__ void normal_from_neighbours(int cnt, NB nb, float px,
 
 // smem per warp (register path): coords[(kk*3)][33] f32 + cnt[32] + pos[32]
 template <bool kSmem, int QPW>
-__global__ void __launch_bounds__(kThreads) normals_kernel(LevelArgs a, const float4 *__restrict__ orig4, int kk, float vx,
+__global__ void __launch_bounds__(kThreads, (!kSmem && QPW == kQPWS) ? 8 : 1) normals_kernel(LevelArgs a, const float4 *__restrict__ orig4, int kk, float vx,
                                                            float vy, float vz, float *__restrict__ nx, float *__restrict__ ny,
                                                            float *__restrict__ nz) {
     extern __shared__ unsigned long long smem_raw[];
+    __shared__ WarpSelScratch s_sel[kWarps];
+    constexpr int kCol = QPW + 1;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t nq = a.nq_dev ? min(a.nq, *a.nq_dev) : a.nq;  // (a launch for a capacity strides over the real count)
     for (uint32_t q0 = (blockIdx.x * kWarps + w) * QPW; q0 < nq; q0 += gridDim.x * kWarps * QPW) {
     if constexpr (!kSmem) {
-        float *sc = reinterpret_cast<float *>(smem_raw) + (size_t)w * (kk * 3 * 33 + 64);
-        int *scnt = reinterpret_cast<int *>(sc + kk * 3 * 33);
+        float *sc = reinterpret_cast<float *>(smem_raw) + (size_t)w * (kk * 3 * kCol + 64);
+        int *scnt = reinterpret_cast<int *>(sc + kk * 3 * kCol);
         uint32_t *spos = reinterpret_cast<uint32_t *>(scnt + 32);
         RegTopK tk;
         tk.kk = kk;
@@ -333,16 +339,16 @@ __global__ void __launch_bounds__(kThreads) normals_kernel(LevelArgs a, const fl
                 if (lane == 0) scnt[t] = -1;
                 continue;
             }
-            bool done = warp_knn_search(tk, g, a.cell_start, a.pts, q.x, q.y, q.z, a.max_rings, a.last_level != 0);
+            bool done = warp_knn_search(tk, g, a.cell_start, a.pts, q.x, q.y, q.z, a.max_rings, a.last_level != 0, PCR_EMPTY_KEY, QPW == kQPWS ? &s_sel[w] : nullptr);
             int cnt = tk.count();
             if (!done) {
                 defer_query(a, pos, lane);
                 cnt = -1;
             } else if (lane < cnt) {  // gather the neighbour's coordinates once (one 16 B load per lane)
                 float4 p = __ldg(&orig4[key_idx(tk.K)]);
-                sc[(lane * 3 + 0) * 33 + t] = p.x;
-                sc[(lane * 3 + 1) * 33 + t] = p.y;
-                sc[(lane * 3 + 2) * 33 + t] = p.z;
+                sc[(lane * 3 + 0) * kCol + t] = p.x;
+                sc[(lane * 3 + 1) * kCol + t] = p.y;
+                sc[(lane * 3 + 2) * kCol + t] = p.z;
             }
             if (lane == 0) {
                 scnt[t] = cnt;
@@ -353,7 +359,7 @@ __global__ void __launch_bounds__(kThreads) normals_kernel(LevelArgs a, const fl
         if (lane < QPW && q0 + lane < nq && scnt[lane] >= 0) {
             float4 q = __ldg(&a.qpts[spos[lane]]);
             float ox, oy, oz;
-            normal_from_neighbours(scnt[lane], [&](int j, int c) { return sc[(j * 3 + c) * 33 + lane]; }, q.x, q.y, q.z, vx, vy,
+            normal_from_neighbours(scnt[lane], [&](int j, int c) { return sc[(j * 3 + c) * kCol + lane]; }, q.x, q.y, q.z, vx, vy,
                                    vz, ox, oy, oz);
             uint32_t oi = __float_as_uint(q.w);
             nx[oi] = ox;
@@ -720,15 +726,19 @@ __global__ void __launch_bounds__(kTQThreads, 6) knn_sel_kernel(LevelArgs a, Thr
     }
 }
 
-enum KnnImpl { kImplInsert = 0, kImplSelect = 1 };
-inline int knn_impl() {  // A/B hook: PCR_KNN_IMPL=insert restores the round-1 insertion kernels
+enum KnnImpl { kImplInsert = 0, kImplSelect = 1, kImplWarp = 2 };
+inline int knn_impl() {  // A/B hook: PCR_KNN_IMPL = insert (round-1 insertion kernels) | select (thread per query, selection) | warp
     static const int impl = [] {
         const char *e = getenv("PCR_KNN_IMPL");
-        return e && !strcmp(e, "insert") ? kImplInsert : kImplSelect;
+        if (e && !strcmp(e, "insert")) return (int)kImplInsert;
+        if (e && !strcmp(e, "warp")) return (int)kImplWarp;
+        return (int)kImplSelect;
     }();
     return impl;
 }
 inline bool use_select(int kk) { return kk <= kSelMaxK && knn_impl() == kImplSelect; }
+// level 0 with a warp per query (warp_select_cube front-end), kQPWS consecutive queries per warp
+inline bool use_warp(int kk) { return kk > 0 && kk <= 32 && knn_impl() == kImplWarp; }
 // shells the thread-per-query pass walks before it hands a query to the follow-up pass (tuning hook PCR_FIRST_SHELLS)
 inline int first_shells() {
     static const int n = [] {
@@ -855,29 +865,125 @@ int set_smem(Ctx *ctx, Kern kern, size_t bytes) {
 // Runs `launch(args, qpw)` level by level until no query is left deferred.  Reading the deferred
 // count costs one small D2H + sync per level that is actually needed (clouds without far outliers
 // finish on level 0 and pay exactly one).
+// ---- classification of the level-0 queries ---------------------------------------------------------------------
+// A frame mixes three kinds of query, and one launch over all of them is as slow as its slowest kind (ncu, round 2:
+// the warps inside a dense object ran five times longer than the rest and WERE the kernel's duration; the ~2 % of
+// isolated outliers cost a grid level, a launch and a round trip after it).  One cheap kernel therefore sorts the
+// queries by the number of points in their 27 cells into three lists, and the three kinds run AT THE SAME TIME:
+//   sparse  (fewer than kk / 4 candidates: the first shell would end with "deferred")   -> the next-coarser level
+//           is built and searched on a side stream while level 0 is still running,
+//   dense   (more than kSelHistMaxN candidates: a volume, not a surface)                -> own launch, side stream,
+//   normal  everything else                                                             -> the main launch.
+// The lists keep the cell-sorted order inside every block of 256 queries (one atomic per block and class), so
+// neighbouring threads still hold neighbouring queries.  Every path is exact; the classes only decide where a query runs.
+constexpr int kClsThreads = 256;
+struct ClassArgs {
+    uint32_t *list[3];       // normal, dense, sparse
+    uint32_t *counts;        // [3]
+    const float *qx, *qy, *qz;  // external queries (nullptr: the indexed points themselves)
+    int kk;
+};
+
+__global__ void __launch_bounds__(kClsThreads) classify_kernel(LevelArgs a, ClassArgs c) {
+    const uint32_t slot = blockIdx.x * kClsThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t q = a.q_offset + slot;
+    int cls = 3;  // no query in this slot
+    if (slot < a.nq) {
+        float px, py, pz;
+        int f = 0;
+        bool searchable;
+        if (c.qx) {
+            px = __ldg(&c.qx[q]);
+            py = __ldg(&c.qy[q]);
+            pz = __ldg(&c.qz[q]);
+            searchable = finite3(px, py, pz);
+        } else {
+            const float4 p = __ldg(&a.qpts[q]);
+            px = p.x; py = p.y; pz = p.z;
+            f = frame_of_sorted(a.grids, a.n_frames, q);
+            searchable = px == px;
+        }
+        cls = 0;  // (queries that are not searched still produce their empty result in the main launch)
+        if (searchable) {
+            const GridDesc *gp = a.grids + f;
+            const uint32_t m = gp->pt_end - gp->pt_begin;
+            if (m > kBruteFrame && m > (uint32_t)c.kk) {
+                const uint32_t n27 = count_27_cells(gp, a.cell_start, px, py, pz);
+                cls = n27 * 4u < (uint32_t)c.kk ? 2 : (n27 > kSelHistMaxN ? 1 : 0);
+            }
+        }
+    }
+    __shared__ uint32_t s_warp[3][kClsThreads / 32];
+    __shared__ uint32_t s_base[3];
+    uint32_t my_rank = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const unsigned mask = __ballot_sync(PCR_FULL, cls == k);
+        if (lane == 0) s_warp[k][w] = __popc(mask);
+        if (cls == k) my_rank = __popc(mask & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        uint32_t tot = 0;
+        for (int i = 0; i < kClsThreads / 32; i++) tot += s_warp[threadIdx.x][i];
+        s_base[threadIdx.x] = tot ? atomicAdd(&c.counts[threadIdx.x], tot) : 0u;
+    }
+    __syncthreads();
+    if (cls < 3) {
+        uint32_t off = s_base[cls] + my_rank;
+        for (int i = 0; i < w; i++) off += s_warp[cls][i];
+        c.list[cls][off] = q;
+    }
+}
+
+struct StreamSwap {  // the library's helpers launch on ctx->stream: run a few of them on a side stream
+    Ctx *c;
+    cudaStream_t saved;
+    StreamSwap(Ctx *ctx, cudaStream_t s) : c(ctx), saved(ctx->stream) { c->stream = s; }
+    ~StreamSwap() { c->stream = saved; }
+};
+
+int ensure_side_streams(Ctx *ctx) {
+    if (ctx->side[0]) return PCR_OK;
+    for (int i = 0; i < 2; i++) {
+        PCR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking));
+        PCR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+    }
+    PCR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    return PCR_OK;
+}
+
 template <class Launch>
 int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *init_list = nullptr, const uint32_t *nq_dev = nullptr,
                int sel_kk = 0 /* > 0: level 0 is a thread-per-query launch for this many neighbours */,
-               uint32_t q_offset = 0 /* level 0 takes the queries q_offset .. q_offset + nq (a rank's shard) */) {
+               uint32_t q_offset = 0 /* level 0 takes the queries q_offset .. q_offset + nq (a rank's shard) */,
+               const float *eqx = nullptr, const float *eqy = nullptr, const float *eqz = nullptr /* external queries (device) */) {
     // init_list: level 0 runs over these nq query ids only (warp kernels) instead of over all queries
     // nq_dev:    the length of init_list is still on the device; nq is the capacity level 0 is launched for
     Ctx *ctx = ix->ctx;
     if (nq == 0) return PCR_OK;
-    // the selection kernels walk only the 27 cells in their first pass and queue what needs more shells for a second
-    // launch over that list (counters[2], cont); the launch is sized for the worst case and reads the count itself
+    // Selection kernels (two_pass): level 0 = classification, then three concurrent launches (see classify_kernel); the
+    // thread-per-query launches walk first_shells() shells and queue what needs more for a warp-per-query follow-up.
     const bool two_pass = !init_list && sel_kk > 0 && use_select(sel_kk);
-    PCR_TRY(ensure(ctx, ctx->b_list, (size_t)nq * (two_pass ? 3 : 2) * sizeof(uint32_t) + 256));
-    uint32_t *counters = (uint32_t *)ctx->b_list.p;  // [0], [1]: deferred counts of even / odd levels, [2]: follow-up count
+    static const bool no_split = getenv("PCR_NO_CLASS_SPLIT") != nullptr;  // A/B hook: one launch over all queries
+    const bool split = two_pass && !no_split;
+    PCR_TRY(ensure(ctx, ctx->b_list, (size_t)nq * (two_pass ? 6 : 2) * sizeof(uint32_t) + 256));
+    // counters: [0], [1] deferred counts of even / odd levels, [2] follow-up count, [3..5] normal / dense / sparse counts
+    uint32_t *counters = (uint32_t *)ctx->b_list.p;
     uint32_t *lists[2] = {counters + 64, counters + 64 + nq};
     uint32_t *cont = counters + 64 + 2 * (size_t)nq;
+    uint32_t *cls_list[3] = {cont + nq, cont + 2 * (size_t)nq, cont + 3 * (size_t)nq};
     Index *cur = ix;
     const uint32_t *qlist = init_list;
     uint32_t n_cur = nq;
+    bool pre_level1 = false;  // the sparse queries have already been searched on level 1 (their own deferrals sit in lists[1])
+    static const bool dbg = getenv("PCR_DEBUG") != nullptr;
     for (int level = 0;; level++) {
         const bool last = level == kMaxLevels - 1;
         uint32_t *cnt = counters + (level & 1);
-        if (level == 0) PCR_CUDA(ctx, cudaMemsetAsync(counters, 0, 3 * sizeof(uint32_t), ctx->stream));
-        else PCR_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(uint32_t), ctx->stream));
+        if (level == 0) PCR_CUDA(ctx, cudaMemsetAsync(counters, 0, 8 * sizeof(uint32_t), ctx->stream));
+        else if (!(level == 1 && pre_level1)) PCR_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(uint32_t), ctx->stream));
         LevelArgs a;
         a.grids = cur->grids;
         a.n_frames = cur->n_frames;
@@ -898,18 +1004,81 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
         a.first_only = first_of_two ? first_shells() : 0;
         a.cont_list = first_of_two ? cont : nullptr;
         a.cont_count = first_of_two ? counters + 2 : nullptr;
-        {
+        if (first_of_two && split) {
+            PCR_TRY(ensure_side_streams(ctx));
+            ClassArgs ca;
+            for (int k = 0; k < 3; k++) ca.list[k] = cls_list[k];
+            ca.counts = counters + 3;
+            ca.qx = eqx; ca.qy = eqy; ca.qz = eqz;
+            ca.kk = sel_kk;
+            {
+                TimeScope ts(ctx, kTagKnnDeferred);
+                classify_kernel<<<(n_cur + kClsThreads - 1) / kClsThreads, kClsThreads, 0, ctx->stream>>>(a, ca);
+                PCR_LAUNCH_CHECK(ctx);
+            }
+            PCR_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+            for (int i = 0; i < 2; i++) PCR_CUDA(ctx, cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
+            // side 0: the sparse queries on the next-coarser level (built here, behind the fork, while level 0 runs)
+            if (!last) {
+                StreamSwap sw(ctx, ctx->side[0]);
+                TimeScope ts(ctx, kTagKnnDeferred);
+                Index *next = nullptr;
+                PCR_TRY(index_coarser_level(cur, &next));
+                LevelArgs s1 = a;
+                s1.grids = next->grids;
+                s1.cell_start = next->cell_start;
+                s1.pts = next->sorted;
+                s1.qlist = cls_list[2];
+                s1.q_offset = 0;
+                s1.nq_dev = counters + 5;
+                s1.defer_list = lists[1];
+                s1.defer_count = counters + 1;
+                const bool last1 = kMaxLevels - 1 == 1;
+                s1.max_rings = last1 ? kMaxRings : kLevelRings;
+                s1.last_level = last1 ? 1 : 0;
+                s1.first_only = 0;
+                s1.cont_list = nullptr;
+                s1.cont_count = nullptr;
+                s1.stats = nullptr;
+                PCR_TRY(launch(s1, kQPWL));
+                pre_level1 = true;
+            }
+            if (pre_level1) PCR_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], ctx->side[0]));
+            {  // side 1: the dense queries
+                StreamSwap sw(ctx, ctx->side[1]);
+                LevelArgs d = a;
+                d.qlist = cls_list[1];
+                d.q_offset = 0;
+                d.nq_dev = counters + 4;
+                {
+                    TimeScope ts(ctx, kTagKnnDeferred);
+                    PCR_TRY(launch(d, kQPW0));
+                }
+                PCR_CUDA(ctx, cudaEventRecord(ctx->ev_join[1], ctx->stream));
+            }
+            {  // main: everything else
+                LevelArgs m = a;
+                m.qlist = cls_list[0];
+                m.q_offset = 0;
+                m.nq_dev = counters + 3;
+                TimeScope ts(ctx, tag0);
+                PCR_TRY(launch(m, kQPW0));
+            }
+            for (int i = pre_level1 ? 0 : 1; i < 2; i++) PCR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+        } else {
             TimeScope ts(ctx, level == 0 ? tag0 : kTagKnnDeferred);
-            PCR_TRY(launch(a, level == 0 && !init_list ? kQPW0 : kQPWL));
+            PCR_TRY(launch(a, level == 0 && !init_list ? (use_warp(sel_kk) ? kQPWS : kQPW0) : kQPWL));
         }
         if (first_of_two) {
-            // the queries that need more than their 27 cells: warp per query over the shells of the same level (they
-            // are few and far apart in the list: a thread-per-query launch would leave most of the GPU idle)
+            // the queries that need more than the first pass's shells: warp per query over the shells of the same level
+            // (they are few and far apart in the list: a thread-per-query launch would leave most of the GPU idle)
             LevelArgs b = a;
             b.first_only = 0;
             b.cont_list = nullptr;
             b.cont_count = nullptr;
+            b.stats = nullptr;
             b.qlist = cont;
+            b.q_offset = 0;
             b.nq_dev = counters + 2;
             b.follow_up = 1;
             TimeScope ts(ctx, kTagKnnDeferred);
@@ -917,9 +1086,7 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
         }
         if (last) break;
         uint32_t *mail = (uint32_t *)ctx->pinned + 32;
-        PCR_CUDA(ctx, cudaMemcpyAsync(mail, cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        static const bool dbg = getenv("PCR_DEBUG") != nullptr;
-        if (dbg && first_of_two) PCR_CUDA(ctx, cudaMemcpyAsync(mail + 1, counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        PCR_CUDA(ctx, cudaMemcpyAsync(mail, counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         for (const auto &pg : ctx->piggy)  // small results other steps want from the same round trip
             PCR_CUDA(ctx, cudaMemcpyAsync(pg.dst, pg.src, pg.bytes, cudaMemcpyDeviceToHost, ctx->stream));
         ctx->piggy.clear();
@@ -940,12 +1107,34 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
             PCR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         }
         PCR_MARK("levels: got deferred count");
-        n_cur = *mail;
+        n_cur = mail[level & 1];
         if (speculate) (n_cur > 0 ? ctx->stat_spec_hits : ctx->stat_spec_misses)++;
-        if (level == 0 && !init_list) ctx->spec_coarser = n_cur > 0;
+        if (level == 0 && !init_list && !split) ctx->spec_coarser = n_cur > 0;
         if (dbg) fprintf(stderr, "[pcr] level %d: %u of %u queries deferred (cell %.4g)\n", level, n_cur, a.nq, cur->grids_h[0].h);
-        if (dbg && first_of_two) fprintf(stderr, "[pcr] level 0: %u of %u queries needed more than their 27 cells\n", mail[1], a.nq);
-        if (n_cur == 0) break;
+        if (dbg && first_of_two)
+            fprintf(stderr, "[pcr] level 0: %u normal / %u dense / %u sparse queries, %u needed more than the first pass's shells, %u of the sparse deferred again\n",
+                    mail[3], mail[4], mail[5], mail[2], mail[1]);
+        if (level == 0 && pre_level1) (mail[5] > 0 ? ctx->stat_spec_hits : ctx->stat_spec_misses)++;  // was the level built ahead needed?
+        if (level == 0 && pre_level1) {
+            // the sparse queries are done on level 1; what they deferred there sits in lists[1] (count mail[1]).  Level 0's own
+            // leftovers (n_cur) go through level 1 next and append to the same list.
+            if (n_cur == 0) {
+                if (mail[1] == 0 || kMaxLevels < 3) break;
+                // nothing for level 1: continue with level 2 over the sparse pass's leftovers
+                Index *l2 = nullptr;
+                {
+                    TimeScope ts(ctx, kTagKnnDeferred);
+                    PCR_TRY(index_coarser_level(cur->coarser, &l2));
+                }
+                cur = l2;
+                qlist = lists[1];
+                n_cur = mail[1];
+                level = 1;
+                continue;
+            }
+        } else if (n_cur == 0) {
+            break;
+        }
         Index *next = nullptr;
         {
             TimeScope ts(ctx, kTagKnnDeferred);
@@ -1034,6 +1223,11 @@ int knn_queries_dev(Index *ix, const float *dqx, const float *dqy, const float *
     return run_levels(ix, (uint32_t)nq, kTagKnn, [&](const LevelArgs &a, int qpw) -> int {
         if (qpw == kQPW0 && k <= 32) return launch_thread_kernel<0>(ctx, a, ta);
         unsigned blocks = blocks_for(ctx, a, qpw);
+        if (qpw == kQPWS) {
+            knn_queries_kernel<false, kQPWS><<<blocks, kThreads, 0, ctx->stream>>>(a, dqx, dqy, dqz, kk, d_idx, d_dist, d_counts);
+            PCR_LAUNCH_CHECK(ctx);
+            return PCR_OK;
+        }
         size_t smem = k <= 32 ? 0 : sizeof(unsigned long long) * k * kWarps;
         if (k <= 32) {
             if (qpw == kQPW0) knn_queries_kernel<false, kQPW0><<<blocks, kThreads, 0, ctx->stream>>>(a, dqx, dqy, dqz, kk, d_idx, d_dist, d_counts);
@@ -1044,7 +1238,7 @@ int knn_queries_dev(Index *ix, const float *dqx, const float *dqy, const float *
         }
         PCR_LAUNCH_CHECK(ctx);
         return PCR_OK;
-    }, nullptr, nullptr, k <= 32 ? kk : 0);
+    }, nullptr, nullptr, k <= 32 ? kk : 0, 0, dqx, dqy, dqz);
 }
 
 int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep_lists, bool allow_shard) {
@@ -1090,8 +1284,16 @@ int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep
         if (qpw == kQPW0 && keep_lists) return launch_thread_kernel<3>(ctx, a, ta);
         if (qpw == kQPW0 && kk <= 32) return launch_thread_kernel<1>(ctx, a, ta);
         unsigned blocks = blocks_for(ctx, a, qpw);
+        if (qpw == kQPWS) {  // level 0, a warp per query
+            const int kw = keep_lists ? ta.kk : (int)kk;
+            const size_t smem_w = ((size_t)kw * (kQPWS + 1) + 64) * sizeof(float) * kWarps;
+            if (keep_lists) sor_mean_kernel<false, kQPWS><<<blocks, kThreads, smem_w, ctx->stream>>>(a, kw, d_mean_d, ta.lists, ta.list_cnt, ta.list_stride, ta.kk_sor);
+            else sor_mean_kernel<false, kQPWS><<<blocks, kThreads, smem_w, ctx->stream>>>(a, kw, d_mean_d, nullptr, nullptr, 0, kw);
+            PCR_LAUNCH_CHECK(ctx);
+            return PCR_OK;
+        }
         if (a.follow_up && keep_lists) {  // the first pass's leftovers on the same level: K neighbours, lists kept
-            const size_t smem_k = ((size_t)ta.kk * 33 + 64) * sizeof(float) * kWarps;
+            const size_t smem_k = ((size_t)ta.kk * (kQPWL + 1) + 64) * sizeof(float) * kWarps;
             sor_mean_kernel<false, kQPWL><<<blocks, kThreads, smem_k, ctx->stream>>>(a, ta.kk, d_mean_d, ta.lists, ta.list_cnt, ta.list_stride, ta.kk_sor);
         } else if (kk <= 32) {
             if (qpw == kQPW0) sor_mean_kernel<false, kQPW0><<<blocks, kThreads, smem, ctx->stream>>>(a, (int)kk, d_mean_d, nullptr, nullptr, 0, (int)kk);
@@ -1143,6 +1345,12 @@ int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny
     const int rc = run_levels(ix, q_count, kTagKnnNormals, [&](const LevelArgs &a, int qpw) -> int {
         if (qpw == kQPW0 && k <= 32) return launch_thread_kernel<2>(ctx, a, ta);
         unsigned blocks = blocks_for(ctx, a, qpw);
+        if (qpw == kQPWS) {  // level 0, a warp per query
+            const size_t smem_w = ((size_t)k * 3 * (kQPWS + 1) + 64) * sizeof(float) * kWarps;
+            normals_kernel<false, kQPWS><<<blocks, kThreads, smem_w, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);
+            PCR_LAUNCH_CHECK(ctx);
+            return PCR_OK;
+        }
         if (k <= 32) {
             if (qpw == kQPW0) normals_kernel<false, kQPW0><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);
             else normals_kernel<false, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, ix->orig4, (int)k, v0, v1, v2, d_nx, d_ny, d_nz);

@@ -21,12 +21,15 @@
 #include "pcr_internal.cuh"
 #include "sortnet32.cuh"
 
+#include <type_traits>
+
 namespace pcr {
 
 constexpr int kMaxRings = 12;         // thread-per-query search (ICP) and the coarsest level
 constexpr int kLevelRings = 4;        // shells scanned per grid level before a query is deferred
 constexpr int kMaxLevels = 4;
 constexpr uint32_t kBruteFrame = 96;  // frames this small are scanned directly
+constexpr uint32_t kSelHistMaxN = 384;  // more candidates than this in the 27 cells: a volume (dense object), not a surface
 
 // Squared lower bound (metres^2) on the distance from the query to anything outside the scanned cube
 // of radius R cells around cell (c0,c1,c2); f = fractional position of the query in that cell
@@ -206,12 +209,136 @@ __device__ __forceinline__ bool trim_row(float tau_c, float gp, int c2, float f2
     return z0 <= z1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Selection front-end of the warp-per-query search (round 2): the 3 x 3 x 3 cube of a query without a single
+// insertion.  The 9 rows of the cube are ONE flat candidate list (prefix sums of the run lengths in shared memory, a
+// 4-step search maps a flat index to its run), the warp walks it 32 candidates at a time -- every lane busy, whatever
+// the run lengths -- twice:
+//   pass 1  d^2 -> one of 64 linear bins, counted with shared-memory atomics; a warp scan of the counters finds the
+//           first bin edge with at least kk candidates below it;
+//   pass 2  the candidates up to that edge (kk plus the rest of one bin, <= 32) are compacted into shared memory with
+//           a ballot,
+// then one bitonic sort across the lanes on the packed (d^2, index) keys leaves lane j with the j-th best: exactly
+// the state RegTopK keeps, so the ring rule and the outer shells continue as before.  More than 32 candidates up to the
+// edge (ties, a kk-th beyond the last bin) or kk > 24: the function declines and the caller scans the rows the old
+// way.  The bins span four times the kk-th d^2 of a uniform sheet (three times that of a uniform volume for more than
+// kSelHistMaxN candidates) with as many points in the cube: a wrong guess only costs the fallback.
+// Why a warp per query at all: one thread per query leaves a B200 with 6 warps per scheduler on a 120 K-point frame
+// (and the 80 registers + 32 KB of its selection buffers cap it there even on an 8 M-point batch); a warp that issues
+// one instruction every ~17 cycles cannot hide its own latencies.  This form needs ~40 registers and 0.7 KB per warp.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWarpSelMaxK = 24;
+struct WarpSelScratch {
+    uint32_t hist[64];
+    unsigned long long keys[32];
+    uint32_t run_end[16];   // inclusive prefix of the run lengths (entries 9..15: 0xffffffff)
+    uint32_t run_base[16];  // pts index of flat candidate 0 of the run, minus the run's first flat index
+};
+
+__device__ __forceinline__ uint32_t warp_sel_locate(const WarpSelScratch &S, uint32_t i) {  // pts index of flat candidate i
+    uint32_t lo = 0;
+    if (S.run_end[lo + 7] <= i) lo += 8;
+    if (S.run_end[lo + 3] <= i) lo += 4;
+    if (S.run_end[lo + 1] <= i) lo += 2;
+    if (S.run_end[lo] <= i) lo += 1;
+    return S.run_base[lo] + i;
+}
+
+// b, e: this lane's run (lanes 0..8, empty elsewhere).  Returns true if tk now holds the exact kk best of the 9 runs.
+__device__ __forceinline__ bool warp_select_cube(RegTopK &tk, WarpSelScratch &S, const float4 *__restrict__ pts, uint32_t b, uint32_t e,
+                                                 float qx, float qy, float qz, float h2) {
+    const int lane = tk.lane, kk = tk.kk;
+    const uint32_t n = e - b;
+    uint32_t inc = n;
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(PCR_FULL, inc, d);
+        if (lane >= d) inc += t;
+    }
+    const uint32_t N = __shfl_sync(PCR_FULL, inc, 15);  // (runs only in lanes 0..8)
+    if (N == 0) return true;  // nothing in the cube: tk stays empty
+    __syncwarp();
+    if (lane < 16) {
+        S.run_end[lane] = lane < 9 ? inc : 0xffffffffu;
+        S.run_base[lane] = b - (inc - n);
+    }
+    S.hist[lane] = 0;
+    S.hist[lane + 32] = 0;
+    __syncwarp();
+    unsigned long long key = PCR_EMPTY_KEY;
+    if (N <= 32) {  // one batch: sort it
+        if ((uint32_t)lane < N) {
+            const float4 p = __ldg(&pts[warp_sel_locate(S, lane)]);
+            const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+            if (d2 == d2) key = make_key(d2, __float_as_uint(p.w));  // (NaN: a tombstoned point)
+        }
+    } else {
+        const float q = (float)kk / (float)N;
+        const float r2 = N > kSelHistMaxN ? h2 * cbrtf(6.4456f * q) * cbrtf(6.4456f * q) : 2.8648f * h2 * q;
+        const float scale = 64.0f / ((N > kSelHistMaxN ? 3.0f : 4.0f) * r2);
+        for (uint32_t i = lane; i < N; i += 32) {
+            const float4 p = __ldg(&pts[warp_sel_locate(S, i)]);
+            const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+            atomicAdd(&S.hist[__float2int_rz(fminf(__fmul_rn(d2, scale), 63.0f))], 1u);  // (NaN lands in bin 63, which never counts)
+        }
+        __syncwarp();
+        // first bin edge with at least kk candidates below it: lane l owns bins 2l, 2l+1
+        const uint32_t c0 = S.hist[2 * lane], c1 = lane < 31 ? S.hist[2 * lane + 1] : 0u;  // (bin 63 is the open one)
+        uint32_t cum = c0 + c1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(PCR_FULL, cum, d);
+            if (lane >= d) cum += t;
+        }
+        const unsigned reached = __ballot_sync(PCR_FULL, cum >= (uint32_t)kk);
+        if (!reached) return false;  // the kk-th best lies beyond the bins
+        const int L = __ffs(reached) - 1;
+        const uint32_t cumL = __shfl_sync(PCR_FULL, cum, L), c0L = __shfl_sync(PCR_FULL, c0, L), c1L = __shfl_sync(PCR_FULL, c1, L);
+        const bool first_half = cumL - c1L >= (uint32_t)kk;
+        const int bstar = 2 * L + (first_half ? 0 : 1);
+        const uint32_t A = first_half ? cumL - c1L : cumL;
+        (void)c0L;
+        if (A > 32u) return false;  // too many up to that edge (ties / a dense bin): the caller's insertion scan handles it
+        uint32_t base = 0;
+        for (uint32_t i0 = 0; i0 < N; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            bool take = false;
+            unsigned long long k2 = 0;
+            if (i < N) {
+                const float4 p = __ldg(&pts[warp_sel_locate(S, i)]);
+                const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+                take = d2 == d2 && __float2int_rz(fminf(__fmul_rn(d2, scale), 63.0f)) <= bstar;
+                k2 = make_key(d2, __float_as_uint(p.w));
+            }
+            const unsigned m = __ballot_sync(PCR_FULL, take);
+            if (take) S.keys[base + __popc(m & ((1u << lane) - 1u))] = k2;
+            base += __popc(m);
+        }
+        __syncwarp();
+        if ((uint32_t)lane < base) key = S.keys[lane];
+    }
+    // bitonic sort across the lanes, ascending
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(PCR_FULL, key, j);
+            const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
+            key = (other < key) == keep_min ? other : key;
+        }
+    tk.K = lane < kk ? key : PCR_EMPTY_KEY;
+    const unsigned long long kth_ = __shfl_sync(PCR_FULL, tk.K, kk - 1);
+    tk.thr = kth_ < tk.cap ? kth_ : tk.cap;
+    return true;
+}
+
 // Warp-cooperative exact k-NN of (qx,qy,qz) in frame g.  All arguments are warp-uniform.
 // Returns false if the query has to be re-run on a coarser level (only when !last_level).
 template <class TopK>
 __device__ __forceinline__ bool warp_knn_search(TopK &tk, const GridDesc &g, const uint32_t *__restrict__ cell_start,
                                                 const float4 *__restrict__ pts, float qx, float qy, float qz,
-                                                int max_rings, bool last_level, unsigned long long seed = PCR_EMPTY_KEY) {
+                                                int max_rings, bool last_level, unsigned long long seed = PCR_EMPTY_KEY,
+                                                WarpSelScratch *sel = nullptr) {
     tk.reset(PCR_EMPTY_KEY);
     if (seed != PCR_EMPTY_KEY) tk.insert(seed);  // a known candidate (ICP: last iteration's neighbour) bounds the search from the start
     const uint32_t m = g.pt_end - g.pt_begin;
@@ -249,7 +376,11 @@ __device__ __forceinline__ bool warp_knn_search(TopK &tk, const GridDesc &g, con
                 }
             }
         }
-        scan_runs(tk, pts, b, e, 1u << 4, qx, qy, qz, gp, inv_h2);
+        bool selected = false;
+        if constexpr (std::is_same<TopK, RegTopK>::value) {
+            if (sel && seed == PCR_EMPTY_KEY && tk.kk <= kWarpSelMaxK) selected = warp_select_cube(tk, *sel, pts, b, e, qx, qy, qz, (float)(g.h * g.h));
+        }
+        if (!selected) scan_runs(tk, pts, b, e, 1u << 4, qx, qy, qz, gp, inv_h2);
     }
     for (int R = 1;; R++) {
         // nearest face of the scanned cube that still has cells behind it
@@ -660,7 +791,6 @@ constexpr int kSelStride = 128;  // threads per block
 constexpr int kSelMaxK = 21;     // kk <= kSelCap - 11: at least two groups of candidates fit between compactions
 constexpr uint32_t kSelPad = 0xffffffe0u;  // rank key of an empty slot (| slot): behind every real d^2 (bits <= 0x7f800000)
 constexpr int kSelBins = 2 * kSelCap;      // the threshold histogram lives in the (still empty) slots: 64 u32 counters
-constexpr uint32_t kSelHistMaxN = 384;     // more candidates than this in the 27 cells: a dense object, see ws_grid_search
 
 // 32 u64 slots per thread, laid out [warp][slot][lane] (file scope: every access below is a plain LDS / STS): a warp's
 // slots are one contiguous 8 KB block that no other warp touches (the warps of a block are not in step with each
@@ -837,6 +967,27 @@ __device__ __forceinline__ void ws_scan_run(ThreadSel &acc, const float4 *__rest
         }
         if (!kHist) acc.make_room();
     }
+}
+
+// points in the 3 x 3 x 3 cells around a query (what the first shell of every search reads): 9 row lookups
+__device__ __forceinline__ uint32_t count_27_cells(const GridDesc *__restrict__ gp, const uint32_t *__restrict__ cell_start, float qx, float qy,
+                                                   float qz) {
+    const GridDesc g = *gp;
+    const int c0 = cell_coord(g, 0, pick_axis(g.ax[0], qx, qy, qz), nullptr);
+    const int c1 = cell_coord(g, 1, pick_axis(g.ax[1], qx, qy, qz), nullptr);
+    const int c2 = cell_coord(g, 2, pick_axis(g.ax[2], qx, qy, qz), nullptr);
+    const int z0 = max(c2 - 1, 0), z1 = min(c2 + 1, g.dims[2] - 1);
+    uint32_t n = 0;
+#pragma unroll
+    for (int e0 = -1; e0 <= 1; e0++)
+#pragma unroll
+        for (int e1 = -1; e1 <= 1; e1++) {
+            const int a0 = c0 + e0, a1 = c1 + e1;
+            if (a0 < 0 || a0 >= g.dims[0] || a1 < 0 || a1 >= g.dims[1]) continue;
+            const uint32_t lin = cell_linear(g, a0, a1, z0);
+            n += __ldg(&cell_start[lin + (uint32_t)(z1 - z0) + 1u]) - __ldg(&cell_start[lin]);
+        }
+    return n;
 }
 
 enum SelOutcome { kSelDone = 0, kSelDefer = 1, kSelContinue = 2 };

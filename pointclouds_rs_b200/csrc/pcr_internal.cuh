@@ -111,6 +111,9 @@ struct Ctx {
     std::vector<Piggy> piggy;
     bool spec_coarser = false;         // frame stream: the previous frame's level-0 pass deferred queries
     cudaEvent_t ev_count = nullptr;    // marks the deferred count's copy when work is queued behind it
+    // level 0 of the KNN runs three ways at once (knn.cu run_levels): side streams + fork / join events, created on first use
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     DevBuf b_scan;     // single-pass scan: ticket + one state word per tile (tagged with scan_epoch, never cleared between scans)
     uint32_t scan_epoch = 0;
     DevBuf b_list;     // deferred-query lists of the level loop

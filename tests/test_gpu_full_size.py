@@ -16,7 +16,35 @@ def _ang(a, b):
     return np.arctan2(np.linalg.norm(np.cross(a, b), axis=1), np.abs(np.sum(a * b, axis=1)))
 
 
-def _check_normals(pts, nrm, o, k, oracle):
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BOUNDS_FILE = os.path.join(ROOT, "tests", "golden", "degenerate_normals.json")
+
+
+def _bound(name, n):
+    """Upper bound on the exactly-degenerate normals of config `name`: the count observed on a B200 and recorded in
+    tests/golden/degenerate_normals.json (tracked), not a percentage."""
+    import json
+
+    with open(BOUNDS_FILE) as f:
+        return int(json.load(f)["observed_on_b200"][name])
+
+
+def _record(name, count, n):
+    import json
+
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    path = os.path.join(out, "degenerate_normals_observed.json")
+    seen = {}
+    if os.path.exists(path):
+        with open(path) as f:
+            seen = json.load(f)
+    seen[name] = {"over_1e-4_rad_and_exactly_degenerate": int(count), "points": int(n)}
+    with open(path, "w") as f:
+        json.dump(seen, f, indent=1)
+
+
+def _check_normals(pts, nrm, o, k, oracle, name):
     """<= 1e-4 rad (north_star) everywhere except on EXACTLY degenerate neighbourhoods.
 
     The aerial scene has wall points that share one coordinate exactly (x = cx + w/2 ...): their
@@ -26,7 +54,8 @@ def _check_normals(pts, nrm, o, k, oracle):
     reference code; such points are counted, must be rare, and must really be degenerate."""
     ang = _ang(nrm, o)
     bad = np.nonzero(ang > 1e-4)[0]
-    assert len(bad) <= 0.01 * len(pts), f"{len(bad)} normals over tolerance"
+    _record(name, len(bad), len(pts))
+    assert len(bad) <= _bound(name, len(pts)), f"{len(bad)} normals over tolerance (recorded bound {_bound(name, len(pts))})"
     if len(bad):
         idx, _, _ = oracle.Tree(pts).knn_batch(pts[bad], k, threads=T)
         nb = pts[idx.astype(np.int64)]  # (n_bad, k, 3)
@@ -41,7 +70,7 @@ def test_config3_aerial_241k_normals_and_radius(pcr, oracle):
     cloud = pcr.PointCloud.from_numpy(pts)
     nrm = pcr.normals_array(cloud, 20)
     o = oracle.normals(pts, 20, threads=T)
-    n_deg = _check_normals(pts, nrm, o, 20, oracle)
+    n_deg = _check_normals(pts, nrm, o, 20, oracle, "config3_aerial_241k_k20")
     print(f"config 3: {n_deg} exactly-degenerate wall normals took the other branch")
     assert np.allclose(np.linalg.norm(nrm, axis=1), 1.0, atol=1e-5)
     keep, kept = pcr.ror_mask(cloud, 2.0, 5)
@@ -66,7 +95,7 @@ def test_config4_icp_point_to_plane_1m_30_iterations(pcr, oracle):
     tn = oracle.normals(tgt, 20, threads=T)
     t = pcr.PointCloud.from_numpy(tgt)
     gn = pcr.normals_array(t, 20)
-    _check_normals(tgt, gn, tn, 20, oracle)
+    _check_normals(tgt, gn, tn, 20, oracle, "config4_aerial_1m_k20")
     t.normals = tn  # same normals on both sides: isolates the ICP loop
     res = pcr.icp_point_to_plane(pcr.PointCloud.from_numpy(src), t, max_iterations=30, tolerance=0.0)
     o = oracle.icp_point_to_plane(src, tgt, tn, 30, 0.0, threads=T)

@@ -109,3 +109,26 @@ def test_scene_shapes():
     assert scenes.kitti_scene(0, scenes.KITTI_COUNTS["frame80k"]).shape == (80_000, 3)
     assert scenes.kitti_scene(0, scenes.KITTI_COUNTS["demo68k"]).shape == (68_000, 3)
     assert scenes.aerial_scene(42, 0.1).shape == (241_000, 3)
+
+
+def test_scipy_cross_check_full_bench_frame(oracle):
+    """The oracle's KNN on the FULL configs[1] frame (122 K points after voxel 0.05, K = 21 = the fused SOR + normals search)
+    against scipy's f64 cKDTree, an implementation that shares nothing with it: wherever the gap between the k-th and the
+    (k+1)-th f64 distance exceeds what f32 rounding of d^2 can move (1e-5 relative), the index SETS must be equal, and all
+    distances must agree to f32 accuracy.  Pins the oracle on a realistic input (SURVEY 8c secondary cross-check)."""
+    import os
+
+    from scipy.spatial import cKDTree
+
+    pts = scenes.voxel_downsample_np(scenes.kitti_scene(), 0.05)
+    k = 21
+    threads = max(1, min(16, os.cpu_count() or 1))
+    idx, dist, cnt = oracle.Tree(pts).knn_batch(pts, k, threads=threads)
+    d64, i64 = cKDTree(pts.astype(np.float64)).query(pts.astype(np.float64), k=k + 1, workers=-1)
+    assert (cnt == k).all()
+    gap = (d64[:, k] - d64[:, k - 1]) > 1e-5 * np.maximum(d64[:, k], 1e-12)  # the k-th neighbour is unambiguous
+    assert gap.mean() > 0.99
+    a = np.sort(idx[gap].astype(np.int64), axis=1)
+    b = np.sort(i64[gap, :k].astype(np.int64), axis=1)
+    assert np.array_equal(a, b)
+    assert np.allclose(dist, d64[:, :k], rtol=2e-6, atol=1e-7)

@@ -178,6 +178,21 @@ def test_icp_identity(oracle):  # :326-344, :428-434
     assert r.rmse < 1e-4 and abs(r.fitness - 1.0) < 1e-6 and r.converged
 
 
+@pytest.mark.xfail(strict=True, reason=(
+    "icp.rs:347-371 `known_translation` as the reference states it (shift exactly 1.0): iteration 1 pairs every source with the "
+    "face x = 1 and moves the cube by 0.5; in iteration 2 the sources at x = 1.5 are EXACTLY equidistant from the target faces "
+    "x = 1 and x = 2 (a 4-way tie per point).  Under the (d^2, index) order this engine and its oracle define -- north_star: "
+    "'KNN index sets bit-exact under a (distance, index) tie-break' -- the lower index wins, the pairing does not change and ICP "
+    "stalls at rmse 0.5; the reference passes only through kiddo's unspecified traversal order.  Kept verbatim so that a "
+    "maintainer running the reference's own suite sees the one red test and its cause; the intent is pinned tie-free below."))
+def test_icp_known_translation_as_in_the_reference(oracle):
+    tgt = oracle.apply_transform(CUBE, I3, [1.0, 0, 0])
+    r = oracle.icp_point_to_point(CUBE, tgt, 100, 1e-8)
+    assert r.converged
+    assert r.rmse < 1e-3
+    assert np.allclose(r.translation, [1.0, 0, 0], atol=0.05)
+
+
 def test_icp_known_translation_tie_free(oracle):
     # icp.rs:347-371 shifts by exactly 1.0, which makes the second iteration an exact 4-way tie
     # (sources at x = 1.5 between target faces x = 1 and x = 2): its outcome rests on kiddo's
