@@ -562,6 +562,7 @@ static int sor_core(Ctx *c, const float *dx, const float *dy, const float *dz, s
                     float *d_mean, float *d_stats, unsigned long long *d_kept) {
     BuildOpts bo;
     bo.k_hint = k + 1;
+    bo.self_knn = true;
     bo.transient = true;
     Index *ix = nullptr;
     PCR_TRY(index_build_dev(c, dx, dy, dz, n, bo, &ix));
@@ -833,6 +834,7 @@ int pcr_estimate_normals_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, c
     DevSetter ds(c);
     BuildOpts bo;
     bo.k_hint = k;
+    bo.self_knn = true;
     bo.transient = true;
     Index *ix = nullptr;
     PCR_TRY(index_build_dev(c, d_x, d_y, d_z, n, bo, &ix));
@@ -858,6 +860,7 @@ int pcr_estimate_normals(pcr_ctx *ctx, const float *x, const float *y, const flo
     float *dnx = (float *)c->b_out.p, *dny = dnx + stride, *dnz = dny + stride;
     BuildOpts bo;
     bo.k_hint = k;
+    bo.self_knn = true;
     bo.transient = true;
     Index *ix = nullptr;
     PCR_TRY(index_build_dev(c, dx, dy, dz, n, bo, &ix));
@@ -1041,6 +1044,7 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
     // tombstoned in place (NaN coordinates) and the normals of the kept points run on the same grid.
     BuildOpts bo;
     bo.k_hint = std::max(k_sor + 1, k_normals);
+    bo.self_knn = true;
     if (const char *e = getenv("PCR_BATCH_KHINT")) bo.k_hint = (size_t)atoi(e);
     bo.n_frames = F;
     bo.transient = true;

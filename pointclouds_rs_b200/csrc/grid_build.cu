@@ -15,6 +15,7 @@
 #include "pcr_internal.cuh"
 
 #include <algorithm>
+#include <cstring>
 #include <chrono>
 #include <cmath>
 
@@ -530,9 +531,16 @@ struct FrameBox {
 
 // occupancy target: points sharing a cell with a typical point.  Tuned with the scalar model
 // (oracle/orc_grid_knn_model) on the KITTI / aerial / uniform-cube shapes.
-double occupancy_target(size_t k_hint) {
+// Self-queries with k <= 24 run as cell tiles (knn_tile.cuh): one shell only, so the cells are sized for the k-th
+// neighbour to lie inside the 27-cell cube's guaranteed radius for all but ~1 % of the queries (swept on the 122 K frame:
+// 0.4 -> 8 758 continuations, 0.5 -> 1 456, 0.6 -> 3 360 with more of the frame in the dense class).
+double occupancy_target(size_t k_hint, bool self_knn) {
     double k = k_hint ? (double)k_hint : 10.0;
-    double scale = 0.25;
+    static const bool tile_off = [] {
+        const char *e = getenv("PCR_KNN_TILE");
+        return e && !strcmp(e, "0");
+    }();
+    double scale = self_knn && !tile_off && k_hint <= 24 ? 0.5 : 0.25;
     if (const char *e = getenv("PCR_OCC_SCALE")) scale = atof(e);  // tuning hook
     return std::min(64.0, std::max(2.0, scale * k));
 }
@@ -807,7 +815,8 @@ int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz,
         }
     }
 
-    const double target = occupancy_target(opts.k_hint);
+    const double target = occupancy_target(opts.k_hint, opts.self_knn);
+    const size_t hint_key = opts.k_hint + (opts.self_knn ? (size_t)1 << 20 : 0);  // (what the cached cell size was chosen for)
     const uint64_t cap = std::max<uint64_t>(1, std::min<uint64_t>(kMaxCellsPerFrame, kMaxCellsTotal / (uint64_t)F));
     std::vector<double> hsel(F);
     const bool forced = ctx->forced_cell > 0.f;
@@ -842,7 +851,7 @@ int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz,
     if (dbg_t) { cudaStreamSynchronize(st); fprintf(stderr, "[build] bbox done +%.0f us\n", now_us() - t_begin); }
     // ---- probe rounds: measure occupancy, solve for the cell size ------------------------------
     bool cached = false;
-    if (!forced && F == 1 && n_indexed > 0 && ctx->frame_stream && ctx->cell_cache.valid && ctx->cell_cache.k_hint == opts.k_hint &&
+    if (!forced && F == 1 && n_indexed > 0 && ctx->frame_stream && ctx->cell_cache.valid && ctx->cell_cache.k_hint == hint_key &&
         !getenv("PCR_NO_CELL_CACHE")) {
         const auto &cc = ctx->cell_cache;
         auto close = [](double a, double b) { return a <= b * 1.125 + 1e-9 && b <= a * 1.125 + 1e-9; };
@@ -891,7 +900,7 @@ int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz,
     if (dbg_t) { cudaStreamSynchronize(st); fprintf(stderr, "[build] probe done +%.0f us\n", now_us() - t_begin); }
     if (!forced && !cached && F == 1 && n_indexed > 0) {
         ctx->cell_cache.valid = true;
-        ctx->cell_cache.k_hint = opts.k_hint;
+        ctx->cell_cache.k_hint = hint_key;
         ctx->cell_cache.count = box[0].count;
         for (int a = 0; a < 3; a++) ctx->cell_cache.ext[a] = box[0].ext[a];
         ctx->cell_cache.h = hsel[0];

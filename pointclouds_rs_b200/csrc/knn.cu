@@ -12,8 +12,10 @@
 // query -- the epilogues are sequential f32 folds in neighbour order (that order is part of the
 // reference's arithmetic), which would waste 31 lanes if done warp-wide.
 #include "knn_search.cuh"
+#include "knn_tile.cuh"
 
 #include <algorithm>
+#include <vector>
 #include <type_traits>
 
 namespace pcr {
@@ -35,6 +37,8 @@ struct LevelArgs {
     const float4 *pts;         // this level's cell-sorted points
     const float4 *qpts;        // level-0 sorted points: where self-queries are read from
     const uint32_t *qlist;     // nullptr on level 0 (query id == position)
+    const uint32_t *qlist2;    // tile kernel: a second list that is taken FIRST (its length in *nq2_dev), then qlist
+    const uint32_t *nq2_dev;
     uint32_t nq;
     uint32_t q_offset;         // level 0 without a list: query id = q_offset + slot (this rank's query shard)
     const uint32_t *nq_dev;    // optional: the real count, still on the device (nq is then the launch capacity)
@@ -48,6 +52,11 @@ struct LevelArgs {
     uint32_t *cont_list;
     uint32_t *cont_count;
     int follow_up;  // this launch takes cont_list of the first pass (warp per query, same grid level)
+    // cell-tile kernel (knn_tile_kernel): queries it hands back to the thread-per-query selection kernel
+    uint32_t *ovf_list;
+    uint32_t *ovf_count;
+    int no_tile;    // this launch is the dense class / the overflow list: thread per query
+    unsigned long long *prof;  // PCR_TILE_PROF: per-warp cycle counters of the tile kernel (8 words per warp)
     unsigned long long *stats;  // optional {queries, distance evaluations} counters of the selection kernel (timing on)
 };
 
@@ -115,7 +124,7 @@ __global__ void __launch_bounds__(kThreads, (!kSmem && QPW == kQPWS) ? 8 : 1) kn
         int cnt = 0;
         tk.reset(PCR_EMPTY_KEY);
         if (finite3(x, y, z)) {  // kdtree.rs:65
-            if (!warp_knn_search(tk, g, a.cell_start, a.pts, x, y, z, a.max_rings, a.last_level != 0, PCR_EMPTY_KEY, QPW == kQPWS ? &s_sel[w] : nullptr)) {
+            if (!warp_knn_search(tk, g, a.cell_start, a.pts, x, y, z, a.max_rings, a.last_level != 0, PCR_EMPTY_KEY, (QPW == kQPWS || a.no_tile) ? &s_sel[w] : nullptr)) {
                 defer_query(a, qi, lane);
                 continue;
             }
@@ -161,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, (!kSmem && QPW == kQPWS) ? 8 : 1) so
                 if (lane == 0) scnt[t] = -1;
                 continue;
             }
-            bool done = warp_knn_search(tk, g, a.cell_start, a.pts, q.x, q.y, q.z, a.max_rings, a.last_level != 0, PCR_EMPTY_KEY, QPW == kQPWS ? &s_sel[w] : nullptr);
+            bool done = warp_knn_search(tk, g, a.cell_start, a.pts, q.x, q.y, q.z, a.max_rings, a.last_level != 0, PCR_EMPTY_KEY, (QPW == kQPWS || a.no_tile) ? &s_sel[w] : nullptr);
             int cnt = tk.count();
             if (!done) {
                 defer_query(a, pos, lane);
@@ -339,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, (!kSmem && QPW == kQPWS) ? 8 : 1) no
                 if (lane == 0) scnt[t] = -1;
                 continue;
             }
-            bool done = warp_knn_search(tk, g, a.cell_start, a.pts, q.x, q.y, q.z, a.max_rings, a.last_level != 0, PCR_EMPTY_KEY, QPW == kQPWS ? &s_sel[w] : nullptr);
+            bool done = warp_knn_search(tk, g, a.cell_start, a.pts, q.x, q.y, q.z, a.max_rings, a.last_level != 0, PCR_EMPTY_KEY, (QPW == kQPWS || a.no_tile) ? &s_sel[w] : nullptr);
             int cnt = tk.count();
             if (!done) {
                 defer_query(a, pos, lane);
@@ -573,6 +582,8 @@ __global__ void __launch_bounds__(kTQThreads) knn_thread_kernel(LevelArgs a, Thr
 template <int MODE>
 int launch_sel_kernel(Ctx *ctx, const LevelArgs &a, const ThreadArgs &t);
 inline bool use_select(int kk);
+template <class Kern>
+int set_smem(Ctx *ctx, Kern kern, size_t bytes);
 
 template <int MODE>
 int launch_thread_kernel(Ctx *ctx, const LevelArgs &a, const ThreadArgs &t) {
@@ -726,6 +737,248 @@ __global__ void __launch_bounds__(kTQThreads, 6) knn_sel_kernel(LevelArgs a, Thr
     }
 }
 
+
+// ---- level 0 as a cell-tile program (knn_tile.cuh): MODE 1 SOR, 2 normals, 3 SOR + lists kept ------------------------
+enum TileOutcome { kTileDone = 0, kTileDefer = 1, kTileContinue = 2, kTileDense = 3, kTileSkip = 4 };
+
+template <int MODE>
+__global__ void __launch_bounds__(kTileThreads, 16 / kTileWarps) knn_tile_kernel(LevelArgs a, ThreadArgs t) {
+    extern __shared__ __align__(16) unsigned char tile_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    TileWarp &S = reinterpret_cast<TileWarp *>(tile_raw)[w];
+    const uint32_t n2 = a.nq2_dev ? *a.nq2_dev : 0u;  // (the heavy queries lead)
+    const uint32_t nq = a.nq_dev ? min(a.nq, *a.nq_dev + n2) : a.nq;
+    const uint32_t slot = blockIdx.x * kTileThreads + threadIdx.x;
+    if ((slot & ~31u) >= nq) return;  // (warp-uniform: the launch is for a capacity)
+    const bool active = slot < nq;
+    const uint32_t q = active ? (slot < n2 ? a.qlist2[slot] : (a.qlist ? a.qlist[slot - n2] : a.q_offset + slot)) : 0u;
+    const int kk = t.kk;
+    if (lane == 0) mbar_init(&S.bar, 1);
+    fence_mbar_init();
+    __syncwarp();
+    float4 qp = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+    if (active) qp = __ldg(&a.qpts[q]);
+    const float px = qp.x, py = qp.y, pz = qp.z;
+    const uint32_t out = __float_as_uint(qp.w);
+    const int f = active ? frame_of_sorted(a.grids, a.n_frames, q) : 0;
+    bool pending = active && px == px;  // a tombstoned point (index_apply_mask_dev) is not a query
+    int outcome = pending ? kTileDone : kTileSkip;
+    int c0 = 0, c1 = 0, c2 = 0;
+    float ff0 = 0.f, ff1 = 0.f, ff2 = 0.f;
+    if (pending) {
+        const GridDesc g = a.grids[f];
+        const uint32_t m = g.pt_end - g.pt_begin;
+        if (m <= kBruteFrame || m <= (uint32_t)kk) {  // tiny frame: the follow-up pass scans it whole
+            outcome = kTileContinue;
+            pending = false;
+        } else {
+            double f0, f1, f2;
+            c0 = cell_coord(g, 0, pick_axis(g.ax[0], px, py, pz), &f0);
+            c1 = cell_coord(g, 1, pick_axis(g.ax[1], px, py, pz), &f1);
+            c2 = cell_coord(g, 2, pick_axis(g.ax[2], px, py, pz), &f2);
+            ff0 = (float)f0;
+            ff1 = (float)f1;
+            ff2 = (float)f2;
+        }
+    }
+    uint32_t phase = 0, n_eval = 0;
+    long long pt0 = clock64(), pt_stage = 0, pt_collect = 0, pt_rank = 0, pt_epi = 0, pt_mark = 0;
+    unsigned n_sub = 0, n_max = 0;
+#define PCR_PROF_MARK(acc)                \
+    if (a.prof) {                         \
+        const long long now_ = clock64(); \
+        acc += now_ - pt_mark;            \
+        pt_mark = now_;                   \
+    }
+    while (true) {
+        const unsigned pm = __ballot_sync(PCR_FULL, pending);
+        if (!pm) break;
+        n_sub++;
+        pt_mark = clock64();
+        // ---- the sub-tile: pending queries of the first pending query's layer, up to kTileRowSpan rows from its row and
+        // kTileZReach cells from its cell; if that is too much for the buffer its row alone, then its cell alone ---------
+        const int leader = __ffs(pm) - 1;
+        const int Lf = __shfl_sync(PCR_FULL, f, leader), L0 = __shfl_sync(PCR_FULL, c0, leader), L1 = __shfl_sync(PCR_FULL, c1, leader),
+                  L2 = __shfl_sync(PCR_FULL, c2, leader);
+        const GridDesc *lg = a.grids + Lf;
+        const int d0n = lg->dims[0], d1n = lg->dims[1], d2n = lg->dims[2];
+        const uint32_t cell_base = lg->cell_base;
+        bool member = false;
+        int W = 3;  // staged rows per layer: the members' rows and one on either side
+        uint32_t lin = 0, gb = 0, n = 0, inc = 0, Nu = 0;
+#pragma unroll 1
+        for (int attempt = 0; attempt < 3; attempt++) {
+            member = pending && f == Lf && c0 == L0 &&
+                     (attempt == 0 ? ((unsigned)(c1 - L1) < (unsigned)kTileRowSpan && abs(c2 - L2) <= kTileZReach)
+                                   : (c1 == L1 && (attempt == 1 ? abs(c2 - L2) <= kTileZReach : c2 == L2)));
+            const int a1hi = __reduce_max_sync(PCR_FULL, member ? c1 : L1);
+            const int zlo = __reduce_min_sync(PCR_FULL, member ? c2 : 0x7fffffff), zhi = __reduce_max_sync(PCR_FULL, member ? c2 : -1);
+            W = a1hi - L1 + 3;
+            // lanes 0 .. 3 W - 1: rows (L0 - 1 .. L0 + 1) x (L1 - 1 .. a1hi + 1), cells [zlo - 1, zhi + 1]
+            const int a0 = L0 + lane / W - 1, a1 = L1 - 1 + lane % W;
+            const bool rvalid = lane < 3 * W && a0 >= 0 && a0 < d0n && a1 >= 0 && a1 < d1n;
+            lin = rvalid ? cell_base + ((uint32_t)a0 * (uint32_t)d1n + (uint32_t)a1) * (uint32_t)d2n : 0u;
+            const int zb = max(zlo - 1, 0), ze = min(zhi + 1, d2n - 1);
+            uint32_t ge = 0;
+            gb = 0;
+            if (rvalid) {
+                gb = __ldg(&a.cell_start[lin + (uint32_t)zb]);
+                ge = __ldg(&a.cell_start[lin + (uint32_t)ze + 1u]);
+            }
+            n = ge - gb;
+            inc = n;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(PCR_FULL, inc, d);
+                if (lane >= d) inc += up;
+            }
+            Nu = __shfl_sync(PCR_FULL, inc, 31);
+            if (Nu <= (uint32_t)kTileCap) break;
+        }
+        if (Nu > (uint32_t)kTileCap) {  // (warp-uniform) a dense object: not a tile's job
+            if (member) {
+                outcome = kTileDense;
+                pending = false;
+            }
+            continue;
+        }
+        __syncwarp();  // every lane is done with the previous sub-tile
+        if (lane < 3 * W) S.row[lane] = make_int4((int)lin, (int)gb, (int)(inc - n), (int)n);
+        fence_proxy_async();  // generic reads / writes of the staging buffer before the async proxy overwrites it
+        __syncwarp();
+        if (lane == 0) mbar_expect_tx(&S.bar, Nu * 16u);
+        __syncwarp();
+        if (n) bulk_g2s(&S.stage[inc - n], a.pts + gb, n * 16u, &S.bar);
+        // while the copies fly: every member's window in each staged row
+        uint32_t N = 0;
+        if (member) {
+            const int z0 = max(c2 - 1, 0), z1 = min(c2 + 1, d2n - 1);
+#pragma unroll
+            for (int r = 0; r < 9; r++) {
+                const int4 R = S.row[(r / 3) * W + (c1 - L1) + r % 3];
+                uint32_t b = 0, e = 0;
+                if (R.w) {
+                    const uint32_t wb = __ldg(&a.cell_start[(uint32_t)R.x + (uint32_t)z0]), we = __ldg(&a.cell_start[(uint32_t)R.x + (uint32_t)z1 + 1u]);
+                    b = (uint32_t)R.z + (wb - (uint32_t)R.y);
+                    e = (uint32_t)R.z + (we - (uint32_t)R.y);
+                }
+                S.seg[r][lane] = b | (e << 16);
+                N += e - b;
+            }
+        }
+        mbar_wait(&S.bar, phase);
+        phase ^= 1u;
+        PCR_PROF_MARK(pt_stage)
+        n_max = max(n_max, __reduce_max_sync(PCR_FULL, N));
+
+        const float h2 = (float)(lg->h * lg->h);
+        // ---- the 27 cells: threshold, collection, ranking --------------------------------------------------------
+        bool live = member;
+        int cnt = 0;
+        if (live) {
+            cnt = tile_collect(S, lane, kk, N, px, py, pz, h2, n_eval);
+            if (cnt > kTileSlots || cnt < 0) {  // more than the slots hold below the threshold: exact ties
+                outcome = kTileDense;
+                live = false;
+            }
+        }
+        if (!live) cnt = 0;
+        PCR_PROF_MARK(pt_collect)
+        const int m = cnt < kk ? cnt : kk;
+        {
+            uint32_t k[kTileSlots];
+            tile_rank(S, lane, cnt, k);
+            if (live) tile_fix(S, lane, cnt, m, k, px, py, pz);
+            // the ranked list back into the slots: the k-th and the epilogue read it from there (a select chain over k[]
+            // makes the compiler index a local-memory copy of it)
+#pragma unroll
+            for (int j = 0; j < kTileMaxK; j++)
+                if (j < m) S.slot[j][lane] = k[j];
+        }
+        bool fin = false;
+        if (live) {
+            // ---- is the list final?  (the ring rule of every search in this library, shell 1) -----------------------
+            unsigned long long kth_key = PCR_EMPTY_KEY;
+            if (m == kk) kth_key = tile_full_key(S, S.slot[kk - 1][lane], px, py, pz);
+            const GridDesc g = *lg;
+            double f0, f1, f2, bound2;
+            cell_coord(g, 0, pick_axis(g.ax[0], px, py, pz), &f0);
+            cell_coord(g, 1, pick_axis(g.ax[1], px, py, pz), &f1);
+            cell_coord(g, 2, pick_axis(g.ax[2], px, py, pz), &f2);
+            if (!ring_bound2(g, c0, c1, c2, f0, f1, f2, 1, bound2)) {
+                fin = true;  // the whole grid has been scanned
+            } else if (kth_key != PCR_EMPTY_KEY && (double)key_d2(kth_key) < bound2 * (1.0 - 1e-6)) {
+                fin = true;
+            } else if (!a.last_level && (1 >= a.max_rings || m * 4 < kk)) {
+                outcome = kTileDefer;  // same rule as every level-0 search: a sparse neighbourhood belongs to the coarser grid
+            } else {
+                // a second shell: rows read from global memory, trimmed to the k-th distance.  One thread doing that costs
+                // 20 K cycles of dependent loads (measured, in-tile variant of round 2) and stalls its 31 neighbours: the
+                // follow-up pass gives such a query a whole warp.  The cell size keeps them rare (occupancy_target).
+                outcome = kTileContinue;
+            }
+        }
+        PCR_PROF_MARK(pt_rank)
+        if (fin) {
+            // ---- epilogue: the list is slot[0 .. m), ascending by (d^2, index) -------------------------------------
+            if (MODE == 1 || MODE == 3) {
+                // statistical_outlier.rs:28-37: drop the first (self) if there is more than one result, sequential f32 sum
+                // in ascending-distance order, divide by the count.  MODE 3 searched kk >= kk_sor neighbours and keeps the list.
+                const int cs = MODE == 3 ? (m < t.kk_sor ? m : t.kk_sor) : m;
+                const int first = cs > 1 ? 1 : 0;
+                float sum = 0.0f;
+#pragma unroll 4
+                for (int j = 0; j < kk; j++) {
+                    float4 p = make_float4(0.f, 0.f, 0.f, __uint_as_float(0xffffffffu));
+                    if (j < m) p = S.stage[S.slot[j][lane] & kTilePos];
+                    if (j >= first && j < cs) sum = __fadd_rn(sum, __fsqrt_rn(dist2_exact(px, py, pz, p.x, p.y, p.z)));  // kdtree.rs:76
+                    if (MODE == 3) t.lists[(size_t)j * t.list_stride + q] = __float_as_uint(p.w);
+                }
+                const int mm = cs - first;
+                t.mean_d[out] = mm > 0 ? __fdiv_rn(sum, (float)mm) : INFINITY;
+                if (MODE == 3) t.list_cnt[q] = (uint8_t)m;
+            } else {
+                // estimate.rs:47-109; the neighbours' coordinates are the staged points themselves
+                float ox, oy, oz;
+                normal_from_neighbours(
+                    m,
+                    [&](int j, int c) {
+                        const float4 p = S.stage[S.slot[j][lane] & kTilePos];
+                        return c == 0 ? p.x : (c == 1 ? p.y : p.z);
+                    },
+                    px, py, pz, t.vx, t.vy, t.vz, ox, oy, oz);
+                t.nx[out] = ox;
+                t.ny[out] = oy;
+                t.nz[out] = oz;
+            }
+        }
+        PCR_PROF_MARK(pt_epi)
+        pending = pending && !member;
+    }
+    if (a.prof && lane == 0) {
+        unsigned long long *pr = a.prof + (size_t)(slot >> 5) * 8;
+        pr[0] = (unsigned long long)(clock64() - pt0);
+        pr[1] = (unsigned long long)pt_stage;
+        pr[2] = (unsigned long long)pt_collect;
+        pr[3] = (unsigned long long)pt_rank;
+        pr[4] = 0ull;
+        pr[5] = (unsigned long long)pt_epi;
+        pr[6] = ((unsigned long long)n_sub << 32) | n_max;
+        pr[7] = q;
+    }
+#undef PCR_PROF_MARK
+    push_list(outcome == kTileDefer, a.defer_list, a.defer_count, q, lane);
+    push_list(outcome == kTileContinue, a.cont_list, a.cont_count, q, lane);
+    push_list(outcome == kTileDense, a.ovf_list, a.ovf_count, q, lane);
+    if (a.stats) {
+        const unsigned evals = __reduce_add_sync(PCR_FULL, n_eval), nqw = __popc(__ballot_sync(PCR_FULL, outcome != kTileSkip && outcome != kTileDense));
+        if (lane == 0) {
+            atomicAdd(&a.stats[0], (unsigned long long)nqw);
+            atomicAdd(&a.stats[1], (unsigned long long)evals);
+        }
+    }
+}
+
 enum KnnImpl { kImplInsert = 0, kImplSelect = 1, kImplWarp = 2 };
 inline int knn_impl() {  // A/B hook: PCR_KNN_IMPL = insert (round-1 insertion kernels) | select (thread per query, selection) | warp
     static const int impl = [] {
@@ -749,9 +1002,62 @@ inline int first_shells() {
     return n;
 }
 
+// level 0 as a cell-tile program (A/B hook: PCR_KNN_TILE=0 keeps the thread-per-query selection kernel for everything)
+inline bool use_tile(int kk) {
+    static const bool on = [] {
+        const char *e = getenv("PCR_KNN_TILE");
+        return !(e && !strcmp(e, "0"));
+    }();
+    return on && kk > 0 && kk <= kTileMaxK;
+}
+
 template <int MODE>
 int launch_sel_kernel(Ctx *ctx, const LevelArgs &a, const ThreadArgs &t) {
     const unsigned blocks = (a.nq + kTQThreads - 1) / kTQThreads;
+    if constexpr (MODE != 0) {
+        if (use_tile(t.kk) && !a.no_tile && a.ovf_list && a.cont_list) {
+            constexpr size_t smem = sizeof(TileWarp) * kTileWarps;
+            static bool attr_set = false;  // (one device per process)
+            if (!attr_set) {
+                PCR_TRY(set_smem(ctx, knn_tile_kernel<MODE>, smem));
+                attr_set = true;
+            }
+            static const bool prof = getenv("PCR_TILE_PROF") != nullptr;  // debug: per-warp cycle counters, ten slowest warps printed
+            if (prof) {
+                LevelArgs ap = a;
+                const size_t nw = (a.nq + 31) / 32;
+                unsigned long long *d = nullptr;
+                PCR_CUDA(ctx, cudaMalloc(&d, nw * 64));
+                PCR_CUDA(ctx, cudaMemset(d, 0, nw * 64));
+                ap.prof = d;
+                knn_tile_kernel<MODE><<<(a.nq + kTileThreads - 1) / kTileThreads, kTileThreads, smem, ctx->stream>>>(ap, t);
+                PCR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                std::vector<unsigned long long> h(nw * 8);
+                PCR_CUDA(ctx, cudaMemcpy(h.data(), d, nw * 64, cudaMemcpyDeviceToHost));
+                cudaFree(d);
+                std::vector<size_t> order(nw);
+                for (size_t i = 0; i < nw; i++) order[i] = i;
+                std::sort(order.begin(), order.end(), [&](size_t x, size_t y) { return h[x * 8] > h[y * 8]; });
+                unsigned long long tot[6] = {0, 0, 0, 0, 0, 0}, subs = 0;
+                for (size_t i = 0; i < nw; i++) {
+                    for (int j = 0; j < 6; j++) tot[j] += h[i * 8 + j];
+                    subs += h[i * 8 + 6] >> 32;
+                }
+                fprintf(stderr, "[pcr] tile profile: %zu warps, %.2f sub-tiles / warp; mean cycles total %.0f = stage %.0f + collect %.0f + rank %.0f + shell2 %.0f + epilogue %.0f\n",
+                        nw, (double)subs / nw, (double)tot[0] / nw, (double)tot[1] / nw, (double)tot[2] / nw, (double)tot[3] / nw, (double)tot[4] / nw,
+                        (double)tot[5] / nw);
+                for (size_t r = 0; r < 10 && r < nw; r++) {
+                    const unsigned long long *e = &h[order[r] * 8];
+                    fprintf(stderr, "[pcr]   warp %zu (q %llu): total %llu = stage %llu + collect %llu + rank %llu + shell2 %llu + epilogue %llu; %llu sub-tiles, max N %llu\n",
+                            order[r], e[7], e[0], e[1], e[2], e[3], e[4], e[5], e[6] >> 32, e[6] & 0xffffffffull);
+                }
+                return PCR_OK;
+            }
+            knn_tile_kernel<MODE><<<(a.nq + kTileThreads - 1) / kTileThreads, kTileThreads, smem, ctx->stream>>>(a, t);
+            PCR_LAUNCH_CHECK(ctx);
+            return PCR_OK;  // (run_levels launches a warp-per-query pass over what the tiles handed back)
+        }
+    }
     knn_sel_kernel<MODE><<<blocks, kTQThreads, 0, ctx->stream>>>(a, t);
     PCR_LAUNCH_CHECK(ctx);
     return PCR_OK;
@@ -878,17 +1184,23 @@ int set_smem(Ctx *ctx, Kern kern, size_t bytes) {
 // neighbouring threads still hold neighbouring queries.  Every path is exact; the classes only decide where a query runs.
 constexpr int kClsThreads = 256;
 struct ClassArgs {
-    uint32_t *list[3];       // normal, dense, sparse
-    uint32_t *counts;        // [3]
+    uint32_t *list[4];       // normal, dense, sparse, heavy normal (tile kernel: the queries with many candidates start first)
+    uint32_t *count[4];
     const float *qx, *qy, *qz;  // external queries (nullptr: the indexed points themselves)
     int kk;
+    // tile kernel in use: a query with fewer than kk candidates in its 27 cells goes straight to the follow-up pass (warp
+    // per query, all shells): inside a tile it is a sub-tile of its own whose second shell has no threshold to trim it
+    uint32_t *thin;
+    uint32_t *thin_count;
+    uint32_t dense_n;  // more candidates than this in the 27 cells: the dense class
+    uint32_t heavy_n;  // more than this: heavy normal (0: no such class)
 };
 
 __global__ void __launch_bounds__(kClsThreads) classify_kernel(LevelArgs a, ClassArgs c) {
     const uint32_t slot = blockIdx.x * kClsThreads + threadIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t q = a.q_offset + slot;
-    int cls = 3;  // no query in this slot
+    int cls = 7;  // no query in this slot
     if (slot < a.nq) {
         float px, py, pz;
         int f = 0;
@@ -909,32 +1221,38 @@ __global__ void __launch_bounds__(kClsThreads) classify_kernel(LevelArgs a, Clas
             const GridDesc *gp = a.grids + f;
             const uint32_t m = gp->pt_end - gp->pt_begin;
             if (m > kBruteFrame && m > (uint32_t)c.kk) {
-                const uint32_t n27 = count_27_cells(gp, a.cell_start, px, py, pz);
-                cls = n27 * 4u < (uint32_t)c.kk ? 2 : (n27 > kSelHistMaxN ? 1 : 0);
+                // (fewer than kk in the cube: the search needs more shells whatever happens -- a warp's job, see thin)
+                // and so does a query with at most one neighbour in the three cells of its own row: an off-surface point, a
+                // sub-tile of its own wherever it sits in the order)
+                uint32_t n_row = 0;
+                const uint32_t n27 = count_27_cells(gp, a.cell_start, px, py, pz, &n_row);
+                cls = n27 * 4u < (uint32_t)c.kk ? 2 : (n27 > c.dense_n ? 1 : (c.thin && (n27 < (uint32_t)c.kk || n_row <= 2u) ? 4 : 0));
+                if (cls == 0 && c.heavy_n && n27 > c.heavy_n) cls = 3;
             }
         }
     }
-    __shared__ uint32_t s_warp[3][kClsThreads / 32];
-    __shared__ uint32_t s_base[3];
+    __shared__ uint32_t s_warp[4][kClsThreads / 32];
+    __shared__ uint32_t s_base[4];
     uint32_t my_rank = 0;
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < 4; k++) {
         const unsigned mask = __ballot_sync(PCR_FULL, cls == k);
         if (lane == 0) s_warp[k][w] = __popc(mask);
         if (cls == k) my_rank = __popc(mask & ((1u << lane) - 1u));
     }
     __syncthreads();
-    if (threadIdx.x < 3) {
+    if (threadIdx.x < 4) {
         uint32_t tot = 0;
         for (int i = 0; i < kClsThreads / 32; i++) tot += s_warp[threadIdx.x][i];
-        s_base[threadIdx.x] = tot ? atomicAdd(&c.counts[threadIdx.x], tot) : 0u;
+        s_base[threadIdx.x] = tot ? atomicAdd(c.count[threadIdx.x], tot) : 0u;
     }
     __syncthreads();
-    if (cls < 3) {
+    if (cls < 4) {
         uint32_t off = s_base[cls] + my_rank;
         for (int i = 0; i < w; i++) off += s_warp[cls][i];
         c.list[cls][off] = q;
     }
+    push_list(cls == 4, c.thin, c.thin_count, q, lane);
 }
 
 struct StreamSwap {  // the library's helpers launch on ctx->stream: run a few of them on a side stream
@@ -958,7 +1276,8 @@ template <class Launch>
 int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *init_list = nullptr, const uint32_t *nq_dev = nullptr,
                int sel_kk = 0 /* > 0: level 0 is a thread-per-query launch for this many neighbours */,
                uint32_t q_offset = 0 /* level 0 takes the queries q_offset .. q_offset + nq (a rank's shard) */,
-               const float *eqx = nullptr, const float *eqy = nullptr, const float *eqz = nullptr /* external queries (device) */) {
+               const float *eqx = nullptr, const float *eqy = nullptr, const float *eqz = nullptr /* external queries (device) */,
+               bool tile_ok = false /* level 0 may run as the cell-tile kernel (self-queries with a fused consumer) */) {
     // init_list: level 0 runs over these nq query ids only (warp kernels) instead of over all queries
     // nq_dev:    the length of init_list is still on the device; nq is the capacity level 0 is launched for
     Ctx *ctx = ix->ctx;
@@ -967,13 +1286,18 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
     // thread-per-query launches walk first_shells() shells and queue what needs more for a warp-per-query follow-up.
     const bool two_pass = !init_list && sel_kk > 0 && use_select(sel_kk);
     static const bool no_split = getenv("PCR_NO_CLASS_SPLIT") != nullptr;  // A/B hook: one launch over all queries
+    static const bool dense_warp = getenv("PCR_DENSE_THREAD") == nullptr;   // A/B hook: the dense class thread per query
+    static const int dense_qpw = getenv("PCR_DENSE_QPW1") ? kQPWL : kQPWS;  // A/B hook: one query per warp and grid step (85 vs 97 us alone on
+                                                                            // the 122 K frame, but 14.9 vs 12.5 ms on the 8 M batch)
     const bool split = two_pass && !no_split;
-    PCR_TRY(ensure(ctx, ctx->b_list, (size_t)nq * (two_pass ? 6 : 2) * sizeof(uint32_t) + 256));
+    PCR_TRY(ensure(ctx, ctx->b_list, (size_t)nq * (two_pass ? 8 : 2) * sizeof(uint32_t) + 256));
     // counters: [0], [1] deferred counts of even / odd levels, [2] follow-up count, [3..5] normal / dense / sparse counts
     uint32_t *counters = (uint32_t *)ctx->b_list.p;
     uint32_t *lists[2] = {counters + 64, counters + 64 + nq};
     uint32_t *cont = counters + 64 + 2 * (size_t)nq;
     uint32_t *cls_list[3] = {cont + nq, cont + 2 * (size_t)nq, cont + 3 * (size_t)nq};
+    uint32_t *ovf = cont + 4 * (size_t)nq;    // counters[6]: queries the tile kernel hands back
+    uint32_t *heavy = cont + 5 * (size_t)nq;  // counters[7]: normal queries with many candidates (they lead the tile launch)
     Index *cur = ix;
     const uint32_t *qlist = init_list;
     uint32_t n_cur = nq;
@@ -991,6 +1315,8 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
         a.pts = cur->sorted;
         a.qpts = ix->sorted;
         a.qlist = qlist;
+        a.qlist2 = nullptr;
+        a.nq2_dev = nullptr;
         a.q_offset = (level == 0 && !init_list) ? q_offset : 0u;
         a.nq = n_cur;
         a.nq_dev = level == 0 ? nq_dev : nullptr;
@@ -1004,13 +1330,41 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
         a.first_only = first_of_two ? first_shells() : 0;
         a.cont_list = first_of_two ? cont : nullptr;
         a.cont_count = first_of_two ? counters + 2 : nullptr;
+        a.ovf_list = first_of_two && tile_ok && use_tile(sel_kk) ? ovf : nullptr;
+        a.ovf_count = counters + 6;
+        a.no_tile = 0;
+        a.prof = nullptr;
+        // what the tile kernel hands back (exact ties, a dense cell in a non-split launch): a warp per query
+        auto launch_ovf = [&]() -> int {
+            LevelArgs o = a;
+            o.qlist = ovf;
+            o.q_offset = 0;
+            o.nq_dev = counters + 6;
+            o.no_tile = 1;
+            o.stats = nullptr;
+            TimeScope ts(ctx, kTagKnnDeferred);
+            return launch(o, kQPWS);
+        };
         if (first_of_two && split) {
             PCR_TRY(ensure_side_streams(ctx));
             ClassArgs ca;
-            for (int k = 0; k < 3; k++) ca.list[k] = cls_list[k];
-            ca.counts = counters + 3;
+            for (int k = 0; k < 3; k++) {
+                ca.list[k] = cls_list[k];
+                ca.count[k] = counters + 3 + k;
+            }
+            ca.list[3] = heavy;
+            ca.count[3] = counters + 7;
             ca.qx = eqx; ca.qy = eqy; ca.qz = eqz;
             ca.kk = sel_kk;
+            ca.thin = a.ovf_list ? cont : nullptr;
+            ca.thin_count = counters + 2;
+            // (a tile's warp is as slow as its heaviest query: with tiles the dense class starts lower)
+            static const uint32_t tile_dense_n = getenv("PCR_TILE_DENSE_N") ? (uint32_t)atoi(getenv("PCR_TILE_DENSE_N")) : kTileDenseN;
+            ca.dense_n = a.ovf_list ? tile_dense_n : kSelHistMaxN;
+            // (heavy-first order measured WORSE, 123 -> 144 us: pulling the many-candidate cells out of the cell order leaves
+            // both lists with gaps, i.e. more sub-tiles per warp; PCR_TILE_HEAVY_N re-enables the split for experiments)
+            static const uint32_t heavy_n = getenv("PCR_TILE_HEAVY_N") ? (uint32_t)atoi(getenv("PCR_TILE_HEAVY_N")) : 0u;
+            ca.heavy_n = a.ovf_list ? heavy_n : 0u;
             {
                 TimeScope ts(ctx, kTagKnnDeferred);
                 classify_kernel<<<(n_cur + kClsThreads - 1) / kClsThreads, kClsThreads, 0, ctx->stream>>>(a, ca);
@@ -1050,9 +1404,12 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
                 d.qlist = cls_list[1];
                 d.q_offset = 0;
                 d.nq_dev = counters + 4;
+                d.no_tile = 1;
                 {
+                    // (a warp per query: a dense query reads thousands of candidates, 32 at a time instead of one thread's
+                    // serial walk -- the thread-per-query launch of this class took 0.34 ms and bounded the step)
                     TimeScope ts(ctx, kTagKnnDeferred);
-                    PCR_TRY(launch(d, kQPW0));
+                    PCR_TRY(launch(d, dense_warp ? dense_qpw : kQPW0));
                 }
                 PCR_CUDA(ctx, cudaEventRecord(ctx->ev_join[1], ctx->stream));
             }
@@ -1061,13 +1418,21 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
                 m.qlist = cls_list[0];
                 m.q_offset = 0;
                 m.nq_dev = counters + 3;
+                if (a.ovf_list) {
+                    m.qlist2 = heavy;
+                    m.nq2_dev = counters + 7;
+                }
                 TimeScope ts(ctx, tag0);
                 PCR_TRY(launch(m, kQPW0));
             }
+            if (a.ovf_list) PCR_TRY(launch_ovf());
             for (int i = pre_level1 ? 0 : 1; i < 2; i++) PCR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
         } else {
-            TimeScope ts(ctx, level == 0 ? tag0 : kTagKnnDeferred);
-            PCR_TRY(launch(a, level == 0 && !init_list ? (use_warp(sel_kk) ? kQPWS : kQPW0) : kQPWL));
+            {
+                TimeScope ts(ctx, level == 0 ? tag0 : kTagKnnDeferred);
+                PCR_TRY(launch(a, level == 0 && !init_list ? (use_warp(sel_kk) ? kQPWS : kQPW0) : kQPWL));
+            }
+            if (a.ovf_list) PCR_TRY(launch_ovf());
         }
         if (first_of_two) {
             // the queries that need more than the first pass's shells: warp per query over the shells of the same level
@@ -1112,8 +1477,8 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
         if (level == 0 && !init_list && !split) ctx->spec_coarser = n_cur > 0;
         if (dbg) fprintf(stderr, "[pcr] level %d: %u of %u queries deferred (cell %.4g)\n", level, n_cur, a.nq, cur->grids_h[0].h);
         if (dbg && first_of_two)
-            fprintf(stderr, "[pcr] level 0: %u normal / %u dense / %u sparse queries, %u needed more than the first pass's shells, %u of the sparse deferred again\n",
-                    mail[3], mail[4], mail[5], mail[2], mail[1]);
+            fprintf(stderr, "[pcr] level 0: %u normal / %u dense / %u sparse queries, %u needed more than the first pass's shells, %u of the sparse deferred again, %u handed back by the tiles\n",
+                    mail[3] + mail[7], mail[4], mail[5], mail[2], mail[1], mail[6]);
         if (level == 0 && pre_level1) (mail[5] > 0 ? ctx->stat_spec_hits : ctx->stat_spec_misses)++;  // was the level built ahead needed?
         if (level == 0 && pre_level1) {
             // the sparse queries are done on level 1; what they deferred there sits in lists[1] (count mail[1]).  Level 0's own
@@ -1292,7 +1657,7 @@ int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep
             PCR_LAUNCH_CHECK(ctx);
             return PCR_OK;
         }
-        if (a.follow_up && keep_lists) {  // the first pass's leftovers on the same level: K neighbours, lists kept
+        if ((a.follow_up || a.no_tile) && keep_lists) {  // the first pass's leftovers / the dense class on the same level: K neighbours, lists kept
             const size_t smem_k = ((size_t)ta.kk * (kQPWL + 1) + 64) * sizeof(float) * kWarps;
             sor_mean_kernel<false, kQPWL><<<blocks, kThreads, smem_k, ctx->stream>>>(a, ta.kk, d_mean_d, ta.lists, ta.list_cnt, ta.list_stride, ta.kk_sor);
         } else if (kk <= 32) {
@@ -1304,7 +1669,7 @@ int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep
         }
         PCR_LAUNCH_CHECK(ctx);
         return PCR_OK;
-    }, nullptr, nullptr, keep_lists ? ta.kk : (kk <= 32 ? (int)kk : 0), q_begin);
+    }, nullptr, nullptr, keep_lists ? ta.kk : (kk <= 32 ? (int)kk : 0), q_begin, nullptr, nullptr, nullptr, true);
     PCR_TRY(rc);
     if (shard) PCR_TRY(comm_allreduce_u32(ctx, reinterpret_cast<uint32_t *>(d_mean_d), ix->n));
     return PCR_OK;
@@ -1360,7 +1725,7 @@ int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny
         }
         PCR_LAUNCH_CHECK(ctx);
         return PCR_OK;
-    }, nullptr, nullptr, k <= 32 ? (int)k : 0, q_begin);
+    }, nullptr, nullptr, k <= 32 ? (int)k : 0, q_begin, nullptr, nullptr, nullptr, true);
     PCR_TRY(rc);
     if (shard)
         for (float *p : {d_nx, d_ny, d_nz}) PCR_TRY(comm_allreduce_u32(ctx, reinterpret_cast<uint32_t *>(p), ix->n));

@@ -971,7 +971,7 @@ __device__ __forceinline__ void ws_scan_run(ThreadSel &acc, const float4 *__rest
 
 // points in the 3 x 3 x 3 cells around a query (what the first shell of every search reads): 9 row lookups
 __device__ __forceinline__ uint32_t count_27_cells(const GridDesc *__restrict__ gp, const uint32_t *__restrict__ cell_start, float qx, float qy,
-                                                   float qz) {
+                                                   float qz, uint32_t *own_row = nullptr /* the three cells of the query's own row */) {
     const GridDesc g = *gp;
     const int c0 = cell_coord(g, 0, pick_axis(g.ax[0], qx, qy, qz), nullptr);
     const int c1 = cell_coord(g, 1, pick_axis(g.ax[1], qx, qy, qz), nullptr);
@@ -985,7 +985,9 @@ __device__ __forceinline__ uint32_t count_27_cells(const GridDesc *__restrict__ 
             const int a0 = c0 + e0, a1 = c1 + e1;
             if (a0 < 0 || a0 >= g.dims[0] || a1 < 0 || a1 >= g.dims[1]) continue;
             const uint32_t lin = cell_linear(g, a0, a1, z0);
-            n += __ldg(&cell_start[lin + (uint32_t)(z1 - z0) + 1u]) - __ldg(&cell_start[lin]);
+            const uint32_t nr = __ldg(&cell_start[lin + (uint32_t)(z1 - z0) + 1u]) - __ldg(&cell_start[lin]);
+            n += nr;
+            if (own_row && e0 == 0 && e1 == 0) *own_row = nr;
         }
     return n;
 }

@@ -211,6 +211,7 @@ struct CloudStats {
 struct BuildOpts {
     const CloudStats *known_stats = nullptr;  // host; single unmasked frame only
     size_t k_hint = 0;
+    bool self_knn = false;  // the index serves the self-queries of SOR / normals (cell-tile kernel: larger cells, see occupancy_target)
     int n_frames = 1;
     const uint64_t *frame_offsets = nullptr;  // host, n_frames + 1 (nullptr if n_frames == 1)
     const uint8_t *d_mask = nullptr;          // optional device keep-mask: index only points with mask != 0
