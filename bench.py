@@ -362,7 +362,10 @@ def main():
     # lists the normals are later computed from.  Algorithmic bytes per query: read the
     # cell-sorted float4 (16), write the mean distance (4), the K list entries (4 K) and the list length (1).
     K_LIST = max(K_SOR, K_NORMALS) + 1
-    bytes_knn = n_in * (16 + 4 + 4 * K_LIST + 1)
+    # The kernel counts the queries it finishes or hands on itself (the dense / sparse / thin classes run in other launches,
+    # concurrently): the bytes are those of ITS queries.
+    q_per_launch = (knn_counters["queries"] / max(knn_s_cnt, 1)) if knn_counters["queries"] else n_in
+    bytes_knn = q_per_launch * (16 + 4 + 4 * K_LIST + 1)
     dur_knn = knn_s_ms / max(knn_s_cnt, 1) * 1e-3
     achieved = bytes_knn / dur_knn / 1e9 if dur_knn > 0 else 0.0
     props = torch.cuda.get_device_properties(local_rank)
@@ -392,12 +395,16 @@ def main():
     }
     roofline = {
         "bound": "hbm",
-        "kernel": f"knn_sel_kernel<3> (grid KNN K={K_LIST}: SOR mean distance + neighbour lists kept for the normals; level 0, thread per query, "
-                  "selection by histogram threshold + register sorting network)",
+        "kernel": f"knn_tile_kernel<3> (grid KNN K={K_LIST}: SOR mean distance + neighbour lists kept for the normals; level 0 as cell tiles: 32 "
+                  "neighbouring queries per warp, their cubes' cell runs staged in shared memory by cp.async.bulk, threshold histogram + "
+                  "register sorting network on 23-bit keys)",
+        "queries_per_launch": q_per_launch,
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
         "traffic": prof.get("dominant_kernel_dram_bytes_per_launch"),
         "algorithmic_bytes_per_launch": bytes_knn, "avg_launch_ms": dur_knn * 1e3,
-        "note": "a 119 K-point frame is L2-resident: the kernel is bound by instruction issue and per-warp latency, not by HBM (DESIGN.md)",
+        "note": "a 119 K-point frame is L2-resident: the kernel is bound by instruction issue and per-warp latency, not by HBM (DESIGN.md); "
+                "avg_launch_ms is the event time on the launching stream, during which the dense- and sparse-class launches share the GPU "
+                "(alone, under ncu, the kernel takes 0.094-0.099 ms: profiles/)",
         "fp32": fp32,
         # (the library's catch-all tag "other" holds only the voxel step in this pipeline)
         "stage_ms_per_step": {("voxel" if k == "other" else k): v[0] / args.steps for k, v in stage.items() if v[1]},

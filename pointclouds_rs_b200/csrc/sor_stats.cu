@@ -18,15 +18,23 @@ struct SorFrameStats {
     uint32_t n_finite;
 };
 
+static __device__ __noinline__ float slow_fold(const float *__restrict__ v, size_t b, size_t e, FoldTerm term, FoldShared &sh, uint32_t *n_used) {
+    return cluster_exact_fold(v, b, e, term, sh, n_used);
+}
+
 // one block CLUSTER per frame: two exact left-to-right folds (seq_fold.cuh), then the threshold
 __global__ void __launch_bounds__(kFoldThreads) sor_stats_kernel(const float *__restrict__ mean_d,
                                                                   const uint32_t *__restrict__ frame_off, size_t n,
-                                                                  float std_mul, SorFrameStats *__restrict__ stats) {
+                                                                  float std_mul, SorFrameStats *__restrict__ stats, int use_fast) {
     __shared__ FoldShared sh;
+    __shared__ SpecShared sp;
     const int f = blockIdx.x / cooperative_groups::this_cluster().num_blocks();
     const size_t b = frame_off ? frame_off[f] : 0, e = frame_off ? frame_off[f + 1] : n;
     uint32_t nf = 0;
-    const float sum = cluster_exact_fold(mean_d, b, e, [](float v) { return v; }, sh, &nf);
+    // (fast: crossings predicted from an f64 prefix and verified; the pass-per-crossing fold is the fallback -- same bits)
+    float sum;
+    FoldTerm term = {0, 0.0f};
+    if (!use_fast || !cluster_exact_fold_fast(mean_d, b, e, term, sp, &sum, &nf, use_fast == 2)) sum = slow_fold(mean_d, b, e, term, sh, &nf);
     SorFrameStats s;
     s.n_finite = nf;
     if (nf == 0) {  // statistical_outlier.rs:49-51 -> empty result (NaN threshold keeps nothing)
@@ -34,13 +42,10 @@ __global__ void __launch_bounds__(kFoldThreads) sor_stats_kernel(const float *__
     } else {
         const float nn = (float)nf;
         const float gmean = __fdiv_rn(sum, nn);
-        float var = cluster_exact_fold(
-            mean_d, b, e,
-            [gmean](float v) {
-                float d = __fsub_rn(v, gmean);
-                return __fmul_rn(d, d);  // powi(2)
-            },
-            sh, nullptr);
+        term.squared_deviation = 1;
+        term.mean = gmean;
+        float var;
+        if (!use_fast || !cluster_exact_fold_fast(mean_d, b, e, term, sp, &var, nullptr, use_fast == 2)) var = slow_fold(mean_d, b, e, term, sh, nullptr);
         var = __fdiv_rn(var, nn);
         const float sd = __fsqrt_rn(var);
         s.mean = gmean;
@@ -105,7 +110,11 @@ int sor_threshold_mask_dev(Ctx *ctx, const float *d_mean_d, const uint32_t *d_fr
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, sor_stats_kernel, d_mean_d, d_frame_off, n, std_mul, (SorFrameStats *)d_stats);
+            static const int use_fast = getenv("PCR_FOLD_SLOW") ? 0 : (getenv("PCR_FOLD_DEBUG") ? 2 : 1);  // A/B hook: the pass-per-crossing fold only
+            // (many frames: the GPU is full of independent clusters and the pass-per-crossing fold's smaller code wins -- 12.55 vs
+            // 12.9 ms on the 100-frame batch; the predicted-crossing fold is for the single long frame, 85 -> 60 us)
+            const int fast = n_frames <= 4 ? use_fast : 0;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, sor_stats_kernel, d_mean_d, d_frame_off, n, std_mul, (SorFrameStats *)d_stats, fast);
             if (e == cudaSuccess) break;
             cudaGetLastError();
             if (use <= 8) return fail(ctx, PCR_ERR_CUDA, "sor_stats_kernel launch failed: %s", cudaGetErrorString(e));
