@@ -34,7 +34,8 @@ constexpr int kTileWarps = 1;                   // one warp per block: a warp is
 constexpr uint32_t kTileDenseN = 128;           // more candidates than this in a query's 27 cells: not a tile's job (classify_kernel)
 constexpr int kTileThreads = 32 * kTileWarps;
 constexpr int kTileCap = 512;                   // staged candidates per warp
-constexpr uint32_t kTilePos = kTileCap - 1;     // low bits of a rank key: position in the staged tile
+constexpr uint32_t kTilePos = 511;              // low 9 bits of a rank key: position in the staged tile
+static_assert(kTileCap <= 512, "a staged position has 9 bits");
 constexpr int kTileSlots = 32;                  // accepted candidates per query (the sorting network's width)
 constexpr int kTileBins = 32;                   // threshold histogram (lives in the slot words before anything is accepted)
 constexpr int kTileMaxK = 24;                   // k <= this: at least 8 slots of margin behind the k-th

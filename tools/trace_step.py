@@ -12,7 +12,7 @@ import pointclouds_rs_b200 as pcr  # noqa: E402
 
 
 def main():
-    raw, _ = bench.make_frame(0)
+    raw = bench.make_frames(0, 1)[0]
     ctx = pcr.Context(device=0)
     ctx.set_frame_stream(True)
     d = pcr.DeviceCloud.from_numpy(raw, ctx)
