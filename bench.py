@@ -580,8 +580,10 @@ def icp_measurement(pcr, pdist, D, device, rank, world):
     wall = time.perf_counter() - t0
     stage = ctx.get_timing()
     ctx.set_timing(False)
+    wall_local = wall
     wall = pdist.max_over_ranks(D, wall, "cuda")
     step_ms, step_cnt = stage["icp_step"]
+    solve_ms, solve_cnt = stage["icp_solve"]
     one = pcr.icp_point_to_plane(full, tgt, 30, 0.0, ctx=solo)  # the unsharded run on this GPU
     v = torch.tensor([x for row in res.rotation for x in row] + list(res.translation) + [res.rmse, res.fitness, float(res.num_iterations)],
                      dtype=torch.float64, device="cuda")
@@ -598,6 +600,12 @@ def icp_measurement(pcr, pdist, D, device, rank, world):
         "scaling": "strong", "points": len(src_np), "source_points_on_rank0": e - b, "iterations": res.num_iterations,
         "ms_per_iter_e2e": wall * 1e3 / max(res.num_iterations, 1),
         "ms_per_iter_step_kernels_rank0": step_ms / max(step_cnt, 1),
+        # reduce kernel + [all-reduce] + solve kernel: event time on the library's stream, so at N > 1 it contains the collective
+        # AND the wait for the slowest rank to reach it
+        "ms_per_iter_reduce_allreduce_solve_rank0": solve_ms / max(solve_cnt, 1),
+        # what is not the iteration loop: upload of the shard and the (replicated) target + normals, target index build,
+        # source binning, result download -- paid once per call whatever the number of ranks
+        "ms_setup_and_host_rank0": wall_local * 1e3 - step_ms - solve_ms,
         "collective": "none (one rank)" if world == 1 else "ncclAllReduce of 30 f64 on the library's stream, every iteration",
         "identical_on_all_ranks": bool(identical), "equals_unsharded": close,
         "rmse": res.rmse, "translation": res.translation,

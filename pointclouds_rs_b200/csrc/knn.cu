@@ -1265,7 +1265,10 @@ struct StreamSwap {  // the library's helpers launch on ctx->stream: run a few o
 int ensure_side_streams(Ctx *ctx) {
     if (ctx->side[0]) return PCR_OK;
     for (int i = 0; i < 2; i++) {
-        PCR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking));
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // (lo = the numerically greatest = the least urgent)
+        static const bool flat = getenv("PCR_SIDE_FIRST") != nullptr;
+        PCR_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side[i], cudaStreamNonBlocking, flat ? hi : lo));
         PCR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
     }
     PCR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -1372,6 +1375,27 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
             }
             PCR_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
             for (int i = 0; i < 2; i++) PCR_CUDA(ctx, cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
+            // The main launch goes first and the side streams have the lowest priority: the tile kernel's blocks take every
+            // SM's shared memory (15 x 14 KB), so whichever kernel starts first runs alone -- and the tile kernel is the one
+            // with the long tail (its SMs are busy half of its duration) that the two small classes can fill.
+            auto launch_main = [&]() -> int {
+                LevelArgs m = a;
+                m.qlist = cls_list[0];
+                m.q_offset = 0;
+                m.nq_dev = counters + 3;
+                if (a.ovf_list) {
+                    m.qlist2 = heavy;
+                    m.nq2_dev = counters + 7;
+                }
+                {
+                    TimeScope ts(ctx, tag0);
+                    PCR_TRY(launch(m, kQPW0));
+                }
+                if (a.ovf_list) PCR_TRY(launch_ovf());
+                return PCR_OK;
+            };
+            static const bool side_first = getenv("PCR_SIDE_FIRST") != nullptr;  // A/B hook: the round-2a order
+            if (!side_first) PCR_TRY(launch_main());
             // side 0: the sparse queries on the next-coarser level (built here, behind the fork, while level 0 runs)
             if (!last) {
                 StreamSwap sw(ctx, ctx->side[0]);
@@ -1394,6 +1418,8 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
                 s1.cont_list = nullptr;
                 s1.cont_count = nullptr;
                 s1.stats = nullptr;
+                // (the selection front-end is NOT used here: measured 58 -> 137 us -- the 27 coarse cells of a point above the
+                // ground hold thousands of candidates, and the insertion walk trims most rows by the k-th distance instead)
                 PCR_TRY(launch(s1, kQPWL));
                 pre_level1 = true;
             }
@@ -1413,19 +1439,7 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
                 }
                 PCR_CUDA(ctx, cudaEventRecord(ctx->ev_join[1], ctx->stream));
             }
-            {  // main: everything else
-                LevelArgs m = a;
-                m.qlist = cls_list[0];
-                m.q_offset = 0;
-                m.nq_dev = counters + 3;
-                if (a.ovf_list) {
-                    m.qlist2 = heavy;
-                    m.nq2_dev = counters + 7;
-                }
-                TimeScope ts(ctx, tag0);
-                PCR_TRY(launch(m, kQPW0));
-            }
-            if (a.ovf_list) PCR_TRY(launch_ovf());
+            if (side_first) PCR_TRY(launch_main());
             for (int i = pre_level1 ? 0 : 1; i < 2; i++) PCR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
         } else {
             {

@@ -276,10 +276,23 @@ __device__ __forceinline__ bool warp_select_cube(RegTopK &tk, WarpSelScratch &S,
         const float q = (float)kk / (float)N;
         const float r2 = N > kSelHistMaxN ? h2 * cbrtf(6.4456f * q) * cbrtf(6.4456f * q) : 2.8648f * h2 * q;
         const float scale = 64.0f / ((N > kSelHistMaxN ? 3.0f : 4.0f) * r2);
-        for (uint32_t i = lane; i < N; i += 32) {
-            const float4 p = __ldg(&pts[warp_sel_locate(S, i)]);
-            const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
-            atomicAdd(&S.hist[__float2int_rz(fminf(__fmul_rn(d2, scale), 63.0f))], 1u);  // (NaN lands in bin 63, which never counts)
+        // four loads in flight per lane (a dense query reads thousands of candidates from L2: one dependent load per step was
+        // the whole pass); the open last bin is not counted at all -- most candidates of a volume land there, and 32 lanes
+        // incrementing one shared word serialise.  (Measured and dropped: widening / refining the range in further passes as
+        // the tile kernel does -- 64 -> 69 us for the dense class; what the first range misses goes to the insertion scan.)
+        for (uint32_t i0 = lane; i0 < N; i0 += 128) {
+            float4 p[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = i0 + 32u * u;
+                p[u] = __ldg(&pts[warp_sel_locate(S, i < N ? i : N - 1u)]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float d2 = dist2_exact(qx, qy, qz, p[u].x, p[u].y, p[u].z);
+                const int bin = __float2int_rz(fminf(__fmul_rn(d2, scale), 63.0f));  // (NaN lands in bin 63)
+                if (i0 + 32u * u < N && bin < 63) atomicAdd(&S.hist[bin], 1u);
+            }
         }
         __syncwarp();
         // first bin edge with at least kk candidates below it: lane l owns bins 2l, 2l+1
@@ -293,26 +306,27 @@ __device__ __forceinline__ bool warp_select_cube(RegTopK &tk, WarpSelScratch &S,
         const unsigned reached = __ballot_sync(PCR_FULL, cum >= (uint32_t)kk);
         if (!reached) return false;  // the kk-th best lies beyond the bins
         const int L = __ffs(reached) - 1;
-        const uint32_t cumL = __shfl_sync(PCR_FULL, cum, L), c0L = __shfl_sync(PCR_FULL, c0, L), c1L = __shfl_sync(PCR_FULL, c1, L);
+        const uint32_t cumL = __shfl_sync(PCR_FULL, cum, L), c1L = __shfl_sync(PCR_FULL, c1, L);
         const bool first_half = cumL - c1L >= (uint32_t)kk;
         const int bstar = 2 * L + (first_half ? 0 : 1);
         const uint32_t A = first_half ? cumL - c1L : cumL;
-        (void)c0L;
         if (A > 32u) return false;  // too many up to that edge (ties / a dense bin): the caller's insertion scan handles it
         uint32_t base = 0;
-        for (uint32_t i0 = 0; i0 < N; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            bool take = false;
-            unsigned long long k2 = 0;
-            if (i < N) {
-                const float4 p = __ldg(&pts[warp_sel_locate(S, i)]);
-                const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
-                take = d2 == d2 && __float2int_rz(fminf(__fmul_rn(d2, scale), 63.0f)) <= bstar;
-                k2 = make_key(d2, __float_as_uint(p.w));
+        for (uint32_t i0 = 0; i0 < N; i0 += 128) {
+            float4 p[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = i0 + 32u * u + lane;
+                p[u] = __ldg(&pts[warp_sel_locate(S, i < N ? i : N - 1u)]);
             }
-            const unsigned m = __ballot_sync(PCR_FULL, take);
-            if (take) S.keys[base + __popc(m & ((1u << lane) - 1u))] = k2;
-            base += __popc(m);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float d2 = dist2_exact(qx, qy, qz, p[u].x, p[u].y, p[u].z);
+                const bool take = i0 + 32u * u + lane < N && d2 == d2 && __float2int_rz(fminf(__fmul_rn(d2, scale), 63.0f)) <= bstar;
+                const unsigned m = __ballot_sync(PCR_FULL, take);
+                if (take) S.keys[base + __popc(m & ((1u << lane) - 1u))] = make_key(d2, __float_as_uint(p[u].w));
+                base += __popc(m);
+            }
         }
         __syncwarp();
         if ((uint32_t)lane < base) key = S.keys[lane];
