@@ -1304,6 +1304,7 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
     Index *cur = ix;
     const uint32_t *qlist = init_list;
     uint32_t n_cur = nq;
+    bool join_pending = false;  // the side streams of the class split have not been joined yet
     bool pre_level1 = false;  // the sparse queries have already been searched on level 1 (their own deferrals sit in lists[1])
     static const bool dbg = getenv("PCR_DEBUG") != nullptr;
     for (int level = 0;; level++) {
@@ -1440,7 +1441,7 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
                 PCR_CUDA(ctx, cudaEventRecord(ctx->ev_join[1], ctx->stream));
             }
             if (side_first) PCR_TRY(launch_main());
-            for (int i = pre_level1 ? 0 : 1; i < 2; i++) PCR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+            join_pending = true;  // (after the follow-up pass: it only needs the main launch's list, and runs beside the side streams' tails)
         } else {
             {
                 TimeScope ts(ctx, level == 0 ? tag0 : kTagKnnDeferred);
@@ -1462,6 +1463,10 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
             b.follow_up = 1;
             TimeScope ts(ctx, kTagKnnDeferred);
             PCR_TRY(launch(b, kQPWL));
+        }
+        if (join_pending) {
+            for (int i = pre_level1 ? 0 : 1; i < 2; i++) PCR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+            join_pending = false;
         }
         if (last) break;
         uint32_t *mail = (uint32_t *)ctx->pinned + 32;

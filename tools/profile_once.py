@@ -14,6 +14,17 @@ if which == "batch":
         pcr.sor_normals_batch(pts, off, 10, 1.0, 20)
     print("done", pcr.default_context().launch_count)
     sys.exit(0)
+if which == "frame":  # the bench step on device-resident clouds: voxel -> fused SOR + normals (frame stream on)
+    import bench
+    ctx = pcr.Context(device=0)
+    ctx.set_frame_stream(True)
+    d = pcr.DeviceCloud.from_numpy(bench.make_frames(0, 1)[0], ctx)
+    for _ in range(reps):
+        v = d.voxel_downsample(bench.VOXEL)
+        o = v.sor_normals(bench.K_SOR, bench.STD_MUL, bench.K_NORMALS)
+        v.free(); o.free()
+    print("done", ctx.launch_count)
+    sys.exit(0)
 if which in ("sor", "normals", "knn"):
     c = pcr.PointCloud.from_numpy(scenes.kitti_scene())
 elif which == "aerial":
