@@ -258,6 +258,8 @@ void pcr_ctx_destroy(pcr_ctx *ctx) {
     free_buf(c, c->b_small);
     free_buf(c, c->b_table);
     free_buf(c, c->b_scan);
+    free_buf(c, c->b_fine_misc);
+    free_buf(c, c->b_fine_scan);
     free_buf(c, c->b_list);
     for (auto &b : c->b_cells) free_buf(c, b);
     cudaStreamSynchronize(c->stream);

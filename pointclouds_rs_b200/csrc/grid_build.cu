@@ -483,23 +483,26 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_u64_kernel(const uint
 
 }  // namespace
 
-int exclusive_scan_u32_dev(Ctx *ctx, uint32_t *d_data, size_t n) {
+// (scratch: ticket + tile states; scans that may run at the same time on different streams need their own)
+static int exclusive_scan_u32_with(Ctx *ctx, uint32_t *d_data, size_t n, DevBuf &scratch, uint32_t &scan_epoch) {
     if (n == 0) return PCR_OK;
     const size_t tiles = (n + kScanTile - 1) / kScanTile;
-    const size_t cap_before = ctx->b_scan.cap;
-    PCR_TRY(ensure(ctx, ctx->b_scan, 16 + tiles * sizeof(unsigned long long)));
-    if (ctx->b_scan.cap != cap_before || ctx->scan_epoch >= (1u << 30) - 2) {  // fresh memory (or epoch wrap): no tag may match
-        PCR_CUDA(ctx, cudaMemsetAsync(ctx->b_scan.p, 0, ctx->b_scan.cap, ctx->stream));
-        ctx->scan_epoch = 0;
+    const size_t cap_before = scratch.cap;
+    PCR_TRY(ensure(ctx, scratch, 16 + tiles * sizeof(unsigned long long)));
+    if (scratch.cap != cap_before || scan_epoch >= (1u << 30) - 2) {  // fresh memory (or epoch wrap): no tag may match
+        PCR_CUDA(ctx, cudaMemsetAsync(scratch.p, 0, scratch.cap, ctx->stream));
+        scan_epoch = 0;
     }
-    const uint32_t epoch = ++ctx->scan_epoch;
-    uint32_t *ticket = (uint32_t *)ctx->b_scan.p;
-    unsigned long long *state = (unsigned long long *)((char *)ctx->b_scan.p + 16);
+    const uint32_t epoch = ++scan_epoch;
+    uint32_t *ticket = (uint32_t *)scratch.p;
+    unsigned long long *state = (unsigned long long *)((char *)scratch.p + 16);
     const int vec = ((uintptr_t)d_data & 15) == 0;
     scan_lookback_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(d_data, n, state, ticket, epoch, (uint32_t)tiles, vec);
     PCR_LAUNCH_CHECK(ctx);
     return PCR_OK;
 }
+
+int exclusive_scan_u32_dev(Ctx *ctx, uint32_t *d_data, size_t n) { return exclusive_scan_u32_with(ctx, d_data, n, ctx->b_scan, ctx->scan_epoch); }
 
 int exclusive_scan_u64_from_u32_dev(Ctx *ctx, const uint32_t *d_in, uint64_t *d_out, size_t n) {
     if (n == 0) {
@@ -592,6 +595,7 @@ void shape_grid(GridDesc &g, const FrameBox &b, double h, uint64_t cap) {
 void index_free(Index *ix) {
     if (!ix) return;
     if (ix->coarser) index_free(ix->coarser);
+    if (ix->finer) index_free(ix->finer);
     if (ix->owns_memory && ix->ctx) {
         cudaStream_t s = ix->ctx->stream;
         if (ix->grids) cudaFreeAsync(ix->grids, s);
@@ -618,22 +622,28 @@ int index_apply_mask_dev(Index *ix, const uint8_t *d_keep) {
         n_max = 0;
         return PCR_OK;
     };
-    for (Index *l = ix; l; l = l->coarser) {
+    auto add = [&](Index *l) -> int {
         l->d_mask = d_keep;  // levels built from now on leave the removed points out
-        if (!l->n_indexed) continue;
+        if (!l->n_indexed) return PCR_OK;
         t.sorted[t.levels] = l->sorted;
         t.n[t.levels] = (uint32_t)l->n_indexed;
         n_max = std::max(n_max, t.n[t.levels]);
         if (++t.levels == 4) PCR_TRY(flush());
-    }
+        return PCR_OK;
+    };
+    for (Index *l = ix; l; l = l->coarser) PCR_TRY(add(l));
+    if (ix->finer) PCR_TRY(add(ix->finer));
     return flush();
 }
 
 // Next-coarser level: same points, same frames, cell size x kLevelFactor.  Reuses the bounding
 // boxes and the AoS copy of level 0, so it costs one count + scan + scatter (no host round trip).
-int index_coarser_level(Index *ix, Index **out) {
-    if (ix->coarser) {
-        *out = ix->coarser;
+// fine = the other direction: cell size / 2 (or as fine as the cell-table cap allows), attached as ix->finer; it is built
+// on its own side stream at the same time as the coarser level, hence its own scratch.
+static int index_level_build(Index *ix, bool fine, Index **out) {
+    Index *&slot_ptr = fine ? ix->finer : ix->coarser;
+    if (slot_ptr) {
+        *out = slot_ptr;
         return PCR_OK;
     }
     Ctx *ctx = ix->ctx;
@@ -674,6 +684,10 @@ int index_coarser_level(Index *ix, Index **out) {
         GridDesc &g = c->grids_h[f];
         double factor = kLevelFactor;
         if (const char *ev = getenv("PCR_LEVEL_FACTOR")) factor = atof(ev);  // tuning hook
+        if (fine) {
+            factor = 0.6;  // (swept on the 122 K frame: 0.35 -> 0.592 ms per step, 0.42 -> 0.530, 0.5 -> 0.523, 0.6 -> 0.511, 0.7 -> 0.515)
+            if (const char *ev = getenv("PCR_FINE_FACTOR")) factor = atof(ev);  // tuning hook
+        }
         shape_grid(g, b, ix->grids_h[f].h * factor, cap);
         g.cell_base = (uint32_t)base;
         base += g.n_cells;
@@ -685,8 +699,9 @@ int index_coarser_level(Index *ix, Index **out) {
     }
     c->total_cells = (uint32_t)base;
     PCR_CUDA(ctx, cudaMemcpyAsync(c->grids, c->grids_h.data(), sizeof(GridDesc) * F, cudaMemcpyHostToDevice, st));
-    if (ix->cell_slot >= 0 && ix->cell_slot + 1 < (int)(sizeof(ctx->b_cells) / sizeof(ctx->b_cells[0]))) {
-        c->cell_slot = ix->cell_slot + 1;
+    constexpr int kSlots = (int)(sizeof(ctx->b_cells) / sizeof(ctx->b_cells[0]));
+    if (fine ? ix->cell_slot == 0 : (ix->cell_slot >= 0 && ix->cell_slot + 1 < kSlots - 1)) {
+        c->cell_slot = fine ? kSlots - 1 : ix->cell_slot + 1;  // (the last slot is the finer level's)
         PCR_TRY(ensure(ctx, ctx->b_cells[c->cell_slot], sizeof(uint32_t) * ((size_t)base + 1)));
         c->cell_start = (uint32_t *)ctx->b_cells[c->cell_slot].p;
     } else {
@@ -694,8 +709,9 @@ int index_coarser_level(Index *ix, Index **out) {
     }
     PCR_CUDA(ctx, cudaMemsetAsync(c->cell_start, 0, sizeof(uint32_t) * ((size_t)base + 1), st));
     PCR_CUDA(ctx, cudaMallocAsync((void **)&c->sorted, sizeof(float4) * std::max<size_t>(n, 1), st));
-    PCR_TRY(ensure(ctx, ctx->b_misc, sizeof(uint32_t) * 2 * std::max<size_t>(n, 1)));
-    uint32_t *d_cell_id = (uint32_t *)ctx->b_misc.p;
+    DevBuf &scratch = fine ? ctx->b_fine_misc : ctx->b_misc;
+    PCR_TRY(ensure(ctx, scratch, sizeof(uint32_t) * 2 * std::max<size_t>(n, 1)));
+    uint32_t *d_cell_id = (uint32_t *)scratch.p;
     uint32_t *d_rank = d_cell_id + std::max<size_t>(n, 1);
     const uint32_t ns = (uint32_t)ix->n_indexed;
     if (ns > 0) {
@@ -703,17 +719,21 @@ int index_coarser_level(Index *ix, Index **out) {
                                                                                                d_cell_id, d_rank);
         PCR_LAUNCH_CHECK(ctx);
     }
-    PCR_TRY(exclusive_scan_u32_dev(ctx, c->cell_start, (size_t)base + 1));
+    if (fine) PCR_TRY(exclusive_scan_u32_with(ctx, c->cell_start, (size_t)base + 1, ctx->b_fine_scan, ctx->fine_scan_epoch));
+    else PCR_TRY(exclusive_scan_u32_dev(ctx, c->cell_start, (size_t)base + 1));
     if (ns > 0) {
         scatter_sorted_kernel<<<(ns + kBuildThreads - 1) / kBuildThreads, kBuildThreads, 0, st>>>(ix->sorted, ns, c->cell_start, d_cell_id,
                                                                                                  d_rank, c->sorted);
         PCR_LAUNCH_CHECK(ctx);
     }
     guard.ix = nullptr;
-    ix->coarser = c;
+    slot_ptr = c;
     *out = c;
     return PCR_OK;
 }
+
+int index_coarser_level(Index *ix, Index **out) { return index_level_build(ix, false, out); }
+int index_finer_level(Index *ix, Index **out) { return index_level_build(ix, true, out); }
 
 int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz, size_t n, const BuildOpts &opts,
                     Index **out) {

@@ -1016,7 +1016,9 @@ int launch_sel_kernel(Ctx *ctx, const LevelArgs &a, const ThreadArgs &t) {
     const unsigned blocks = (a.nq + kTQThreads - 1) / kTQThreads;
     if constexpr (MODE != 0) {
         if (use_tile(t.kk) && !a.no_tile && a.ovf_list && a.cont_list) {
-            constexpr size_t smem = sizeof(TileWarp) * kTileWarps;
+            // (tuning hook PCR_TILE_PAD_SMEM: extra bytes per block = fewer resident tile blocks per SM, room for the other classes)
+            static const size_t pad = getenv("PCR_TILE_PAD_SMEM") ? (size_t)atoi(getenv("PCR_TILE_PAD_SMEM")) : 0;
+            const size_t smem = sizeof(TileWarp) * kTileWarps + pad;
             static bool attr_set = false;  // (one device per process)
             if (!attr_set) {
                 PCR_TRY(set_smem(ctx, knn_tile_kernel<MODE>, smem));
@@ -1290,6 +1292,7 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
     const bool two_pass = !init_list && sel_kk > 0 && use_select(sel_kk);
     static const bool no_split = getenv("PCR_NO_CLASS_SPLIT") != nullptr;  // A/B hook: one launch over all queries
     static const bool dense_warp = getenv("PCR_DENSE_THREAD") == nullptr;   // A/B hook: the dense class thread per query
+    static const bool dense_fine = getenv("PCR_DENSE_NO_FINE") == nullptr;  // A/B hook: the dense class on level 0, warp per query
     static const int dense_qpw = getenv("PCR_DENSE_QPW1") ? kQPWL : kQPWS;  // A/B hook: one query per warp and grid step (85 vs 97 us alone on
                                                                             // the 122 K frame, but 14.9 vs 12.5 ms on the 8 M batch)
     const bool split = two_pass && !no_split;
@@ -1310,7 +1313,7 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
     for (int level = 0;; level++) {
         const bool last = level == kMaxLevels - 1;
         uint32_t *cnt = counters + (level & 1);
-        if (level == 0) PCR_CUDA(ctx, cudaMemsetAsync(counters, 0, 8 * sizeof(uint32_t), ctx->stream));
+        if (level == 0) PCR_CUDA(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(uint32_t), ctx->stream));
         else if (!(level == 1 && pre_level1)) PCR_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(uint32_t), ctx->stream));
         LevelArgs a;
         a.grids = cur->grids;
@@ -1432,10 +1435,24 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
                 d.q_offset = 0;
                 d.nq_dev = counters + 4;
                 d.no_tile = 1;
-                {
+                TimeScope ts(ctx, kTagKnnDeferred);
+                if (a.ovf_list && dense_fine) {
+                    // Dense means "too many points per cell", so these queries get smaller cells: the FINER level (cell / 2,
+                    // built here on this side stream), same warp-per-query kernel -- an eighth of the candidates.  A dense query
+                    // on level 0 costs 15 ns of the whole GPU (1 900 candidates, two passes) against 0.4 ns for a tile query:
+                    // 2.9 of the 8 M batch's 11.7 ms for 2.4 % of its queries.  (Measured and dropped: the fine level under the
+                    // TILE kernel -- 165 us for 11 K queries: 240 candidates per thread is a long serial chain, and only 350
+                    // warps carry it; its leftovers then need lists of their own for the level-0 warp kernels.)
+                    Index *fine = nullptr;
+                    PCR_TRY(index_finer_level(cur, &fine));
+                    d.grids = fine->grids;
+                    d.cell_start = fine->cell_start;
+                    d.pts = fine->sorted;
+                    d.stats = nullptr;
+                    PCR_TRY(launch(d, dense_qpw));
+                } else {
                     // (a warp per query: a dense query reads thousands of candidates, 32 at a time instead of one thread's
                     // serial walk -- the thread-per-query launch of this class took 0.34 ms and bounded the step)
-                    TimeScope ts(ctx, kTagKnnDeferred);
                     PCR_TRY(launch(d, dense_warp ? dense_qpw : kQPW0));
                 }
                 PCR_CUDA(ctx, cudaEventRecord(ctx->ev_join[1], ctx->stream));
@@ -1470,7 +1487,7 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
         }
         if (last) break;
         uint32_t *mail = (uint32_t *)ctx->pinned + 32;
-        PCR_CUDA(ctx, cudaMemcpyAsync(mail, counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        PCR_CUDA(ctx, cudaMemcpyAsync(mail, counters, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));  // (words 32 .. 47 of the block)
         for (const auto &pg : ctx->piggy)  // small results other steps want from the same round trip
             PCR_CUDA(ctx, cudaMemcpyAsync(pg.dst, pg.src, pg.bytes, cudaMemcpyDeviceToHost, ctx->stream));
         ctx->piggy.clear();

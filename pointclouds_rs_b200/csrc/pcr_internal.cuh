@@ -60,6 +60,7 @@ struct Index {
     std::vector<uint32_t> box_count;
     const uint8_t *d_mask = nullptr;  // keep-mask the index was built with (caller memory)
     Index *coarser = nullptr;         // next grid level (8x the cell size), built on demand
+    Index *finer = nullptr;           // half the cell size: where the dense class of level 0 is searched (knn.cu), built on demand
     bool shares_orig4 = false;        // coarser levels borrow orig4 / grids layout from level 0
     int cell_slot = -1;               // >= 0: cell_start lives in ctx->b_cells[cell_slot] (transient index), not owned
     // query shard of this rank (sorted positions): set by index_shard_queries, default = every indexed point
@@ -100,6 +101,9 @@ struct Ctx {
     DevBuf b_in2;      // second cloud (ICP source)
     DevBuf b_out;      // staged outputs
     DevBuf b_misc;     // per-point scratch (cell ids, ranks, mean distances ...)
+    // the finer level is built on a side stream while the coarser one is built on another: own per-point and scan scratch
+    DevBuf b_fine_misc, b_fine_scan;
+    uint32_t fine_scan_epoch = 0;
     DevBuf b_misc2;
     DevBuf b_small;    // reductions, statistics, ICP state
     DevBuf b_table;    // probe cell table
@@ -222,6 +226,8 @@ int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz,
 void index_free(Index *ix);
 // The next-coarser level of `ix` (cell size x kLevelFactor), built on first use and owned by `ix`.
 int index_coarser_level(Index *ix, Index **out);
+// The finer level of `ix` (cell size / 2, or as fine as the cell-table cap allows), built on first use and owned by `ix`.
+int index_finer_level(Index *ix, Index **out);
 
 // KNN over external queries (n_frames == 1).  d_idx/d_dist row-major nq x k.
 int knn_queries_dev(Index *ix, const float *dqx, const float *dqy, const float *dqz, size_t nq,
