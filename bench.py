@@ -603,6 +603,7 @@ def icp_measurement(pcr, pdist, D, device, rank, world):
         # reduce kernel + [all-reduce] + solve kernel: event time on the library's stream, so at N > 1 it contains the collective
         # AND the wait for the slowest rank to reach it
         "ms_per_iter_reduce_allreduce_solve_rank0": solve_ms / max(solve_cnt, 1),
+        "ms_per_iter_loop_rank0": step_ms / max(step_cnt, 1) + solve_ms / max(solve_cnt, 1),  # the iteration itself: what sharding can shrink
         # what is not the iteration loop: upload of the shard and the (replicated) target + normals, target index build,
         # source binning, result download -- paid once per call whatever the number of ranks
         "ms_setup_and_host_rank0": wall_local * 1e3 - step_ms - solve_ms,
