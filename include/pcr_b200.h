@@ -49,8 +49,8 @@
 extern "C" {
 #endif
 
-#define PCR_B200_VERSION 120 /* 0.1.1: + voxel, cluster, RANSAC, device-resident clouds; 111/112: + block upload / download, nowait;
-                                0.2.0 (120): + query sharding over a communicator, frame-stream hint statistics */
+#define PCR_B200_VERSION 121 /* 0.1.1: + voxel, cluster, RANSAC, device-resident clouds; 111/112: + block upload / download, nowait;
+                                0.2.0 (120): + query sharding over a communicator, frame-stream hint statistics; 121: + pcr_ctx_comm_kind */
 
 typedef enum pcr_status {
     PCR_OK = 0,
@@ -119,6 +119,14 @@ int pcr_comm_unique_id(void *out_id /* PCR_UNIQUE_ID_BYTES */);
 int pcr_ctx_comm_init(pcr_ctx *ctx, const void *id, int rank, int world_size);
 int pcr_ctx_comm_rank(const pcr_ctx *ctx);
 int pcr_ctx_comm_size(const pcr_ctx *ctx);
+/* How the ICP normal equations (icp_plane.rs:55-79, icp.rs:221-244 summed over a sharded source) are all-reduced on this
+ * context: 0 = no exchange (one rank), 1 = ncclAllReduce, 2 = a one-shot all-reduce over NVLink peer memory fused into the
+ * reduction kernel (one process per GPU on one node, blocks shared through CUDA IPC; chosen by pcr_ctx_comm_init when
+ * every rank could map every peer, PCR_ICP_NCCL=1 forces 1). */
+#define PCR_COMM_NONE 0
+#define PCR_COMM_NCCL 1
+#define PCR_COMM_PEER 2
+int pcr_ctx_comm_kind(const pcr_ctx *ctx);
 /* Query sharding of ONE cloud over the ranks of the context's communicator (the reference's
  * loops this parallelises: crates/normals/src/estimate.rs:42-45, crates/filters/src/statistical_outlier.rs:19-39,
  * crates/filters/src/radius_outlier.rs:8-16).  When enabled (and pcr_ctx_comm_init gave the context more than one

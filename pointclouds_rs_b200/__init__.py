@@ -136,6 +136,11 @@ class Context:
         buf = C.create_string_buffer(uid, _ffi.PCR_UNIQUE_ID_BYTES)
         _ffi.check(_ffi.load().pcr_ctx_comm_init(self._h, buf, rank, world_size), self._h)
 
+    @property
+    def comm_kind(self) -> str:
+        """How the sharded ICP all-reduces its normal equations on this context: 'none', 'nccl' or 'peer' (NVLink peer memory)."""
+        return ("none", "nccl", "peer")[_ffi.load().pcr_ctx_comm_kind(self._h)]
+
 
 _default_ctx: Optional[Context] = None
 

@@ -78,6 +78,7 @@ SIGNATURES = {
     "pcr_ctx_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
     "pcr_ctx_comm_rank": (C.c_int, [vp]),
     "pcr_ctx_comm_size": (C.c_int, [vp]),
+    "pcr_ctx_comm_kind": (C.c_int, [vp]),
     "pcr_index_build": (C.c_int, [vp, f32p, f32p, f32p, C.c_size_t, C.c_size_t, C.POINTER(vp)]),
     "pcr_index_build_dev": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.POINTER(vp)]),
     "pcr_index_free": (None, [vp]),

@@ -395,6 +395,10 @@ int pcr_ctx_comm_init(pcr_ctx *ctx, const void *id, int rank, int world_size) {
 }
 int pcr_ctx_comm_rank(const pcr_ctx *ctx) { return ctx ? ctx->c.rank : 0; }
 int pcr_ctx_comm_size(const pcr_ctx *ctx) { return ctx ? ctx->c.world : 1; }
+int pcr_ctx_comm_kind(const pcr_ctx *ctx) {
+    if (!ctx || ctx->c.world <= 1 || ctx->c.fake_comm) return PCR_COMM_NONE;
+    return ctx->c.peer_ok ? PCR_COMM_PEER : PCR_COMM_NCCL;
+}
 
 /* ---- index ------------------------------------------------------------------------------------ */
 static int wrap_index(pcr_ctx *ctx, Index *ix, pcr_index **out) {

@@ -8,6 +8,8 @@
 
 #include <dlfcn.h>
 
+#include <vector>
+
 namespace pcr {
 
 namespace {
@@ -81,6 +83,77 @@ int comm_unique_id(void *out) {
     return PCR_OK;
 }
 
+int comm_allgather_bytes(Ctx *ctx, const void *d_send, void *d_recv, size_t bytes);
+int comm_allreduce_u32(Ctx *ctx, uint32_t *d_buf, size_t count);
+
+// ---- exchange blocks for the one-shot all-reduce of the ICP sums (icp.cu: icp_reduce_kernel) ----------------------------
+// Every rank allocates one block with cudaMalloc (pool memory cannot be exported), exports it with cudaIpcGetMemHandle, the
+// handles travel through ncclAllGather, every rank opens its peers' blocks (one process per GPU: CUDA IPC; NVLink peer access is
+// enabled lazily by the open).  All ranks must take the same path, so the outcome is agreed on with an integer all-reduce: if
+// any rank failed anywhere, all fall back to ncclAllReduce.  PCR_ICP_NCCL=1 forces that (A/B hook).
+static void peer_teardown(Ctx *ctx) {
+    for (int p = 0; p < kPeerMaxWorld; p++) {
+        if (ctx->peer_open[p]) cudaIpcCloseMemHandle(ctx->peer_open[p]);
+        ctx->peer_open[p] = nullptr;
+    }
+    if (ctx->peer_block) cudaFree(ctx->peer_block);
+    ctx->peer_block = nullptr;
+    ctx->peer_ok = false;
+    ctx->peer = {};
+    cudaGetLastError();
+}
+
+static void peer_setup(Ctx *ctx) {
+    const int W = ctx->world, R = ctx->rank;
+    if (W <= 1 || W > kPeerMaxWorld) return;
+    bool ok = getenv("PCR_ICP_NCCL") == nullptr;
+    unsigned char *d_tmp = nullptr;  // [0, 64 W): the handles; then one u32 for the agreement
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    std::vector<cudaIpcMemHandle_t> handles(W);
+    if (cudaMalloc((void **)&d_tmp, hb * W + 64) != cudaSuccess) {
+        cudaGetLastError();
+        return;  // (no collective has been issued yet: returning here cannot desynchronise the ranks only if ALL fail; see below)
+    }
+    if (ok && cudaMalloc(&ctx->peer_block, kPeerBlockBytes) != cudaSuccess) ok = false;
+    if (ok && cudaMemset(ctx->peer_block, 0, kPeerBlockBytes) != cudaSuccess) ok = false;
+    cudaIpcMemHandle_t mine = {};
+    if (ok && cudaIpcGetMemHandle(&mine, ctx->peer_block) != cudaSuccess) ok = false;
+    cudaGetLastError();
+    // the collectives below are issued by every rank whatever happened above
+    cudaMemcpy(d_tmp + hb * R, &mine, hb, cudaMemcpyHostToDevice);
+    bool coll = comm_allgather_bytes(ctx, d_tmp + hb * R, d_tmp, hb) == PCR_OK;
+    coll = coll && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    if (coll) cudaMemcpy(handles.data(), d_tmp, hb * W, cudaMemcpyDeviceToHost);
+    ok = ok && coll;
+    for (int p = 0; ok && p < W; p++) {
+        if (p == R) continue;
+        if (cudaIpcOpenMemHandle(&ctx->peer_open[p], handles[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = false;
+    }
+    cudaGetLastError();
+    uint32_t good = ok ? 1u : 0u, *d_good = (uint32_t *)(d_tmp + hb * W);
+    cudaMemcpy(d_good, &good, sizeof(good), cudaMemcpyHostToDevice);
+    if (comm_allreduce_u32(ctx, d_good, 1) == PCR_OK && cudaStreamSynchronize(ctx->stream) == cudaSuccess)
+        cudaMemcpy(&good, d_good, sizeof(good), cudaMemcpyDeviceToHost);
+    else
+        good = 0;
+    cudaFree(d_tmp);
+    cudaGetLastError();
+    if (good != (uint32_t)W) {
+        peer_teardown(ctx);
+        return;
+    }
+    ctx->peer.rank = R;
+    ctx->peer.world = W;
+    for (int p = 0; p < W; p++) {
+        char *base = (char *)(p == R ? ctx->peer_block : ctx->peer_open[p]);
+        ctx->peer.data[p] = (double *)base;
+        ctx->peer.flag[p] = (unsigned long long *)(base + kPeerDataBytes);
+    }
+    ctx->peer_seq = 0;
+    ctx->peer_ok = true;
+}
+
 int comm_init(Ctx *ctx, const void *id, int rank, int world) {
     if (world < 1 || rank < 0 || rank >= world) return fail(ctx, PCR_ERR_INVALID_ARG, "bad rank/world");
     comm_destroy(ctx);
@@ -100,11 +173,13 @@ int comm_init(Ctx *ctx, const void *id, int rank, int world) {
         return fail(ctx, PCR_ERR_NCCL, "ncclCommInitRank: %s", a.GetErrorString ? a.GetErrorString(r) : "error");
     }
     ctx->nccl_comm = comm;
+    peer_setup(ctx);  // (best effort: without it the ICP sums go through ncclAllReduce)
     return PCR_OK;
 }
 
 void comm_destroy(Ctx *ctx) {
     ctx->fake_comm = false;
+    peer_teardown(ctx);
     if (ctx->nccl_comm) {
         NcclApi &a = api();
         if (a.ok) a.CommDestroy((ncclComm_t_)ctx->nccl_comm);

@@ -254,15 +254,73 @@ __global__ void __launch_bounds__(kIcpThreads) icp_accum_kernel(const float4 *__
 
 // Folds the per-block partials in a fixed order: 32 lanes per value take strided subsets, then a
 // shuffle tree -- deterministic for a given launch configuration.
+//
+// Sharded source, pc.world > 1: the reduction is followed IN THE SAME KERNEL by a one-shot all-reduce over NVLink peer
+// memory instead of an ncclAllReduce launch (whose span -- small-message latency plus launch -- was 0.13 ms of a 0.19 ms
+// iteration at 8 GPUs).  Every rank owns an exchange block that all peers have mapped (comm.cu: CUDA IPC):
+//   1. warp j, lane p < world, stores this rank's sum j into peer p's block at [slot][this rank][j]   (NVLink stores)
+//   2. __threadfence_system + block barrier, then thread p publishes flag[slot][this rank] = seq in peer p's block (release)
+//   3. thread p waits for flag[slot][p] == seq in the OWN block (acquire), block barrier
+//   4. warp j adds the world's contributions in RANK order: every rank computes the same bits, as after ncclAllReduce.
+// slot = seq & 1: a rank can be at most one exchange ahead of the slowest (it needs everybody's flag of exchange n to leave
+// it), so exchange n + 2 never overwrites data somebody still reads.  All ranks skip the same exchanges (state->done is
+// computed from the all-reduced sums, and the host queues passes in lock step), and seq counts the queued ones on every rank.
+// A peer that never arrives (a crashed rank) must not hang this GPU: after ~2e7 polls the kernel gives up and marks the
+// state as failed (rmse NaN, done), which the host reports.
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __global__ void __launch_bounds__(NP * 32) icp_reduce_kernel(const double *__restrict__ partials, int n_blocks, size_t ns_local,
-                                                             IcpState *state) {
+                                                             IcpState *state, PeerComm pc, unsigned long long seq) {
     if (state->done) return;
     const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double v = 0.0;
     for (int b = lane; b < n_blocks; b += 32) v += partials[(size_t)b * NP + j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PCR_FULL, v, o);
-    if (lane == 0) state->sums[j] = j == kSrcN ? (double)ns_local : v;
+    v = j == kSrcN ? (double)ns_local : v;  // (every lane holds the sum)
+    if (pc.world <= 1) {
+        if (lane == 0) state->sums[j] = v;
+        return;
+    }
+    const int slot = (int)(seq & 1ull);
+    if (lane < pc.world) pc.data[lane][((size_t)slot * kPeerMaxWorld + pc.rank) * kPeerWords + j] = v;
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_failed;
+    if (threadIdx.x == 0) s_failed = 0;
+    if (threadIdx.x < pc.world) st_release_sys_u64(&pc.flag[threadIdx.x][slot * kPeerMaxWorld + pc.rank], seq);
+    __syncthreads();
+    if (threadIdx.x < pc.world) {
+        const unsigned long long *f = &pc.flag[pc.rank][slot * kPeerMaxWorld + threadIdx.x];
+        unsigned polls = 0;
+        while (ld_acquire_sys_u64(f) != seq)
+            if (++polls > 20000000u) {
+                s_failed = 1;
+                break;
+            }
+    }
+    __syncthreads();
+    if (s_failed) {
+        if (threadIdx.x == 0) {
+            state->last_rmse = __int_as_float(0x7fc00000);
+            state->converged = 0;
+            state->done = 1;
+        }
+        return;
+    }
+    if (lane == 0) {
+        const volatile double *mine = pc.data[pc.rank] + (size_t)slot * kPeerMaxWorld * kPeerWords;
+        double t = 0.0;
+        for (int p = 0; p < pc.world; p++) t += mine[(size_t)p * kPeerWords + j];
+        state->sums[j] = t;
+    }
 }
 
 // ---- device-side solves ----------------------------------------------------------------------------
@@ -744,9 +802,12 @@ int icp_dev(Ctx *ctx, const IcpArgs &a, pcr_icp_result *result) {
                     levels[0]->grids_h[0].h, levels[1]->grids_h[0].h);
         }
         TimeScope ts2(ctx, kTagIcpSolve);
-        icp_reduce_kernel<<<1, NP * 32, 0, st>>>(partials, n_blocks, ns, d_state);
+        const bool peer = ctx->world > 1 && ctx->peer_ok;
+        PeerComm pc = {};
+        if (peer) pc = ctx->peer;
+        icp_reduce_kernel<<<1, NP * 32, 0, st>>>(partials, n_blocks, ns, d_state, pc, peer ? ++ctx->peer_seq : 0ull);
         PCR_LAUNCH_CHECK(ctx);
-        if (ctx->world > 1) PCR_TRY(comm_allreduce_f64(ctx, d_state->sums, NP));
+        if (ctx->world > 1 && !peer) PCR_TRY(comm_allreduce_f64(ctx, d_state->sums, NP));
         if (plane) icp_solve_kernel<true><<<1, 32, 0, st>>>(d_state, metrics_only, a.params.tolerance, (int *)h_done);
         else icp_solve_kernel<false><<<1, 32, 0, st>>>(d_state, metrics_only, a.params.tolerance, (int *)h_done);
         PCR_LAUNCH_CHECK(ctx);

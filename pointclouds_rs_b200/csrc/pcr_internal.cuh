@@ -41,6 +41,17 @@ struct DevBuf {  // grow-only device scratch buffer
 
 struct Ctx;
 
+// Exchange block of one rank: data[2 slots][kPeerMaxWorld senders][kPeerWords] f64, then flag[2][kPeerMaxWorld] u64.
+constexpr int kPeerMaxWorld = 8;
+constexpr int kPeerWords = 32;
+constexpr size_t kPeerDataBytes = 2 * kPeerMaxWorld * kPeerWords * sizeof(double);
+constexpr size_t kPeerBlockBytes = kPeerDataBytes + 2 * kPeerMaxWorld * sizeof(unsigned long long);
+struct PeerComm {
+    double *data[kPeerMaxWorld];              // rank p's block as mapped on this device
+    unsigned long long *flag[kPeerMaxWorld];
+    int rank, world;                          // world == 0: no peer exchange (one rank, or NCCL is used)
+};
+
 // Device-resident index over one cloud or a batch of frames.
 struct Index {
     Ctx *ctx = nullptr;
@@ -139,6 +150,13 @@ struct Ctx {
     // NCCL (loaded lazily with dlopen, see comm.cu)
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
+    // One-shot all-reduce of the ICP sums over NVLink peer memory (comm.cu sets it up, icp.cu's reduce kernel uses it): every
+    // rank owns one exchange block (cudaMalloc, shared through CUDA IPC) and holds a pointer into every peer's.
+    PeerComm peer = {};
+    void *peer_block = nullptr;             // this rank's block
+    void *peer_open[kPeerMaxWorld] = {};    // peers' blocks as opened here (cudaIpcOpenMemHandle), nullptr for the own rank
+    bool peer_ok = false;                   // all ranks agreed to use it
+    unsigned long long peer_seq = 0;        // exchanges issued so far: the value the flags of the next one carry
     // pcr_ctx_set_query_sharding: with a communicator, sor / estimate_normals / radius_outlier_removal of ONE cloud
     // given in full on every rank search only this rank's share of the queries and merge the results over NCCL
     bool shard_queries = false;
