@@ -104,13 +104,16 @@ int pcr_ctx_set_cell_size(pcr_ctx *ctx, float cell_size);
  * and bounding box are within 12.5 % of it, which skips the probe grid and its host round trip.  Results never
  * depend on the cell size; an unrepresentative reuse only costs speed.  The same hint lets voxel_downsample size
  * its table from the previous frame's key box (padded) without measuring the new frame first -- a point outside the
- * box is detected and the frame redone the exact way -- and lets the KNN levels queue the next-coarser grid before
- * the count that decides whether it is needed has come back.  Off by default. */
+ * box is detected and the frame redone the exact way -- lets the KNN levels queue the next-coarser grid before
+ * the count that decides whether it is needed has come back, and lets the fused SOR -> normals call skip the round trip
+ * for the number of queries its first grid level left over when that number was zero on the previous frame (it is then
+ * read with the call's last round trip; non-zero: the call is redone with the wait).  Off by default. */
 int pcr_ctx_set_frame_stream(pcr_ctx *ctx, int enable);
 /* How often the frame-stream hints held since the context was created: {cell size reused, cell size probed again,
  * voxel key box guess held, guess missed (frame redone the exact way), coarser KNN level built ahead and needed,
- * built ahead and not needed}.  bench.py reports them so that the timed steps cannot be a best case by construction. */
-#define PCR_NUM_HINT_STATS 6
+ * built ahead and not needed, deferred counts of the fused SOR pass not awaited and zero, not awaited and non-zero (call
+ * redone)}.  bench.py reports them so that the timed steps cannot be a best case by construction. */
+#define PCR_NUM_HINT_STATS 8
 int pcr_ctx_get_hint_stats(pcr_ctx *ctx, uint64_t out[PCR_NUM_HINT_STATS]);
 
 /* ---- multi-GPU (one process per GPU; the host exchanges the id, e.g. torch.distributed) ------ */

@@ -107,10 +107,10 @@ class Context:
 
     def hint_stats(self) -> dict:
         """How often the frame-stream hints held (pcr_ctx_get_hint_stats)."""
-        out = (C.c_uint64 * 6)()
+        out = (C.c_uint64 * 8)()
         _ffi.check(_ffi.load().pcr_ctx_get_hint_stats(self._h, out), self._h)
         names = ("cell_size_reused", "cell_size_probed", "voxel_box_guess_held", "voxel_box_guess_missed", "coarser_level_ahead_needed",
-                 "coarser_level_ahead_unneeded")
+                 "coarser_level_ahead_unneeded", "deferred_counts_not_awaited_zero", "deferred_counts_not_awaited_nonzero")
         return {k: int(v) for k, v in zip(names, out)}
 
     def set_query_sharding(self, enable: bool = True):

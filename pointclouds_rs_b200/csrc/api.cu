@@ -368,7 +368,8 @@ int pcr_ctx_debug_set_shard(pcr_ctx *ctx, int rank, int world_size) {
 int pcr_ctx_get_hint_stats(pcr_ctx *ctx, uint64_t out[PCR_NUM_HINT_STATS]) {
     if (!ctx || !out) return fail(ctx ? &ctx->c : nullptr, PCR_ERR_INVALID_ARG, "null pointer");
     const Ctx &c = ctx->c;
-    const uint64_t v[PCR_NUM_HINT_STATS] = {c.stat_cell_hits, c.stat_cell_misses, c.stat_vox_hits, c.stat_vox_misses, c.stat_spec_hits, c.stat_spec_misses};
+    const uint64_t v[PCR_NUM_HINT_STATS] = {c.stat_cell_hits, c.stat_cell_misses, c.stat_vox_hits, c.stat_vox_misses, c.stat_spec_hits, c.stat_spec_misses,
+                                             c.stat_nowait_hits, c.stat_nowait_misses};
     for (int i = 0; i < PCR_NUM_HINT_STATS; i++) out[i] = v[i];
     return PCR_OK;
 }
@@ -1032,7 +1033,8 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
                       size_t n, size_t k_sor, float std_mul, size_t k_normals, const float vp[3], uint8_t *d_keep, float *d_nx,
                       float *d_ny, float *d_nz, unsigned long long *d_kept /* n_frames */,
                       unsigned long long *h_kept0 = nullptr /* single frame: set if the count came back with another round trip */,
-                      const CloudStats *known_stats = nullptr /* single frame: its box and finite count, if already measured */) {
+                      const CloudStats *known_stats = nullptr /* single frame: its box and finite count, if already measured */,
+                      bool allow_nowait = true /* false: the redo of a call whose unawaited deferred counts were not zero */) {
     const int F = (int)n_frames;
     float *d_mean = nullptr, *d_stats = nullptr;
     PCR_CUDA(c, cudaMallocAsync((void **)&d_mean, sizeof(float) * std::max<size_t>(n, 1), c->stream));
@@ -1088,7 +1090,11 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
         PCR_CUDA(c, cudaMemsetAsync(d_keep, 0, n, c->stream));
         PCR_CUDA(c, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long) * F, c->stream));
     } else {
-        PCR_TRY(sor_mean_dist_dev(ix, k_sor, d_mean, fused ? &sl : nullptr));
+        c->spec_request = fused && allow_nowait && F == 1 && k_normals > 0 && !c->shard_queries;
+        c->spec_pending = false;
+        const int ss = sor_mean_dist_dev(ix, k_sor, d_mean, fused ? &sl : nullptr);
+        c->spec_request = false;
+        PCR_TRY(ss);
         PCR_MARK("core: sor search done");
         PCR_TRY(sor_threshold_mask_dev(c, d_mean, ix->frame_in_off, F, n, std_mul, d_keep, d_stats, d_kept));
         PCR_MARK("core: stats queued");
@@ -1100,7 +1106,22 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
     if (k_normals == 0) return PCR_OK;
     PCR_TRY(index_apply_mask_dev(ix, d_keep));
     // removed points get 0 and kept non-finite points (0,0,1) inside normals_dev / normals_from_lists_dev
-    if (fused) return normals_from_lists_dev(ix, k_normals, vp, sl, d_keep, d_nx, d_ny, d_nz, F == 1 ? d_kept : nullptr, h_kept0);
+    if (fused) {
+        const int sn = normals_from_lists_dev(ix, k_normals, vp, sl, d_keep, d_nx, d_ny, d_nz, F == 1 ? d_kept : nullptr, h_kept0);
+        if (c->spec_pending) {  // the SOR pass's deferred counts, read by the round trip that just ended
+            c->spec_pending = false;
+            if (sn == PCR_OK) {
+                const uint32_t *m2 = (const uint32_t *)c->pinned + 128;
+                const bool zero = m2[0] == 0 && m2[1] == 0;
+                c->spec_zero = zero;
+                (zero ? c->stat_nowait_hits : c->stat_nowait_misses)++;
+                if (!zero)  // queries were left for the coarser levels: everything downstream saw incomplete mean distances
+                    return batch_core(c, dx, dy, dz, frame_offsets, (size_t)F, n, k_sor, std_mul, k_normals, vp, d_keep, d_nx, d_ny, d_nz, d_kept,
+                                      h_kept0, known_stats, false);
+            }
+        }
+        return sn;
+    }
     return normals_dev(ix, k_normals, vp, d_nx, d_ny, d_nz, d_keep);
 }
 

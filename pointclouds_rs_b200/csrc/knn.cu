@@ -1486,11 +1486,19 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
             join_pending = false;
         }
         if (last) break;
-        uint32_t *mail = (uint32_t *)ctx->pinned + 32;
+        // (see Ctx::spec_request: a frame stream does not wait for counts that were zero on the previous frame)
+        static const bool no_nowait = getenv("PCR_WAIT_COUNTS") != nullptr;  // A/B hook
+        const bool nowait = level == 0 && !init_list && split && pre_level1 && ctx->spec_request && ctx->frame_stream && ctx->spec_zero && !no_nowait;
+        uint32_t *mail = (uint32_t *)ctx->pinned + (nowait ? 128 : 32);
         PCR_CUDA(ctx, cudaMemcpyAsync(mail, counters, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));  // (words 32 .. 47 of the block)
         for (const auto &pg : ctx->piggy)  // small results other steps want from the same round trip
             PCR_CUDA(ctx, cudaMemcpyAsync(pg.dst, pg.src, pg.bytes, cudaMemcpyDeviceToHost, ctx->stream));
         ctx->piggy.clear();
+        if (nowait) {
+            ctx->spec_pending = true;
+            PCR_MARK("levels: deferred count left for the last round trip");
+            return PCR_OK;
+        }
         // A frame stream whose previous frame needed the next level will need it again: queue its build behind the
         // count's copy and wait on an event, so the GPU builds while the host wakes up and reads the count.
         const bool speculate = level == 0 && !init_list && ctx->frame_stream && ctx->spec_coarser && !cur->coarser;
@@ -1511,6 +1519,7 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
         n_cur = mail[level & 1];
         if (speculate) (n_cur > 0 ? ctx->stat_spec_hits : ctx->stat_spec_misses)++;
         if (level == 0 && !init_list && !split) ctx->spec_coarser = n_cur > 0;
+        if (level == 0 && !init_list && split && pre_level1) ctx->spec_zero = mail[0] == 0 && mail[1] == 0;
         if (dbg) fprintf(stderr, "[pcr] level %d: %u of %u queries deferred (cell %.4g)\n", level, n_cur, a.nq, cur->grids_h[0].h);
         if (dbg && first_of_two)
             fprintf(stderr, "[pcr] level 0: %u normal / %u dense / %u sparse queries, %u needed more than the first pass's shells, %u of the sparse deferred again, %u handed back by the tiles\n",

@@ -125,6 +125,13 @@ struct Ctx {
     };
     std::vector<Piggy> piggy;
     bool spec_coarser = false;         // frame stream: the previous frame's level-0 pass deferred queries
+    // Frame stream, fused SOR -> normals: when the previous frame's level-0 pass left nothing for the coarser levels, the
+    // next frame's deferred counts are copied to a mailbox of their own and NOT awaited; the pipeline goes on, and the
+    // counts are checked at the call's last round trip.  Non-zero (rare) = the whole call is redone the careful way.
+    bool spec_request = false;   // set by the caller that can redo (batch_core)
+    bool spec_pending = false;   // the counts of this call are still unchecked (mailbox: pinned + 128 words)
+    bool spec_zero = false;      // the previous frame's counts were all zero
+    uint64_t stat_nowait_hits = 0, stat_nowait_misses = 0;
     cudaEvent_t ev_count = nullptr;    // marks the deferred count's copy when work is queued behind it
     // level 0 of the KNN runs three ways at once (knn.cu run_levels): side streams + fork / join events, created on first use
     cudaStream_t side[2] = {nullptr, nullptr};

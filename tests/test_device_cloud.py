@@ -133,3 +133,27 @@ def test_frames_in_flight_on_independent_contexts(pcr):
     for t in th:
         t.join()
     assert not errors, errors
+
+
+def test_frame_stream_deferred_counts_not_awaited_and_redone(pcr):
+    """Frame stream, fused SOR -> normals: after a frame whose first grid level left nothing over, the next frame's
+    leftover counts are not awaited (pcr_ctx_set_frame_stream).  Frames that DO leave queries over --
+    a handful of points hundreds of metres away need the third grid level -- must then be redone the careful way:
+    same bits as a context without the hint, and the miss is counted."""
+    base = scenes.kitti_scene(11, (20_000, 1000, 170, 430))
+    far = np.array([[900.0, 0, 0], [0, -850.0, 5], [910.0, 3.0, 1], [-700, 600, 40], [905.0, -2.0, 0.5]], np.float32)
+    frames = [base, scenes.kitti_scene(12, (20_000, 1000, 170, 430)), np.vstack([scenes.kitti_scene(13, (20_000, 1000, 170, 430)), far]),
+              scenes.kitti_scene(14, (20_000, 1000, 170, 430)), scenes.kitti_scene(15, (20_000, 1000, 170, 430))]
+    plain = pcr.Context(device=0)
+    stream = pcr.Context(device=0)
+    stream.set_frame_stream(True)
+    for pts in frames:
+        want = pcr.DeviceCloud.from_numpy(pts, plain).sor_normals(10, 1.0, 20)
+        got = pcr.DeviceCloud.from_numpy(pts, stream).sor_normals(10, 1.0, 20)
+        assert np.array_equal(got.to_numpy(), want.to_numpy())
+        assert np.array_equal(got.normals_to_numpy(), want.normals_to_numpy())
+    h = stream.hint_stats()
+    assert h["deferred_counts_not_awaited_zero"] >= 1           # frames 2 and 5 ran without the round trip
+    assert h["deferred_counts_not_awaited_nonzero"] >= 1        # frame 3 was redone
+    plain.close()
+    stream.close()
