@@ -1235,6 +1235,7 @@ int cloud_alloc(pcr_ctx *ctx, size_t n, bool normals, pcr_cloud **out) {
 }
 
 __global__ void mask_to_u32_kernel(const uint8_t *__restrict__ keep, size_t n, uint32_t *__restrict__ flag) {
+    PCR_GRID_DEP_SYNC();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= n) flag[i] = (i < n && keep[i]) ? 1u : 0u;
 }
@@ -1244,6 +1245,7 @@ __global__ void mask_to_u32_kernel(const uint8_t *__restrict__ keep, size_t n, u
 __global__ void compact_kernel(const float *__restrict__ a, size_t a_stride, int n_a, const float *__restrict__ b, size_t b_stride, int n_b,
                                size_t n, const uint32_t *__restrict__ pos /* exclusive scan of the flags, n + 1 */,
                                float *__restrict__ dst, size_t dst_stride) {
+    PCR_GRID_DEP_SYNC();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t p = pos[i];
@@ -1269,8 +1271,8 @@ int cloud_compact(const pcr_cloud *in, const uint8_t *d_keep, pcr_cloud **out, c
     const size_t n = in->n;
     PCR_TRY(ensure(c, c->b_list, sizeof(uint32_t) * (n + 1)));
     uint32_t *pos = (uint32_t *)c->b_list.p;
-    mask_to_u32_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, c->stream>>>(d_keep, n, pos);
-    PCR_LAUNCH_CHECK(c);
+    PCR_CUDA(c, launch_chained(mask_to_u32_kernel, dim3((unsigned)((n + 1 + 255) / 256)), dim3(256), 0, c->stream, d_keep, n, pos));
+    c->launches++;
     PCR_TRY(exclusive_scan_u32_dev(c, pos, n + 1));
     size_t m = known_m;
     if (m == SIZE_MAX) {
@@ -1284,10 +1286,9 @@ int cloud_compact(const pcr_cloud *in, const uint8_t *d_keep, pcr_cloud **out, c
     PCR_TRY(cloud_alloc(in->owner, m, with_normals, &tmp));
     if (m) {
         const int n_a = nrm ? 3 : (in->has_normals ? 6 : 3), n_b = nrm ? 3 : 0;
-        compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(in->base, in->stride, n_a, nrm, nrm_stride, n_b, n, pos, tmp->base,
-                                                                           tmp->stride);
+        const cudaError_t e = launch_chained(compact_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, c->stream, in->base, in->stride, n_a, nrm,
+                                             nrm_stride, n_b, n, pos, tmp->base, tmp->stride);
         c->launches++;
-        const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) {
             pcr_cloud_free(tmp);
             return fail(c, PCR_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e), __FILE__, __LINE__);

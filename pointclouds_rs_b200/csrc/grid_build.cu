@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(kBuildThreads) count_kernel(const float *__res
                                                               uint32_t *__restrict__ cell_count,
                                                               uint32_t *__restrict__ cell_id, uint32_t *__restrict__ rank,
                                                               float4 *__restrict__ orig4) {
+    PCR_GRID_DEP_SYNC();
     const int f = blockIdx.y;
     const uint32_t b = frame_off ? frame_off[f] : 0u;
     const uint32_t e = frame_off ? frame_off[f + 1] : (uint32_t)n;
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(kBuildThreads) count_sorted_kernel(const float
                                                                      const GridDesc *__restrict__ grids, int n_frames,
                                                                      uint32_t *__restrict__ cell_count,
                                                                      uint32_t *__restrict__ cell_id, uint32_t *__restrict__ rank) {
+    PCR_GRID_DEP_SYNC();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     uint32_t cid = 0xffffffffu;
@@ -187,6 +189,7 @@ __global__ void __launch_bounds__(kBuildThreads) scatter_sorted_kernel(const flo
                                                                        const uint32_t *__restrict__ cell_id,
                                                                        const uint32_t *__restrict__ rank,
                                                                        float4 *__restrict__ sorted) {
+    PCR_GRID_DEP_SYNC();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_sorted) return;
     uint32_t cid = cell_id[i];
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(kBuildThreads) scatter_kernel(const float4 *__
                                                                 const uint32_t *__restrict__ cell_id,
                                                                 const uint32_t *__restrict__ rank,
                                                                 float4 *__restrict__ sorted) {
+    PCR_GRID_DEP_SYNC();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t cid = cell_id[i];
@@ -274,6 +278,7 @@ struct TombLevels {
     int levels;
 };
 __global__ void __launch_bounds__(256) tombstone_kernel(TombLevels t, const uint8_t *__restrict__ keep) {
+    PCR_GRID_DEP_SYNC();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     for (int l = 0; l < t.levels; l++) {
         if (i >= t.n[l]) continue;
@@ -354,6 +359,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(uint32_t *_
     constexpr int kWarps = kScanThreads / 32, kRows = kScanItems / 4;
     __shared__ uint32_t s_tile, s_pre;
     __shared__ uint32_t warp_tot[kWarps];
+    PCR_GRID_DEP_SYNC();
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -497,8 +503,9 @@ static int exclusive_scan_u32_with(Ctx *ctx, uint32_t *d_data, size_t n, DevBuf 
     uint32_t *ticket = (uint32_t *)scratch.p;
     unsigned long long *state = (unsigned long long *)((char *)scratch.p + 16);
     const int vec = ((uintptr_t)d_data & 15) == 0;
-    scan_lookback_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(d_data, n, state, ticket, epoch, (uint32_t)tiles, vec);
-    PCR_LAUNCH_CHECK(ctx);
+    PCR_CUDA(ctx, launch_chained(scan_lookback_kernel, dim3((unsigned)tiles), dim3(kScanThreads), 0, ctx->stream, d_data, n, state, ticket, epoch,
+                                 (uint32_t)tiles, vec));
+    ctx->launches++;
     return PCR_OK;
 }
 
@@ -615,8 +622,8 @@ int index_apply_mask_dev(Index *ix, const uint8_t *d_keep) {
     uint32_t n_max = 0;
     auto flush = [&]() -> int {  // (all levels of an index fit one launch; the loop is for generality)
         if (t.levels && n_max) {
-            tombstone_kernel<<<(n_max + 255) / 256, 256, 0, ctx->stream>>>(t, d_keep);
-            PCR_LAUNCH_CHECK(ctx);
+            PCR_CUDA(ctx, launch_chained(tombstone_kernel, dim3((n_max + 255) / 256), dim3(256), 0, ctx->stream, t, d_keep));
+            ctx->launches++;
         }
         t = {};
         n_max = 0;
@@ -722,9 +729,9 @@ static int index_level_build(Index *ix, bool fine, Index **out) {
     if (fine) PCR_TRY(exclusive_scan_u32_with(ctx, c->cell_start, (size_t)base + 1, ctx->b_fine_scan, ctx->fine_scan_epoch));
     else PCR_TRY(exclusive_scan_u32_dev(ctx, c->cell_start, (size_t)base + 1));
     if (ns > 0) {
-        scatter_sorted_kernel<<<(ns + kBuildThreads - 1) / kBuildThreads, kBuildThreads, 0, st>>>(ix->sorted, ns, c->cell_start, d_cell_id,
-                                                                                                 d_rank, c->sorted);
-        PCR_LAUNCH_CHECK(ctx);
+        PCR_CUDA(ctx, launch_chained(scatter_sorted_kernel, dim3((ns + kBuildThreads - 1) / kBuildThreads), dim3(kBuildThreads), 0, st, ix->sorted, ns,
+                                     c->cell_start, d_cell_id, d_rank, c->sorted));
+        ctx->launches++;
     }
     guard.ix = nullptr;
     slot_ptr = c;
@@ -948,9 +955,9 @@ int index_build_dev(Ctx *ctx, const float *dx, const float *dy, const float *dz,
     PCR_TRY(exclusive_scan_u32_dev(ctx, ix->cell_start, (size_t)total + 1));
     if (dbg_t) { cudaStreamSynchronize(st); fprintf(stderr, "[build] scan done +%.0f us\n", now_us() - t_begin); }
     if (n > 0) {
-        scatter_kernel<<<(unsigned)((n + kBuildThreads - 1) / kBuildThreads), kBuildThreads, 0, st>>>(
-            ix->orig4, n, ix->cell_start, d_cell_id, d_rank, ix->sorted);
-        PCR_LAUNCH_CHECK(ctx);
+        PCR_CUDA(ctx, launch_chained(scatter_kernel, dim3((unsigned)((n + kBuildThreads - 1) / kBuildThreads)), dim3(kBuildThreads), 0, st,
+                                     ix->orig4, n, ix->cell_start, d_cell_id, d_rank, ix->sorted));
+        ctx->launches++;
     }
     if (dbg_t) { cudaStreamSynchronize(st); fprintf(stderr, "[build] final done +%.0f us (total cells %u)\n", now_us() - t_begin, total); }
     guard.ix = nullptr;

@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(kThreads, (!kSmem && QPW == kQPWS) ? 8 : 1) kn
 template <bool kSmem, int QPW>
 __global__ void __launch_bounds__(kThreads, (!kSmem && QPW == kQPWS) ? 8 : 1) sor_mean_kernel(LevelArgs a, int kk, float *__restrict__ mean_d, uint32_t *__restrict__ lists,
                                                             uint8_t *__restrict__ list_cnt, size_t list_stride, int kk_sor) {
+    PCR_GRID_DEP_SYNC();
     extern __shared__ unsigned long long smem_raw[];
     __shared__ WarpSelScratch s_sel[kWarps];
     constexpr int kCol = QPW + 1;  // column stride of the parked results (conflict-free transposed reads)
@@ -743,6 +744,7 @@ enum TileOutcome { kTileDone = 0, kTileDefer = 1, kTileContinue = 2, kTileDense 
 
 template <int MODE>
 __global__ void __launch_bounds__(kTileThreads, 16 / kTileWarps) knn_tile_kernel(LevelArgs a, ThreadArgs t) {
+    PCR_GRID_DEP_SYNC();
     extern __shared__ __align__(16) unsigned char tile_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     TileWarp &S = reinterpret_cast<TileWarp *>(tile_raw)[w];
@@ -1055,8 +1057,8 @@ int launch_sel_kernel(Ctx *ctx, const LevelArgs &a, const ThreadArgs &t) {
                 }
                 return PCR_OK;
             }
-            knn_tile_kernel<MODE><<<(a.nq + kTileThreads - 1) / kTileThreads, kTileThreads, smem, ctx->stream>>>(a, t);
-            PCR_LAUNCH_CHECK(ctx);
+            PCR_CUDA(ctx, launch_chained(knn_tile_kernel<MODE>, dim3((a.nq + kTileThreads - 1) / kTileThreads), dim3(kTileThreads), smem, ctx->stream, a, t));
+            ctx->launches++;
             return PCR_OK;  // (run_levels launches a warp-per-query pass over what the tiles handed back)
         }
     }
@@ -1199,6 +1201,7 @@ struct ClassArgs {
 };
 
 __global__ void __launch_bounds__(kClsThreads) classify_kernel(LevelArgs a, ClassArgs c) {
+    PCR_GRID_DEP_SYNC();
     const uint32_t slot = blockIdx.x * kClsThreads + threadIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t q = a.q_offset + slot;
@@ -1374,8 +1377,8 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
             ca.heavy_n = a.ovf_list ? heavy_n : 0u;
             {
                 TimeScope ts(ctx, kTagKnnDeferred);
-                classify_kernel<<<(n_cur + kClsThreads - 1) / kClsThreads, kClsThreads, 0, ctx->stream>>>(a, ca);
-                PCR_LAUNCH_CHECK(ctx);
+                PCR_CUDA(ctx, launch_chained(classify_kernel, dim3((n_cur + kClsThreads - 1) / kClsThreads), dim3(kClsThreads), 0, ctx->stream, a, ca));
+                ctx->launches++;
             }
             PCR_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
             for (int i = 0; i < 2; i++) PCR_CUDA(ctx, cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
@@ -1697,14 +1700,19 @@ int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep
         if (qpw == kQPWS) {  // level 0, a warp per query
             const int kw = keep_lists ? ta.kk : (int)kk;
             const size_t smem_w = ((size_t)kw * (kQPWS + 1) + 64) * sizeof(float) * kWarps;
-            if (keep_lists) sor_mean_kernel<false, kQPWS><<<blocks, kThreads, smem_w, ctx->stream>>>(a, kw, d_mean_d, ta.lists, ta.list_cnt, ta.list_stride, ta.kk_sor);
-            else sor_mean_kernel<false, kQPWS><<<blocks, kThreads, smem_w, ctx->stream>>>(a, kw, d_mean_d, nullptr, nullptr, 0, kw);
-            PCR_LAUNCH_CHECK(ctx);
+            if (keep_lists)
+                PCR_CUDA(ctx, launch_chained(sor_mean_kernel<false, kQPWS>, dim3(blocks), dim3(kThreads), smem_w, ctx->stream, a, kw, d_mean_d, ta.lists,
+                                             ta.list_cnt, ta.list_stride, ta.kk_sor));
+            else
+                PCR_CUDA(ctx, launch_chained(sor_mean_kernel<false, kQPWS>, dim3(blocks), dim3(kThreads), smem_w, ctx->stream, a, kw, d_mean_d,
+                                             (uint32_t *)nullptr, (uint8_t *)nullptr, (size_t)0, kw));
+            ctx->launches++;
             return PCR_OK;
         }
         if ((a.follow_up || a.no_tile) && keep_lists) {  // the first pass's leftovers / the dense class on the same level: K neighbours, lists kept
             const size_t smem_k = ((size_t)ta.kk * (kQPWL + 1) + 64) * sizeof(float) * kWarps;
-            sor_mean_kernel<false, kQPWL><<<blocks, kThreads, smem_k, ctx->stream>>>(a, ta.kk, d_mean_d, ta.lists, ta.list_cnt, ta.list_stride, ta.kk_sor);
+            PCR_CUDA(ctx, launch_chained(sor_mean_kernel<false, kQPWL>, dim3(blocks), dim3(kThreads), smem_k, ctx->stream, a, ta.kk, d_mean_d, ta.lists,
+                                         ta.list_cnt, ta.list_stride, ta.kk_sor));
         } else if (kk <= 32) {
             if (qpw == kQPW0) sor_mean_kernel<false, kQPW0><<<blocks, kThreads, smem, ctx->stream>>>(a, (int)kk, d_mean_d, nullptr, nullptr, 0, (int)kk);
             else sor_mean_kernel<false, kQPWL><<<blocks, kThreads, smem, ctx->stream>>>(a, (int)kk, d_mean_d, nullptr, nullptr, 0, (int)kk);
@@ -1788,6 +1796,7 @@ __global__ void __launch_bounds__(128) normals_from_lists_kernel(const float4 *_
                                                                  const float4 *__restrict__ orig4, float vx_, float vy_, float vz_,
                                                                  float *__restrict__ nx, float *__restrict__ ny, float *__restrict__ nz,
                                                                  uint32_t *__restrict__ fallback, uint32_t *__restrict__ fallback_count) {
+    PCR_GRID_DEP_SYNC();
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     const float4 p = __ldg(&qpts[q]);
@@ -1877,10 +1886,9 @@ int normals_from_lists_dev(Index *ix, size_t k, const float vp[3], const SorList
     PCR_CUDA(ctx, cudaMemsetAsync(d_fb_count, 0, sizeof(uint32_t), ctx->stream));
     {
         TimeScope ts(ctx, kTagKnnNormals);
-        normals_from_lists_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(ix->sorted, nq, sl.lists, sl.cnt, sl.stride, (int)sl.K, (int)k,
-                                                                            d_keep, ix->orig4, vp[0], vp[1], vp[2], d_nx, d_ny, d_nz,
-                                                                            sl.fallback, d_fb_count);
-        PCR_LAUNCH_CHECK(ctx);
+        PCR_CUDA(ctx, launch_chained(normals_from_lists_kernel, dim3((nq + 127) / 128), dim3(128), 0, ctx->stream, ix->sorted, nq, sl.lists, sl.cnt,
+                                     sl.stride, (int)sl.K, (int)k, d_keep, ix->orig4, vp[0], vp[1], vp[2], d_nx, d_ny, d_nz, sl.fallback, d_fb_count));
+        ctx->launches++;
     }
     // The queries that fall back are few, and their count is still on the device: launch their level-0 pass now for a
     // fixed capacity (the kernel reads the count itself) and let the count, the kept count the caller's compaction

@@ -1,5 +1,6 @@
 // pcr_internal.cuh -- shared declarations of the sm_100a KNN engine (not part of the C ABI).
 #pragma once
+#include <cstdlib>
 
 #include <cuda_runtime.h>
 #include <math.h>
@@ -352,6 +353,29 @@ struct pcr_index {
 namespace pcr {
 
 #ifdef __CUDACC__
+
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_chained() may be scheduled while its predecessor in
+// the stream is still draining; it must call PCR_GRID_DEP_SYNC() before it touches anything the predecessor wrote (here:
+// as its first statement).  The predecessors never trigger early, so the wait returns when they have completed and
+// flushed: what overlaps is the launch itself -- 2-4 us per kernel boundary, and the step is a chain of ~28 small kernels.
+// A kernel WITHOUT the wait must never be launched this way.  PCR_NO_PDL=1 turns the attribute off (A/B hook).
+#define PCR_GRID_DEP_SYNC() cudaGridDependencySynchronize()
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    static const bool off = getenv("PCR_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 #define PCR_FULL 0xffffffffu
 // "no entry" sentinel: just above every real key (d^2 bits <= 0x7f800000 = +inf).  A candidate whose

@@ -26,6 +26,7 @@ static __device__ __noinline__ float slow_fold(const float *__restrict__ v, size
 __global__ void __launch_bounds__(kFoldThreads) sor_stats_kernel(const float *__restrict__ mean_d,
                                                                   const uint32_t *__restrict__ frame_off, size_t n,
                                                                   float std_mul, SorFrameStats *__restrict__ stats, int use_fast) {
+    PCR_GRID_DEP_SYNC();
     __shared__ FoldShared sh;
     __shared__ SpecShared sp;
     const int f = blockIdx.x / cooperative_groups::this_cluster().num_blocks();
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(kFoldThreads) sor_stats_kernel(const float *__
 __global__ void __launch_bounds__(256) sor_mask_kernel(const float *__restrict__ mean_d, const uint32_t *__restrict__ frame_off,
                                                        int n_frames, size_t n, const SorFrameStats *__restrict__ stats,
                                                        uint8_t *__restrict__ keep, unsigned long long *__restrict__ kept) {
+    PCR_GRID_DEP_SYNC();
     const int f = blockIdx.y;
     const size_t b = frame_off ? frame_off[f] : 0, e = frame_off ? frame_off[f + 1] : n;
     const SorFrameStats s = stats[f];
@@ -84,6 +86,7 @@ int sor_threshold_mask_dev(Ctx *ctx, const float *d_mean_d, const uint32_t *d_fr
     static_assert(sizeof(SorFrameStats) == 4 * sizeof(float), "stats layout");
     if (n == 0) return PCR_OK;
     TimeScope ts(ctx, kTagSorStats);
+    PCR_CUDA(ctx, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long) * n_frames, ctx->stream));  // (before the kernels: they chain)
     {
         // a cluster of 8 CTAs per frame (one CTA for small frames: fewer cluster barriers)
         // 16 CTAs per frame for long frames (non-portable cluster size: fewer cluster-wide passes per fold)
@@ -103,13 +106,16 @@ int sor_threshold_mask_dev(Ctx *ctx, const float *d_mean_d, const uint32_t *d_fr
             cfg.gridDim = dim3((unsigned)n_frames * use);
             cfg.blockDim = dim3(kFoldThreads);
             cfg.stream = ctx->stream;
-            cudaLaunchAttribute attr[1];
+            cudaLaunchAttribute attr[2];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = use;
             attr[0].val.clusterDim.y = 1;
             attr[0].val.clusterDim.z = 1;
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // (see launch_chained)
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            static const bool no_pdl = getenv("PCR_NO_PDL") != nullptr;
             cfg.attrs = attr;
-            cfg.numAttrs = 1;
+            cfg.numAttrs = no_pdl ? 1 : 2;
             static const int use_fast = getenv("PCR_FOLD_SLOW") ? 0 : (getenv("PCR_FOLD_DEBUG") ? 2 : 1);  // A/B hook: the pass-per-crossing fold only
             // (many frames: the GPU is full of independent clusters and the pass-per-crossing fold's smaller code wins -- 12.55 vs
             // 12.9 ms on the 100-frame batch; the predicted-crossing fold is for the single long frame, 85 -> 60 us)
@@ -122,12 +128,11 @@ int sor_threshold_mask_dev(Ctx *ctx, const float *d_mean_d, const uint32_t *d_fr
         }
         ctx->launches++;
     }
-    PCR_CUDA(ctx, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long) * n_frames, ctx->stream));
     size_t per = n / (size_t)n_frames + 1;
     unsigned bx = (unsigned)std::min<size_t>((per + 255) / 256, (size_t)ctx->sm_count * 8);
-    sor_mask_kernel<<<dim3(bx ? bx : 1, n_frames), 256, 0, ctx->stream>>>(d_mean_d, d_frame_off, n_frames, n,
-                                                                          (const SorFrameStats *)d_stats, d_keep, d_kept);
-    PCR_LAUNCH_CHECK(ctx);
+    PCR_CUDA(ctx, launch_chained(sor_mask_kernel, dim3(bx ? bx : 1, n_frames), dim3(256), 0, ctx->stream, d_mean_d, d_frame_off, n_frames, n,
+                                 (const SorFrameStats *)d_stats, d_keep, d_kept));
+    ctx->launches++;
     return PCR_OK;
 }
 

@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(256) vox_col_scatter_kernel(const float *__res
                                                               float voxel, int mn1, int mn2, int ys,
                                                               const uint32_t *__restrict__ start, const uint32_t *__restrict__ col_of,
                                                               const uint32_t *__restrict__ rank_of, unsigned long long *__restrict__ members) {
+    PCR_GRID_DEP_SYNC();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t col = col_of[i];
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(256) vox_col_sort_kernel(const uint32_t *__res
                                                            size_t n, const uint32_t *__restrict__ start,
                                                            unsigned long long *__restrict__ members, uint32_t *__restrict__ nvox,
                                                            unsigned *__restrict__ tall) {
+    PCR_GRID_DEP_SYNC();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t c = col_of[i];
@@ -366,6 +368,7 @@ __global__ void __launch_bounds__(256) vox_col_emit_kernel(const float *__restri
                                                            const uint32_t *__restrict__ start, const uint32_t *__restrict__ vstart,
                                                            const unsigned long long *__restrict__ members, float *__restrict__ ox,
                                                            float *__restrict__ oy, float *__restrict__ oz) {
+    PCR_GRID_DEP_SYNC();
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // again the thread of the column's first arrival
     if (t >= n) return;
     const uint32_t c = col_of[t];
@@ -397,6 +400,7 @@ __global__ void __launch_bounds__(256) vox_col_emit_kernel(const float *__restri
 __global__ void __launch_bounds__(256) vox_out_stats_kernel(const float *__restrict__ x, const float *__restrict__ y,
                                                             const float *__restrict__ z, const uint32_t *__restrict__ d_n,
                                                             VoxHeader *hdr) {
+    PCR_GRID_DEP_SYNC();
     const uint32_t n = *d_n;
     if (blockIdx.x == 0 && threadIdx.x == 0) hdr->total = n;
     unsigned mn_c[3] = {0u, 0u, 0u}, mx[3] = {0u, 0u, 0u}, cnt = 0;
@@ -560,17 +564,19 @@ int voxel_downsample_dev(Ctx *ctx, const float *dx, const float *dy, const float
                                                       (uint32_t)nyc64, ys, count, col_of, rank_of, &d_hdr->outside);
             PCR_LAUNCH_CHECK(ctx);
             PCR_TRY(exclusive_scan_u32_dev(ctx, count, (size_t)n_cols + 1));
-            vox_col_scatter_kernel<<<nbp, 256, 0, st>>>(dy, dz, n, voxel, h_range->mn[1], h_range->mn[2], ys, count, col_of, rank_of, members);
-            PCR_LAUNCH_CHECK(ctx);
-            vox_col_sort_kernel<<<nbp, 256, 0, st>>>(col_of, rank_of, n, count, members, nvox, &d_hdr->tall);
-            PCR_LAUNCH_CHECK(ctx);
+            // (a chain of small kernels: programmatic dependent launches, see launch_chained)
+            PCR_CUDA(ctx, launch_chained(vox_col_scatter_kernel, dim3(nbp), dim3(256), 0, st, dy, dz, n, voxel, h_range->mn[1], h_range->mn[2], ys,
+                                         count, col_of, rank_of, members));
+            PCR_CUDA(ctx, launch_chained(vox_col_sort_kernel, dim3(nbp), dim3(256), 0, st, col_of, rank_of, n, count, members, nvox, &d_hdr->tall));
+            ctx->launches += 2;
             PCR_TRY(exclusive_scan_u32_dev(ctx, nvox, (size_t)n_cols + 1));
-            vox_col_emit_kernel<<<nbp, 256, 0, st>>>(dx, dy, dz, col_of, rank_of, n, count, nvox, members, d_ox, d_oy, d_oz);
-            PCR_LAUNCH_CHECK(ctx);
+            PCR_CUDA(ctx, launch_chained(vox_col_emit_kernel, dim3(nbp), dim3(256), 0, st, dx, dy, dz, col_of, rank_of, n, count, nvox, members, d_ox,
+                                         d_oy, d_oz));
+            ctx->launches++;
             // the box and count of what was written (the next step's index build wants them), the voxel count and the
             // outside flag come back together
-            vox_out_stats_kernel<<<(unsigned)ctx->sm_count, 256, 0, st>>>(d_ox, d_oy, d_oz, nvox + n_cols, d_hdr);
-            PCR_LAUNCH_CHECK(ctx);
+            PCR_CUDA(ctx, launch_chained(vox_out_stats_kernel, dim3((unsigned)ctx->sm_count), dim3(256), 0, st, d_ox, d_oy, d_oz, nvox + n_cols, d_hdr));
+            ctx->launches++;
             VoxHeader *mail = (VoxHeader *)((uint32_t *)ctx->pinned + 64);
             PCR_CUDA(ctx, cudaMemcpyAsync(mail, d_hdr, sizeof(VoxHeader), cudaMemcpyDeviceToHost, st));
             PCR_MARK("voxel: wait for count");
