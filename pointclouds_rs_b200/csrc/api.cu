@@ -1074,8 +1074,16 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
     static const bool no_fuse = getenv("PCR_NO_LIST_REUSE") != nullptr;  // A/B hook
     const bool fused = !no_fuse && k_sor > 0 && k_normals > 0 && K <= 32 && n > 1 && ix->n_indexed > 0;
     SorLists sl;
+    bool early = false;
     void *list_mem = nullptr;
     FreeLater f3{nullptr, c->stream};
+    struct EarlyJoin {  // an error return between the early normals pass and its join: the lists are freed in stream order
+        Ctx *c;
+        bool *armed;
+        ~EarlyJoin() {
+            if (*armed) cudaStreamWaitEvent(c->stream, c->ev_join[0], 0);
+        }
+    } early_join{c, &early};
     if (fused) {
         sl.K = K;
         sl.stride = (ix->n_indexed + 63) & ~(size_t)63;
@@ -1096,6 +1104,9 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
         c->spec_request = false;
         PCR_TRY(ss);
         PCR_MARK("core: sor search done");
+        // the normals of every query as if SOR removed nothing, beside the exact fold (which occupies 16 SMs per frame);
+        // the pass after the mask only redoes the queries that lost one of their first k neighbours
+        if (fused) PCR_TRY(normals_early_from_lists_dev(ix, k_normals, vp, sl, d_nx, d_ny, d_nz, &early));
         PCR_TRY(sor_threshold_mask_dev(c, d_mean, ix->frame_in_off, F, n, std_mul, d_keep, d_stats, d_kept));
         PCR_MARK("core: stats queued");
         if (F > 1 || n == 1) {  // a one-point frame is returned as is, even if the point is not finite
@@ -1104,10 +1115,11 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
         }
     }
     if (k_normals == 0) return PCR_OK;
+    if (early) PCR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[0], 0));  // (the early pass reads the coordinates the mask is about to overwrite)
     PCR_TRY(index_apply_mask_dev(ix, d_keep));
     // removed points get 0 and kept non-finite points (0,0,1) inside normals_dev / normals_from_lists_dev
     if (fused) {
-        const int sn = normals_from_lists_dev(ix, k_normals, vp, sl, d_keep, d_nx, d_ny, d_nz, F == 1 ? d_kept : nullptr, h_kept0);
+        const int sn = normals_from_lists_dev(ix, k_normals, vp, sl, d_keep, d_nx, d_ny, d_nz, F == 1 ? d_kept : nullptr, h_kept0, early);
         if (c->spec_pending) {  // the SOR pass's deferred counts, read by the round trip that just ended
             c->spec_pending = false;
             if (sn == PCR_OK) {

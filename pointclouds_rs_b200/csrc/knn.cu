@@ -1790,31 +1790,24 @@ int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny
 // points, in the same (d^2, index) order -- as long as k of them survive (or the list is complete).
 // Queries without a usable list go to `fallback` and are searched again on the tombstoned index.
 namespace {
-__global__ void __launch_bounds__(128) normals_from_lists_kernel(const float4 *__restrict__ qpts, uint32_t nq,
-                                                                 const uint32_t *__restrict__ lists, const uint8_t *__restrict__ list_cnt,
-                                                                 size_t stride, int K, int k, const uint8_t *__restrict__ keep,
-                                                                 const float4 *__restrict__ orig4, float vx_, float vy_, float vz_,
-                                                                 float *__restrict__ nx, float *__restrict__ ny, float *__restrict__ nz,
-                                                                 uint32_t *__restrict__ fallback, uint32_t *__restrict__ fallback_count) {
-    PCR_GRID_DEP_SYNC();
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    const float4 p = __ldg(&qpts[q]);
-    if (p.x != p.x) {  // removed by SOR (tombstoned): not a point of the kept cloud -> 0 (like the unindexed fill)
-        const uint32_t oi = __float_as_uint(p.w);
-        nx[oi] = 0.f;
-        ny[oi] = 0.f;
-        nz[oi] = 0.f;
-        return;
-    }
-    const int c = list_cnt[q];
+// MODE 0: every query, filtered by the keep mask (the plain form).
+// MODE 1: EARLY pass, launched before the mask exists (it overlaps the exact fold, which occupies 16 SMs): every query as if
+//         nothing were removed -- its first min(c, k) list entries.  Never falls back (a list shorter than k is complete).
+// MODE 2: FIX-UP pass after the mask: removed queries get 0; a query none of whose first min(c, k) entries was removed keeps
+//         the early result (the filtered walk would take exactly those entries); the others are gathered per CTA and
+//         recomputed by its first threads, so that a warp does not pay a full evaluation for one lane in thirty.
+template <bool kFilter>
+__device__ __forceinline__ void normal_from_list(uint32_t q, float4 p, int c, const uint32_t *__restrict__ lists, size_t stride, int K, int k,
+                                                 const uint8_t *__restrict__ keep, const float4 *__restrict__ orig4, float vx_, float vy_,
+                                                 float vz_, float *__restrict__ nx, float *__restrict__ ny, float *__restrict__ nz,
+                                                 uint32_t *__restrict__ fallback, uint32_t *__restrict__ fallback_count) {
     bool ok = c != 0xff;
     int taken = 0;
     float cx = 0.f, cy = 0.f, cz = 0.f;
     if (ok) {
         for (int j = 0; j < c && taken < k; j++) {  // estimate.rs:54-65, neighbour order
             const uint32_t i = __ldg(&lists[(size_t)j * stride + q]);
-            if (!keep[i]) continue;
+            if (kFilter && !keep[i]) continue;
             const float4 t = __ldg(&orig4[i]);
             cx = __fadd_rn(cx, t.x);
             cy = __fadd_rn(cy, t.y);
@@ -1824,8 +1817,8 @@ __global__ void __launch_bounds__(128) normals_from_lists_kernel(const float4 *_
         ok = taken == k || c < K;  // a truncated list with fewer than k survivors cannot be trusted
     }
     if (!ok) {
-        fallback[atomicAdd(fallback_count, 1u)] = q;
-        return;
+        if (kFilter) fallback[atomicAdd(fallback_count, 1u)] = q;
+        return;  // (early pass: a query without a list is left to the fix-up pass)
     }
     float ox = 0.f, oy = 0.f, oz = 1.f;
     if (taken >= 1) {
@@ -1837,7 +1830,7 @@ __global__ void __launch_bounds__(128) normals_from_lists_kernel(const float4 *_
         int seen = 0;
         for (int j = 0; j < c && seen < k; j++) {  // estimate.rs:68-84
             const uint32_t i = __ldg(&lists[(size_t)j * stride + q]);
-            if (!keep[i]) continue;
+            if (kFilter && !keep[i]) continue;
             const float4 t = __ldg(&orig4[i]);
             const float dx = __fsub_rn(t.x, cx), dy = __fsub_rn(t.y, cy), dz = __fsub_rn(t.z, cz);
             c00 = __fadd_rn(c00, __fmul_rn(dx, dx));
@@ -1868,12 +1861,91 @@ __global__ void __launch_bounds__(128) normals_from_lists_kernel(const float4 *_
     ny[oi] = oy;
     nz[oi] = oz;
 }
+
+constexpr int kNflThreads = 128;
+template <int MODE>
+__global__ void __launch_bounds__(kNflThreads) normals_from_lists_kernel(const float4 *__restrict__ qpts, uint32_t nq,
+                                                                 const uint32_t *__restrict__ lists, const uint8_t *__restrict__ list_cnt,
+                                                                 size_t stride, int K, int k, const uint8_t *__restrict__ keep,
+                                                                 const float4 *__restrict__ orig4, float vx_, float vy_, float vz_,
+                                                                 float *__restrict__ nx, float *__restrict__ ny, float *__restrict__ nz,
+                                                                 uint32_t *__restrict__ fallback, uint32_t *__restrict__ fallback_count) {
+    PCR_GRID_DEP_SYNC();
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (MODE == 1) {
+        if (q >= nq) return;
+        normal_from_list<false>(q, __ldg(&qpts[q]), list_cnt[q], lists, stride, K, k, nullptr, orig4, vx_, vy_, vz_, nx, ny, nz, nullptr, nullptr);
+        return;
+    }
+    __shared__ uint32_t s_redo[kNflThreads];
+    __shared__ int s_n;
+    if (MODE == 2) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+    }
+    bool work = q < nq;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (work) {
+        p = __ldg(&qpts[q]);
+        if (p.x != p.x) {  // removed by SOR (tombstoned): not a point of the kept cloud -> 0 (like the unindexed fill)
+            const uint32_t oi = __float_as_uint(p.w);
+            nx[oi] = 0.f;
+            ny[oi] = 0.f;
+            nz[oi] = 0.f;
+            work = false;
+        }
+    }
+    if (MODE == 2) {
+        if (work) {
+            const int c = list_cnt[q];
+            bool redo = c == 0xff;
+            if (!redo) {
+                const int m = min(c, k);
+#pragma unroll 4
+                for (int j = 0; j < m; j++) redo |= keep[__ldg(&lists[(size_t)j * stride + q])] == 0;
+            }
+            if (redo) s_redo[atomicAdd(&s_n, 1)] = q;
+        }
+        __syncthreads();
+        work = (int)threadIdx.x < s_n;
+        if (work) {
+            q = s_redo[threadIdx.x];
+            p = __ldg(&qpts[q]);
+        }
+    }
+    if (!work) return;
+    normal_from_list<true>(q, p, list_cnt[q], lists, stride, K, k, keep, orig4, vx_, vy_, vz_, nx, ny, nz, fallback, fallback_count);
+}
 }  // namespace
 
 // normals of the kept points of `ix` (already tombstoned with d_keep) from the lists of the SOR pass;
 // the few queries without a usable list are searched again (warp kernels on the tombstoned levels)
+// The early pass (MODE 1 above) on a side stream, forked from the main stream's current position (the searches are done, the
+// lists complete); `ev_join[0]` marks its end.  The caller makes the main stream wait for that event before the index is
+// tombstoned and the fix-up pass runs (normals_from_lists_dev with early = true).
+int normals_early_from_lists_dev(Index *ix, size_t k, const float vp[3], const SorLists &sl, float *d_nx, float *d_ny, float *d_nz, bool *launched) {
+    Ctx *ctx = ix->ctx;
+    *launched = false;
+    static const bool off = getenv("PCR_NO_EARLY_NORMALS") != nullptr;  // A/B hook
+    const uint32_t nq = (uint32_t)ix->n_indexed;
+    if (off || ix->n == 0 || k == 0 || nq == 0) return PCR_OK;
+    PCR_TRY(ensure_side_streams(ctx));
+    PCR_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    PCR_CUDA(ctx, cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork, 0));
+    {
+        StreamSwap sw(ctx, ctx->side[0]);
+        TimeScope ts(ctx, kTagKnnNormals);
+        normals_from_lists_kernel<1><<<(nq + kNflThreads - 1) / kNflThreads, kNflThreads, 0, ctx->stream>>>(
+            ix->sorted, nq, sl.lists, sl.cnt, sl.stride, (int)sl.K, (int)k, nullptr, ix->orig4, vp[0], vp[1], vp[2], d_nx, d_ny, d_nz, nullptr, nullptr);
+        PCR_LAUNCH_CHECK(ctx);
+    }
+    PCR_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], ctx->side[0]));
+    *launched = true;
+    return PCR_OK;
+}
+
 int normals_from_lists_dev(Index *ix, size_t k, const float vp[3], const SorLists &sl, const uint8_t *d_keep, float *d_nx, float *d_ny,
-                           float *d_nz, const unsigned long long *d_kept0, unsigned long long *h_kept0) {
+                           float *d_nz, const unsigned long long *d_kept0, unsigned long long *h_kept0, bool early) {
     Ctx *ctx = ix->ctx;
     if (ix->n == 0 || k == 0) return PCR_OK;
     if (ix->n_indexed < ix->n) {  // points outside the index (non-finite); the removed indexed ones are zeroed by the kernel below
@@ -1886,8 +1958,9 @@ int normals_from_lists_dev(Index *ix, size_t k, const float vp[3], const SorList
     PCR_CUDA(ctx, cudaMemsetAsync(d_fb_count, 0, sizeof(uint32_t), ctx->stream));
     {
         TimeScope ts(ctx, kTagKnnNormals);
-        PCR_CUDA(ctx, launch_chained(normals_from_lists_kernel, dim3((nq + 127) / 128), dim3(128), 0, ctx->stream, ix->sorted, nq, sl.lists, sl.cnt,
-                                     sl.stride, (int)sl.K, (int)k, d_keep, ix->orig4, vp[0], vp[1], vp[2], d_nx, d_ny, d_nz, sl.fallback, d_fb_count));
+        PCR_CUDA(ctx, launch_chained(early ? normals_from_lists_kernel<2> : normals_from_lists_kernel<0>, dim3((nq + kNflThreads - 1) / kNflThreads),
+                                     dim3(kNflThreads), 0, ctx->stream, ix->sorted, nq, sl.lists, sl.cnt, sl.stride, (int)sl.K, (int)k, d_keep, ix->orig4,
+                                     vp[0], vp[1], vp[2], d_nx, d_ny, d_nz, sl.fallback, d_fb_count));
         ctx->launches++;
     }
     // The queries that fall back are few, and their count is still on the device: launch their level-0 pass now for a
