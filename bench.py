@@ -479,7 +479,7 @@ def _sync_all(torch, D):
         torch.cuda.synchronize()
 
 
-def batch8m_measurement(pcr, pdist, D, device, rank, world, n_frames=100, reps=3):
+def batch8m_measurement(pcr, pdist, D, device, rank, world, n_frames=100, reps=5):
     """BASELINE configs[4]: 100 frames x 80 000 points, SOR k=10 + normals k=20, frames dealt round-robin over the ranks
     (strong scaling), one pcr_sor_normals_batch call per rank."""
     import torch
@@ -518,20 +518,21 @@ def batch8m_measurement(pcr, pdist, D, device, rank, world, n_frames=100, reps=3
         host_call()
         dev_call()
     _sync_all(torch, D)
-    t_host = 0.0
+    t_host, t_dev = [], []
     for _ in range(reps):
         flush.fill_(1)
         _sync_all(torch, D)
         t0 = time.perf_counter()
         host_call()
-        t_host += time.perf_counter() - t0
-    t_dev = 0.0
+        t_host.append(time.perf_counter() - t0)
     for _ in range(reps):
         flush.fill_(2)
         _sync_all(torch, D)
         t0 = time.perf_counter()
         dev_call()
-        t_dev += time.perf_counter() - t0
+        t_dev.append(time.perf_counter() - t0)
+    spread = {"host_api_ms": [round(t * 1e3, 3) for t in t_host], "device_ms": [round(t * 1e3, 3) for t in t_dev]}
+    t_host, t_dev = float(np.median(t_host)) * reps, float(np.median(t_dev)) * reps  # (the median of the repetitions)
     # both arms must agree (same kernels): the host arm's mask and normals against the device arm's
     same = True
     if n:
@@ -550,6 +551,7 @@ def batch8m_measurement(pcr, pdist, D, device, rank, world, n_frames=100, reps=3
                      "h2d_bytes": 12 * int(n_all), "d2h_bytes": 13 * int(n_all),
                      "timer": "wall clock around pcr_sor_normals_batch (pinned host buffers, copies inside), max over ranks"},
         "host_and_device_results_identical": bool(same_all),
+        "repetitions_rank0": spread, "statistic": "median of %d calls after 2 warm-up calls" % reps,
     }
 
 

@@ -44,6 +44,7 @@ struct VoxHeader {
 // Members one thread sorts in place.  A coarse voxel, a wall or a dense small-footprint cloud can put 10^5..10^7 points
 // into one column; a serial sort of that in global memory would take seconds, the radix path sorts it in 4 passes.
 constexpr uint32_t kTallColumn = 256;
+constexpr uint32_t kLocalColumn = 32;  // columns up to this many members are sorted in local memory
 static_assert(sizeof(VoxHeader) == 64, "header layout");
 
 struct VoxRange {
@@ -322,16 +323,40 @@ __global__ void __launch_bounds__(256) vox_col_sort_kernel(const uint32_t *__res
         return;
     }
     unsigned long long *a = members + b;
-    if (m <= 24) {  // insertion sort
-        for (uint32_t i = 1; i < m; i++) {
-            const unsigned long long v = a[i];
+    if (m == 1) {  // (nine columns in ten of a LiDAR frame)
+        nvox[c] = 1u;
+        return;
+    }
+    if (m <= kLocalColumn) {
+        // A wall or a pedestrian puts 10-30 points in a column.  Sorted in place in global memory every compare of the
+        // insertion sort was a dependent L2 round trip (the kernel took as long as its slowest column: 29 us); the column
+        // is copied to local memory instead (eight independent loads in flight), sorted there and written back.
+        unsigned long long loc[kLocalColumn];
+        for (uint32_t j0 = 0; j0 < m; j0 += 8) {
+            unsigned long long t[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) t[u] = a[min(j0 + u, m - 1)];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (j0 + u < m) loc[j0 + u] = t[u];
+        }
+        for (uint32_t i = 1; i < m; i++) {  // insertion sort
+            const unsigned long long v = loc[i];
             uint32_t j = i;
-            while (j > 0 && a[j - 1] > v) {
-                a[j] = a[j - 1];
+            while (j > 0 && loc[j - 1] > v) {
+                loc[j] = loc[j - 1];
                 j--;
             }
-            a[j] = v;
+            loc[j] = v;
         }
+        uint32_t nv = 1;
+        a[0] = loc[0];
+        for (uint32_t i = 1; i < m; i++) {
+            a[i] = loc[i];
+            nv += (uint32_t)(loc[i] >> 32) != (uint32_t)(loc[i - 1] >> 32) ? 1u : 0u;
+        }
+        nvox[c] = nv;
+        return;
     } else {  // heapsort: O(m log m) for the rare tall column (a wall, a whole cloud in one column)
         for (uint32_t s0 = m / 2; s0-- > 0;) {
             uint32_t root = s0;
@@ -375,24 +400,48 @@ __global__ void __launch_bounds__(256) vox_col_emit_kernel(const float *__restri
     if (c == 0xffffffffu || rank_of[t] != 0u) return;
     const uint32_t b = start[c], e = start[c + 1];
     if (e - b > kTallColumn) return;  // flagged by vox_col_sort_kernel: this pass is void
+    // Eight members at a time: their keys, then their coordinates, are independent loads; only the additions are a chain
+    // (one member after the other was two dependent L2 round trips per member: 15 us for the tallest column).
     uint32_t v = vstart[c];
-    uint32_t i = b;
-    while (i < e) {
-        const uint32_t kz = (uint32_t)(members[i] >> 32);
-        float sx = 0.f, sy = 0.f, sz = 0.f;
-        uint32_t cnt = 0;
-        for (; i < e && (uint32_t)(members[i] >> 32) == kz; i++, cnt++) {  // :38-42, input order
-            const uint32_t p = (uint32_t)members[i];
-            sx = __fadd_rn(sx, x[p]);
-            sy = __fadd_rn(sy, y[p]);
-            sz = __fadd_rn(sz, z[p]);
+    uint32_t cur = (uint32_t)(members[b] >> 32);
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    uint32_t cnt = 0;
+    for (uint32_t i = b; i < e; i += 8) {
+        unsigned long long mm[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) mm[u] = members[min(i + u, e - 1)];
+        float X[8], Y[8], Z[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t p = (uint32_t)mm[u];
+            X[u] = x[p];
+            Y[u] = y[p];
+            Z[u] = z[p];
         }
-        const float denom = (float)cnt;  // :56
-        ox[v] = __fdiv_rn(sx, denom);
-        oy[v] = __fdiv_rn(sy, denom);
-        oz[v] = __fdiv_rn(sz, denom);
-        v++;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (i + u >= e) break;
+            const uint32_t kz = (uint32_t)(mm[u] >> 32);
+            if (kz != cur) {
+                const float denom = (float)cnt;  // :56
+                ox[v] = __fdiv_rn(sx, denom);
+                oy[v] = __fdiv_rn(sy, denom);
+                oz[v] = __fdiv_rn(sz, denom);
+                v++;
+                sx = sy = sz = 0.f;
+                cnt = 0;
+                cur = kz;
+            }
+            sx = __fadd_rn(sx, X[u]);  // :38-42, input order
+            sy = __fadd_rn(sy, Y[u]);
+            sz = __fadd_rn(sz, Z[u]);
+            cnt++;
+        }
     }
+    const float denom = (float)cnt;  // :56
+    ox[v] = __fdiv_rn(sx, denom);
+    oy[v] = __fdiv_rn(sy, denom);
+    oz[v] = __fdiv_rn(sz, denom);
 }
 
 // Bounding box and finite count of the cloud just written, its length still on the device: what the index
