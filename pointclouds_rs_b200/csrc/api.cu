@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <cstring>
 #include <utility>
 #include <vector>
 #include <algorithm>
@@ -63,8 +64,17 @@ bool g_trace_on = getenv("PCR_TRACE") != nullptr;
 namespace {
 thread_local std::vector<std::pair<const char *, double>> t_trace;
 }
+static void trace_dump();
+// PCR_TRACE_SLOW_US=<t>: keep only the marks of calls that took longer than t (a call = a mark ending in "enter" ... "exit")
+static const double g_trace_slow_us = getenv("PCR_TRACE_SLOW_US") ? atof(getenv("PCR_TRACE_SLOW_US")) : 0.0;
 void trace_mark(const char *label) {
+    const size_t len = strlen(label);
+    if (g_trace_slow_us > 0.0 && len >= 5 && !strcmp(label + len - 5, "enter")) t_trace.clear();
     t_trace.emplace_back(label, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count());
+    if (g_trace_slow_us > 0.0 && len >= 4 && !strcmp(label + len - 4, "exit")) {
+        if (t_trace.back().second - t_trace.front().second > g_trace_slow_us) trace_dump();
+        else t_trace.clear();
+    }
 }
 static void trace_dump() {
     if (!g_trace_on || t_trace.empty()) return;
@@ -262,6 +272,8 @@ void pcr_ctx_destroy(pcr_ctx *ctx) {
     free_buf(c, c->b_fine_scan);
     free_buf(c, c->b_list);
     for (auto &b : c->b_cells) free_buf(c, b);
+    for (auto &b : c->b_lsorted) free_buf(c, b);
+    for (auto &b : c->b_lgrids) free_buf(c, b);
     cudaStreamSynchronize(c->stream);
     for (auto &sp : c->spans) {
         cudaEventDestroy(sp.a);
@@ -1093,6 +1105,7 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
         sl.lists = (uint32_t *)list_mem;
         sl.fallback = sl.lists + K * sl.stride;
         sl.cnt = (uint8_t *)(sl.fallback + sl.stride + 64);
+        PCR_MARK("core: lists allocated");
     }
     if (k_sor == 0) {  // statistical_outlier.rs:5-7: empty result
         PCR_CUDA(c, cudaMemsetAsync(d_keep, 0, n, c->stream));
@@ -1154,11 +1167,16 @@ int pcr_sor_normals_batch_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, 
     if (n_frames > 65535) return fail(c, PCR_ERR_UNSUPPORTED, "at most 65535 frames per batch");
     PCR_API_BEGIN
     DevSetter ds(c);
+    PCR_MARK("batch_dev: enter");
     unsigned long long *d_kept = nullptr;
     PCR_CUDA(c, cudaMallocAsync((void **)&d_kept, sizeof(unsigned long long) * n_frames, c->stream));
     int s = batch_core(c, d_x, d_y, d_z, frame_offsets, n_frames, n, k_sor, std_mul, k_normals, viewpoint, d_keep, d_nx, d_ny, d_nz,
                        d_kept);
     cudaFreeAsync(d_kept, c->stream);
+    if (g_trace_on) {  // (tracing only: the entry point itself is asynchronous)
+        cudaStreamSynchronize(c->stream);
+        PCR_MARK("batch_dev: synced, exit");
+    }
     return s;
     PCR_API_END(c)
 }

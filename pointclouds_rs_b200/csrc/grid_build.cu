@@ -605,8 +605,8 @@ void index_free(Index *ix) {
     if (ix->finer) index_free(ix->finer);
     if (ix->owns_memory && ix->ctx) {
         cudaStream_t s = ix->ctx->stream;
-        if (ix->grids) cudaFreeAsync(ix->grids, s);
-        if (ix->sorted) cudaFreeAsync(ix->sorted, s);
+        if (ix->grids && !ix->level_bufs_borrowed) cudaFreeAsync(ix->grids, s);
+        if (ix->sorted && !ix->level_bufs_borrowed) cudaFreeAsync(ix->sorted, s);
         if (ix->cell_start && ix->cell_slot < 0) cudaFreeAsync(ix->cell_start, s);
         if (!ix->shares_orig4) {
             if (ix->frame_in_off) cudaFreeAsync(ix->frame_in_off, s);
@@ -677,7 +677,15 @@ static int index_level_build(Index *ix, bool fine, Index **out) {
             if (ix) index_free(ix);
         }
     } guard{c};
-    PCR_CUDA(ctx, cudaMallocAsync((void **)&c->grids, sizeof(GridDesc) * F, st));
+    constexpr int kSlots = (int)(sizeof(ctx->b_cells) / sizeof(ctx->b_cells[0]));
+    if (fine ? ix->cell_slot == 0 : (ix->cell_slot >= 0 && ix->cell_slot + 1 < kSlots - 1)) {
+        c->cell_slot = fine ? kSlots - 1 : ix->cell_slot + 1;  // (the last slot is the finer level's)
+        c->level_bufs_borrowed = true;  // a level of a transient index: every array comes from the context's slot
+        PCR_TRY(ensure(ctx, ctx->b_lgrids[c->cell_slot], sizeof(GridDesc) * F));
+        c->grids = (GridDesc *)ctx->b_lgrids[c->cell_slot].p;
+    } else {
+        PCR_CUDA(ctx, cudaMallocAsync((void **)&c->grids, sizeof(GridDesc) * F, st));
+    }
     const uint64_t cap = std::max<uint64_t>(1, std::min<uint64_t>(kMaxCellsPerFrame, kMaxCellsTotal / (uint64_t)F));
     uint64_t base = 0;
     uint32_t max_frame = 0;
@@ -706,16 +714,16 @@ static int index_level_build(Index *ix, bool fine, Index **out) {
     }
     c->total_cells = (uint32_t)base;
     PCR_CUDA(ctx, cudaMemcpyAsync(c->grids, c->grids_h.data(), sizeof(GridDesc) * F, cudaMemcpyHostToDevice, st));
-    constexpr int kSlots = (int)(sizeof(ctx->b_cells) / sizeof(ctx->b_cells[0]));
-    if (fine ? ix->cell_slot == 0 : (ix->cell_slot >= 0 && ix->cell_slot + 1 < kSlots - 1)) {
-        c->cell_slot = fine ? kSlots - 1 : ix->cell_slot + 1;  // (the last slot is the finer level's)
+    if (c->level_bufs_borrowed) {
         PCR_TRY(ensure(ctx, ctx->b_cells[c->cell_slot], sizeof(uint32_t) * ((size_t)base + 1)));
         c->cell_start = (uint32_t *)ctx->b_cells[c->cell_slot].p;
+        PCR_TRY(ensure(ctx, ctx->b_lsorted[c->cell_slot], sizeof(float4) * std::max<size_t>(n, 1)));
+        c->sorted = (float4 *)ctx->b_lsorted[c->cell_slot].p;
     } else {
         PCR_CUDA(ctx, cudaMallocAsync((void **)&c->cell_start, sizeof(uint32_t) * ((size_t)base + 1), st));
+        PCR_CUDA(ctx, cudaMallocAsync((void **)&c->sorted, sizeof(float4) * std::max<size_t>(n, 1), st));
     }
     PCR_CUDA(ctx, cudaMemsetAsync(c->cell_start, 0, sizeof(uint32_t) * ((size_t)base + 1), st));
-    PCR_CUDA(ctx, cudaMallocAsync((void **)&c->sorted, sizeof(float4) * std::max<size_t>(n, 1), st));
     DevBuf &scratch = fine ? ctx->b_fine_misc : ctx->b_misc;
     PCR_TRY(ensure(ctx, scratch, sizeof(uint32_t) * 2 * std::max<size_t>(n, 1)));
     uint32_t *d_cell_id = (uint32_t *)scratch.p;

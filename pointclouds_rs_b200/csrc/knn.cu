@@ -1402,13 +1402,16 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
                 return PCR_OK;
             };
             static const bool side_first = getenv("PCR_SIDE_FIRST") != nullptr;  // A/B hook: the round-2a order
+            PCR_MARK("levels: classes queued");
             if (!side_first) PCR_TRY(launch_main());
+            PCR_MARK("levels: main launch queued");
             // side 0: the sparse queries on the next-coarser level (built here, behind the fork, while level 0 runs)
             if (!last) {
                 StreamSwap sw(ctx, ctx->side[0]);
                 TimeScope ts(ctx, kTagKnnDeferred);
                 Index *next = nullptr;
                 PCR_TRY(index_coarser_level(cur, &next));
+                PCR_MARK("levels: coarser level queued");
                 LevelArgs s1 = a;
                 s1.grids = next->grids;
                 s1.cell_start = next->cell_start;
@@ -1447,7 +1450,9 @@ int run_levels(Index *ix, uint32_t nq, int tag0, Launch launch, const uint32_t *
                     // TILE kernel -- 165 us for 11 K queries: 240 candidates per thread is a long serial chain, and only 350
                     // warps carry it; its leftovers then need lists of their own for the level-0 warp kernels.)
                     Index *fine = nullptr;
+                    PCR_MARK("levels: sparse class queued");
                     PCR_TRY(index_finer_level(cur, &fine));
+                    PCR_MARK("levels: finer level queued");
                     d.grids = fine->grids;
                     d.cell_start = fine->cell_start;
                     d.pts = fine->sorted;
@@ -1801,18 +1806,33 @@ __device__ __forceinline__ void normal_from_list(uint32_t q, float4 p, int c, co
                                                  const uint8_t *__restrict__ keep, const float4 *__restrict__ orig4, float vx_, float vy_,
                                                  float vz_, float *__restrict__ nx, float *__restrict__ ny, float *__restrict__ nz,
                                                  uint32_t *__restrict__ fallback, uint32_t *__restrict__ fallback_count) {
+    // The list is walked eight entries at a time: the indices, then the keep flags, then the points are independent loads
+    // (one entry after the other was three dependent L2 round trips per neighbour); only the additions are a chain.
     bool ok = c != 0xff;
     int taken = 0;
     float cx = 0.f, cy = 0.f, cz = 0.f;
+    uint32_t used = 0;  // bit j: list entry j is one of the (at most k) neighbours taken
     if (ok) {
-        for (int j = 0; j < c && taken < k; j++) {  // estimate.rs:54-65, neighbour order
-            const uint32_t i = __ldg(&lists[(size_t)j * stride + q]);
-            if (kFilter && !keep[i]) continue;
-            const float4 t = __ldg(&orig4[i]);
-            cx = __fadd_rn(cx, t.x);
-            cy = __fadd_rn(cy, t.y);
-            cz = __fadd_rn(cz, t.z);
-            taken++;
+        for (int j0 = 0; j0 < c && taken < k; j0 += 8) {  // estimate.rs:54-65, neighbour order
+            uint32_t id[8];
+            bool kp[8];
+            float4 t[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) id[u] = __ldg(&lists[(size_t)min(j0 + u, c - 1) * stride + q]);
+#pragma unroll
+            for (int u = 0; u < 8; u++) kp[u] = j0 + u < c && (!kFilter || keep[id[u]] != 0);
+#pragma unroll
+            for (int u = 0; u < 8; u++) t[u] = kp[u] ? __ldg(&orig4[id[u]]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (kp[u] && taken < k) {
+                    cx = __fadd_rn(cx, t[u].x);
+                    cy = __fadd_rn(cy, t[u].y);
+                    cz = __fadd_rn(cz, t[u].z);
+                    taken++;
+                    used |= 1u << (j0 + u);
+                }
+            }
         }
         ok = taken == k || c < K;  // a truncated list with fewer than k survivors cannot be trusted
     }
@@ -1827,19 +1847,23 @@ __device__ __forceinline__ void normal_from_list(uint32_t q, float4 p, int c, co
         cy = __fdiv_rn(cy, count);
         cz = __fdiv_rn(cz, count);
         float c00 = 0.f, c01 = 0.f, c02 = 0.f, c11 = 0.f, c12 = 0.f, c22 = 0.f;
-        int seen = 0;
-        for (int j = 0; j < c && seen < k; j++) {  // estimate.rs:68-84
-            const uint32_t i = __ldg(&lists[(size_t)j * stride + q]);
-            if (kFilter && !keep[i]) continue;
-            const float4 t = __ldg(&orig4[i]);
-            const float dx = __fsub_rn(t.x, cx), dy = __fsub_rn(t.y, cy), dz = __fsub_rn(t.z, cz);
-            c00 = __fadd_rn(c00, __fmul_rn(dx, dx));
-            c01 = __fadd_rn(c01, __fmul_rn(dx, dy));
-            c02 = __fadd_rn(c02, __fmul_rn(dx, dz));
-            c11 = __fadd_rn(c11, __fmul_rn(dy, dy));
-            c12 = __fadd_rn(c12, __fmul_rn(dy, dz));
-            c22 = __fadd_rn(c22, __fmul_rn(dz, dz));
-            seen++;
+        for (int j0 = 0; j0 < 32 && (used >> j0) != 0u; j0 += 8) {  // estimate.rs:68-84
+            float4 t[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                t[u] = ((used >> (j0 + u)) & 1u) ? __ldg(&orig4[__ldg(&lists[(size_t)(j0 + u) * stride + q])]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if ((used >> (j0 + u)) & 1u) {
+                    const float dx = __fsub_rn(t[u].x, cx), dy = __fsub_rn(t[u].y, cy), dz = __fsub_rn(t[u].z, cz);
+                    c00 = __fadd_rn(c00, __fmul_rn(dx, dx));
+                    c01 = __fadd_rn(c01, __fmul_rn(dx, dy));
+                    c02 = __fadd_rn(c02, __fmul_rn(dx, dz));
+                    c11 = __fadd_rn(c11, __fmul_rn(dy, dy));
+                    c12 = __fadd_rn(c12, __fmul_rn(dy, dz));
+                    c22 = __fadd_rn(c22, __fmul_rn(dz, dz));
+                }
+            }
         }
         float ex, ey, ez;
         smallest_eigenvector_3x3(c00, c01, c02, c11, c12, c22, ex, ey, ez);

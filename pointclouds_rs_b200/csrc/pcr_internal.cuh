@@ -75,6 +75,7 @@ struct Index {
     Index *finer = nullptr;           // half the cell size: where the dense class of level 0 is searched (knn.cu), built on demand
     bool shares_orig4 = false;        // coarser levels borrow orig4 / grids layout from level 0
     int cell_slot = -1;               // >= 0: cell_start lives in ctx->b_cells[cell_slot] (transient index), not owned
+    bool level_bufs_borrowed = false; // sorted and grids live in ctx->b_lsorted / b_lgrids[cell_slot], not owned
     // query shard of this rank (sorted positions): set by index_shard_queries, default = every indexed point
     uint32_t q_begin = 0;
     uint32_t q_count = 0xffffffffu;
@@ -144,6 +145,10 @@ struct Ctx {
     // level.  A 100-frame batch needs a 280 MB table: taking it from the stream-ordered pool on every
     // call cost 4-16 ms (the pool had just carved the freed block up for the smaller arrays).
     DevBuf b_cells[6];
+    // ... and, for the levels built on the side streams (coarser / finer), their sorted points and grid descriptors too: a
+    // side-stream cudaMallocAsync finds the blocks the main stream freed after the previous call only some of the time
+    // (otherwise it carves up a larger block or maps new memory: intermittent 20-700 ms host stalls on the 8 M-point batch)
+    DevBuf b_lsorted[6], b_lgrids[6];
     void *pinned = nullptr;  // small pinned host mailbox
     size_t pinned_cap = 0;
     // optional per-stage device timing (cudaEvents on the context's stream; bench.py's roofline)
