@@ -1925,8 +1925,13 @@ __global__ void __launch_bounds__(kNflThreads) normals_from_lists_kernel(const f
             bool redo = c == 0xff;
             if (!redo) {
                 const int m = min(c, k);
-#pragma unroll 4
-                for (int j = 0; j < m; j++) redo |= keep[__ldg(&lists[(size_t)j * stride + q])] == 0;
+                for (int j0 = 0; j0 < m; j0 += 8) {  // (eight independent index loads, then eight independent flag loads)
+                    uint32_t id[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) id[u] = __ldg(&lists[(size_t)min(j0 + u, m - 1) * stride + q]);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) redo |= keep[id[u]] == 0;
+                }
             }
             if (redo) s_redo[atomicAdd(&s_n, 1)] = q;
         }

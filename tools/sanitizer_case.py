@@ -19,4 +19,8 @@ src = (tgt @ scenes.rot_z(0.03).T + np.array([0.1, 0.0, -0.05], np.float32)).ast
 tc = pcr.estimate_normals(pcr.PointCloud.from_numpy(tgt), 15)
 print(pcr.icp_point_to_plane(pcr.PointCloud.from_numpy(np.ascontiguousarray(src)), tc, 10, 1e-6))
 print(pcr.icp_point_to_point(pcr.PointCloud.from_numpy(np.ascontiguousarray(src)), tc, 10, 1e-6))
+v = pcr.voxel_downsample(c, 0.3)
+d = pcr.DeviceCloud.from_numpy(pts)
+o = d.voxel_downsample(0.05).sor_normals(10, 1.0, 20)
+print("device pipeline", o.len(), "voxels", v.len())
 print("sanitizer case done", kept)
