@@ -578,18 +578,22 @@ def icp_measurement(pcr, pdist, D, device, rank, world):
     shard_np = np.ascontiguousarray(src_np[rank::world])
     b, e = 0, len(shard_np)
     shard = pcr.PointCloud.from_numpy(shard_np)
-    pcr.icp_point_to_plane(shard, tgt, 30, 0.0, ctx=ctx)  # warm-up
+    for _ in range(2):
+        pcr.icp_point_to_plane(shard, tgt, 30, 0.0, ctx=ctx)  # warm-up
     ctx.set_timing(True)
     ctx.get_timing()
-    _sync_all(torch, D)
-    t0 = time.perf_counter()
-    res = pcr.icp_point_to_plane(shard, tgt, 30, 0.0, ctx=ctx)
-    wall = time.perf_counter() - t0
+    walls = []
+    ICP_REPS = 5
+    for _ in range(ICP_REPS):  # (the median of the repetitions)
+        _sync_all(torch, D)
+        t0 = time.perf_counter()
+        res = pcr.icp_point_to_plane(shard, tgt, 30, 0.0, ctx=ctx)
+        walls.append(time.perf_counter() - t0)
     stage = ctx.get_timing()
     ctx.set_timing(False)
-    wall_local = wall
+    wall_local = wall = float(np.median(walls))
     wall = pdist.max_over_ranks(D, wall, "cuda")
-    step_ms, step_cnt = stage["icp_step"]
+    step_ms, step_cnt = stage["icp_step"]      # (sums over the timed calls; used per iteration below)
     solve_ms, solve_cnt = stage["icp_solve"]
     one = pcr.icp_point_to_plane(full, tgt, 30, 0.0, ctx=solo)  # the unsharded run on this GPU
     v = torch.tensor([x for row in res.rotation for x in row] + list(res.translation) + [res.rmse, res.fitness, float(res.num_iterations)],
@@ -613,7 +617,8 @@ def icp_measurement(pcr, pdist, D, device, rank, world):
         "ms_per_iter_loop_rank0": step_ms / max(step_cnt, 1) + solve_ms / max(solve_cnt, 1),  # the iteration itself: what sharding can shrink
         # what is not the iteration loop: upload of the shard and the (replicated) target + normals, target index build,
         # source binning, result download -- paid once per call whatever the number of ranks
-        "ms_setup_and_host_rank0": wall_local * 1e3 - step_ms - solve_ms,
+        "ms_setup_and_host_rank0": wall_local * 1e3 - (step_ms + solve_ms) / ICP_REPS,
+        "ms_per_call_rank0": [round(w * 1e3, 3) for w in walls], "statistic": "median of %d calls after 2 warm-up calls" % ICP_REPS,
         "collective": {"none": "none (one rank)",
                        "nccl": "ncclAllReduce of 30 f64 on the library's stream, every iteration",
                        "peer": "one-shot all-reduce of 30 f64 over NVLink peer memory (CUDA IPC blocks), fused into the reduction kernel, "

@@ -167,6 +167,7 @@ class PointCloud:
         self.y = np.empty(0, np.float32)
         self.z = np.empty(0, np.float32)
         self.normals: Optional[np.ndarray] = None  # (N,3) f32
+        self._nsoa = None  # (the array `normals` was when split, (nx, ny, nz)): the reference's Normals are SoA (cloud.rs:13-18)
 
     @staticmethod
     def _from_xyz(x, y, z, normals=None) -> "PointCloud":
@@ -188,6 +189,12 @@ class PointCloud:
             raise ValueError("expected shape (N, 3)")
         a = array.astype(np.float32, copy=False)
         return PointCloud._from_xyz(*_soa(a))
+
+    def _normals_soa(self):
+        """nx, ny, nz as contiguous arrays, split once per normals array (a 1 M-point split costs more than an ICP setup)."""
+        if self._nsoa is None or self._nsoa[0] is not self.normals:
+            self._nsoa = (self.normals, _soa(np.asarray(self.normals, np.float32).reshape(-1, 3)))
+        return self._nsoa[1]
 
     def to_numpy(self) -> np.ndarray:
         return np.stack([self.x, self.y, self.z], axis=1) if len(self.x) else np.zeros((0, 3), np.float32)
@@ -554,8 +561,7 @@ def icp_point_to_plane(source: PointCloud, target: PointCloud, max_iterations: i
     if target.normals is None:  # crates/python/src/registration.rs:66-71
         raise ValueError("target cloud must have normals for point-to-plane ICP. Use estimate_normals(target, k) first.")
     p = _icp_params(max_iterations, tolerance, max_correspondence_distance)
-    nr = np.asarray(target.normals, np.float32).reshape(-1, 3)
-    nx, ny, nz = _soa(nr)
+    nx, ny, nz = target._normals_soa()
     res = _ffi.IcpResultC()
     st = _ffi.load().pcr_icp_point_to_plane(ctx._h, _p(source.x, _ffi.f32p), _p(source.y, _ffi.f32p), _p(source.z, _ffi.f32p),
                                             len(source), _p(target.x, _ffi.f32p), _p(target.y, _ffi.f32p), _p(target.z, _ffi.f32p),
