@@ -441,72 +441,6 @@ __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(uint32_t *_
     if (tile == tiles - 1 && threadIdx.x == 0) *ticket = 0;  // every ticket has been handed out by now
 }
 
-// ---- keep-mask compaction in one pass ---------------------------------------------------------------
-// flags -> tile scan -> look-back -> scatter, instead of flag kernel + scan + scatter kernel (two kernel boundaries and
-// two passes over a 4 B-per-point array less at the end of every frame).  Rows 0..n_a-1 of the output come from `a`, rows
-// n_a..n_a+n_b-1 from `b`; kept points keep their order (cloud.rs:103-140).  Same ticket / state words as the scan.
-constexpr int kCompItems = 8, kCompTile = kScanThreads * kCompItems;
-__global__ void __launch_bounds__(kScanThreads) compact_lookback_kernel(const uint8_t *__restrict__ keep, size_t n, const float *__restrict__ a,
-                                                                        size_t a_stride, int n_a, const float *__restrict__ b, size_t b_stride,
-                                                                        int n_b, float *__restrict__ dst, size_t dst_stride,
-                                                                        unsigned long long *state, uint32_t *ticket, uint32_t epoch,
-                                                                        uint32_t tiles, int vec) {
-    constexpr int kWarps = kScanThreads / 32;
-    __shared__ uint32_t s_tile, s_pre;
-    __shared__ uint32_t warp_tot[kWarps];
-    PCR_GRID_DEP_SYNC();
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    if (tile >= tiles) return;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const size_t base = (size_t)tile * kCompTile + (size_t)threadIdx.x * kCompItems;
-    uint32_t flags = 0;
-    if (vec && base + kCompItems <= n) {
-        const uint2 v = *reinterpret_cast<const uint2 *>(keep + base);
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            flags |= ((v.x >> (8 * u)) & 0xffu) ? 1u << u : 0u;
-            flags |= ((v.y >> (8 * u)) & 0xffu) ? 1u << (4 + u) : 0u;
-        }
-    } else {
-#pragma unroll
-        for (int u = 0; u < kCompItems; u++)
-            if (base + u < n && keep[base + u]) flags |= 1u << u;
-    }
-    const uint32_t cnt = __popc(flags);
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t u = __shfl_up_sync(PCR_FULL, incl, o);
-        if (lane >= o) incl += u;
-    }
-    if (lane == 31) warp_tot[w] = incl;
-    __syncthreads();
-    uint32_t woff = 0, total = 0;
-#pragma unroll
-    for (int j = 0; j < kWarps; j++) {
-        const uint32_t t = warp_tot[j];
-        if (j < w) woff += t;
-        total += t;
-    }
-    if (w == 0) {
-        const uint32_t pre = scan_lookback_warp0(state, tile, epoch, total, lane);
-        if (lane == 0) s_pre = pre;
-    }
-    __syncthreads();
-    size_t p = (size_t)s_pre + woff + (incl - cnt);
-#pragma unroll
-    for (int u = 0; u < kCompItems; u++) {
-        if (!((flags >> u) & 1u)) continue;
-        const size_t i = base + u;
-        for (int r = 0; r < n_a; r++) dst[(size_t)r * dst_stride + p] = a[(size_t)r * a_stride + i];
-        for (int r = 0; r < n_b; r++) dst[(size_t)(n_a + r) * dst_stride + p] = b[(size_t)r * b_stride + i];
-        p++;
-    }
-    if (tile == tiles - 1 && threadIdx.x == 0) *ticket = 0;  // every ticket has been handed out by now
-}
-
 __global__ void __launch_bounds__(kScanThreads) scan_apply_u64_kernel(const uint32_t *__restrict__ in,
                                                                       uint64_t *__restrict__ out, size_t n,
                                                                       const uint32_t *__restrict__ tile_sums) {
@@ -581,27 +515,6 @@ static int exclusive_scan_u32_with(Ctx *ctx, uint32_t *d_data, size_t n, DevBuf 
 }
 
 int exclusive_scan_u32_dev(Ctx *ctx, uint32_t *d_data, size_t n) { return exclusive_scan_u32_with(ctx, d_data, n, ctx->b_scan, ctx->scan_epoch); }
-
-int compact_by_mask_dev(Ctx *ctx, const uint8_t *d_keep, size_t n, const float *a, size_t a_stride, int n_a, const float *b, size_t b_stride, int n_b,
-                        float *dst, size_t dst_stride) {
-    if (n == 0) return PCR_OK;
-    DevBuf &scratch = ctx->b_scan;
-    const size_t tiles = (n + kCompTile - 1) / kCompTile;
-    const size_t cap_before = scratch.cap;
-    PCR_TRY(ensure(ctx, scratch, 16 + tiles * sizeof(unsigned long long)));
-    if (scratch.cap != cap_before || ctx->scan_epoch >= (1u << 30) - 2) {  // (as exclusive_scan_u32_with)
-        PCR_CUDA(ctx, cudaMemsetAsync(scratch.p, 0, scratch.cap, ctx->stream));
-        ctx->scan_epoch = 0;
-    }
-    const uint32_t epoch = ++ctx->scan_epoch;
-    uint32_t *ticket = (uint32_t *)scratch.p;
-    unsigned long long *state = (unsigned long long *)((char *)scratch.p + 16);
-    const int vec = ((uintptr_t)d_keep & 7) == 0;
-    PCR_CUDA(ctx, launch_chained(compact_lookback_kernel, dim3((unsigned)tiles), dim3(kScanThreads), 0, ctx->stream, d_keep, n, a, a_stride, n_a, b,
-                                 b_stride, n_b, dst, dst_stride, state, ticket, epoch, (uint32_t)tiles, vec));
-    ctx->launches++;
-    return PCR_OK;
-}
 
 int exclusive_scan_u64_from_u32_dev(Ctx *ctx, const uint32_t *d_in, uint64_t *d_out, size_t n) {
     if (n == 0) {

@@ -301,9 +301,6 @@ int sor_threshold_mask_dev(Ctx *ctx, const float *d_mean_d, const uint32_t *d_fr
                            unsigned long long *d_kept);
 
 int exclusive_scan_u32_dev(Ctx *ctx, uint32_t *d_data, size_t n_plus_1);
-// one-pass compaction by a keep mask (rows 0..n_a-1 from a, then n_b rows from b), kept points in order
-int compact_by_mask_dev(Ctx *ctx, const uint8_t *d_keep, size_t n, const float *a, size_t a_stride, int n_a, const float *b, size_t b_stride, int n_b,
-                        float *dst, size_t dst_stride);
 int exclusive_scan_u64_from_u32_dev(Ctx *ctx, const uint32_t *d_in, uint64_t *d_out, size_t n);
 
 struct IcpArgs {
