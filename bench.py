@@ -404,7 +404,7 @@ def main():
         "algorithmic_bytes_per_launch": bytes_knn, "avg_launch_ms": dur_knn * 1e3,
         "note": "a 119 K-point frame is L2-resident: the kernel is bound by instruction issue and per-warp latency, not by HBM (DESIGN.md); "
                 "avg_launch_ms is the event time on the launching stream, during which the dense- and sparse-class launches share the GPU "
-                "(alone, under ncu, the kernel takes 0.094-0.099 ms: profiles/)",
+                "(alone, under ncu, the kernel takes 0.089-0.092 ms: profiles/)",
         "fp32": fp32,
         # (the library's catch-all tag "other" holds only the voxel step in this pipeline)
         "stage_ms_per_step": {("voxel" if k == "other" else k): v[0] / args.steps for k, v in stage.items() if v[1]},
