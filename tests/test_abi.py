@@ -103,6 +103,26 @@ def test_python_surface_mirrors_reference_names():
         pcr.PointCloud.from_numpy(__import__("numpy").asfortranarray(__import__("numpy").zeros((3, 3), "float32")))
 
 
+def test_normals_are_split_once_per_array():
+    """The reference's Normals are SoA (crates/core/src/cloud.rs:13-18); the mirror keeps an (N, 3) array and its split
+    form together: the split is redone only when another array is attached (a 1 M-point split costs more than the rest
+    of an ICP call's setup)."""
+    import numpy as np
+
+    import pointclouds_rs_b200 as pcr
+
+    pc = pcr.PointCloud.from_numpy(np.arange(12, dtype=np.float32).reshape(4, 3))
+    pc.normals = np.arange(12, 24, dtype=np.float32).reshape(4, 3)
+    a = pc._normals_soa()
+    assert [x.tolist() for x in a] == [[12, 15, 18, 21], [13, 16, 19, 22], [14, 17, 20, 23]]
+    assert all(x.flags["C_CONTIGUOUS"] and x.dtype == np.float32 for x in a)
+    assert pc._normals_soa()[0] is a[0]                     # same array attached: nothing recomputed
+    pc.normals = np.zeros((4, 3), np.float32)               # another array: split again
+    assert pc._normals_soa()[0] is not a[0] and pc._normals_soa()[0].tolist() == [0, 0, 0, 0]
+    sub = pc.select([1, 3])                                 # select carries the normals (cloud.rs:103-140) with a split of its own
+    assert sub.normals.shape == (2, 3) and sub._normals_soa()[1].shape == (2,)
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` needs no GPU: one bounded step of the CPU port, one JSON line with the contract's keys."""
     import json
