@@ -1062,6 +1062,35 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
 
     // ONE index serves both stages: built for the larger k, then the points SOR removes are
     // tombstoned in place (NaN coordinates) and the normals of the kept points run on the same grid.
+    // Fused form: the SOR pass searches K = max(k_sor, k_normals) + 1 neighbours once and keeps the lists;
+    // the normals of the kept points are computed from them (a kept point's nearest kept neighbours are
+    // its nearest neighbours minus the removed ones), and only the queries that lose more neighbours
+    // than the margin allows are searched again.  One KNN pass instead of two.
+    // The lists are allocated -- and their lengths, the fallback counter and the kept counters initialised -- BEFORE the
+    // index build: a memset between two kernels of the chain costs its own 2-3 us and breaks the programmatic launch
+    // behind it; up here the device is still waiting for the host.
+    const size_t K = std::max(k_sor, k_normals) + 1;
+    static const bool no_fuse = getenv("PCR_NO_LIST_REUSE") != nullptr;  // A/B hook
+    const bool may_fuse = !no_fuse && k_sor > 0 && k_normals > 0 && K <= 32 && n > 1;
+    SorLists sl;
+    bool early = false;
+    void *list_mem = nullptr;
+    FreeLater f3{nullptr, c->stream};
+    if (may_fuse) {
+        sl.K = K;
+        sl.stride = (n + 63) & ~(size_t)63;  // (>= the indexed points, whose number the build has yet to report)
+        const size_t bytes = sizeof(uint32_t) * (K * sl.stride + sl.stride + 64) + sl.stride;
+        PCR_CUDA(c, cudaMallocAsync(&list_mem, bytes, c->stream));
+        f3.p = list_mem;
+        sl.lists = (uint32_t *)list_mem;
+        sl.fallback = sl.lists + K * sl.stride;
+        sl.cnt = (uint8_t *)(sl.fallback + sl.stride + 64);
+        PCR_CUDA(c, cudaMemsetAsync(sl.fallback + sl.stride, 0, 64 * sizeof(uint32_t), c->stream));  // the fallback counter (and its padding)
+        PCR_CUDA(c, cudaMemsetAsync(sl.cnt, 0xff, sl.stride, c->stream));                            // "no list yet"
+        sl.initialised = true;
+        PCR_MARK("core: lists allocated");
+    }
+    if (k_sor > 0) PCR_CUDA(c, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long) * F, c->stream));
     BuildOpts bo;
     bo.k_hint = std::max(k_sor + 1, k_normals);
     bo.self_knn = true;
@@ -1078,17 +1107,7 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
         Index *ix;
         ~IxGuard() { index_free(ix); }
     } g{ix};
-    // Fused form: the SOR pass searches K = max(k_sor, k_normals) + 1 neighbours once and keeps the lists;
-    // the normals of the kept points are computed from them (a kept point's nearest kept neighbours are
-    // its nearest neighbours minus the removed ones), and only the queries that lose more neighbours
-    // than the margin allows are searched again.  One KNN pass instead of two.
-    const size_t K = std::max(k_sor, k_normals) + 1;
-    static const bool no_fuse = getenv("PCR_NO_LIST_REUSE") != nullptr;  // A/B hook
-    const bool fused = !no_fuse && k_sor > 0 && k_normals > 0 && K <= 32 && n > 1 && ix->n_indexed > 0;
-    SorLists sl;
-    bool early = false;
-    void *list_mem = nullptr;
-    FreeLater f3{nullptr, c->stream};
+    const bool fused = may_fuse && ix->n_indexed > 0;
     struct EarlyJoin {  // an error return between the early normals pass and its join: the lists are freed in stream order
         Ctx *c;
         bool *armed;
@@ -1096,17 +1115,6 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
             if (*armed) cudaStreamWaitEvent(c->stream, c->ev_join[0], 0);
         }
     } early_join{c, &early};
-    if (fused) {
-        sl.K = K;
-        sl.stride = (ix->n_indexed + 63) & ~(size_t)63;
-        const size_t bytes = sizeof(uint32_t) * (K * sl.stride + sl.stride + 64) + sl.stride;
-        PCR_CUDA(c, cudaMallocAsync(&list_mem, bytes, c->stream));
-        f3.p = list_mem;
-        sl.lists = (uint32_t *)list_mem;
-        sl.fallback = sl.lists + K * sl.stride;
-        sl.cnt = (uint8_t *)(sl.fallback + sl.stride + 64);
-        PCR_MARK("core: lists allocated");
-    }
     if (k_sor == 0) {  // statistical_outlier.rs:5-7: empty result
         PCR_CUDA(c, cudaMemsetAsync(d_keep, 0, n, c->stream));
         PCR_CUDA(c, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long) * F, c->stream));
@@ -1120,7 +1128,7 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
         // the normals of every query as if SOR removed nothing, beside the exact fold (which occupies 16 SMs per frame);
         // the pass after the mask only redoes the queries that lost one of their first k neighbours
         if (fused) PCR_TRY(normals_early_from_lists_dev(ix, k_normals, vp, sl, d_nx, d_ny, d_nz, &early));
-        PCR_TRY(sor_threshold_mask_dev(c, d_mean, ix->frame_in_off, F, n, std_mul, d_keep, d_stats, d_kept));
+        PCR_TRY(sor_threshold_mask_dev(c, d_mean, ix->frame_in_off, F, n, std_mul, d_keep, d_stats, d_kept, true));
         PCR_MARK("core: stats queued");
         if (F > 1 || n == 1) {  // a one-point frame is returned as is, even if the point is not finite
             single_point_frames_kernel<<<(F + 127) / 128, 128, 0, c->stream>>>(ix->frame_in_off, F, n, d_keep, d_kept);

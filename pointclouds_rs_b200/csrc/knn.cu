@@ -1696,7 +1696,7 @@ int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep
         ta.lists = keep_lists->lists;
         ta.list_cnt = keep_lists->cnt;
         ta.list_stride = keep_lists->stride;
-        PCR_CUDA(ctx, cudaMemsetAsync(keep_lists->cnt, 0xff, keep_lists->stride, ctx->stream));
+        if (!keep_lists->initialised) PCR_CUDA(ctx, cudaMemsetAsync(keep_lists->cnt, 0xff, keep_lists->stride, ctx->stream));
     }
     const int rc = run_levels(ix, q_count, kTagKnn, [&](const LevelArgs &a, int qpw) -> int {
         if (qpw == kQPW0 && keep_lists) return launch_thread_kernel<3>(ctx, a, ta);
@@ -1984,7 +1984,7 @@ int normals_from_lists_dev(Index *ix, size_t k, const float vp[3], const SorList
     const uint32_t nq = (uint32_t)ix->n_indexed;
     if (nq == 0) return PCR_OK;
     uint32_t *d_fb_count = sl.fallback + sl.stride;  // one counter behind the list
-    PCR_CUDA(ctx, cudaMemsetAsync(d_fb_count, 0, sizeof(uint32_t), ctx->stream));
+    if (!sl.initialised) PCR_CUDA(ctx, cudaMemsetAsync(d_fb_count, 0, sizeof(uint32_t), ctx->stream));
     {
         TimeScope ts(ctx, kTagKnnNormals);
         PCR_CUDA(ctx, launch_chained(early ? normals_from_lists_kernel<2> : normals_from_lists_kernel<0>, dim3((nq + kNflThreads - 1) / kNflThreads),

@@ -272,6 +272,7 @@ struct SorLists {
     uint32_t *lists = nullptr;
     uint8_t *cnt = nullptr;
     uint32_t *fallback = nullptr;  // stride + 1 entries: query ids without a usable list, then their count
+    bool initialised = false;      // cnt (0xff) and the fallback counter (0) were set by the caller, ahead of the kernels
 };
 int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep_lists = nullptr, bool allow_shard = false);
 int normals_from_lists_dev(Index *ix, size_t k, const float vp[3], const SorLists &sl, const uint8_t *d_keep, float *d_nx, float *d_ny,
@@ -298,7 +299,7 @@ int radius_fill_dev(Index *ix, const float *dqx, const float *dqy, const float *
 // per frame {mean, stddev, threshold, n_finite(as float bits)}; d_kept per-frame kept counts.
 int sor_threshold_mask_dev(Ctx *ctx, const float *d_mean_d, const uint32_t *d_frame_off /*dev, n_frames+1*/,
                            int n_frames, size_t n, float std_mul, uint8_t *d_keep, float *d_stats,
-                           unsigned long long *d_kept);
+                           unsigned long long *d_kept, bool kept_zeroed = false /* the caller zeroed d_kept earlier in the stream */);
 
 int exclusive_scan_u32_dev(Ctx *ctx, uint32_t *d_data, size_t n_plus_1);
 int exclusive_scan_u64_from_u32_dev(Ctx *ctx, const uint32_t *d_in, uint64_t *d_out, size_t n);

@@ -82,11 +82,11 @@ __global__ void __launch_bounds__(256) sor_mask_kernel(const float *__restrict__
 }  // namespace
 
 int sor_threshold_mask_dev(Ctx *ctx, const float *d_mean_d, const uint32_t *d_frame_off, int n_frames, size_t n, float std_mul,
-                           uint8_t *d_keep, float *d_stats, unsigned long long *d_kept) {
+                           uint8_t *d_keep, float *d_stats, unsigned long long *d_kept, bool kept_zeroed) {
     static_assert(sizeof(SorFrameStats) == 4 * sizeof(float), "stats layout");
     if (n == 0) return PCR_OK;
     TimeScope ts(ctx, kTagSorStats);
-    PCR_CUDA(ctx, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long) * n_frames, ctx->stream));  // (before the kernels: they chain)
+    if (!kept_zeroed) PCR_CUDA(ctx, cudaMemsetAsync(d_kept, 0, sizeof(unsigned long long) * n_frames, ctx->stream));  // (before the kernels: they chain)
     {
         // a cluster of 8 CTAs per frame (one CTA for small frames: fewer cluster barriers)
         // 16 CTAs per frame for long frames (non-portable cluster size: fewer cluster-wide passes per fold)
