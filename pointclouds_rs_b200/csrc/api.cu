@@ -1127,8 +1127,9 @@ static int batch_core(Ctx *c, const float *dx, const float *dy, const float *dz,
         PCR_MARK("core: sor search done");
         // the normals of every query as if SOR removed nothing, beside the exact fold (which occupies 16 SMs per frame);
         // the pass after the mask only redoes the queries that lost one of their first k neighbours
-        if (fused) PCR_TRY(normals_early_from_lists_dev(ix, k_normals, vp, sl, d_nx, d_ny, d_nz, &early));
+        if (fused) PCR_TRY(normals_early_fork(c));
         PCR_TRY(sor_threshold_mask_dev(c, d_mean, ix->frame_in_off, F, n, std_mul, d_keep, d_stats, d_kept, true));
+        if (fused) PCR_TRY(normals_early_from_lists_dev(ix, k_normals, vp, sl, d_nx, d_ny, d_nz, &early));
         PCR_MARK("core: stats queued");
         if (F > 1 || n == 1) {  // a one-point frame is returned as is, even if the point is not finite
             single_point_frames_kernel<<<(F + 127) / 128, 128, 0, c->stream>>>(ix->frame_in_off, F, n, d_keep, d_kept);

@@ -1952,15 +1952,22 @@ __global__ void __launch_bounds__(kNflThreads) normals_from_lists_kernel(const f
 // The early pass (MODE 1 above) on a side stream, forked from the main stream's current position (the searches are done, the
 // lists complete); `ev_join[0]` marks its end.  The caller makes the main stream wait for that event before the index is
 // tombstoned and the fix-up pass runs (normals_from_lists_dev with early = true).
+// (the fork: where in the main stream the side stream's pass may start -- recorded BEFORE the fold is launched, the pass
+// itself queued AFTER it, so that the fold's cluster, which needs 16 empty SMs, is first in line.  Measured: no difference
+// on the single frame -- the fold reads 65 us beside the pass either way, 58 us without it -- 10.8 -> 10.7 ms on the batch.)
+int normals_early_fork(Ctx *ctx) {
+    PCR_TRY(ensure_side_streams(ctx));
+    PCR_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    return PCR_OK;
+}
+
 int normals_early_from_lists_dev(Index *ix, size_t k, const float vp[3], const SorLists &sl, float *d_nx, float *d_ny, float *d_nz, bool *launched) {
     Ctx *ctx = ix->ctx;
     *launched = false;
     static const bool off = getenv("PCR_NO_EARLY_NORMALS") != nullptr;  // A/B hook
     const uint32_t nq = (uint32_t)ix->n_indexed;
     if (off || ix->n == 0 || k == 0 || nq == 0) return PCR_OK;
-    PCR_TRY(ensure_side_streams(ctx));
-    PCR_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-    PCR_CUDA(ctx, cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork, 0));
+    PCR_CUDA(ctx, cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork, 0));  // (normals_early_fork)
     {
         StreamSwap sw(ctx, ctx->side[0]);
         TimeScope ts(ctx, kTagKnnNormals);

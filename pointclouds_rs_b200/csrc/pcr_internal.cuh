@@ -278,6 +278,7 @@ int sor_mean_dist_dev(Index *ix, size_t k, float *d_mean_d, const SorLists *keep
 int normals_from_lists_dev(Index *ix, size_t k, const float vp[3], const SorLists &sl, const uint8_t *d_keep, float *d_nx, float *d_ny,
                            float *d_nz,
                            const unsigned long long *d_kept0 = nullptr, unsigned long long *h_kept0 = nullptr, bool early = false);
+int normals_early_fork(Ctx *ctx);
 int normals_early_from_lists_dev(Index *ix, size_t k, const float vp[3], const SorLists &sl, float *d_nx, float *d_ny, float *d_nz, bool *launched);
 // normals of every point of the indexed cloud(s); points not indexed get (0,0,1) (no neighbours)
 int normals_dev(Index *ix, size_t k, const float vp[3], float *d_nx, float *d_ny, float *d_nz,
