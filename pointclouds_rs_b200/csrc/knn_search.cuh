@@ -189,10 +189,17 @@ __device__ __forceinline__ void scan_runs(TopK &tk, const float4 *__restrict__ p
         pri &= pri - 1;
         scan_run(tk, pts, __shfl_sync(PCR_FULL, b, s), __shfl_sync(PCR_FULL, e, s), qx, qy, qz);
     }
-    while (ne) {
-        int s = __ffs(ne) - 1;
-        ne &= ne - 1;
-        if (__shfl_sync(PCR_FULL, gp, s) > warp_tau_cells(tk, inv_h2)) continue;
+    // Nearest run first (one redux per run on gap bits | lane): the list tightens as early as it can, and the runs beyond
+    // the current k-th best are skipped when their turn comes.  A point metres above a
+    // dense surface used to stream the whole footprint of the shell in which the surface first appears (the rows were
+    // taken in lane order, the far corner first); now it reads the row below it and little else.
+    uint32_t order = ((ne >> tk.lane) & 1u) ? ((__float_as_uint(gp) & ~31u) | (uint32_t)tk.lane) : 0xffffffffu;  // (gp >= 0: its bits order like its value)
+    for (;;) {
+        const uint32_t m = __reduce_min_sync(PCR_FULL, order);
+        if (m == 0xffffffffu) break;
+        const int s = (int)(m & 31u);
+        if (tk.lane == s) order = 0xffffffffu;
+        if (__shfl_sync(PCR_FULL, gp, s) > warp_tau_cells(tk, inv_h2)) continue;  // (not "break": the order key drops 5 bits of the gap)
         scan_run(tk, pts, __shfl_sync(PCR_FULL, b, s), __shfl_sync(PCR_FULL, e, s), qx, qy, qz);
     }
 }
