@@ -49,8 +49,9 @@
 extern "C" {
 #endif
 
-#define PCR_B200_VERSION 121 /* 0.1.1: + voxel, cluster, RANSAC, device-resident clouds; 111/112: + block upload / download, nowait;
-                                0.2.0 (120): + query sharding over a communicator, frame-stream hint statistics; 121: + pcr_ctx_comm_kind */
+#define PCR_B200_VERSION 122 /* 0.1.1: + voxel, cluster, RANSAC, device-resident clouds; 111/112: + block upload / download, nowait;
+                                0.2.0 (120): + query sharding over a communicator, frame-stream hint statistics; 121: + pcr_ctx_comm_kind;
+                                122: + pcr_cloud_upload_rows / _download_rows */
 
 typedef enum pcr_status {
     PCR_OK = 0,
@@ -317,6 +318,12 @@ int pcr_cloud_upload_block(pcr_ctx *ctx, const float *xyz, size_t stride, size_t
  * depends on the cloud (any filter's result, a download) or pcr_ctx_synchronize has returned. */
 int pcr_cloud_upload_block_nowait(pcr_ctx *ctx, const float *xyz, size_t stride, size_t n, pcr_cloud **out);
 int pcr_cloud_download_block(const pcr_cloud *cloud, float *dst, size_t stride, int with_normals);
+/* The PyO3 surface takes and returns row-major (N, 3) arrays (crates/python/src/cloud.rs:25-53, from_numpy / to_numpy,
+ * which copy between that layout and the SoA vectors on the host).  Here the copy crosses PCIe as it is -- one contiguous
+ * transfer -- and the (de)interleaving runs on the device: `xyz` is n rows of x, y, z; `normals` (NULL: not wanted) n rows
+ * of nx, ny, nz, PCR_ERR_INVALID_ARG if wanted from a cloud without normals. */
+int pcr_cloud_upload_rows(pcr_ctx *ctx, const float *xyz, size_t n, pcr_cloud **out);
+int pcr_cloud_download_rows(const pcr_cloud *cloud, float *xyz, float *normals);
 /* device pointers of the SoA arrays (valid until the cloud is freed; normals NULL if absent) */
 int pcr_cloud_device_pointers(const pcr_cloud *cloud, const float **d_x, const float **d_y, const float **d_z,
                               const float **d_nx, const float **d_ny, const float **d_nz);

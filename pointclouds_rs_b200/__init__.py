@@ -609,7 +609,15 @@ class DeviceCloud:
 
     @staticmethod
     def from_numpy(array, ctx: Optional[Context] = None) -> "DeviceCloud":
-        return DeviceCloud.from_cloud(PointCloud.from_numpy(array), ctx)
+        """(N, 3) float32 / float64, C-contiguous (crates/python/src/cloud.rs:25-37).  A float32 array crosses PCIe as it is
+        and is split into SoA on the device (pcr_cloud_upload_rows): splitting 122 K points with numpy costs more than the
+        whole voxel -> SOR -> normals pipeline."""
+        if isinstance(array, np.ndarray) and array.dtype == np.float32 and array.ndim == 2 and array.shape[1] == 3 and array.flags["C_CONTIGUOUS"]:
+            ctx = ctx or default_context()
+            h = C.c_void_p()
+            _ffi.check(_ffi.load().pcr_cloud_upload_rows(ctx._h, array.ctypes.data, len(array), C.byref(h)), ctx._h)
+            return DeviceCloud(h, ctx)
+        return DeviceCloud.from_cloud(PointCloud.from_numpy(array), ctx)  # (same checks and errors as the host class)
 
     @staticmethod
     def from_cloud(cloud: PointCloud, ctx: Optional[Context] = None) -> "DeviceCloud":
@@ -672,18 +680,16 @@ class DeviceCloud:
         return f"DeviceCloud(n={self.len()}, normals={self.has_normals()})"
 
     def to_numpy(self) -> np.ndarray:
-        n = self.len()
-        x, y, z = (np.zeros(max(n, 1), np.float32) for _ in range(3))
-        _ffi.check(_ffi.load().pcr_cloud_download(self._h, x.ctypes.data, y.ctypes.data, z.ctypes.data), self._ctx._h)
-        return np.stack([x[:n], y[:n], z[:n]], axis=1)
+        out = np.empty((self.len(), 3), np.float32)  # (interleaved on the device: one contiguous transfer)
+        _ffi.check(_ffi.load().pcr_cloud_download_rows(self._h, out.ctypes.data, None), self._ctx._h)
+        return out
 
     def normals_to_numpy(self) -> Optional[np.ndarray]:
         if not self.has_normals():
             return None
-        n = self.len()
-        x, y, z = (np.zeros(max(n, 1), np.float32) for _ in range(3))
-        _ffi.check(_ffi.load().pcr_cloud_download_normals(self._h, x.ctypes.data, y.ctypes.data, z.ctypes.data), self._ctx._h)
-        return np.stack([x[:n], y[:n], z[:n]], axis=1)
+        out = np.empty((self.len(), 3), np.float32)
+        _ffi.check(_ffi.load().pcr_cloud_download_rows(self._h, None, out.ctypes.data), self._ctx._h)
+        return out
 
     def to_cloud(self) -> PointCloud:
         a = self.to_numpy()

@@ -113,6 +113,8 @@ SIGNATURES = {
     "pcr_cloud_has_normals": (C.c_int, [vp]),
     "pcr_cloud_download": (C.c_int, [vp, vp, vp, vp]),
     "pcr_cloud_download_normals": (C.c_int, [vp, vp, vp, vp]),
+    "pcr_cloud_upload_rows": (C.c_int, [vp, vp, C.c_size_t, C.POINTER(vp)]),
+    "pcr_cloud_download_rows": (C.c_int, [vp, vp, vp]),
     "pcr_cloud_device_pointers": (C.c_int, [vp] + [C.POINTER(vp)] * 6),
     "pcr_cloud_select": (C.c_int, [vp, u32p, C.c_size_t, C.POINTER(vp)]),
     "pcr_cloud_voxel_downsample": (C.c_int, [vp, C.c_float, C.POINTER(vp)]),

@@ -1293,6 +1293,26 @@ __global__ void compact_kernel(const float *__restrict__ a, size_t a_stride, int
     for (int r = 0; r < n_b; r++) dst[(size_t)(n_a + r) * dst_stride + p] = b[(size_t)r * b_stride + i];
 }
 
+// (N, 3) rows <-> SoA rows, 256 points per block through shared memory so that both sides are coalesced
+__global__ void __launch_bounds__(256) rows_to_soa_kernel(const float *__restrict__ rows, size_t n, float *__restrict__ dst, size_t dst_stride) {
+    __shared__ float sh[768];
+    const size_t p0 = (size_t)blockIdx.x * 256;
+    const size_t m = min((size_t)256, n - p0);
+    for (size_t i = threadIdx.x; i < 3 * m; i += 256) sh[i] = rows[3 * p0 + i];
+    __syncthreads();
+    if (threadIdx.x < m)
+        for (int r = 0; r < 3; r++) dst[(size_t)r * dst_stride + p0 + threadIdx.x] = sh[3 * threadIdx.x + r];
+}
+__global__ void __launch_bounds__(256) soa_to_rows_kernel(const float *__restrict__ src, size_t src_stride, size_t n, float *__restrict__ rows) {
+    __shared__ float sh[768];
+    const size_t p0 = (size_t)blockIdx.x * 256;
+    const size_t m = min((size_t)256, n - p0);
+    if (threadIdx.x < m)
+        for (int r = 0; r < 3; r++) sh[3 * threadIdx.x + r] = src[(size_t)r * src_stride + p0 + threadIdx.x];
+    __syncthreads();
+    for (size_t i = threadIdx.x; i < 3 * m; i += 256) rows[3 * p0 + i] = sh[i];
+}
+
 __global__ void gather_kernel(const float *__restrict__ src, size_t src_stride, int n_arrays, const uint32_t *__restrict__ idx, size_t m,
                               float *__restrict__ dst, size_t dst_stride) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1424,6 +1444,66 @@ int pcr_cloud_download_normals(const pcr_cloud *cloud, float *nx, float *ny, flo
     PCR_CUDA(c, cudaMemcpyAsync(nx, cloud->nx(), sizeof(float) * cloud->n, cudaMemcpyDeviceToHost, c->stream));
     PCR_CUDA(c, cudaMemcpyAsync(ny, cloud->ny(), sizeof(float) * cloud->n, cudaMemcpyDeviceToHost, c->stream));
     PCR_CUDA(c, cudaMemcpyAsync(nz, cloud->nz(), sizeof(float) * cloud->n, cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+// Row-major (N, 3) in and out (the PyO3 surface's layout): one contiguous transfer, (de)interleaved on the device.
+int pcr_cloud_upload_rows(pcr_ctx *ctx, const float *xyz, size_t n, pcr_cloud **out) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (!out || (n && !xyz)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    pcr_cloud *cl = nullptr;
+    PCR_TRY(cloud_alloc(ctx, n, false, &cl));
+    cudaError_t e = cudaSuccess;
+    if (n) {
+        if (ensure(c, c->b_in, sizeof(float) * 3 * n) != PCR_OK) {
+            pcr_cloud_free(cl);
+            return PCR_ERR_CUDA;
+        }
+        e = cudaMemcpyAsync(c->b_in.p, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) {
+            rows_to_soa_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const float *)c->b_in.p, n, cl->base, cl->stride);
+            c->launches++;
+            e = cudaGetLastError();
+        }
+    }
+    const cudaError_t es = cudaStreamSynchronize(c->stream);  // the caller's buffer is free again on return
+    if (e == cudaSuccess) e = es;
+    if (e != cudaSuccess) {
+        pcr_cloud_free(cl);
+        return fail(c, PCR_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = cl;
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
+int pcr_cloud_download_rows(const pcr_cloud *cloud, float *xyz, float *normals) {
+    PCR_CLOUD_CHECK(cloud)
+    if (normals && !cloud->has_normals) return fail(c, PCR_ERR_INVALID_ARG, "the cloud has no normals");
+    if (cloud->n && !xyz && !normals) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (!cloud->n) return PCR_OK;
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    const size_t n = cloud->n, row = sizeof(float) * 3 * n;
+    PCR_TRY(ensure(c, c->b_out, 2 * row));
+    float *d_xyz = (float *)c->b_out.p, *d_nrm = d_xyz + 3 * n;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (xyz) {
+        soa_to_rows_kernel<<<blocks, 256, 0, c->stream>>>(cloud->base, cloud->stride, n, d_xyz);
+        PCR_LAUNCH_CHECK(c);
+        PCR_CUDA(c, cudaMemcpyAsync(xyz, d_xyz, row, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (normals) {
+        soa_to_rows_kernel<<<blocks, 256, 0, c->stream>>>(cloud->nx(), cloud->stride, n, d_nrm);
+        PCR_LAUNCH_CHECK(c);
+        PCR_CUDA(c, cudaMemcpyAsync(normals, d_nrm, row, cudaMemcpyDeviceToHost, c->stream));
+    }
     PCR_CUDA(c, cudaStreamSynchronize(c->stream));
     return PCR_OK;
     PCR_API_END(c)

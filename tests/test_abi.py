@@ -24,7 +24,7 @@ def test_header_symbols_are_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in pcr_b200.h but not exported"
     assert set(names) == set(_ffi.SIGNATURES), set(names) ^ set(_ffi.SIGNATURES)
-    assert lib.pcr_version() == 121
+    assert lib.pcr_version() == 122
 
 
 def test_no_torch_in_library_dependencies():

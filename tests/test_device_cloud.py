@@ -8,6 +8,30 @@ from pointclouds_rs_b200 import scenes
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("n", [0, 1, 2, 255, 256, 257, 100_003])
+def test_rows_in_and_out_are_the_soa_arrays(pcr, n):
+    """(N, 3) rows cross PCIe as they are and are split / interleaved on the device (pcr_cloud_upload_rows /
+    _download_rows): same bits as the SoA transfers, NaN / inf / -0.0 included, whatever the tail of the last block."""
+    rng = np.random.default_rng(n)
+    pts = rng.uniform(-50, 50, (n, 3)).astype(np.float32)
+    if n > 2:
+        pts[1] = [np.nan, -0.0, np.inf]
+    d = pcr.DeviceCloud.from_numpy(pts)                                  # rows path (float32, C-contiguous)
+    s = pcr.DeviceCloud.from_cloud(pcr.PointCloud.from_numpy(pts))       # SoA path
+    assert len(d) == n == len(s)
+    x, y, z = (np.zeros(max(n, 1), np.float32) for _ in range(3))
+    d.download_raw(x.ctypes.data, y.ctypes.data, z.ctypes.data)          # SoA download of the rows upload
+    assert np.array_equal(np.stack([x[:n], y[:n], z[:n]], 1).view(np.uint32), pts.view(np.uint32))
+    assert np.array_equal(s.to_numpy().view(np.uint32), pts.view(np.uint32))   # rows download of the SoA upload
+    assert pcr.DeviceCloud.from_numpy(pts.astype(np.float64)).to_numpy().shape == (n, 3)   # other dtypes: the host class's path
+    if n >= 256:
+        dn = d.estimate_normals(8)
+        nx, ny, nz = (np.zeros(n, np.float32) for _ in range(3))
+        dn.download_raw(x.ctypes.data, y.ctypes.data, z.ctypes.data, nx.ctypes.data, ny.ctypes.data, nz.ctypes.data)
+        assert np.array_equal(dn.normals_to_numpy().view(np.uint32), np.stack([nx, ny, nz], 1).view(np.uint32))
+    assert d.normals_to_numpy() is None
+
+
 def test_upload_download_select(pcr):
     rng = np.random.default_rng(0)
     pts = rng.uniform(-5, 5, (5000, 3)).astype(np.float32)
