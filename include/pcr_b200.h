@@ -51,7 +51,7 @@ extern "C" {
 
 #define PCR_B200_VERSION 122 /* 0.1.1: + voxel, cluster, RANSAC, device-resident clouds; 111/112: + block upload / download, nowait;
                                 0.2.0 (120): + query sharding over a communicator, frame-stream hint statistics; 121: + pcr_ctx_comm_kind;
-                                122: + pcr_cloud_upload_rows / _download_rows */
+                                122: + pcr_cloud_upload_rows / _download_rows, pcr_sor_normals_batch_rows */
 
 typedef enum pcr_status {
     PCR_OK = 0,
@@ -290,6 +290,11 @@ int pcr_sor_normals_batch(pcr_ctx *ctx, const float *x, const float *y, const fl
                           const uint64_t *frame_offsets, size_t n_frames, size_t k_sor,
                           float std_mul, size_t k_normals, const float viewpoint[3], uint8_t *keep,
                           float *nx, float *ny, float *nz, uint64_t *n_kept_per_frame);
+/* The same for the PyO3 surface's layout: `xyz` and `normals` are row-major (N, 3) blocks (see pcr_cloud_upload_rows);
+ * one contiguous transfer each way, split / interleaved on the device. */
+int pcr_sor_normals_batch_rows(pcr_ctx *ctx, const float *xyz, const uint64_t *frame_offsets, size_t n_frames,
+                               size_t k_sor, float std_mul, size_t k_normals, const float viewpoint[3],
+                               uint8_t *keep, float *normals, uint64_t *n_kept_per_frame);
 int pcr_sor_normals_batch_dev(pcr_ctx *ctx, const float *d_x, const float *d_y, const float *d_z,
                               const uint64_t *frame_offsets /* HOST */, size_t n_frames,
                               size_t k_sor, float std_mul, size_t k_normals,

@@ -1509,6 +1509,54 @@ int pcr_cloud_download_rows(const pcr_cloud *cloud, float *xyz, float *normals) 
     PCR_API_END(c)
 }
 
+int pcr_sor_normals_batch_rows(pcr_ctx *ctx, const float *xyz, const uint64_t *frame_offsets, size_t n_frames, size_t k_sor, float std_mul,
+                               size_t k_normals, const float viewpoint[3], uint8_t *keep, float *normals, uint64_t *n_kept_per_frame) {
+    if (!ctx) return fail(nullptr, PCR_ERR_INVALID_ARG, "ctx is NULL");
+    Ctx *c = &ctx->c;
+    if (n_frames == 0) return PCR_OK;
+    if (!frame_offsets) return fail(c, PCR_ERR_INVALID_ARG, "frame_offsets is NULL");
+    const size_t n = (size_t)frame_offsets[n_frames];
+    if (n_kept_per_frame) memset(n_kept_per_frame, 0, sizeof(uint64_t) * n_frames);
+    if (n == 0) return PCR_OK;
+    if (!xyz || !keep || !viewpoint || (k_normals && !normals)) return fail(c, PCR_ERR_INVALID_ARG, "null pointer");
+    if (!std::isfinite(std_mul) || std_mul < 0.f) return fail(c, PCR_ERR_INVALID_ARG, "std_mul must be >= 0 and finite");
+    if (k_sor + 1 > PCR_MAX_K || k_normals > PCR_MAX_K) return fail(c, PCR_ERR_UNSUPPORTED, "k exceeds PCR_MAX_K");
+    if (n_frames > 65535) return fail(c, PCR_ERR_UNSUPPORTED, "at most 65535 frames per batch");
+    PCR_API_BEGIN
+    DevSetter ds(c);
+    const size_t stride = (n + 63) & ~(size_t)63;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    // b_in: x | y | z (stride apart) | the rows as uploaded;  b_out: nx | ny | nz | keep | kept | the normals as rows
+    PCR_TRY(ensure(c, c->b_in, sizeof(float) * (3 * stride + 3 * n)));
+    float *dx = (float *)c->b_in.p, *d_rows = dx + 3 * stride;
+    PCR_CUDA(c, cudaMemcpyAsync(d_rows, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    rows_to_soa_kernel<<<blocks, 256, 0, c->stream>>>(d_rows, n, dx, stride);
+    PCR_LAUNCH_CHECK(c);
+    const size_t o_keep = stride * 3 * sizeof(float);
+    const size_t o_kept = o_keep + ((n + 255) & ~(size_t)255);
+    const size_t o_rows = (o_kept + sizeof(unsigned long long) * n_frames + 255) & ~(size_t)255;
+    PCR_TRY(ensure(c, c->b_out, o_rows + sizeof(float) * 3 * n));
+    float *dnx = (float *)c->b_out.p, *dny = dnx + stride, *dnz = dny + stride;
+    uint8_t *d_keep = (uint8_t *)c->b_out.p + o_keep;
+    unsigned long long *d_kept = (unsigned long long *)((char *)c->b_out.p + o_kept);
+    float *d_nrows = (float *)((char *)c->b_out.p + o_rows);
+    PCR_TRY(batch_core(c, dx, dx + stride, dx + 2 * stride, frame_offsets, n_frames, n, k_sor, std_mul, k_normals, viewpoint, d_keep, dnx, dny, dnz,
+                       d_kept));
+    PCR_CUDA(c, cudaMemcpyAsync(keep, d_keep, n, cudaMemcpyDeviceToHost, c->stream));
+    if (k_normals) {
+        soa_to_rows_kernel<<<blocks, 256, 0, c->stream>>>(dnx, stride, n, d_nrows);
+        PCR_LAUNCH_CHECK(c);
+        PCR_CUDA(c, cudaMemcpyAsync(normals, d_nrows, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    }
+    std::vector<unsigned long long> hk(n_frames);
+    PCR_CUDA(c, cudaMemcpyAsync(hk.data(), d_kept, sizeof(unsigned long long) * n_frames, cudaMemcpyDeviceToHost, c->stream));
+    PCR_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (n_kept_per_frame)
+        for (size_t f = 0; f < n_frames; f++) n_kept_per_frame[f] = hk[f];
+    return PCR_OK;
+    PCR_API_END(c)
+}
+
 // One strided copy each way for callers that keep their SoA arrays in one block (x | y | z [| nx | ny | nz], `stride`
 // floats apart): a single cudaMemcpy2DAsync instead of three or six separate transfers.
 static int upload_block(pcr_ctx *ctx, const float *xyz, size_t stride, size_t n, pcr_cloud **out, bool wait);
